@@ -1,0 +1,95 @@
+"""ctypes binding of libpp_b200.so (include/pp_b200.h).
+
+There is no CPU fallback: if the shared object is missing and cannot be built, or a call returns
+an error, this module raises.  PyTorch is only used by the callers for device memory and streams.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+PP_OK = 0
+PP_F32, PP_F64, PP_I64 = 0, 1, 2
+PP_MAX_SWEEPS = 64
+STATUS_NEG_IOU, STATUS_BAD_POINT, STATUS_BAD_INDEX, STATUS_CAND_OVERFLOW = 1, 2, 4, 8
+
+
+class PPGrid(ctypes.Structure):
+    """pp_grid: the nine doubles create_pillars takes positionally (data/pillars.cpp:241-249)."""
+    _fields_ = [(n, ctypes.c_double) for n in (
+        "x_step", "y_step", "x_min", "y_min", "z_min", "x_max", "y_max", "z_max", "canvas_height")]
+
+
+class PPError(RuntimeError):
+    pass
+
+
+_lib = None
+_c = ctypes
+_vp, _i32, _i64, _sz, _f32, _f64 = _c.c_void_p, _c.c_int32, _c.c_int64, _c.c_size_t, _c.c_float, _c.c_double
+_gridp = _c.POINTER(PPGrid)
+_i64p = _c.POINTER(_c.c_int64)
+
+_SIGNATURES = {
+    "pp_version": (_c.c_int, []),
+    "pp_error_string": (_c.c_char_p, [_c.c_int]),
+    "pp_last_cuda_error": (_c.c_int, []),
+    "pp_pillarize_workspace_bytes": (_sz, [_i32, _i64, _gridp, _i32]),
+    "pp_pillarize": (_c.c_int, [_vp, _i32, _i64, _i64, _i64p, _i32, _gridp, _i32, _i32, _vp, _vp,
+                                _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pp_pillarize_compact": (_c.c_int, [_vp, _i32, _i64, _i64, _i64, _gridp, _i32, _i32, _vp, _vp,
+                                        _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pp_pfn_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+    "pp_pfn_forward": (_c.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _i32, _f32, _f32, _vp, _vp, _sz, _vp]),
+    "pp_scatter": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "pp_pfn_scatter": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _vp, _i32, _f32, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _sz,
+                                  _vp]),
+    "pp_make_ious": (_c.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "pp_anchor_index_bytes": (_sz, [_vp, _i64]),
+    "pp_anchor_index_build": (_c.c_int, [_vp, _i64, _vp, _sz, _vp]),
+    "pp_assign_targets_workspace_bytes": (_sz, [_i32, _i64, _i64, _vp]),
+    "pp_assign_targets": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64p,
+                                     _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load libpp_b200.so, building it with nvcc first if it is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or (_build.is_stale() and os.access(os.path.dirname(path), os.W_OK)):
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            if not os.path.exists(path):
+                raise PPError("libpp_b200.so is missing and could not be built (no CPU fallback "
+                              "exists): %s" % e) from e
+    L = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(L, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != PP_OK:
+        L = load()
+        msg = L.pp_error_string(rc).decode()
+        raise PPError("%s failed: %s (code %d, cudaError %d)" % (what, msg, rc, L.pp_last_cuda_error()))
+
+
+def i64_array(values):
+    arr = (ctypes.c_int64 * len(values))(*[int(v) for v in values])
+    return arr

@@ -1,0 +1,586 @@
+// pfn.cu -- K2: PPFeatureNet (1x1 conv 9->C, ReLU, BatchNorm, max over N) and PPScatter for
+// sm_100a.  Replaces model/model.py:31-40 and :53-62 of the reference.
+//
+// Algebra.  ReLU and BatchNorm are per-channel monotone maps, so
+//     max_n BN(relu(y_n)) = BN(relu(max_n y_n))   when gamma*invstd >= 0
+//                         = BN(relu(min_n y_n))   otherwise,
+// with y = W x + b.  One pass over x therefore only has to keep, per (b,p,c), the running max and
+// min of y and, in training mode, the per-channel sums of relu(y) and relu(y)^2 over (B,P,N);
+// the [B,C,P,N] intermediate the reference materialises four times never exists.
+//
+// Kernels
+//   k_pfn_stats   persistent, one CTA per SM, one pillar row per warp at a time.  The nine
+//                 feature rows of a pillar ([9][N] floats) are fetched into a per-warp shared
+//                 memory ring by 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), the
+//                 weights live in registers (2 channels per lane), x is read by warp-wide
+//                 broadcast LDS.128.  Slots whose nine features are all zero give y == b exactly
+//                 and are only counted (the tensor is ~98.7 % padding when no data_mean is used).
+//                 Output: ext[b,p,{max,min},c] (channel-contiguous, coalesced) + per-CTA partial
+//                 sums in fp64 (fixed reduction order => run-to-run deterministic).
+//   k_bn_finalize per-channel batch statistics -> affine (mean, scale, beta, use-min), running
+//                 statistics update exactly as nn.BatchNorm2d.
+//   k_pfn_out     ext -> out[B,C,P] (transpose through shared memory).
+//   k_build_map   inds -> cell->pillar map;  k_canvas  dense, fully coalesced canvas write
+//                 (zeros + gathered pillars), from ext (+affine) or from a [B,C,P] feature tensor.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace pp {
+
+constexpr int kD = 9;
+constexpr int kWarps = 8;          // warps per CTA in k_pfn_stats
+constexpr int kMaxChunk = 256;     // slots per shared-memory tile row
+constexpr int kStages = 3;
+
+// ---- mbarrier / bulk-copy PTX (sm_90+ / sm_100a) -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+struct Affine {   // per channel, produced by k_bn_finalize
+  float mean, scale, beta, use_min;
+};
+
+// ------------------------------------------------------------------------------------------
+// work item = (row r = b*P+p, chunk k of the N axis); rows are dealt round-robin to warps.
+template <int CPL, bool TRAIN>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+k_pfn_stats(const float* __restrict__ x, int B, int P, int N, int chunk, int nchunks, bool use_bulk,
+            const float* __restrict__ conv_w, const float* __restrict__ conv_b,
+            float* __restrict__ ext, double* __restrict__ partials) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int C = CPL * 32;
+  const int warp = threadIdx.x >> 5;
+  const unsigned lane = lane_id();
+  const int tile_floats = kD * chunk;
+  float* tiles = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kStages * tile_floats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * kStages * tile_floats * 4) +
+                   warp * kStages;
+  __shared__ double s_red[kWarps][2][64];
+
+  // weights of this lane's channels in registers
+  float w[CPL][kD], bias[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = CPL * lane + j;
+    bias[j] = conv_b[c];
+#pragma unroll
+    for (int d = 0; d < kD; ++d) w[j][d] = conv_w[c * kD + d];
+  }
+
+  if (use_bulk && lane == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+
+  const long long rows = (long long)B * P;
+  const long long gw = (long long)blockIdx.x * kWarps + warp;   // global warp id
+  const long long nw = (long long)gridDim.x * kWarps;
+  const long long my_rows = gw < rows ? (rows - gw + nw - 1) / nw : 0;
+  const long long my_items = my_rows * nchunks;
+  const size_t PN = (size_t)P * N;
+
+  auto issue = [&](long long item) {
+    const long long r = gw + (item / nchunks) * nw;
+    const int k = (int)(item % nchunks);
+    const int b = (int)(r / P), p = (int)(r % P);
+    const int n0 = k * chunk;
+    const int len = min(chunk, N - n0);
+    const int stage = (int)(item % kStages);
+    float* dst = tiles + (size_t)stage * tile_floats;
+    const float* src = x + (size_t)b * kD * PN + (size_t)p * N + n0;
+    if (use_bulk) {
+      if (lane == 0) {
+        mbar_expect_tx(&bars[stage], (uint32_t)(kD * len * 4));
+#pragma unroll
+        for (int d = 0; d < kD; ++d) bulk_g2s(dst + d * chunk, src + d * PN, (uint32_t)(len * 4), &bars[stage]);
+      }
+    } else {
+      for (int d = 0; d < kD; ++d)
+        for (int n = lane; n < len; n += 32) dst[d * chunk + n] = __ldg(src + d * PN + n);
+    }
+  };
+
+  double accS[CPL], accQ[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { accS[j] = 0.0; accQ[j] = 0.0; }
+
+  if (use_bulk) {
+    for (long long it = 0; it < my_items && it < kStages; ++it) issue(it);
+  }
+
+  float mx[CPL], mn[CPL], rs[CPL], rq[CPL];
+  int nz = 0;
+  for (long long it = 0; it < my_items; ++it) {
+    const int k = (int)(it % nchunks);
+    const int stage = (int)(it % kStages);
+    const int n0 = k * chunk;
+    const int len = min(chunk, N - n0);
+    if (k == 0) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) { mx[j] = -INFINITY; mn[j] = INFINITY; rs[j] = 0.f; rq[j] = 0.f; }
+      nz = 0;
+    }
+    if (use_bulk) {
+      mbar_wait(&bars[stage], (uint32_t)((it / kStages) & 1));
+    } else {
+      __syncwarp();
+      issue(it);
+      __syncwarp();
+    }
+    const float* t = tiles + (size_t)stage * tile_floats;
+
+    auto slot = [&](const float (&xv)[kD]) {
+      unsigned bits = 0;
+#pragma unroll
+      for (int d = 0; d < kD; ++d) bits |= __float_as_uint(xv[d]);
+      if ((bits & 0x7fffffffu) == 0u) { ++nz; return; }   // y == b exactly; accounted per row
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        float y = bias[j];
+#pragma unroll
+        for (int d = 0; d < kD; ++d) y = fmaf(w[j][d], xv[d], y);
+        mx[j] = fmaxf(mx[j], y);
+        mn[j] = fminf(mn[j], y);
+        if (TRAIN) {
+          const float r = fmaxf(y, 0.f);
+          rs[j] += r;
+          rq[j] = fmaf(r, r, rq[j]);
+        }
+      }
+    };
+
+    const int len4 = len & ~3;
+    for (int n = 0; n < len4; n += 4) {
+      float4 v[kD];
+#pragma unroll
+      for (int d = 0; d < kD; ++d) v[d] = *reinterpret_cast<const float4*>(t + d * chunk + n);
+      {
+        float xv[kD];
+#pragma unroll
+        for (int d = 0; d < kD; ++d) xv[d] = v[d].x;
+        slot(xv);
+#pragma unroll
+        for (int d = 0; d < kD; ++d) xv[d] = v[d].y;
+        slot(xv);
+#pragma unroll
+        for (int d = 0; d < kD; ++d) xv[d] = v[d].z;
+        slot(xv);
+#pragma unroll
+        for (int d = 0; d < kD; ++d) xv[d] = v[d].w;
+        slot(xv);
+      }
+    }
+    for (int n = len4; n < len; ++n) {
+      float xv[kD];
+#pragma unroll
+      for (int d = 0; d < kD; ++d) xv[d] = t[d * chunk + n];
+      slot(xv);
+    }
+
+    __syncwarp();
+    if (use_bulk && it + kStages < my_items) issue(it + kStages);
+
+    if (k == nchunks - 1) {
+      const long long r = gw + (it / nchunks) * nw;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        if (nz > 0) {
+          mx[j] = fmaxf(mx[j], bias[j]);
+          mn[j] = fminf(mn[j], bias[j]);
+        }
+        if (TRAIN) {
+          const double rb = (double)fmaxf(bias[j], 0.f);
+          accS[j] += (double)rs[j] + (double)nz * rb;
+          accQ[j] += (double)rq[j] + (double)nz * rb * rb;
+        }
+      }
+      float* e = ext + (size_t)r * 2 * C + CPL * lane;
+      if (CPL == 2) {
+        *reinterpret_cast<float2*>(e) = make_float2(mx[0], mx[CPL - 1]);
+        *reinterpret_cast<float2*>(e + C) = make_float2(mn[0], mn[CPL - 1]);
+      } else {
+        e[0] = mx[0];
+        e[C] = mn[0];
+      }
+    }
+  }
+
+  if (TRAIN) {
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      s_red[warp][0][CPL * lane + j] = accS[j];
+      s_red[warp][1][CPL * lane + j] = accQ[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * C) {
+      const int q = threadIdx.x / C, c = threadIdx.x % C;
+      double v = 0.0;
+      for (int wv = 0; wv < kWarps; ++wv) v += s_red[wv][q][c];
+      partials[((size_t)blockIdx.x * 2 + q) * C + c] = v;
+    }
+  }
+}
+
+__global__ void k_bn_finalize(int C, int nparts, double count, int training, float momentum,
+                              float eps, const double* __restrict__ partials,
+                              const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                              float* __restrict__ running_mean, float* __restrict__ running_var,
+                              long long* __restrict__ num_batches_tracked,
+                              Affine* __restrict__ affine) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  double mean, var;
+  if (training) {
+    double S = 0.0, Q = 0.0;
+    for (int k = 0; k < nparts; ++k) {
+      S += partials[((size_t)k * 2 + 0) * C + c];
+      Q += partials[((size_t)k * 2 + 1) * C + c];
+    }
+    mean = S / count;
+    var = Q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+    running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
+    running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
+    if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+  } else {
+    mean = (double)running_mean[c];
+    var = (double)running_var[c];
+  }
+  const double invstd = 1.0 / sqrt(var + (double)eps);
+  const double scale = (double)bn_w[c] * invstd;
+  Affine a;
+  a.mean = (float)mean;
+  a.scale = (float)scale;
+  a.beta = bn_b[c];
+  a.use_min = scale < 0.0 ? 1.f : 0.f;
+  affine[c] = a;
+}
+
+__device__ __forceinline__ float apply_affine(const Affine& a, float vmax, float vmin) {
+  const float v = fmaxf(a.use_min != 0.f ? vmin : vmax, 0.f);   // relu of the extreme pre-activation
+  return fmaf(v - a.mean, a.scale, a.beta);
+}
+
+// ext [B*P, 2, C] -> out [B, C, P]
+__global__ void __launch_bounds__(256) k_pfn_out(const float* __restrict__ ext,
+                                                 const Affine* __restrict__ affine, int P, int C,
+                                                 float* __restrict__ out) {
+  __shared__ float tile[64][33];
+  __shared__ Affine s_aff[64];
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * 32;
+  if (threadIdx.x < C) s_aff[threadIdx.x] = affine[threadIdx.x];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * C; idx += 256) {
+    const int pp = idx / C, c = idx % C;
+    if (p0 + pp < P) {
+      const float* e = ext + ((size_t)b * P + p0 + pp) * 2 * C;
+      tile[c][pp] = apply_affine(s_aff[c], e[c], e[C + c]);
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * C; idx += 256) {
+    const int c = idx / 32, pp = idx % 32;
+    if (p0 + pp < P) out[((size_t)b * C + c) * P + p0 + pp] = tile[c][pp];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_build_map(const long long* __restrict__ inds, int B, int P,
+                                                   int H, int W, int* __restrict__ map,
+                                                   int* __restrict__ status) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * P) return;
+  const long long* row = inds + i * 3;
+  if (row[0] == 0) return;                       // model/model.py:56 nonzero(inds[:,:,0])
+  const long long cx = row[1], cy = row[2];      // model/model.py:59-61: out[b,:,y_inds,x_inds]
+  if (cx < 0 || cx >= W || cy < 0 || cy >= H) {
+    atomicOr(status, PP_STATUS_BAD_INDEX);
+    return;
+  }
+  const int b = (int)(i / P);
+  atomicMax(&map[(size_t)b * H * W + cy * W + cx], (int)(i % P));
+}
+
+// Dense canvas write.  One CTA owns 128 consecutive cells of one sweep for all channels.
+//   FROM_EXT: source is ext[b*P+p][2][C] + affine (fused path); else feat[b][c][p] (PPScatter).
+template <bool FROM_EXT>
+__global__ void __launch_bounds__(256) k_canvas(const float* __restrict__ src,
+                                                const Affine* __restrict__ affine,
+                                                const int* __restrict__ map, int P, int C, int HW,
+                                                bool vec_ok, float* __restrict__ canvas) {
+  constexpr int kCells = 128, kStride = 132;
+  __shared__ __align__(16) float tile[64 * kStride];
+  __shared__ int s_slot[kCells];
+  __shared__ Affine s_aff[64];
+  const int b = blockIdx.y;
+  const int cell0 = blockIdx.x * kCells;
+  const int warp = threadIdx.x >> 5;
+  const unsigned lane = lane_id();
+  int slot = -1;
+  if (threadIdx.x < kCells) {
+    if (cell0 + (int)threadIdx.x < HW) slot = map[(size_t)b * HW + cell0 + threadIdx.x];
+    s_slot[threadIdx.x] = slot;
+  }
+  if (FROM_EXT && threadIdx.x < C) s_aff[threadIdx.x] = affine[threadIdx.x];
+  const int any = __syncthreads_or(slot >= 0);
+  float* cb = canvas + (size_t)b * C * HW + cell0;
+  const int ncell = min(kCells, HW - cell0);
+
+  if (any) {
+    // stage: warp w fills cells w*16 .. w*16+15 (uniform branch per cell)
+    for (int j = warp * 16; j < warp * 16 + 16; ++j) {
+      const int s = s_slot[j];
+      for (int c = lane; c < C; c += 32) {
+        float v = 0.f;
+        if (s >= 0) {
+          if (FROM_EXT) {
+            const float* e = src + ((size_t)b * P + s) * 2 * C;
+            v = apply_affine(s_aff[c], e[c], e[C + c]);
+          } else {
+            v = src[((size_t)b * C + c) * P + s];
+          }
+        }
+        tile[c * kStride + j] = v;
+      }
+    }
+    __syncthreads();
+  }
+  for (int c = warp; c < C; c += 8) {
+    float* row = cb + (size_t)c * HW;
+    if (vec_ok && ncell == kCells) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (any) v = *reinterpret_cast<const float4*>(&tile[c * kStride + 4 * lane]);
+      __stcs(reinterpret_cast<float4*>(row) + lane, v);
+    } else {
+      for (int j = lane; j < ncell; j += 32) row[j] = any ? tile[c * kStride + j] : 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+struct PfnWs {
+  float* ext;        // [B*P, 2, C]
+  double* partials;  // [nblocks, 2, C]
+  Affine* affine;    // [C]
+  int* map;          // [B, H*W]
+};
+
+template <class A>
+static void pfn_layout(A& a, PfnWs* ws, int B, int P, int C, int H, int W, int nblocks) {
+  auto p0 = a.template take<float>((size_t)B * P * 2 * C);
+  auto p1 = a.template take<double>((size_t)nblocks * 2 * C);
+  auto p2 = a.template take<Affine>(64);
+  auto p3 = a.template take<int>((size_t)B * H * W + 1);
+  if (ws) { ws->ext = p0; ws->partials = p1; ws->affine = p2; ws->map = p3; }
+}
+
+struct SizeArena2 {
+  size_t used = 0;
+  template <class T>
+  T* take(size_t count) { used += align_up(count * sizeof(T)); return nullptr; }
+};
+
+static int stats_blocks(long long rows) {
+  long long nb = (rows + kWarps - 1) / kWarps;
+  const int sms = sm_count();
+  if (nb > sms) nb = sms;
+  if (nb < 1) nb = 1;
+  return (int)nb;
+}
+
+static int launch_stats(const float* d_x, int B, int P, int N, int C, const float* w, const float* bias,
+                        int training, PfnWs& ws, int nblocks, cudaStream_t st) {
+  int chunk = N < kMaxChunk ? N : kMaxChunk;
+  chunk = (chunk + 3) & ~3;
+  const int nchunks = (N + chunk - 1) / chunk;
+  const bool use_bulk = (N % 4 == 0) && ((uintptr_t)d_x % 16 == 0);
+  const size_t smem = (size_t)kWarps * kStages * kD * chunk * 4 + (size_t)kWarps * kStages * 8;
+#define PP_STATS(CPL, TR)                                                                         \
+  do {                                                                                            \
+    PP_CUDA(cudaFuncSetAttribute(k_pfn_stats<CPL, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem));                                                     \
+    k_pfn_stats<CPL, TR><<<nblocks, kWarps * 32, smem, st>>>(d_x, B, P, N, chunk, nchunks, use_bulk, \
+                                                            w, bias, ws.ext, ws.partials);        \
+  } while (0)
+  if (C == 64) {
+    if (training) PP_STATS(2, true); else PP_STATS(2, false);
+  } else {
+    if (training) PP_STATS(1, true); else PP_STATS(1, false);
+  }
+#undef PP_STATS
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+static int pfn_common(const float* d_x, int B, int D, int P, int N, int C, const float* w,
+                      const float* bias, const float* bn_w, const float* bn_b, float* rm, float* rv,
+                      int64_t* nbt, int training, float momentum, float eps, PfnWs& ws, int nblocks,
+                      cudaStream_t st) {
+  int rc = launch_stats(d_x, B, P, N, C, w, bias, training, ws, nblocks, st);
+  if (rc != PP_OK) return rc;
+  k_bn_finalize<<<1, 64, 0, st>>>(C, nblocks, (double)B * P * N, training, momentum, eps,
+                                  ws.partials, bn_w, bn_b, rm, rv, (long long*)nbt, ws.affine);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+static bool pfn_args_ok(const void* x, int B, int D, int P, int N, int C, const void* w,
+                        const void* b, const void* g, const void* be, const void* rm,
+                        const void* rv) {
+  return x && w && b && g && be && rm && rv && B >= 1 && D == kD && P >= 1 && N >= 1 &&
+         (C == 32 || C == 64) && (long long)B * P < 0x7fffffffll;
+}
+
+static int canvas_launch(bool from_ext, const float* src, const Affine* aff, const int* map, int B,
+                         int P, int C, int H, int W, float* d_canvas, cudaStream_t st) {
+  const int HW = H * W;
+  const bool vec_ok = (HW % 4 == 0) && ((uintptr_t)d_canvas % 16 == 0);
+  dim3 grid((HW + 127) / 128, B);
+  if (from_ext)
+    k_canvas<true><<<grid, 256, 0, st>>>(src, aff, map, P, C, HW, vec_ok, d_canvas);
+  else
+    k_canvas<false><<<grid, 256, 0, st>>>(src, aff, map, P, C, HW, vec_ok, d_canvas);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+static int build_map(const int64_t* d_inds, int B, int P, int H, int W, int* map, int32_t* d_status,
+                     cudaStream_t st) {
+  PP_CUDA(cudaMemsetAsync(map, 0xff, (size_t)B * H * W * sizeof(int), st));
+  const long long n = (long long)B * P;
+  k_build_map<<<(int)((n + 255) / 256), 256, 0, st>>>((const long long*)d_inds, B, P, H, W, map,
+                                                      d_status);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+}  // namespace pp
+
+extern "C" {
+
+size_t pp_pfn_workspace_bytes(int32_t B, int32_t P, int32_t C, int32_t canvas_h, int32_t canvas_w) {
+  if (B < 1 || P < 1 || C < 1 || canvas_h < 0 || canvas_w < 0) return 0;
+  pp::SizeArena2 a;
+  pp::pfn_layout(a, (pp::PfnWs*)nullptr, B, P, C, canvas_h, canvas_w, pp::sm_count());
+  return a.used + pp::kAlign;
+}
+
+int pp_pfn_forward(const float* d_x, int32_t B, int32_t D, int32_t P, int32_t N, int32_t C,
+                   const float* d_conv_w, const float* d_conv_b, const float* d_bn_w,
+                   const float* d_bn_b, float* d_running_mean, float* d_running_var,
+                   int64_t* d_num_batches_tracked, int32_t training, float momentum, float eps,
+                   float* d_out, void* d_workspace, size_t workspace_bytes, pp_stream_t stream) {
+  using namespace pp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!pfn_args_ok(d_x, B, D, P, N, C, d_conv_w, d_conv_b, d_bn_w, d_bn_b, d_running_mean,
+                   d_running_var) || d_out == nullptr)
+    return D != kD || !(C == 32 || C == 64) ? PP_ERR_UNSUPPORTED : PP_ERR_INVALID_ARG;
+  Arena arena(d_workspace, workspace_bytes);
+  PfnWs ws{};
+  const int nblocks = stats_blocks((long long)B * P);
+  pfn_layout(arena, &ws, B, P, C, 0, 0, sm_count());
+  if (!arena.ok) return PP_ERR_WORKSPACE;
+  int rc = pfn_common(d_x, B, D, P, N, C, d_conv_w, d_conv_b, d_bn_w, d_bn_b, d_running_mean,
+                      d_running_var, d_num_batches_tracked, training, momentum, eps, ws, nblocks, st);
+  if (rc != PP_OK) return rc;
+  dim3 grid((P + 31) / 32, B);
+  k_pfn_out<<<grid, 256, 0, st>>>(ws.ext, ws.affine, P, C, d_out);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+int pp_scatter(const float* d_feat, const int64_t* d_inds, int32_t B, int32_t C, int32_t P,
+               int32_t canvas_h, int32_t canvas_w, float* d_canvas, int32_t* d_status,
+               void* d_workspace, size_t workspace_bytes, pp_stream_t stream) {
+  using namespace pp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_feat || !d_inds || !d_canvas || !d_status || B < 1 || P < 1 || C < 1 || canvas_h < 1 ||
+      canvas_w < 1 || (long long)canvas_h * canvas_w > 0x3fffffffll)
+    return PP_ERR_INVALID_ARG;
+  if (C > 64) return PP_ERR_UNSUPPORTED;
+  Arena arena(d_workspace, workspace_bytes);
+  int* map = arena.take<int>((size_t)B * canvas_h * canvas_w + 1);
+  if (!arena.ok) return PP_ERR_WORKSPACE;
+  int rc = build_map(d_inds, B, P, canvas_h, canvas_w, map, d_status, st);
+  if (rc != PP_OK) return rc;
+  return canvas_launch(false, d_feat, nullptr, map, B, P, C, canvas_h, canvas_w, d_canvas, st);
+}
+
+int pp_pfn_scatter(const float* d_x, const int64_t* d_inds, int32_t B, int32_t D, int32_t P,
+                   int32_t N, int32_t C, const float* d_conv_w, const float* d_conv_b,
+                   const float* d_bn_w, const float* d_bn_b, float* d_running_mean,
+                   float* d_running_var, int64_t* d_num_batches_tracked, int32_t training,
+                   float momentum, float eps, int32_t canvas_h, int32_t canvas_w, float* d_canvas,
+                   float* d_out, int32_t* d_status, void* d_workspace, size_t workspace_bytes,
+                   pp_stream_t stream) {
+  using namespace pp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!pfn_args_ok(d_x, B, D, P, N, C, d_conv_w, d_conv_b, d_bn_w, d_bn_b, d_running_mean,
+                   d_running_var))
+    return D != kD || !(C == 32 || C == 64) ? PP_ERR_UNSUPPORTED : PP_ERR_INVALID_ARG;
+  if (!d_inds || !d_canvas || !d_status || canvas_h < 1 || canvas_w < 1 ||
+      (long long)canvas_h * canvas_w > 0x3fffffffll)
+    return PP_ERR_INVALID_ARG;
+  Arena arena(d_workspace, workspace_bytes);
+  PfnWs ws{};
+  const int nblocks = stats_blocks((long long)B * P);
+  pfn_layout(arena, &ws, B, P, C, canvas_h, canvas_w, sm_count());
+  if (!arena.ok) return PP_ERR_WORKSPACE;
+  int rc = build_map(d_inds, B, P, canvas_h, canvas_w, ws.map, d_status, st);
+  if (rc != PP_OK) return rc;
+  rc = pfn_common(d_x, B, D, P, N, C, d_conv_w, d_conv_b, d_bn_w, d_bn_b, d_running_mean,
+                  d_running_var, d_num_batches_tracked, training, momentum, eps, ws, nblocks, st);
+  if (rc != PP_OK) return rc;
+  rc = canvas_launch(true, ws.ext, ws.affine, ws.map, B, P, C, canvas_h, canvas_w, d_canvas, st);
+  if (rc != PP_OK) return rc;
+  if (d_out != nullptr) {
+    dim3 grid((P + 31) / 32, B);
+    k_pfn_out<<<grid, 256, 0, st>>>(ws.ext, ws.affine, P, C, d_out);
+    PP_LAUNCH_CHECK();
+  }
+  return PP_OK;
+}
+
+}  // extern "C"

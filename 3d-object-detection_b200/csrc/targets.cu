@@ -1,0 +1,542 @@
+// targets.cu -- K3: rotated anchor-vs-GT IoU and target assignment for sm_100a.
+// Replaces data/pillars.cpp:132-172 (iou), :400-427 (make_ious) and utils/box_utils.py:70-109,
+// 162-232 (make_target, create_target) of the reference.
+//
+// IoU: the anchor ring (counter-clockwise) is clipped against the four half-planes of the GT
+// ring (clockwise, walked backwards) with Sutherland-Hodgman in fp64; every multiply, add and
+// divide is separately rounded (__dmul_rn/__dadd_rn/__ddiv_rn, no FMA contraction) so the value is
+// the one a plain IEEE-double CPU evaluation of the same formulae gives.
+//
+// Assignment never materialises the [A,G] matrix.  A uniform bucket index over anchor centres
+// (built once per anchor set) lets each GT visit only the anchors that can pass the centre
+// prefilter (|dcx|<=10 and |dcy|<=10, data/pillars.cpp:418-419).  Exact fp64 comparisons and
+// first-index tie-breaks of np.argmax are reproduced with 64-bit atomicMax on the IoU bit
+// pattern followed by atomicMin on the index among the maximisers:
+//   k_iou_pass<0>  one CTA per GT: IoU of its candidates -> atomicMax(best[a]); CTA reduction ->
+//                  top_anchor[g] (first anchor among the GT's maximisers; 0 when all IoU are 0)
+//   k_iou_pass<1>  same enumeration: candidates whose IoU equals best[a] -> atomicMin(arg[a], g);
+//                  positives (best > thresh) set a bit in posmask
+//   k_encode       dense, vectorised write of cls[A,K] and reg[A,9] (zeros + positives)
+//   k_forced       per sweep: the per-GT best-anchor overrides, in the reference's order
+#include <vector>
+
+#include "common.cuh"
+
+namespace pp {
+
+constexpr double kRadius = 10.0;  // data/pillars.cpp:418-419, hard-coded in the reference
+
+struct IndexHeader {  // first 64 bytes of the anchor index
+  double x0, y0, cell;
+  int nbx, nby;
+  long long A;
+  int max_bucket;
+  int magic;
+  long long pad[2];
+};
+static_assert(sizeof(IndexHeader) == 64, "index header must be 64 bytes");
+constexpr int kIndexMagic = 0x50504958;
+
+// ---- geometry ------------------------------------------------------------------------------
+__device__ __forceinline__ double ring_area_ccw(const double* v, int n) {
+  if (n < 3) return 0.0;
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const int j = (i + 1 == n) ? 0 : i + 1;
+    s = __dadd_rn(s, __dsub_rn(__dmul_rn(v[2 * i], v[2 * j + 1]), __dmul_rn(v[2 * j], v[2 * i + 1])));
+  }
+  return __dmul_rn(0.5, s);
+}
+
+// a: 4 corners counter-clockwise; g: 4 corners clockwise (both open rings, x,y interleaved)
+__device__ double quad_iou(const double* __restrict__ a, const double* __restrict__ g) {
+  double buf0[16], buf1[16];
+  double* subj = buf0;
+  double* nxt = buf1;
+  int n = 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) subj[i] = a[i];
+  for (int e = 0; e < 4 && n > 0; ++e) {
+    const double c0x = g[2 * (3 - e)], c0y = g[2 * (3 - e) + 1];
+    const int e1 = (6 - e) & 3;
+    const double ex = __dsub_rn(g[2 * e1], c0x), ey = __dsub_rn(g[2 * e1 + 1], c0y);
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+      const int ip = (i == 0) ? n - 1 : i - 1;
+      const double cx = subj[2 * i], cy = subj[2 * i + 1];
+      const double px = subj[2 * ip], py = subj[2 * ip + 1];
+      const double dc = __dsub_rn(__dmul_rn(ex, __dsub_rn(cy, c0y)), __dmul_rn(ey, __dsub_rn(cx, c0x)));
+      const double dp = __dsub_rn(__dmul_rn(ex, __dsub_rn(py, c0y)), __dmul_rn(ey, __dsub_rn(px, c0x)));
+      const bool cin = dc >= 0.0, pin = dp >= 0.0;
+      if (cin != pin) {
+        const double t = __ddiv_rn(dp, __dsub_rn(dp, dc));
+        nxt[2 * m] = __dadd_rn(px, __dmul_rn(t, __dsub_rn(cx, px)));
+        nxt[2 * m + 1] = __dadd_rn(py, __dmul_rn(t, __dsub_rn(cy, py)));
+        ++m;
+      }
+      if (cin) {
+        nxt[2 * m] = cx;
+        nxt[2 * m + 1] = cy;
+        ++m;
+      }
+    }
+    double* t2 = subj; subj = nxt; nxt = t2;
+    n = m;
+  }
+  if (n < 3) return 0.0;
+  const double inter = ring_area_ccw(subj, n);
+  if (!(inter > 0.0)) return 0.0;
+  const double area_a = ring_area_ccw(a, 4);
+  const double area_g = -ring_area_ccw(g, 4);
+  return __ddiv_rn(inter, __dsub_rn(__dadd_rn(area_a, area_g), inter));
+}
+
+__device__ __forceinline__ bool prefilter_far(const double* __restrict__ ac, const double* __restrict__ gc) {
+  return (fabs(__dsub_rn(ac[0], gc[0])) > kRadius) || (fabs(__dsub_rn(ac[1], gc[1])) > kRadius);
+}
+
+// ---- dense make_ious ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_make_ious(const double* __restrict__ a_corners,
+                                                   const double* __restrict__ g_corners,
+                                                   const double* __restrict__ a_centers,
+                                                   const double* __restrict__ g_centers,
+                                                   long long A, long long G,
+                                                   double* __restrict__ ious,
+                                                   int* __restrict__ status) {
+  const long long total = A * G;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / G, j = idx % G;
+    double v = 0.0;
+    if (!prefilter_far(a_centers + i * 3, g_centers + j * 3)) {
+      double a[8], g[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a[k] = a_corners[i * 8 + k]; g[k] = g_corners[j * 8 + k]; }
+      v = quad_iou(a, g);
+      if (v < 0.0) atomicOr(status, PP_STATUS_NEG_IOU);
+    }
+    ious[idx] = v;
+  }
+}
+
+// ---- sparse assignment ----------------------------------------------------------------------
+struct GtParams {
+  int n_sweeps;
+  long long off[PP_MAX_SWEEPS + 1];
+};
+
+__device__ __forceinline__ int find_gt_sweep(const GtParams& gp, long long g) {
+  int lo = 0, hi = gp.n_sweeps - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (gp.off[mid] <= g) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// PASS 0: best[a] = max IoU (as bits), top_anchor[g].  PASS 1: arg[a], posmask, counters.
+template <int PASS>
+__global__ void __launch_bounds__(256) k_iou_pass(
+    const double* __restrict__ a_corners, const double* __restrict__ a_centers,
+    const unsigned char* __restrict__ index, long long A, const double* __restrict__ g_corners,
+    const double* __restrict__ g_centers, GtParams gp, double pos_thresh,
+    unsigned long long* __restrict__ best, int* __restrict__ arg, unsigned* __restrict__ posmask,
+    int* __restrict__ top_anchor, int* __restrict__ counts, int* __restrict__ status) {
+  const long long gg = blockIdx.x;  // global GT row
+  const int b = find_gt_sweep(gp, gg);
+  const int gl = (int)(gg - gp.off[b]);  // index of the GT inside its sweep
+  const IndexHeader* hdr = reinterpret_cast<const IndexHeader*>(index);
+  const int* bucket_start = reinterpret_cast<const int*>(index + sizeof(IndexHeader));
+  const int nb = hdr->nbx * hdr->nby;
+  const int* ids = bucket_start + nb + 1;
+
+  double g[8], gc[2];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) g[k] = g_corners[gg * 8 + k];
+  gc[0] = g_centers[gg * 3];
+  gc[1] = g_centers[gg * 3 + 1];
+
+  // bucket window that can contain anchors passing the prefilter (one bucket of slack each side)
+  int bx0 = (int)floor((gc[0] - kRadius - hdr->x0) / hdr->cell) - 1;
+  int bx1 = (int)floor((gc[0] + kRadius - hdr->x0) / hdr->cell) + 1;
+  int by0 = (int)floor((gc[1] - kRadius - hdr->y0) / hdr->cell) - 1;
+  int by1 = (int)floor((gc[1] + kRadius - hdr->y0) / hdr->cell) + 1;
+  bx0 = max(bx0, 0); by0 = max(by0, 0);
+  bx1 = min(bx1, hdr->nbx - 1); by1 = min(by1, hdr->nby - 1);
+  if (!(gc[0] == gc[0]) || !(gc[1] == gc[1])) { bx1 = -1; by1 = -1; }  // NaN centre: out of contract
+
+  unsigned long long my_best = 0ull;
+  int my_a = 0x7fffffff;
+  unsigned long long* best_b = best + (size_t)b * A;
+
+  for (int by = by0; by <= by1; ++by) {
+    if (bx1 < bx0) break;
+    const int s = bucket_start[by * hdr->nbx + bx0];
+    const int e = bucket_start[by * hdr->nbx + bx1 + 1];
+    for (int k = s + (int)threadIdx.x; k < e; k += blockDim.x) {
+      const int a = ids[k];
+      if (prefilter_far(a_centers + (size_t)a * 3, gc)) continue;
+      double ar[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ar[q] = a_corners[(size_t)a * 8 + q];
+      const double v = quad_iou(ar, g);
+      if (v < 0.0) { atomicOr(status, PP_STATUS_NEG_IOU); continue; }
+      if (!(v > 0.0)) continue;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+      if (PASS == 0) {
+        atomicMax(&best_b[a], bits);
+        if (bits > my_best || (bits == my_best && a < my_a)) { my_best = bits; my_a = a; }
+      } else {
+        if (bits == best_b[a]) {
+          atomicMin(&arg[(size_t)b * A + a], gl);
+          if (v > pos_thresh) {
+            const unsigned bit = 1u << (a & 31);
+            const unsigned old = atomicOr(&posmask[(size_t)b * ((A + 31) / 32) + (a >> 5)], bit);
+            if (!(old & bit)) atomicAdd(&counts[b * 4 + 0], 1);
+          }
+          if (fabs(v - pos_thresh) < 1e-6) atomicAdd(&counts[b * 4 + 2], 1);
+        }
+      }
+    }
+  }
+
+  if (PASS == 0) {
+    // CTA reduction: max IoU bits, then min anchor index (np.argmax first-index rule, :200)
+    __shared__ unsigned long long s_best[8];
+    __shared__ int s_a[8];
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ob = __shfl_xor_sync(0xffffffffu, my_best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, my_a, o);
+      if (ob > my_best || (ob == my_best && oa < my_a)) { my_best = ob; my_a = oa; }
+    }
+    if (lane_id() == 0) { s_best[threadIdx.x >> 5] = my_best; s_a[threadIdx.x >> 5] = my_a; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+        if (s_best[w] > my_best || (s_best[w] == my_best && s_a[w] < my_a)) { my_best = s_best[w]; my_a = s_a[w]; }
+      }
+      // all-zero column -> np.argmax returns 0 -> dropped by np.nonzero (utils/box_utils.py:204)
+      top_anchor[gg] = (my_best == 0ull) ? 0 : my_a;
+    }
+  }
+}
+
+// utils/box_utils.py:70-109 in fp64.  gc is the IMAGE-space GT centre (y already flipped, which is
+// what :83 recomputes); gyaw is the unflipped yaw.
+__device__ void make_target(const double* __restrict__ ac, const double* __restrict__ awlh, double at,
+                            const double* __restrict__ gc, const double* __restrict__ gwlh,
+                            double gyaw, double out[9]) {
+  const double aw = awlh[0], al = awlh[1], ah = awlh[2];
+  const double ad = sqrt(__dadd_rn(__dmul_rn(aw, aw), __dmul_rn(al, al)));
+  out[0] = 1.0;
+  out[1] = __ddiv_rn(__dsub_rn(gc[0], ac[0]), ad);
+  out[2] = __ddiv_rn(__dsub_rn(gc[1], ac[1]), ad);
+  out[3] = __ddiv_rn(__dsub_rn(gc[2], ac[2]), ah);
+  out[4] = log(__ddiv_rn(gwlh[0], aw));
+  out[5] = log(__ddiv_rn(gwlh[1], al));
+  out[6] = log(__ddiv_rn(gwlh[2], ah));
+  const double kPi = 3.141592653589793;  // np.pi
+  double gt = gyaw;
+  if (gt <= kPi && gt >= kPi / 2) gt = __dsub_rn(gt, kPi);
+  else if (gt >= -kPi && gt <= -kPi / 2) gt = __dadd_rn(gt, kPi);
+  const double dth = __dsub_rn(gt, at);
+  out[7] = sin(dth);
+  out[8] = ((dth <= kPi && dth >= kPi / 2) || (dth >= -kPi && dth <= -kPi / 2)) ? 1.0 : 0.0;
+}
+
+struct EncodeArgs {
+  const double *a_centers, *a_wlh, *a_yaw, *g_centers, *g_wlh, *g_yaw;
+  const int* g_cls;
+  const int* arg;
+  const unsigned* posmask;
+};
+
+__device__ __forceinline__ bool is_pos(const EncodeArgs& ea, int b, long long A, long long a) {
+  return (ea.posmask[(size_t)b * ((A + 31) / 32) + (a >> 5)] >> (a & 31)) & 1u;
+}
+
+__device__ float encode_value(const EncodeArgs& ea, const GtParams& gp, int b, long long A, long long a,
+                              int col, bool is_reg) {
+  const long long gg = gp.off[b] + ea.arg[(size_t)b * A + a];
+  if (!is_reg) return ea.g_cls[gg] == col ? 1.f : 0.f;   // utils/box_utils.py:211
+  double t[9];
+  make_target(ea.a_centers + a * 3, ea.a_wlh + a * 3, ea.a_yaw[a], ea.g_centers + gg * 3,
+              ea.g_wlh + gg * 3, ea.g_yaw[gg], t);
+  return (float)t[col];                                   // utils/box_utils.py:219-221, then .float()
+}
+
+// dense write of one [A, ncol] float matrix per sweep (cls when !IS_REG, reg when IS_REG)
+template <bool IS_REG>
+__global__ void __launch_bounds__(256) k_encode(EncodeArgs ea, GtParams gp, long long A, int ncol,
+                                                bool vec_ok, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const long long total = A * ncol;
+  float* ob = out + (size_t)b * total;
+  if (vec_ok) {
+    const long long groups = total / 4;
+    for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups;
+         gi += (long long)gridDim.x * blockDim.x) {
+      const long long e0 = gi * 4;
+      const long long a0 = e0 / ncol, a1 = (e0 + 3) / ncol;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool any = is_pos(ea, b, A, a0);
+      for (long long a = a0 + 1; a <= a1; ++a) any = any || is_pos(ea, b, A, a);
+      if (any) {
+        float* vf = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const long long a = (e0 + k) / ncol;
+          const int col = (int)((e0 + k) % ncol);
+          if (is_pos(ea, b, A, a)) vf[k] = encode_value(ea, gp, b, A, a, col, IS_REG);
+        }
+      }
+      __stcs(reinterpret_cast<float4*>(ob) + gi, v);
+    }
+  } else {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+      const long long a = e / ncol;
+      float v = 0.f;
+      if (is_pos(ea, b, A, a)) v = encode_value(ea, gp, b, A, a, (int)(e % ncol), IS_REG);
+      ob[e] = v;
+    }
+  }
+}
+
+// utils/box_utils.py:212-213,226-228: per-GT best anchors override, later GT wins on reg.
+__global__ void __launch_bounds__(256) k_forced(EncodeArgs ea, GtParams gp, long long A, int ncls,
+                                                const int* __restrict__ top_anchor,
+                                                float* __restrict__ cls, float* __restrict__ reg,
+                                                int* __restrict__ counts) {
+  const int b = blockIdx.x;
+  const long long g0 = gp.off[b], g1 = gp.off[b + 1];
+  float* cb = cls + (size_t)b * A * ncls;
+  float* rb = reg + (size_t)b * A * 9;
+  int kept = 0;
+  for (long long g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
+    const int t = top_anchor[g];
+    if (t != 0) {
+      ++kept;
+      for (int c = 0; c < ncls; ++c) cb[(size_t)t * ncls + c] = 0.f;
+    }
+  }
+  __syncthreads();
+  for (long long g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
+    const int t = top_anchor[g];
+    if (t == 0) continue;
+    const int c = ea.g_cls[g];
+    if (c >= 0 && c < ncls) cb[(size_t)t * ncls + c] = 1.f;
+    bool last = true;
+    for (long long h = g + 1; h < g1; ++h) if (top_anchor[h] == t) { last = false; break; }
+    if (last) {
+      double tv[9];
+      make_target(ea.a_centers + (size_t)t * 3, ea.a_wlh + (size_t)t * 3, ea.a_yaw[t],
+                  ea.g_centers + g * 3, ea.g_wlh + g * 3, ea.g_yaw[g], tv);
+      for (int k = 0; k < 9; ++k) rb[(size_t)t * 9 + k] = (float)tv[k];
+    }
+  }
+  if (kept) atomicAdd(&counts[b * 4 + 1], kept);
+}
+
+struct TargetWs {
+  unsigned long long* best;  // [B, A]   zero-init
+  unsigned* posmask;         // [B, ceil(A/32)] zero-init
+  int* arg;                  // [B, A]   0x7f-init
+  size_t zero_bytes;
+};
+
+template <class AR>
+static void targets_layout(AR& a, TargetWs* ws, int B, long long A) {
+  size_t z0 = a.used;
+  auto p0 = a.template take<unsigned long long>((size_t)B * A);
+  auto p1 = a.template take<unsigned>((size_t)B * ((A + 31) / 32));
+  size_t z1 = a.used;
+  auto p2 = a.template take<int>((size_t)B * A);
+  if (ws) { ws->best = p0; ws->posmask = p1; ws->arg = p2; ws->zero_bytes = z1 - z0; }
+}
+
+struct SizeArena3 {
+  size_t used = 0;
+  template <class T>
+  T* take(size_t count) { used += align_up(count * sizeof(T)); return nullptr; }
+};
+
+struct HostIndex {
+  IndexHeader hdr;
+  std::vector<int> start, ids;
+};
+
+static bool build_host_index(const double* c, long long A, HostIndex& hi) {
+  if (c == nullptr || A < 1 || A > 0x7fffffffll) return false;
+  double x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+  bool any = false;
+  for (long long i = 0; i < A; ++i) {
+    const double x = c[i * 3], y = c[i * 3 + 1];
+    if (!(x == x) || !(y == y) || x > 1e300 || x < -1e300 || y > 1e300 || y < -1e300) continue;
+    if (!any) { x0 = x1 = x; y0 = y1 = y; any = true; }
+    if (x < x0) x0 = x;
+    if (x > x1) x1 = x;
+    if (y < y0) y0 = y;
+    if (y > y1) y1 = y;
+  }
+  double cell = 4.0;
+  const double ext = (x1 - x0) > (y1 - y0) ? (x1 - x0) : (y1 - y0);
+  if (ext / cell > 2048.0) cell = ext / 2048.0;
+  IndexHeader& h = hi.hdr;
+  h.x0 = x0; h.y0 = y0; h.cell = cell;
+  h.nbx = (int)floor((x1 - x0) / cell) + 1;
+  h.nby = (int)floor((y1 - y0) / cell) + 1;
+  h.A = A; h.magic = kIndexMagic; h.pad[0] = h.pad[1] = 0;
+  const int nb = h.nbx * h.nby;
+  hi.start.assign((size_t)nb + 1, 0);
+  std::vector<int> bucket((size_t)A);
+  for (long long i = 0; i < A; ++i) {
+    const double x = c[i * 3], y = c[i * 3 + 1];
+    int bx = 0, by = 0;
+    if (x == x && y == y && x <= 1e300 && x >= -1e300 && y <= 1e300 && y >= -1e300) {
+      bx = (int)floor((x - x0) / cell);
+      by = (int)floor((y - y0) / cell);
+      if (bx < 0) bx = 0; if (bx >= h.nbx) bx = h.nbx - 1;
+      if (by < 0) by = 0; if (by >= h.nby) by = h.nby - 1;
+    }
+    bucket[(size_t)i] = by * h.nbx + bx;
+    hi.start[(size_t)bucket[(size_t)i] + 1]++;
+  }
+  int mx = 0;
+  for (int k = 0; k < nb; ++k) {
+    if (hi.start[(size_t)k + 1] > mx) mx = hi.start[(size_t)k + 1];
+    hi.start[(size_t)k + 1] += hi.start[(size_t)k];
+  }
+  h.max_bucket = mx;
+  hi.ids.assign((size_t)A, 0);
+  std::vector<int> cur(hi.start.begin(), hi.start.end() - 1);
+  for (long long i = 0; i < A; ++i) hi.ids[(size_t)cur[(size_t)bucket[(size_t)i]]++] = (int)i;  // ascending ids per bucket
+  return true;
+}
+
+}  // namespace pp
+
+extern "C" {
+
+int pp_make_ious(const double* d_a_corners, const double* d_g_corners, const double* d_a_centers,
+                 const double* d_g_centers, int64_t A, int64_t G, double* d_ious,
+                 int32_t* d_status, pp_stream_t stream) {
+  using namespace pp;
+  if (A < 0 || G < 0 || d_status == nullptr) return PP_ERR_INVALID_ARG;
+  if (A == 0 || G == 0) return PP_OK;
+  if (!d_a_corners || !d_g_corners || !d_a_centers || !d_g_centers || !d_ious) return PP_ERR_INVALID_ARG;
+  const long long total = (long long)A * G;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 64;
+  if (blocks > cap) blocks = cap;
+  k_make_ious<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_a_corners, d_g_corners, d_a_centers,
+                                                            d_g_centers, A, G, d_ious, d_status);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+size_t pp_anchor_index_bytes(const double* h_a_centers, int64_t A) {
+  pp::HostIndex hi;
+  if (!pp::build_host_index(h_a_centers, A, hi)) return 0;
+  return sizeof(pp::IndexHeader) + (hi.start.size() + hi.ids.size()) * sizeof(int) + pp::kAlign;
+}
+
+int pp_anchor_index_build(const double* h_a_centers, int64_t A, void* d_index, size_t index_bytes,
+                          pp_stream_t stream) {
+  using namespace pp;
+  HostIndex hi;
+  if (d_index == nullptr || !build_host_index(h_a_centers, A, hi)) return PP_ERR_INVALID_ARG;
+  const size_t need = sizeof(IndexHeader) + (hi.start.size() + hi.ids.size()) * sizeof(int);
+  if (index_bytes < need) return PP_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* d = (unsigned char*)d_index;
+  PP_CUDA(cudaMemcpyAsync(d, &hi.hdr, sizeof(IndexHeader), cudaMemcpyHostToDevice, st));
+  PP_CUDA(cudaMemcpyAsync(d + sizeof(IndexHeader), hi.start.data(), hi.start.size() * sizeof(int),
+                          cudaMemcpyHostToDevice, st));
+  PP_CUDA(cudaMemcpyAsync(d + sizeof(IndexHeader) + hi.start.size() * sizeof(int), hi.ids.data(),
+                          hi.ids.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  PP_CUDA(cudaStreamSynchronize(st));  // host vectors die at return; one-off call
+  return PP_OK;
+}
+
+size_t pp_assign_targets_workspace_bytes(int32_t n_sweeps, int64_t A, int64_t total_gt,
+                                         const void* h_index_header) {
+  (void)total_gt; (void)h_index_header;
+  if (n_sweeps < 1 || n_sweeps > PP_MAX_SWEEPS || A < 1) return 0;
+  pp::SizeArena3 a;
+  pp::targets_layout(a, (pp::TargetWs*)nullptr, n_sweeps, A);
+  return a.used + pp::kAlign;
+}
+
+int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, const double* d_a_wlh,
+                      const double* d_a_yaw, const void* d_anchor_index, int64_t A,
+                      const double* d_g_corners, const double* d_g_centers, const double* d_g_wlh,
+                      const double* d_g_yaw, const int32_t* d_g_cls, const int64_t* h_gt_offsets,
+                      int32_t n_sweeps, int32_t num_classes, double pos_thresh, float* d_cls,
+                      float* d_reg, int32_t* d_top_anchor, int32_t* d_counts, int32_t* d_status,
+                      void* d_workspace, size_t workspace_bytes, pp_stream_t stream) {
+  using namespace pp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_a_corners || !d_a_centers || !d_a_wlh || !d_a_yaw || !d_anchor_index || A < 1 ||
+      A > 0x7fffffffll || !h_gt_offsets || n_sweeps < 1 || n_sweeps > PP_MAX_SWEEPS ||
+      num_classes < 1 || !d_cls || !d_reg || !d_counts || !d_status)
+    return PP_ERR_INVALID_ARG;
+  GtParams gp;
+  gp.n_sweeps = n_sweeps;
+  for (int s = 0; s <= n_sweeps; ++s) {
+    gp.off[s] = h_gt_offsets[s];
+    if (s > 0 && h_gt_offsets[s] < h_gt_offsets[s - 1]) return PP_ERR_INVALID_ARG;
+  }
+  if (gp.off[0] != 0) return PP_ERR_INVALID_ARG;
+  const long long Gt = gp.off[n_sweeps];
+  if (Gt > 0 && (!d_g_corners || !d_g_centers || !d_g_wlh || !d_g_yaw || !d_g_cls || !d_top_anchor))
+    return PP_ERR_INVALID_ARG;
+  if (Gt > 0x7fffffffll) return PP_ERR_INVALID_ARG;
+  Arena arena(d_workspace, workspace_bytes);
+  TargetWs ws{};
+  targets_layout(arena, &ws, n_sweeps, A);
+  if (!arena.ok) return PP_ERR_WORKSPACE;
+
+  PP_CUDA(cudaMemsetAsync(ws.best, 0, ws.zero_bytes, st));
+  PP_CUDA(cudaMemsetAsync(ws.arg, 0x7f, (size_t)n_sweeps * A * sizeof(int), st));
+  PP_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)n_sweeps * 4 * sizeof(int), st));
+  const unsigned char* idx = (const unsigned char*)d_anchor_index;
+  if (Gt > 0) {
+    k_iou_pass<0><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
+                                           d_g_centers, gp, pos_thresh, ws.best, ws.arg, ws.posmask,
+                                           d_top_anchor, d_counts, d_status);
+    PP_LAUNCH_CHECK();
+    k_iou_pass<1><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
+                                           d_g_centers, gp, pos_thresh, ws.best, ws.arg, ws.posmask,
+                                           d_top_anchor, d_counts, d_status);
+    PP_LAUNCH_CHECK();
+  }
+  EncodeArgs ea{d_a_centers, d_a_wlh, d_a_yaw, d_g_centers, d_g_wlh, d_g_yaw, d_g_cls, ws.arg, ws.posmask};
+  {
+    const long long total = (long long)A * num_classes;
+    const bool vec_ok = (total % 4 == 0) && ((uintptr_t)d_cls % 16 == 0);
+    long long blocks = ((vec_ok ? total / 4 : total) + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)n_sweeps);
+    k_encode<false><<<grid, 256, 0, st>>>(ea, gp, A, num_classes, vec_ok, d_cls);
+    PP_LAUNCH_CHECK();
+  }
+  {
+    const long long total = (long long)A * 9;
+    const bool vec_ok = (total % 4 == 0) && ((uintptr_t)d_reg % 16 == 0);
+    long long blocks = ((vec_ok ? total / 4 : total) + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)n_sweeps);
+    k_encode<true><<<grid, 256, 0, st>>>(ea, gp, A, 9, vec_ok, d_reg);
+    PP_LAUNCH_CHECK();
+  }
+  if (Gt > 0) {
+    k_forced<<<n_sweeps, 256, 0, st>>>(ea, gp, A, num_classes, d_top_anchor, d_cls, d_reg, d_counts);
+    PP_LAUNCH_CHECK();
+  }
+  return PP_OK;
+}
+
+}  // extern "C"

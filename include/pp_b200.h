@@ -1,0 +1,201 @@
+/*
+ * pp_b200.h -- C ABI of libpp_b200.so: the B200 (sm_100a) PointPillars input path.
+ *
+ * This is the drop-in boundary for the per-sweep hot path of mr3543/3d-Object-Detection
+ * (paths below are under the reference checkout):
+ *
+ *   pp_pillarize          replaces  data/pillars.cpp:236-398  create_pillars  (pybind11 export :433)
+ *                         + the tensor glue of                data/dataset.py:99-106
+ *   pp_pfn_forward        replaces  model/model.py:31-40      PPFeatureNet.forward
+ *   pp_scatter            replaces  model/model.py:53-62      PPScatter.forward
+ *   pp_pfn_scatter        the two above fused (canvas written straight from the pillar maxima)
+ *   pp_make_ious          replaces  data/pillars.cpp:400-427  make_ious       (pybind11 export :432)
+ *   pp_assign_targets     replaces  utils/box_utils.py:162-232 create_target + :70-109 make_target
+ *
+ * Conventions
+ *   - Every pointer named d_* is DEVICE memory of the current CUDA device; h_* is host memory.
+ *     No torch / pybind types appear here: plain pointers, sizes and a stream handle.
+ *   - Every function returns PP_OK (0) or a PP_ERR_* code; nothing throws, nothing calls exit().
+ *     (The reference kills the process on a negative IoU, data/pillars.cpp:166-169; here the
+ *     kernels raise bit PP_STATUS_NEG_IOU in the caller's d_status word instead.)
+ *   - All work is enqueued on `stream` and is asynchronous with respect to the host.  No hidden
+ *     allocation, no global state: scratch memory is a caller-provided workspace whose size the
+ *     matching *_workspace_bytes() function reports.  Calls are re-entrant per (device, stream,
+ *     workspace).
+ *   - There is no CPU fallback.  If no CUDA device is usable the calls return PP_ERR_CUDA.
+ */
+#ifndef PP_B200_H_
+#define PP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_B200_VERSION 100 /* major*100 + minor */
+
+typedef void* pp_stream_t; /* a cudaStream_t */
+
+enum {
+  PP_OK = 0,
+  PP_ERR_INVALID_ARG = 1, /* bad size / NULL pointer / unsupported combination */
+  PP_ERR_WORKSPACE = 2,   /* workspace too small or misaligned (needs 256-byte alignment) */
+  PP_ERR_CUDA = 3,        /* a CUDA runtime call failed; see pp_last_cuda_error() */
+  PP_ERR_UNSUPPORTED = 4
+};
+
+/* bits of the device-side status word (d_status), OR-ed in by kernels */
+enum {
+  PP_STATUS_NEG_IOU = 1,       /* wrong corner winding: the reference would exit(1) */
+  PP_STATUS_BAD_POINT = 2,     /* NaN/Inf coordinate met the reference's range filter (out of contract); point dropped */
+  PP_STATUS_BAD_INDEX = 4,     /* scatter index outside the canvas; row skipped */
+  PP_STATUS_CAND_OVERFLOW = 8  /* more candidate anchors for one GT than the anchor index promised */
+};
+
+enum { PP_F32 = 0, PP_F64 = 1, PP_I64 = 2 };
+
+#define PP_MAX_SWEEPS 64   /* sweeps per call (batch); larger batches are split by the caller */
+#define PP_NUM_FEATURES 9  /* x,y,z,r,xp,yp,xc,yc,zc : data/pillars.cpp:48-56 */
+#define PP_REG_DIMS 9      /* [1,dx,dy,dz,dw,dl,dh,sin(dyaw),ort] : utils/box_utils.py:109 */
+
+/* The nine doubles create_pillars receives positionally (data/pillars.cpp:241-249). */
+typedef struct pp_grid {
+  double x_step, y_step;
+  double x_min, y_min, z_min;
+  double x_max, y_max, z_max;
+  double canvas_height;
+} pp_grid;
+
+int pp_version(void);
+const char* pp_error_string(int code);
+/* cudaError_t of the most recent failing CUDA call made by this thread inside the library. */
+int pp_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  point -> pillar binning, order-exact compaction, decoration, per-slot mean subtraction
+ * ----------------------------------------------------------------------------------------
+ * Points of all sweeps are concatenated: element (i, c), c in 0..3 = x,y,z,r, lives at
+ * d_points[(i*stride_point + c*stride_col)] in units of elements of `point_dtype`
+ * (PP_F32 or PP_F64).  Sweep s owns rows h_sweep_offsets[s] .. h_sweep_offsets[s+1]-1.
+ * Semantics per sweep are exactly SURVEY.md App. A.3 / data/pillars.cpp:236-398:
+ * half-open range filter, floor binning in double, pillars in first-touch order, the first
+ * max_pillars kept, the first max_points_per_pillar points of each kept in input order, the
+ * pillar mean taken over ALL its in-range points with the reference's sequential update.
+ */
+size_t pp_pillarize_workspace_bytes(int32_t n_sweeps, int64_t total_points, const pp_grid* grid,
+                                    int32_t max_pillars);
+
+/*
+ * Dense output (the tensor PPDataset.__getitem__ hands to the network, data/dataset.py:99-106):
+ *   d_x        float [n_sweeps, 9, max_pillars, max_points]  = float32(feature) - data_mean
+ *              (every slot written; empty slots hold 0 - data_mean, exactly like the reference's
+ *              flat subtraction).  d_data_mean is [9*max_pillars*max_points] floats or NULL.
+ *   d_indices  int64 [n_sweeps, max_pillars, 3] = [1, canvas_x, canvas_y] for kept pillars, 0 rows after.
+ *   d_num_pillars int32 [n_sweeps].
+ */
+int pp_pillarize(const void* d_points, int32_t point_dtype, int64_t stride_point,
+                 int64_t stride_col, const int64_t* h_sweep_offsets, int32_t n_sweeps,
+                 const pp_grid* grid, int32_t max_points_per_pillar, int32_t max_pillars,
+                 const float* d_data_mean, float* d_x, int64_t* d_indices, int32_t* d_num_pillars,
+                 int32_t* d_status, void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
+
+/*
+ * Compact double-precision output for the numpy-signature drop-in of create_pillars, whose
+ * contract is "only touched slots of the caller's [P,N,9] float64 array are written"
+ * (data/pillars.cpp:48-56,390-392).  One sweep per call.
+ *   d_rows   double [n_points, 9]  features of the i-th kept point in (pillar, rank) order;
+ *   d_slot   int32  [n_points]     pillar*max_points + rank, or -1 for rows past the kept count;
+ *   d_pillar_xy int32 [max_pillars, 2] canvas_x, canvas_y of each kept pillar;
+ *   d_counts int32 [2]             {number of kept pillars, number of valid rows}.
+ */
+int pp_pillarize_compact(const void* d_points, int32_t point_dtype, int64_t stride_point,
+                         int64_t stride_col, int64_t n_points, const pp_grid* grid,
+                         int32_t max_points_per_pillar, int32_t max_pillars, double* d_rows,
+                         int32_t* d_slot, int32_t* d_pillar_xy, int32_t* d_counts,
+                         int32_t* d_status, void* d_workspace, size_t workspace_bytes,
+                         pp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  PPFeatureNet (1x1 conv D->C, ReLU, BatchNorm, max over N) and PPScatter
+ * ----------------------------------------------------------------------------------------
+ * d_x [B, D, P, N] float (D == 9).  Parameters keep nn.Conv2d / nn.BatchNorm2d layouts:
+ * conv weight [C, D] (= conv1.weight[:, :, 0, 0]), conv bias [C], bn weight/bias/running_mean/
+ * running_var [C] (C <= 64, multiple of 32), num_batches_tracked int64[1].
+ * training != 0: batch statistics over (B,P,N) normalise the output and the running statistics
+ * are updated in place (momentum, unbiased variance) exactly like nn.BatchNorm2d.train();
+ * training == 0: running statistics are used and left untouched.
+ */
+size_t pp_pfn_workspace_bytes(int32_t B, int32_t P, int32_t C, int32_t canvas_h, int32_t canvas_w);
+
+/* out [B, C, P] float : the tensor PPFeatureNet.forward returns (model/model.py:39-40). */
+int pp_pfn_forward(const float* d_x, int32_t B, int32_t D, int32_t P, int32_t N, int32_t C,
+                   const float* d_conv_w, const float* d_conv_b, const float* d_bn_w,
+                   const float* d_bn_b, float* d_running_mean, float* d_running_var,
+                   int64_t* d_num_batches_tracked, int32_t training, float momentum, float eps,
+                   float* d_out, void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
+
+/* canvas [B, C, H, W] float, fully written: zeros + feat[b,:,p] at (inds[b,p,2], inds[b,p,1]) for
+ * rows with inds[b,p,0] != 0 (model/model.py:55-61).  d_feat is [B, C, P]. */
+int pp_scatter(const float* d_feat, const int64_t* d_inds, int32_t B, int32_t C, int32_t P,
+               int32_t canvas_h, int32_t canvas_w, float* d_canvas, int32_t* d_status,
+               void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
+
+/* pp_pfn_forward + pp_scatter in one pass over x; d_out ([B,C,P]) may be NULL. */
+int pp_pfn_scatter(const float* d_x, const int64_t* d_inds, int32_t B, int32_t D, int32_t P,
+                   int32_t N, int32_t C, const float* d_conv_w, const float* d_conv_b,
+                   const float* d_bn_w, const float* d_bn_b, float* d_running_mean,
+                   float* d_running_var, int64_t* d_num_batches_tracked, int32_t training,
+                   float momentum, float eps, int32_t canvas_h, int32_t canvas_w, float* d_canvas,
+                   float* d_out, int32_t* d_status, void* d_workspace, size_t workspace_bytes,
+                   pp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  rotated anchor-vs-GT IoU and target assignment
+ * ----------------------------------------------------------------------------------------
+ * Ring conventions are the reference's (data/pillars.cpp:15-16,149-157): anchor corners
+ * [A,4,2] counter-clockwise, GT corners [G,4,2] clockwise (they are after the y flip of
+ * utils/box_utils.py:29-30), both open rings, doubles.  Centres are [.,3] doubles in the same
+ * (image) space.  IoU is 0 when |dcx| > 10 or |dcy| > 10 (data/pillars.cpp:418-419).
+ */
+
+/* Dense [A,G] double IoU matrix, every entry written: make_ious verbatim. */
+int pp_make_ious(const double* d_a_corners, const double* d_g_corners, const double* d_a_centers,
+                 const double* d_g_centers, int64_t A, int64_t G, double* d_ious,
+                 int32_t* d_status, pp_stream_t stream);
+
+/* Anchors are batch-invariant (built once offline in the reference, train_prep.py:115-120).
+ * The index buckets anchor centres on a uniform grid so that each GT visits only the anchors
+ * that can pass the centre prefilter.  Built once per anchor set from HOST centres. */
+size_t pp_anchor_index_bytes(const double* h_a_centers, int64_t A);
+int pp_anchor_index_build(const double* h_a_centers, int64_t A, void* d_index, size_t index_bytes,
+                          pp_stream_t stream);
+
+size_t pp_assign_targets_workspace_bytes(int32_t n_sweeps, int64_t A, int64_t total_gt,
+                                         const void* h_index_header /* first 64 bytes of the index, host copy; may be NULL for a safe upper bound */);
+
+/*
+ * Target assignment for a batch of sweeps (SURVEY.md App. A.7 = utils/box_utils.py:178-232).
+ * Anchors: corners/centres as above plus d_a_wlh [A,3], d_a_yaw [A] (radians).
+ * GT boxes of all sweeps concatenated; sweep s owns rows h_gt_offsets[s]..h_gt_offsets[s+1]-1:
+ *   d_g_corners [Gt,4,2], d_g_centers [Gt,3] in IMAGE space (y already flipped),
+ *   d_g_wlh [Gt,3], d_g_yaw [Gt] (radians, NOT flipped), d_g_cls int32 [Gt].
+ * Outputs (every element written):
+ *   d_cls float [n_sweeps, A, num_classes], d_reg float [n_sweeps, A, 9],
+ *   d_top_anchor int32 [Gt] (per-GT best anchor, 0 = dropped like np.nonzero does, :204),
+ *   d_counts int32 [n_sweeps, 4] = {positives (max IoU > thresh), forced matches kept,
+ *                                   anchors with |max IoU - thresh| < 1e-6, reserved}.
+ */
+int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, const double* d_a_wlh,
+                      const double* d_a_yaw, const void* d_anchor_index, int64_t A,
+                      const double* d_g_corners, const double* d_g_centers, const double* d_g_wlh,
+                      const double* d_g_yaw, const int32_t* d_g_cls, const int64_t* h_gt_offsets,
+                      int32_t n_sweeps, int32_t num_classes, double pos_thresh, float* d_cls,
+                      float* d_reg, int32_t* d_top_anchor, int32_t* d_counts, int32_t* d_status,
+                      void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PP_B200_H_ */
