@@ -34,6 +34,9 @@ _SIGNATURES = {
     "pp_version": (_c.c_int, []),
     "pp_error_string": (_c.c_char_p, [_c.c_int]),
     "pp_last_cuda_error": (_c.c_int, []),
+    "pp_launch_count": (_i64, []),
+    "pp_profile_enable": (_c.c_int, [_c.c_int]),
+    "pp_profile_report": (_i64, [_c.c_char_p, _i64]),
     "pp_pillarize_workspace_bytes": (_sz, [_i32, _i64, _gridp, _i32]),
     "pp_pillarize": (_c.c_int, [_vp, _i32, _i64, _i64, _i64p, _i32, _gridp, _i32, _i32, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -93,3 +96,15 @@ def check(rc, what):
 def i64_array(values):
     arr = (ctypes.c_int64 * len(values))(*[int(v) for v in values])
     return arr
+
+
+def profile_report():
+    """{kernel name: (launches, total_ms)} since pp_profile_enable(1); synchronises the device."""
+    L = load()
+    buf = ctypes.create_string_buffer(1 << 16)
+    L.pp_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split()
+        out[name] = (int(n), float(ms))
+    return out

@@ -1,15 +1,88 @@
 // api.cu -- version / error plumbing of libpp_b200.so.
 #include "common.cuh"
 
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 namespace pp {
 thread_local int g_last_cuda_error = 0;
+
+// ---- launch counter + optional per-kernel CUDA-event timing -----------------------------------
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static thread_local cudaEvent_t t_pending = nullptr;
+
+void prof_begin(const char* name, cudaStream_t st) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  t_pending = nullptr;
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec r{name, nullptr, nullptr};
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  t_pending = r.b;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
 }
+
+void prof_end(cudaStream_t st) {
+  if (t_pending != nullptr) cudaEventRecord(t_pending, st);
+  t_pending = nullptr;
+}
+}  // namespace pp
 
 extern "C" {
 
 int pp_version(void) { return PP_B200_VERSION; }
 
 int pp_last_cuda_error(void) { return pp::g_last_cuda_error; }
+
+int64_t pp_launch_count(void) { return (int64_t)pp::g_launches.load(); }
+
+int pp_profile_enable(int on) {
+  pp::g_prof_on.store(on ? 1 : 0);
+  return PP_OK;
+}
+
+// Synchronises the device, then writes "name launches total_ms\n" per kernel (launch order of first
+// appearance) into buf and clears the records.  Returns the number of bytes needed (like snprintf).
+int64_t pp_profile_report(char* buf, int64_t buf_bytes) {
+  using namespace pp;
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::vector<std::string> order;
+  std::map<std::string, std::pair<long long, double>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (r.a && r.b && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto it = agg.find(r.name);
+      if (it == agg.end()) { order.push_back(r.name); agg[r.name] = {1, (double)ms}; }
+      else { it->second.first += 1; it->second.second += ms; }
+    }
+    if (r.a) cudaEventDestroy(r.a);
+    if (r.b) cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  std::string out;
+  char line[256];
+  for (auto& n : order) {
+    snprintf(line, sizeof line, "%s %lld %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+    out += line;
+  }
+  if (buf != nullptr && buf_bytes > 0) {
+    const size_t k = out.size() < (size_t)(buf_bytes - 1) ? out.size() : (size_t)(buf_bytes - 1);
+    memcpy(buf, out.data(), k);
+    buf[k] = 0;
+  }
+  return (int64_t)out.size() + 1;
+}
 
 const char* pp_error_string(int code) {
   switch (code) {

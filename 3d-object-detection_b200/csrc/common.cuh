@@ -23,6 +23,18 @@ inline int cuda_fail(cudaError_t e) {
 
 #define PP_LAUNCH_CHECK() PP_CUDA(cudaGetLastError())
 
+// Every kernel launch goes through PP_KERNEL: it counts the launch (pp_launch_count) and, when
+// profiling is enabled (pp_profile_enable), brackets it with CUDA events on the launching stream.
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+#define PP_KERNEL(name, st, ...)   \
+  do {                             \
+    ::pp::prof_begin(name, st);    \
+    __VA_ARGS__;                   \
+    ::pp::prof_end(st);            \
+    PP_LAUNCH_CHECK();             \
+  } while (0)
+
 constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 

@@ -441,8 +441,9 @@ static int launch_stats(const float* d_x, int B, int P, int N, int C, const floa
   do {                                                                                            \
     PP_CUDA(cudaFuncSetAttribute(k_pfn_stats<CPL, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  (int)smem));                                                     \
-    k_pfn_stats<CPL, TR><<<nblocks, kWarps * 32, smem, st>>>(d_x, B, P, N, chunk, nchunks, use_bulk, \
-                                                            w, bias, ws.ext, ws.partials);        \
+    PP_KERNEL("k_pfn_stats", st,                                                                  \
+              (k_pfn_stats<CPL, TR><<<nblocks, kWarps * 32, smem, st>>>(                          \
+                  d_x, B, P, N, chunk, nchunks, use_bulk, w, bias, ws.ext, ws.partials)));        \
   } while (0)
   if (C == 64) {
     if (training) PP_STATS(2, true); else PP_STATS(2, false);
@@ -450,7 +451,6 @@ static int launch_stats(const float* d_x, int B, int P, int N, int C, const floa
     if (training) PP_STATS(1, true); else PP_STATS(1, false);
   }
 #undef PP_STATS
-  PP_LAUNCH_CHECK();
   return PP_OK;
 }
 
@@ -460,9 +460,10 @@ static int pfn_common(const float* d_x, int B, int D, int P, int N, int C, const
                       cudaStream_t st) {
   int rc = launch_stats(d_x, B, P, N, C, w, bias, training, ws, nblocks, st);
   if (rc != PP_OK) return rc;
-  k_bn_finalize<<<1, 64, 0, st>>>(C, nblocks, (double)B * P * N, training, momentum, eps,
-                                  ws.partials, bn_w, bn_b, rm, rv, (long long*)nbt, ws.affine);
-  PP_LAUNCH_CHECK();
+  PP_KERNEL("k_bn_finalize", st,
+            k_bn_finalize<<<1, 64, 0, st>>>(C, nblocks, (double)B * P * N, training, momentum, eps,
+                                            ws.partials, bn_w, bn_b, rm, rv, (long long*)nbt,
+                                            ws.affine));
   return PP_OK;
 }
 
@@ -478,11 +479,11 @@ static int canvas_launch(bool from_ext, const float* src, const Affine* aff, con
   const int HW = H * W;
   const bool vec_ok = (HW % 4 == 0) && ((uintptr_t)d_canvas % 16 == 0);
   dim3 grid((HW + 127) / 128, B);
-  if (from_ext)
-    k_canvas<true><<<grid, 256, 0, st>>>(src, aff, map, P, C, HW, vec_ok, d_canvas);
-  else
-    k_canvas<false><<<grid, 256, 0, st>>>(src, aff, map, P, C, HW, vec_ok, d_canvas);
-  PP_LAUNCH_CHECK();
+  if (from_ext) {
+    PP_KERNEL("k_canvas", st, k_canvas<true><<<grid, 256, 0, st>>>(src, aff, map, P, C, HW, vec_ok, d_canvas));
+  } else {
+    PP_KERNEL("k_canvas", st, k_canvas<false><<<grid, 256, 0, st>>>(src, aff, map, P, C, HW, vec_ok, d_canvas));
+  }
   return PP_OK;
 }
 
@@ -490,9 +491,8 @@ static int build_map(const int64_t* d_inds, int B, int P, int H, int W, int* map
                      cudaStream_t st) {
   PP_CUDA(cudaMemsetAsync(map, 0xff, (size_t)B * H * W * sizeof(int), st));
   const long long n = (long long)B * P;
-  k_build_map<<<(int)((n + 255) / 256), 256, 0, st>>>((const long long*)d_inds, B, P, H, W, map,
-                                                      d_status);
-  PP_LAUNCH_CHECK();
+  PP_KERNEL("k_build_map", st, k_build_map<<<(int)((n + 255) / 256), 256, 0, st>>>((const long long*)d_inds, B, P, H, W, map,
+                                                      d_status));
   return PP_OK;
 }
 
@@ -526,8 +526,7 @@ int pp_pfn_forward(const float* d_x, int32_t B, int32_t D, int32_t P, int32_t N,
                       d_running_var, d_num_batches_tracked, training, momentum, eps, ws, nblocks, st);
   if (rc != PP_OK) return rc;
   dim3 grid((P + 31) / 32, B);
-  k_pfn_out<<<grid, 256, 0, st>>>(ws.ext, ws.affine, P, C, d_out);
-  PP_LAUNCH_CHECK();
+  PP_KERNEL("k_pfn_out", st, k_pfn_out<<<grid, 256, 0, st>>>(ws.ext, ws.affine, P, C, d_out));
   return PP_OK;
 }
 
@@ -577,8 +576,7 @@ int pp_pfn_scatter(const float* d_x, const int64_t* d_inds, int32_t B, int32_t D
   if (rc != PP_OK) return rc;
   if (d_out != nullptr) {
     dim3 grid((P + 31) / 32, B);
-    k_pfn_out<<<grid, 256, 0, st>>>(ws.ext, ws.affine, P, C, d_out);
-    PP_LAUNCH_CHECK();
+    PP_KERNEL("k_pfn_out", st, k_pfn_out<<<grid, 256, 0, st>>>(ws.ext, ws.affine, P, C, d_out));
   }
   return PP_OK;
 }

@@ -582,32 +582,25 @@ static int run_stages(const T* pts, long long sp, long long sc, bool vec4, const
   PP_CUDA(cudaMemsetAsync(d_num_pillars, 0, (size_t)B * sizeof(int), st));
   const int pt_blocks = (int)((total + 255) / 256);
   if (total > 0) {
-    k_bin<T><<<pt_blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, ws.cell_of_point, ws.cell_first,
-                                        ws.cell_count, d_status);
-    PP_LAUNCH_CHECK();
-    k_tilecount<<<ntiles, kTile, 0, st>>>(sw, g, ws.cell_of_point, ws.cell_first, ws.tile_count);
-    PP_LAUNCH_CHECK();
-    k_assign<<<ntiles, kTile, 0, st>>>(sw, g, P, ws.cell_of_point, ws.cell_first, ws.cell_count,
+    PP_KERNEL("k_bin", st, k_bin<T><<<pt_blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, ws.cell_of_point, ws.cell_first,
+                                        ws.cell_count, d_status));
+    PP_KERNEL("k_tilecount", st, k_tilecount<<<ntiles, kTile, 0, st>>>(sw, g, ws.cell_of_point, ws.cell_first, ws.tile_count));
+    PP_KERNEL("k_assign", st, k_assign<<<ntiles, kTile, 0, st>>>(sw, g, P, ws.cell_of_point, ws.cell_first, ws.cell_count,
                                        ws.tile_count, ws.cell_slot, ws.pil_cnt, ws.pil_off,
                                        ws.pil_cell, ws.list_cursor, ws.big_count, ws.big_list,
-                                       d_num_pillars);
-    PP_LAUNCH_CHECK();
-    k_scatter<<<pt_blocks, 256, 0, st>>>(sw, g, P, ws.cell_of_point, ws.cell_slot, ws.pil_off,
-                                         ws.pil_cursor, ws.list_u);
-    PP_LAUNCH_CHECK();
-    k_rank<<<pt_blocks, 256, 0, st>>>(sw, g, P, ws.cell_of_point, ws.cell_slot, ws.pil_cnt,
-                                      ws.pil_off, ws.list_u, ws.list_s, ws.rank_of_point);
-    PP_LAUNCH_CHECK();
-    k_rank_big<<<64, kTile, 0, st>>>(sw, P, ws.cell_of_point, ws.pil_off, ws.pil_cell,
-                                     ws.big_count, ws.big_list, ws.list_s, ws.rank_of_point);
-    PP_LAUNCH_CHECK();
+                                       d_num_pillars));
+    PP_KERNEL("k_scatter", st, k_scatter<<<pt_blocks, 256, 0, st>>>(sw, g, P, ws.cell_of_point, ws.cell_slot, ws.pil_off,
+                                         ws.pil_cursor, ws.list_u));
+    PP_KERNEL("k_rank", st, k_rank<<<pt_blocks, 256, 0, st>>>(sw, g, P, ws.cell_of_point, ws.cell_slot, ws.pil_cnt,
+                                      ws.pil_off, ws.list_u, ws.list_s, ws.rank_of_point));
+    PP_KERNEL("k_rank_big", st, k_rank_big<<<64, kTile, 0, st>>>(sw, P, ws.cell_of_point, ws.pil_off, ws.pil_cell,
+                                     ws.big_count, ws.big_list, ws.list_s, ws.rank_of_point));
   }
   const long long warps = (long long)B * P;
   const int mean_blocks = (int)((warps * 32 + 255) / 256);
-  k_mean<T><<<mean_blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, P, d_num_pillars, ws.pil_cnt,
+  PP_KERNEL("k_mean", st, k_mean<T><<<mean_blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, P, d_num_pillars, ws.pil_cnt,
                                          ws.pil_off, ws.pil_cell, ws.list_s, ws.pil_mean,
-                                         d_indices);
-  PP_LAUNCH_CHECK();
+                                         d_indices));
   return PP_OK;
 }
 
@@ -659,15 +652,16 @@ static int pillarize_impl(const T* pts, long long sp, long long sc, const int64_
   const long long cap = (long long)sm_count() * 32;
   if (blocks > cap) blocks = cap;
   if (v4) {
-    k_emit_dense<T, 4><<<(int)blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, P, N, d_mean, d_x,
-                                                    d_num_pillars, ws.pil_cnt, ws.pil_off,
-                                                    ws.pil_cell, ws.pil_mean, ws.list_s);
+    PP_KERNEL("k_emit_dense", st,
+              (k_emit_dense<T, 4><<<(int)blocks, 256, 0, st>>>(
+                  pts, sp, sc, vec4, sw, g, P, N, d_mean, d_x, d_num_pillars, ws.pil_cnt, ws.pil_off,
+                  ws.pil_cell, ws.pil_mean, ws.list_s)));
   } else {
-    k_emit_dense<T, 1><<<(int)blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, P, N, d_mean, d_x,
-                                                    d_num_pillars, ws.pil_cnt, ws.pil_off,
-                                                    ws.pil_cell, ws.pil_mean, ws.list_s);
+    PP_KERNEL("k_emit_dense", st,
+              (k_emit_dense<T, 1><<<(int)blocks, 256, 0, st>>>(
+                  pts, sp, sc, vec4, sw, g, P, N, d_mean, d_x, d_num_pillars, ws.pil_cnt, ws.pil_off,
+                  ws.pil_cell, ws.pil_mean, ws.list_s)));
   }
-  PP_LAUNCH_CHECK();
   return PP_OK;
 }
 
@@ -696,14 +690,14 @@ static int compact_impl(const T* pts, long long sp, long long sc, int64_t n_poin
   if (n_points > 0) {
     PP_CUDA(cudaMemsetAsync(d_slot, 0xff, (size_t)n_points * sizeof(int), st));
     const int blocks = (int)((n_points + 255) / 256);
-    k_emit_compact<T><<<blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, P, N, ws.cell_of_point,
-                                              ws.cell_slot, ws.rank_of_point, ws.pil_off,
-                                              ws.pil_mean, d_rows, d_slot, ws.n_rows);
-    PP_LAUNCH_CHECK();
+    PP_KERNEL("k_emit_compact", st,
+              k_emit_compact<T><<<blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, P, N,
+                                                        ws.cell_of_point, ws.cell_slot,
+                                                        ws.rank_of_point, ws.pil_off, ws.pil_mean,
+                                                        d_rows, d_slot, ws.n_rows));
   }
-  k_pillar_xy<<<(P + 255) / 256, 256, 0, st>>>(g, P, ws.num_pillars_scratch, ws.pil_cell,
-                                               d_pillar_xy, d_counts);
-  PP_LAUNCH_CHECK();
+  PP_KERNEL("k_pillar_xy", st, k_pillar_xy<<<(P + 255) / 256, 256, 0, st>>>(g, P, ws.num_pillars_scratch, ws.pil_cell,
+                                               d_pillar_xy, d_counts));
   PP_CUDA(cudaMemcpyAsync(d_counts + 1, ws.n_rows, sizeof(int), cudaMemcpyDeviceToDevice, st));
   return PP_OK;
 }

@@ -84,7 +84,13 @@ __device__ double quad_iou(const double* __restrict__ a, const double* __restric
     n = m;
   }
   if (n < 3) return 0.0;
-  const double inter = ring_area_ccw(subj, n);
+  // the reference takes bg::area of a clockwise-typed output polygon (data/pillars.cpp:15,164):
+  // walk the intersection ring clockwise and flip the sign
+  for (int i = 0; i < n; ++i) {
+    nxt[2 * i] = subj[2 * (n - 1 - i)];
+    nxt[2 * i + 1] = subj[2 * (n - 1 - i) + 1];
+  }
+  const double inter = -ring_area_ccw(nxt, n);
   if (!(inter > 0.0)) return 0.0;
   const double area_a = ring_area_ccw(a, 4);
   const double area_g = -ring_area_ccw(g, 4);
@@ -429,9 +435,8 @@ int pp_make_ious(const double* d_a_corners, const double* d_g_corners, const dou
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 64;
   if (blocks > cap) blocks = cap;
-  k_make_ious<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_a_corners, d_g_corners, d_a_centers,
-                                                            d_g_centers, A, G, d_ious, d_status);
-  PP_LAUNCH_CHECK();
+  PP_KERNEL("k_make_ious", (cudaStream_t)stream, k_make_ious<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_a_corners, d_g_corners, d_a_centers,
+                                                            d_g_centers, A, G, d_ious, d_status));
   return PP_OK;
 }
 
@@ -502,14 +507,12 @@ int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, cons
   PP_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)n_sweeps * 4 * sizeof(int), st));
   const unsigned char* idx = (const unsigned char*)d_anchor_index;
   if (Gt > 0) {
-    k_iou_pass<0><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
+    PP_KERNEL("k_iou_pass", st, k_iou_pass<0><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
                                            d_g_centers, gp, pos_thresh, ws.best, ws.arg, ws.posmask,
-                                           d_top_anchor, d_counts, d_status);
-    PP_LAUNCH_CHECK();
-    k_iou_pass<1><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
+                                           d_top_anchor, d_counts, d_status));
+    PP_KERNEL("k_iou_pass", st, k_iou_pass<1><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
                                            d_g_centers, gp, pos_thresh, ws.best, ws.arg, ws.posmask,
-                                           d_top_anchor, d_counts, d_status);
-    PP_LAUNCH_CHECK();
+                                           d_top_anchor, d_counts, d_status));
   }
   EncodeArgs ea{d_a_centers, d_a_wlh, d_a_yaw, d_g_centers, d_g_wlh, d_g_yaw, d_g_cls, ws.arg, ws.posmask};
   {
@@ -519,8 +522,7 @@ int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, cons
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)n_sweeps);
-    k_encode<false><<<grid, 256, 0, st>>>(ea, gp, A, num_classes, vec_ok, d_cls);
-    PP_LAUNCH_CHECK();
+    PP_KERNEL("k_encode", st, k_encode<false><<<grid, 256, 0, st>>>(ea, gp, A, num_classes, vec_ok, d_cls));
   }
   {
     const long long total = (long long)A * 9;
@@ -529,12 +531,10 @@ int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, cons
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)n_sweeps);
-    k_encode<true><<<grid, 256, 0, st>>>(ea, gp, A, 9, vec_ok, d_reg);
-    PP_LAUNCH_CHECK();
+    PP_KERNEL("k_encode", st, k_encode<true><<<grid, 256, 0, st>>>(ea, gp, A, 9, vec_ok, d_reg));
   }
   if (Gt > 0) {
-    k_forced<<<n_sweeps, 256, 0, st>>>(ea, gp, A, num_classes, d_top_anchor, d_cls, d_reg, d_counts);
-    PP_LAUNCH_CHECK();
+    PP_KERNEL("k_forced", st, k_forced<<<n_sweeps, 256, 0, st>>>(ea, gp, A, num_classes, d_top_anchor, d_cls, d_reg, d_counts));
   }
   return PP_OK;
 }

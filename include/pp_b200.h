@@ -73,6 +73,14 @@ const char* pp_error_string(int code);
 /* cudaError_t of the most recent failing CUDA call made by this thread inside the library. */
 int pp_last_cuda_error(void);
 
+/* Instrumentation.  pp_launch_count: kernels launched by this library since load (all threads).
+ * pp_profile_enable(1): bracket every kernel launch with CUDA events on its stream;
+ * pp_profile_report: synchronise the device, write one "name launches total_ms" line per kernel
+ * into buf, clear the records, return the bytes needed. */
+int64_t pp_launch_count(void);
+int pp_profile_enable(int on);
+int64_t pp_profile_report(char* buf, int64_t buf_bytes);
+
 /* ------------------------------------------------------------------------------------------
  * K1  point -> pillar binning, order-exact compaction, decoration, per-slot mean subtraction
  * ----------------------------------------------------------------------------------------

@@ -45,3 +45,15 @@ def scatter(x, inds, canvas_h, canvas_w):
     y_inds = inds[batch, pillar][:, 2]
     out[batch, :, y_inds, x_inds] = x[batch, :, pillar]
     return out
+
+
+def reference_forward_f32(x, weight, bias, bn_weight, bn_bias, running_mean, running_var, training,
+                          momentum=0.1, eps=1e-5):
+    """model/model.py:36-39 with the same float32 library ops the reference module calls
+    (conv2d 1x1 -> relu -> batch_norm -> max over dim 3).  Used as the timed CPU baseline of
+    the PFN stage; running statistics are updated in place when training."""
+    import torch.nn.functional as F
+    y = F.conv2d(x, weight.reshape(weight.shape[0], -1, 1, 1), bias)
+    y = F.relu(y)
+    y = F.batch_norm(y, running_mean, running_var, bn_weight, bn_bias, training, momentum, eps)
+    return torch.max(y, dim=3)[0]

@@ -216,7 +216,14 @@ double pp_oracle_iou(const double* a, const double* g) {
     n = m;
   }
   if (n < 3) return 0.0;
-  const double inter = ring_area_ccw(subj, n);
+  /* The reference's output vector holds clockwise-typed polygons (pillars.cpp:15,159), so the
+     intersection ring is presented clockwise and bg::area (pillars.cpp:164) walks it that way:
+     reverse the ring, take the shoelace sum, flip the sign. */
+  for (int i = 0; i < n; ++i) {
+    nxt[2 * i] = subj[2 * (n - 1 - i)];
+    nxt[2 * i + 1] = subj[2 * (n - 1 - i) + 1];
+  }
+  const double inter = -ring_area_ccw(nxt, n);
   if (!(inter > 0.0)) return 0.0;
   const double area_a = ring_area_ccw(a, 4);  /* bg::area of a CCW-typed polygon */
   const double area_g = -ring_area_ccw(g, 4); /* bg::area of a CW-typed polygon */

@@ -150,3 +150,37 @@ def create_target(anchor_corners, gt_corners, anchor_centers, gt_centers, anchor
     if return_ious:
         return cls_targets, reg_targets, ious_dense
     return cls_targets, reg_targets
+
+
+class LazyAnchorBoxes:
+    """Indexable stand-in for the reference's 540000-element ``anchor_box_list``: create_target
+    only indexes it for positive / forced anchors (utils/box_utils.py:219-228)."""
+
+    def __init__(self, centers, wlh, yaw):
+        self.centers, self.wlh, self.yaw = centers, wlh, yaw
+
+    def __len__(self):
+        return self.centers.shape[0]
+
+    def __getitem__(self, a):
+        return Box(self.centers[a], self.wlh[a], self.yaw[a])
+
+
+def anchor_arrays(fm_height=None, fm_width=None):
+    """Vectorised equivalent of make_anchor_boxes() (checked against the loop in
+    tests/test_oracle_targets.py): corners [A,4,2], centers [A,3], wlh [A,3], yaw [A]."""
+    fm_height = int(cfg.FM_HEIGHT if fm_height is None else fm_height)
+    fm_width = int(cfg.FM_WIDTH if fm_width is None else fm_width)
+    nd = len(cfg.ANCHOR_DIMS)
+    ys, xs, ds = np.meshgrid(np.arange(fm_height), np.arange(fm_width), np.arange(nd), indexing="ij")
+    ys, xs, ds = ys.reshape(-1), xs.reshape(-1), ds.reshape(-1)
+    wlh = np.stack(cfg.ANCHOR_DIMS)[ds]
+    yaw = np.deg2rad(np.asarray(cfg.ANCHOR_YAWS, dtype=np.float64))[ds]
+    centers = np.stack([(xs + 0.5) / cfg.FM_SCALE, (ys + 0.5) / cfg.FM_SCALE,
+                        np.asarray(cfg.ANCHOR_ZS, dtype=np.float64)[ds]], axis=1)
+    w, l = wlh[:, 0:1], wlh[:, 1:2]
+    bx = l / 2 * np.array([[1, 1, -1, -1.0]])
+    by = w / 2 * np.array([[-1, 1, 1, -1.0]])
+    c, s = np.cos(yaw)[:, None], np.sin(yaw)[:, None]
+    corners = np.stack([c * bx - s * by + centers[:, 0:1], s * bx + c * by + centers[:, 1:2]], axis=2)
+    return corners, centers, wlh, yaw

@@ -1,0 +1,79 @@
+"""The C-ABI shared library: builds for sm_100a, loads, and exports every symbol
+include/pp_b200.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import pp_b200
+from pp_b200 import _lib, build
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "pp_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build()
+    assert os.path.exists(path)
+    L = ctypes.CDLL(path)
+    syms = declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(L, s), "libpp_b200.so does not export %s" % s
+    assert sorted(_lib.EXPORTED_SYMBOLS) == syms      # the ctypes binding covers exactly the header
+
+
+def test_version_and_error_strings():
+    L = _lib.load()
+    assert L.pp_version() == 100
+    assert L.pp_error_string(0) == b"ok"
+    assert b"workspace" in L.pp_error_string(2)
+
+
+def test_workspace_queries_and_argument_validation_without_gpu():
+    L = _lib.load()
+    grid = pp_b200.PPConfig().grid()
+    n = L.pp_pillarize_workspace_bytes(4, 280000, grid, 24000)
+    assert 20e6 < n < 200e6
+    assert L.pp_pillarize_workspace_bytes(0, 10, grid, 24000) == 0          # n_sweeps < 1
+    assert L.pp_pillarize_workspace_bytes(65, 10, grid, 24000) == 0         # > PP_MAX_SWEEPS
+    bad = pp_b200.PPConfig(x_step=0.0).grid()
+    assert L.pp_pillarize_workspace_bytes(1, 10, bad, 24000) == 0
+    assert L.pp_pfn_workspace_bytes(4, 24000, 64, 600, 600) > 4 * 24000 * 2 * 64 * 4
+    assert L.pp_assign_targets_workspace_bytes(4, 540000, 400, None) >= 4 * 540000 * 12
+    # invalid arguments are rejected before any CUDA call
+    assert L.pp_pillarize(None, 7, 4, 1, _lib.i64_array([0, 0]), 1, grid, 200, 24000, None, None, None,
+                          None, None, None, 0, None) == 1
+    assert L.pp_pfn_forward(None, 1, 9, 1, 1, 64, None, None, None, None, None, None, None, 1, 0.1, 1e-5,
+                            None, None, 0, None) == 1
+    assert L.pp_make_ious(None, None, None, None, -1, 0, None, None, None) == 1
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.dirname(_lib.__file__)
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, f
+
+
+def test_host_mirrors_fail_loudly_without_gpu():
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pp_b200 import pillars, model, pipeline
+    with pytest.raises(_lib.PPError):
+        pillars.create_pillars(np.zeros((3, 4)), np.zeros((4, 4, 9)), np.zeros((4, 3)), 4, 4,
+                               .2, .2, -60, -60, -10, 60, 60, 10, 600)
+    with pytest.raises(_lib.PPError):
+        model.PPFeatureNet(9, 64)(torch.zeros(1, 9, 4, 4))
+    with pytest.raises(_lib.PPError):
+        pipeline.InputPath()

@@ -1,0 +1,76 @@
+"""The whole path through the host-facing call (InputPath.step_host) vs the oracle, plus
+idempotence / batch-order properties at BASELINE sizes."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_step_host_matches_oracle_composition():
+    import pp_b200
+    from oracle import config as ocfg, glue, pfn, targets as T
+    from helpers import boxes_from_gt
+    from pp_b200 import pipeline, synth
+    cfg = pp_b200.PPConfig(max_pillars=2000, max_points_per_pillar=32, fm_height=60, fm_width=60)
+    P, N = cfg.max_pillars, cfg.max_points_per_pillar
+    mean = synth.make_data_mean(P, N, seed=2)
+    prm = synth.make_pfn_params(3, flip_gamma=True)
+    path = pipeline.InputPath(cfg, data_mean=mean, pfn_params=prm, training=True)
+    sweeps = [synth.make_sweep(s)[:15000] for s in (1, 2)]
+    gcfg = pp_b200.PPConfig(canvas_width=120, canvas_height=120)
+    gts = [synth.make_gt(s, G, gcfg) for s, G in ((1, 9), (2, 14))]
+    for g in gts:                       # keep the boxes on the 60x60 anchor lattice, flip uses H=600
+        g["centers"][:, 1] = 599 - g["centers"][:, 1]
+    batch = path.pack_host_batch(sweeps, gts)
+    canvas, cls, reg, npil, counts = path.step_host(batch)
+    torch.cuda.synchronize()
+    # oracle composition
+    xs, inds = [], []
+    for s in sweeps:
+        x, i = glue.pillarize(s.astype(np.float64), torch.from_numpy(mean), P, N)
+        xs.append(x); inds.append(i)
+    x = torch.stack(xs); ind = torch.stack(inds)
+    t = lambda a: torch.from_numpy(a)
+    y, rm, rv = pfn.pfn_forward(x, t(prm["conv_w"]), t(prm["conv_b"]), t(prm["bn_w"]), t(prm["bn_b"]),
+                                t(prm["running_mean"]), t(prm["running_var"]), True)
+    want = pfn.scatter(y, ind, cfg.canvas_height, cfg.canvas_width).numpy()
+    got = canvas.cpu().numpy().astype(np.float64)
+    assert (np.abs(got - want) <= 1e-5 * np.maximum(np.abs(got), np.abs(want)) + 2e-6).all()
+    assert np.array_equal(got != 0, want != 0)
+    boxes, corners, centers, _ = T.make_anchor_boxes(60, 60)
+    for b, gt in enumerate(gts):
+        g = boxes_from_gt(gt, T.Box, ocfg.CLASS_NAMES)
+        gc, gcor = T.boxes_to_image_space(g)
+        c0, r0 = T.create_target(corners, gcor, centers, gc, boxes, g)
+        assert np.array_equal(cls[b].cpu().numpy(), c0.astype(np.float32))
+        r = reg[b].cpu().numpy().astype(np.float64); r0 = r0.astype(np.float32).astype(np.float64)
+        assert (np.abs(r - r0) <= 1e-5 * np.maximum(np.abs(r), np.abs(r0)) + 1e-7).all()
+        assert int(counts[b, 0]) == int((c0.sum(1) > 0).sum()) or int(counts[b, 0]) <= int((c0.sum(1) > 0).sum())
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 2/4 sizes (B=4, P=24000, N=200, C=64, 600x600 canvas, 540000 anchors):
+    idempotence, batch-order independence of pillars/targets, canvas support == pillar cells."""
+    from pp_b200 import pipeline, synth
+    path = pipeline.InputPath(data_mean=synth.make_data_mean(24000, 200, dense=False),
+                              pfn_params=synth.make_pfn_params(0), training=False)
+    sweeps = [synth.make_sweep(s) for s in range(4)]
+    gts = [synth.make_gt(s, 100) for s in range(4)]
+    b1 = path.pack_host_batch(sweeps, gts)
+    c1, cls1, reg1, n1, k1 = [t.clone() for t in path.step_host(b1)]
+    c2, cls2, reg2, n2, k2 = path.step_host(b1)
+    assert torch.equal(c1, c2) and torch.equal(cls1, cls2) and torch.equal(reg1, reg2)     # idempotent
+    b3 = path.pack_host_batch(sweeps[::-1], gts[::-1])
+    c3, cls3, reg3, n3, k3 = path.step_host(b3)
+    assert torch.equal(cls3.flip(0), cls1) and torch.equal(reg3.flip(0), reg1)
+    assert torch.equal(n3.flip(0), n1)
+    assert torch.equal(c3.flip(0), c1)          # eval-mode BN: per-sweep result independent of the batch
+    x, inds, npil = path.pillarize(b1["points"].cuda(), b1["offsets"])
+    for b in range(4):
+        n = int(npil[b]); ii = inds[b, :n].cpu().numpy()
+        support = torch.zeros(600, 600, dtype=torch.bool)
+        support[ii[:, 2], ii[:, 1]] = True
+        nz = (c1[b] != 0).any(0).cpu()
+        assert not (nz & ~support).any()
+    assert int(k1[:, 0].sum()) > 50
