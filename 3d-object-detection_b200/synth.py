@@ -64,7 +64,7 @@ def make_gt(seed, G, cfg=None):
     rng = np.random.default_rng(10_000 + seed)
     dims = class_dims(cfg.x_step)
     cls = rng.choice(len(cfg.class_names), size=G, p=_CLASS_P).astype(np.int32)
-    wlh = np.stack([dims[cfg.class_names[c]] for c in cls]) * rng.uniform(0.8, 1.2, (G, 3))
+    wlh = np.stack([dims[cfg.class_names[c]] for c in cls] + [np.zeros(3)])[:G] * rng.uniform(0.8, 1.2, (G, 3))
     centers = np.stack([rng.uniform(20, cfg.canvas_width - 20, G),
                         rng.uniform(20, cfg.canvas_height - 20, G),
                         rng.uniform(-1.0, 2.0, G)], axis=1)
