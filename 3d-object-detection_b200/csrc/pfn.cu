@@ -262,21 +262,36 @@ k_pfn_stats(const float* __restrict__ x, int B, int P, int N, int chunk, int nch
   }
 }
 
-__global__ void k_bn_finalize(int C, int nparts, double count, int training, float momentum,
-                              float eps, const double* __restrict__ partials,
-                              const float* __restrict__ bn_w, const float* __restrict__ bn_b,
-                              float* __restrict__ running_mean, float* __restrict__ running_var,
-                              long long* __restrict__ num_batches_tracked,
-                              Affine* __restrict__ affine) {
-  const int c = threadIdx.x;
-  if (c >= C) return;
-  double mean, var;
-  if (training) {
+// 64 channels x 8 segments: each thread sums a contiguous run of per-CTA partials, the eight
+// segment sums are combined in fixed order => deterministic, ~8x shorter dependency chain.
+__global__ void __launch_bounds__(512) k_bn_finalize(int C, int nparts, double count, int training,
+                                                     float momentum, float eps,
+                                                     const double* __restrict__ partials,
+                                                     const float* __restrict__ bn_w,
+                                                     const float* __restrict__ bn_b,
+                                                     float* __restrict__ running_mean,
+                                                     float* __restrict__ running_var,
+                                                     long long* __restrict__ num_batches_tracked,
+                                                     Affine* __restrict__ affine) {
+  __shared__ double s_part[2][8][64];
+  const int c = threadIdx.x & 63, seg = threadIdx.x >> 6;
+  if (training && c < C) {
+    const int per = (nparts + 7) / 8;
+    const int k0 = seg * per, k1 = min(nparts, k0 + per);
     double S = 0.0, Q = 0.0;
-    for (int k = 0; k < nparts; ++k) {
+    for (int k = k0; k < k1; ++k) {
       S += partials[((size_t)k * 2 + 0) * C + c];
       Q += partials[((size_t)k * 2 + 1) * C + c];
     }
+    s_part[0][seg][c] = S;
+    s_part[1][seg][c] = Q;
+  }
+  __syncthreads();
+  if (seg != 0 || c >= C) return;
+  double mean, var;
+  if (training) {
+    double S = 0.0, Q = 0.0;
+    for (int k = 0; k < 8; ++k) { S += s_part[0][k][c]; Q += s_part[1][k][c]; }
     mean = S / count;
     var = Q / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -369,32 +384,43 @@ __global__ void __launch_bounds__(256) k_canvas(const float* __restrict__ src,
   const int ncell = min(kCells, HW - cell0);
 
   if (any) {
-    // stage: warp w fills cells w*16 .. w*16+15 (uniform branch per cell)
+    // stage only the occupied cells (~5 % of the canvas): warp w owns cells w*16 .. w*16+15
     for (int j = warp * 16; j < warp * 16 + 16; ++j) {
       const int s = s_slot[j];
+      if (s < 0) continue;                       // warp-uniform
       for (int c = lane; c < C; c += 32) {
-        float v = 0.f;
-        if (s >= 0) {
-          if (FROM_EXT) {
-            const float* e = src + ((size_t)b * P + s) * 2 * C;
-            v = apply_affine(s_aff[c], e[c], e[C + c]);
-          } else {
-            v = src[((size_t)b * C + c) * P + s];
-          }
+        float v;
+        if (FROM_EXT) {
+          const float* e = src + ((size_t)b * P + s) * 2 * C;
+          v = apply_affine(s_aff[c], e[c], e[C + c]);
+        } else {
+          v = src[((size_t)b * C + c) * P + s];
         }
         tile[c * kStride + j] = v;
       }
     }
     __syncthreads();
   }
+  // every (channel, 4-cell group) is one coalesced 16-byte store; zeros unless a cell is occupied
+  int occ4 = 0;                                   // which of this lane's 4 cells are occupied
+  if (any) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) occ4 |= (s_slot[4 * lane + k] >= 0) ? (1 << k) : 0;
+  }
   for (int c = warp; c < C; c += 8) {
     float* row = cb + (size_t)c * HW;
     if (vec_ok && ncell == kCells) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (any) v = *reinterpret_cast<const float4*>(&tile[c * kStride + 4 * lane]);
+      if (occ4) {
+        const float* t = &tile[c * kStride + 4 * lane];
+        if (occ4 & 1) v.x = t[0];
+        if (occ4 & 2) v.y = t[1];
+        if (occ4 & 4) v.z = t[2];
+        if (occ4 & 8) v.w = t[3];
+      }
       __stcs(reinterpret_cast<float4*>(row) + lane, v);
     } else {
-      for (int j = lane; j < ncell; j += 32) row[j] = any ? tile[c * kStride + j] : 0.f;
+      for (int j = lane; j < ncell; j += 32) row[j] = (any && s_slot[j] >= 0) ? tile[c * kStride + j] : 0.f;
     }
   }
 }
@@ -461,7 +487,7 @@ static int pfn_common(const float* d_x, int B, int D, int P, int N, int C, const
   int rc = launch_stats(d_x, B, P, N, C, w, bias, training, ws, nblocks, st);
   if (rc != PP_OK) return rc;
   PP_KERNEL("k_bn_finalize", st,
-            k_bn_finalize<<<1, 64, 0, st>>>(C, nblocks, (double)B * P * N, training, momentum, eps,
+            k_bn_finalize<<<1, 512, 0, st>>>(C, nblocks, (double)B * P * N, training, momentum, eps,
                                             ws.partials, bn_w, bn_b, rm, rv, (long long*)nbt,
                                             ws.affine));
   return PP_OK;

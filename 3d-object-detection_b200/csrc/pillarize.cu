@@ -176,12 +176,35 @@ __global__ void __launch_bounds__(kTile) k_assign(
     if (w < (int)(threadIdx.x >> 5)) before += v;
     total += v;
   }
+  // kept pillars reserve a list segment of `cnt` entries: block-scan the counts and take ONE
+  // atomicAdd per tile (segments only have to be disjoint, not ordered)
+  int slot = -1, cnt = 0;
+  size_t ci = 0;
   if (flag) {
-    const int slot = base + before + in_warp;
-    const size_t ci = (size_t)b * g.ncell + cell;
+    slot = base + before + in_warp;
+    ci = (size_t)b * g.ncell + cell;
+    if (slot < P) cnt = cell_count[ci];
+  }
+  int incl = cnt;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)lane_id() >= o) incl += v;
+  }
+  __shared__ int warp_cnt[kTile / 32];
+  __shared__ int s_seg_base;
+  if (lane_id() == 31) warp_cnt[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  int cnt_before = 0, cnt_total = 0;
+  for (int w = 0; w < kTile / 32; ++w) {
+    const int v = warp_cnt[w];
+    if (w < (int)(threadIdx.x >> 5)) cnt_before += v;
+    cnt_total += v;
+  }
+  if (threadIdx.x == 0) s_seg_base = cnt_total > 0 ? atomicAdd(&list_cursor[b], cnt_total) : 0;
+  __syncthreads();
+  if (flag) {
     if (slot < P) {
-      const int cnt = cell_count[ci];
-      const int off = atomicAdd(&list_cursor[b], cnt);
+      const int off = s_seg_base + cnt_before + incl - cnt;
       const size_t pi = (size_t)b * P + slot;
       cell_slot[ci] = slot;
       pil_cnt[pi] = cnt;
@@ -296,10 +319,13 @@ __global__ void __launch_bounds__(kTile) k_rank_big(SweepParams sw, int P,
   }
 }
 
-// One warp per pillar slot: the reference's sequential running mean (data/pillars.cpp:311-328)
+// Eight lanes per pillar slot (four pillars per warp): the reference's sequential running mean
+// (data/pillars.cpp:311-328)
 //   m <- m*(n/(n+1)) + x/(n+1)
 // evaluated in input order with separately rounded IEEE operations.  The divisions do not depend
-// on m, so the lanes compute them 32 at a time and only the multiply-add chain is sequential.
+// on m, so the lanes of a group compute them 8 at a time and only the multiply-add chain is
+// sequential (median pillar: 2 points, p90: 7).
+constexpr int kMeanGroup = 8;
 template <typename T>
 __global__ void __launch_bounds__(256) k_mean(const T* __restrict__ pts, long long sp, long long sc,
                                               bool vec4, SweepParams sw, GridDev g, int P,
@@ -310,53 +336,58 @@ __global__ void __launch_bounds__(256) k_mean(const T* __restrict__ pts, long lo
                                               const int* __restrict__ list_s,
                                               double* __restrict__ pil_mean,
                                               long long* __restrict__ indices) {
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = (long long)sw.n_sweeps * P;
-  if (warp >= nwarps) return;
-  const int b = (int)(warp / P);
-  const int slot = (int)(warp % P);
+  const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kMeanGroup;
+  const long long ngrp = (long long)sw.n_sweeps * P;
   const unsigned lane = lane_id();
-  if (slot >= num_pillars[b]) {
-    if (indices != nullptr && lane < 3) indices[warp * 3 + lane] = 0;
-    return;
-  }
-  const int c = pil_cnt[warp];
-  const int* seg = list_s + sw.off[b] + pil_off[warp];
+  const unsigned li = lane % kMeanGroup;            // lane inside the group
+  const unsigned gbase = lane - li;                 // first lane of the group
+  const bool in_range = grp < ngrp;
+  const int b = in_range ? (int)(grp / P) : 0;
+  const int slot = in_range ? (int)(grp % P) : 0;
+  const bool live = in_range && slot < num_pillars[b];
+  if (in_range && !live && indices != nullptr && li < 3) indices[grp * 3 + li] = 0;
+  const int c = live ? pil_cnt[grp] : 0;
+  int cmax = c;
+  for (int o = 16; o >= kMeanGroup; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+  const int* seg = live ? list_s + sw.off[b] + pil_off[grp] : nullptr;
   double m0 = 0, m1 = 0, m2 = 0;
-  for (int s = 0; s < c; s += 32) {
-    const int k = s + (int)lane;
+  for (int s = 0; s < cmax; s += kMeanGroup) {
+    const int k = s + (int)li;
     double x = 0, y = 0, z = 0, r = 0;
     if (k < c) load_xyz(pts, sw.off[b] + seg[k], sp, sc, vec4, x, y, z, r);
     const double n = (double)k;
     const double n1 = __dadd_rn(n, 1.0);
     const double a = __ddiv_rn(n, n1);
     const double dx = __ddiv_rn(x, n1), dy = __ddiv_rn(y, n1), dz = __ddiv_rn(z, n1);
-    const int lim = min(32, c - s);
+    const int lim = min(kMeanGroup, cmax - s);
     for (int j = 0; j < lim; ++j) {
-      const double aj = __shfl_sync(0xffffffffu, a, j);
-      const double xj = __shfl_sync(0xffffffffu, (s + j == 0) ? x : dx, j);
-      const double yj = __shfl_sync(0xffffffffu, (s + j == 0) ? y : dy, j);
-      const double zj = __shfl_sync(0xffffffffu, (s + j == 0) ? z : dz, j);
-      if (s + j == 0) {
-        m0 = xj; m1 = yj; m2 = zj;  // data/pillars.cpp:313-317
-      } else {
-        m0 = __dadd_rn(__dmul_rn(m0, aj), xj);  // data/pillars.cpp:324-326
-        m1 = __dadd_rn(__dmul_rn(m1, aj), yj);
-        m2 = __dadd_rn(__dmul_rn(m2, aj), zj);
+      const bool first = (s + j == 0);
+      const double aj = __shfl_sync(0xffffffffu, a, gbase + j);
+      const double xj = __shfl_sync(0xffffffffu, first ? x : dx, gbase + j);
+      const double yj = __shfl_sync(0xffffffffu, first ? y : dy, gbase + j);
+      const double zj = __shfl_sync(0xffffffffu, first ? z : dz, gbase + j);
+      if (s + j < c) {
+        if (first) {
+          m0 = xj; m1 = yj; m2 = zj;  // data/pillars.cpp:313-317
+        } else {
+          m0 = __dadd_rn(__dmul_rn(m0, aj), xj);  // data/pillars.cpp:324-326
+          m1 = __dadd_rn(__dmul_rn(m1, aj), yj);
+          m2 = __dadd_rn(__dmul_rn(m2, aj), zj);
+        }
       }
     }
   }
-  if (lane == 0) {
-    pil_mean[warp * 3 + 0] = m0;
-    pil_mean[warp * 3 + 1] = m1;
-    pil_mean[warp * 3 + 2] = m2;
+  if (live && li == 0) {
+    pil_mean[grp * 3 + 0] = m0;
+    pil_mean[grp * 3 + 1] = m1;
+    pil_mean[grp * 3 + 2] = m2;
     if (indices != nullptr) {
-      const int cell = pil_cell[warp];
+      const int cell = pil_cell[grp];
       const double cx = (double)(cell % g.nx);
       const double cy = __dsub_rn(__dsub_rn(g.canvas_height, 1.0), (double)(cell / g.nx));
-      indices[warp * 3 + 0] = 1;                 // data/pillars.cpp:390-392, then .long()
-      indices[warp * 3 + 1] = (long long)cx;
-      indices[warp * 3 + 2] = (long long)cy;
+      indices[grp * 3 + 0] = 1;                 // data/pillars.cpp:390-392, then .long()
+      indices[grp * 3 + 1] = (long long)cx;
+      indices[grp * 3 + 2] = (long long)cy;
     }
   }
 }
@@ -373,58 +404,64 @@ __device__ __forceinline__ void point_features(double x, double y, double z, dou
   f[8] = __dsub_rn(mean[2], z);
 }
 
-// Dense emit: x[b,d,p,n] = float(feature) - data_mean[d,p,n] for every slot (data/dataset.py:99-105).
-// One thread owns VEC consecutive n of one pillar for all 9 features and all sweeps, so that
-// data_mean is read once per batch and every access is a full-width coalesced vector.  ~98.7 % of
-// the groups hold no point: they stream "0 - mean"; the occupied ones take the out-of-line path.
-template <typename T, int VEC>
-__device__ __noinline__ void emit_occupied(const T* __restrict__ pts, long long sp, long long sc,
-                                           bool vec4, long long pt_base, const GridDev& g, int c,
-                                           int n0, int cell, const double* __restrict__ pmean,
-                                           const int* __restrict__ seg,
-                                           const float* __restrict__ mean_ptr, long long PN,
-                                           float* __restrict__ ob) {
-  const double cx = (double)(cell % g.nx);
-  const double cy = __dsub_rn(__dsub_rn(g.canvas_height, 1.0), (double)(cell / g.nx));
-  const double mean[3] = {pmean[0], pmean[1], pmean[2]};
+constexpr int kFeatGroup = 3;   // features per thread in k_emit_dense (9 = 3 groups -> grid.y)
+
+// Per kept point (rank < N inside a kept pillar): the nine decorated features in fp64, rounded once
+// to fp32 (torch .float(), data/dataset.py:101), stored compactly at the point's position in its
+// pillar's ordered segment.  Keeps all fp64 math out of the streaming kernel below.
+template <typename T>
+__global__ void __launch_bounds__(256) k_feat(const T* __restrict__ pts, long long sp, long long sc,
+                                              bool vec4, SweepParams sw, GridDev g, int P, int N,
+                                              const int* __restrict__ cell_of_point,
+                                              const int* __restrict__ cell_slot,
+                                              const int* __restrict__ rank_of_point,
+                                              const int* __restrict__ pil_off,
+                                              const double* __restrict__ pil_mean,
+                                              float* __restrict__ feat_c) {
+  const long long total = sw.off[sw.n_sweeps];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cell = cell_of_point[i];
+    if (cell < 0) continue;
+    const int b = find_sweep(sw, i);
+    const int slot = cell_slot[(size_t)b * g.ncell + cell];
+    if (slot < 0) continue;
+    const int rank = rank_of_point[i];
+    if (rank >= N) continue;                       // data/pillars.cpp:371 first-N cap
+    const size_t pi = (size_t)b * P + slot;
+    double x, y, z, r, ft[9];
+    load_xyz(pts, i, sp, sc, vec4, x, y, z, r);
+    const double cx = (double)(cell % g.nx);
+    const double cy = __dsub_rn(__dsub_rn(g.canvas_height, 1.0), (double)(cell / g.nx));
+    point_features(x, y, z, r, cx, cy, pil_mean + pi * 3, ft);
+    float* o = feat_c + (size_t)(sw.off[b] + pil_off[pi] + rank) * 9;
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    double ft[9];
-#pragma unroll
-    for (int d = 0; d < 9; ++d) ft[d] = 0.0;
-    if (n0 + k < c) {
-      double x, y, z, r;
-      load_xyz(pts, pt_base + seg[n0 + k], sp, sc, vec4, x, y, z, r);
-      point_features(x, y, z, r, cx, cy, mean, ft);
-    }
-#pragma unroll
-    for (int d = 0; d < 9; ++d) {
-      const float m = mean_ptr != nullptr ? __ldg(mean_ptr + d * PN + k) : 0.f;
-      ob[d * PN + k] = __fsub_rn((float)ft[d], m);  // torch .float() then fp32 subtract
-    }
+    for (int d = 0; d < 9; ++d) o[d] = (float)ft[d];
   }
 }
 
-template <typename T, int VEC>
-__global__ void __launch_bounds__(256, 3) k_emit_dense(
-    const T* __restrict__ pts, long long sp, long long sc, bool vec4, SweepParams sw, GridDev g,
-    int P, int N, const float* __restrict__ data_mean, float* __restrict__ xout,
+// Dense emit: x[b,d,p,n] = float(feature) - data_mean[d,p,n] for every slot (data/dataset.py:99-105).
+// One thread owns VEC consecutive n of one pillar for kFeatGroup features and all sweeps, so that
+// data_mean is read once per batch and every access is a full-width coalesced vector.  ~98.7 % of
+// the groups hold no point and stream "0 - mean"; occupied ones pick their features up from k_feat.
+template <int VEC>
+__global__ void __launch_bounds__(256) k_emit_dense(
+    SweepParams sw, int P, int N, const float* __restrict__ data_mean, float* __restrict__ xout,
     const int* __restrict__ num_pillars, const int* __restrict__ pil_cnt,
-    const int* __restrict__ pil_off, const int* __restrict__ pil_cell,
-    const double* __restrict__ pil_mean, const int* __restrict__ list_s) {
+    const int* __restrict__ pil_off, const float* __restrict__ feat_c) {
   typedef typename std::conditional<VEC == 4, float4, float>::type vec_t;
   const long long PN = (long long)P * N;
-  const long long groups = PN / VEC;
-  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups;
-       gi += (long long)gridDim.x * blockDim.x) {
-    const long long e = gi * VEC;
-    const int p = (int)(e / N);
-    const int n0 = (int)(e % N);
-    vec_t m[9];
+  const unsigned groups = (unsigned)(PN / VEC);
+  const int d0 = blockIdx.y * kFeatGroup;
+  for (unsigned gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
+    const unsigned e = gi * VEC;
+    const int p = (int)(e / (unsigned)N);
+    const int n0 = (int)(e - (unsigned)p * (unsigned)N);
+    vec_t m[kFeatGroup];
 #pragma unroll
-    for (int d = 0; d < 9; ++d) {
+    for (int d = 0; d < kFeatGroup; ++d) {
       if (data_mean != nullptr) {
-        m[d] = __ldg(reinterpret_cast<const vec_t*>(data_mean + d * PN + e));
+        m[d] = __ldg(reinterpret_cast<const vec_t*>(data_mean + (d0 + d) * PN + e));
       } else {
         float* mf = reinterpret_cast<float*>(&m[d]);
 #pragma unroll
@@ -436,20 +473,18 @@ __global__ void __launch_bounds__(256, 3) k_emit_dense(
       int c = 0;
       if (p < num_pillars[b]) c = min(pil_cnt[pi], N);  // data/pillars.cpp:371 first-N cap
       float* ob = xout + (size_t)b * 9 * PN + e;
-      if (n0 < c) {
-        emit_occupied<T, VEC>(pts, sp, sc, vec4, sw.off[b], g, c, n0, pil_cell[pi],
-                              pil_mean + pi * 3, list_s + sw.off[b] + pil_off[pi],
-                              data_mean != nullptr ? data_mean + e : nullptr, PN, ob);
-      } else {
+      const float* fc = (n0 < c) ? feat_c + (size_t)(sw.off[b] + pil_off[pi] + n0) * 9 + d0 : nullptr;
 #pragma unroll
-        for (int d = 0; d < 9; ++d) {
-          vec_t v;
-          float* vf = reinterpret_cast<float*>(&v);
-          const float* mf = reinterpret_cast<const float*>(&m[d]);
+      for (int d = 0; d < kFeatGroup; ++d) {
+        vec_t v;
+        float* vf = reinterpret_cast<float*>(&v);
+        const float* mf = reinterpret_cast<const float*>(&m[d]);
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) vf[k] = __fsub_rn(0.f, mf[k]);  // 0 - mean, like the reference
-          *reinterpret_cast<vec_t*>(ob + d * PN) = v;
+        for (int k = 0; k < VEC; ++k) {
+          const float f = (fc != nullptr && n0 + k < c) ? fc[k * 9 + d] : 0.f;
+          vf[k] = __fsub_rn(f, mf[k]);            // feature (or 0) - mean, like the reference
         }
+        __stcs(reinterpret_cast<vec_t*>(ob + (d0 + d) * PN), v);
       }
     }
   }
@@ -507,6 +542,7 @@ struct PillarWs {
   int *cell_first, *cell_slot, *cell_of_point, *rank_of_point, *tile_count, *list_u, *list_s;
   int *pil_cnt, *pil_off, *pil_cell, *big_list, *num_pillars_scratch;
   double* pil_mean;
+  float* feat_c;
   // zero-initialised block (one memset)
   int* zero_begin;
   int *cell_count, *pil_cursor, *list_cursor, *big_count, *n_rows;
@@ -561,6 +597,7 @@ static void layout(A& a, PillarWs* ws, int B, long long T, long long ntiles, int
   TAKE(pil_cell, int, np);
   TAKE(big_list, int, t / kBig + 2);
   TAKE(pil_mean, double, np * 3);
+  TAKE(feat_c, float, t * 9);
 #undef TAKE
 }
 
@@ -596,8 +633,8 @@ static int run_stages(const T* pts, long long sp, long long sc, bool vec4, const
     PP_KERNEL("k_rank_big", st, k_rank_big<<<64, kTile, 0, st>>>(sw, P, ws.cell_of_point, ws.pil_off, ws.pil_cell,
                                      ws.big_count, ws.big_list, ws.list_s, ws.rank_of_point));
   }
-  const long long warps = (long long)B * P;
-  const int mean_blocks = (int)((warps * 32 + 255) / 256);
+  const long long groups = (long long)B * P;
+  const int mean_blocks = (int)((groups * kMeanGroup + 255) / 256);
   PP_KERNEL("k_mean", st, k_mean<T><<<mean_blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, P, d_num_pillars, ws.pil_cnt,
                                          ws.pil_off, ws.pil_cell, ws.list_s, ws.pil_mean,
                                          d_indices));
@@ -633,7 +670,7 @@ static int pillarize_impl(const T* pts, long long sp, long long sc, const int64_
   int rc = make_sweeps(h_off, B, sw);
   if (rc != PP_OK) return rc;
   if (N < 1 || P < 1 || d_x == nullptr || d_indices == nullptr || d_num_pillars == nullptr ||
-      d_status == nullptr || (pts == nullptr && sw.off[B] > 0))
+      d_status == nullptr || (pts == nullptr && sw.off[B] > 0) || (long long)P * N > 0x7fffffffll)
     return PP_ERR_INVALID_ARG;
   if ((long long)B * g.ncell > 0x7fffffffll || (long long)B * P > 0x3fffffffll) return PP_ERR_INVALID_ARG;
   Arena arena(d_ws, ws_bytes);
@@ -651,16 +688,22 @@ static int pillarize_impl(const T* pts, long long sp, long long sc, const int64_
   long long blocks = (groups + 255) / 256;
   const long long cap = (long long)sm_count() * 32;
   if (blocks > cap) blocks = cap;
+  const dim3 egrid((unsigned)blocks, 9 / kFeatGroup);
+  const long long total = sw.off[B];
+  if (total > 0) {
+    PP_KERNEL("k_feat", st,
+              k_feat<T><<<(int)((total + 255) / 256), 256, 0, st>>>(
+                  pts, sp, sc, vec4, sw, g, P, N, ws.cell_of_point, ws.cell_slot, ws.rank_of_point,
+                  ws.pil_off, ws.pil_mean, ws.feat_c));
+  }
   if (v4) {
     PP_KERNEL("k_emit_dense", st,
-              (k_emit_dense<T, 4><<<(int)blocks, 256, 0, st>>>(
-                  pts, sp, sc, vec4, sw, g, P, N, d_mean, d_x, d_num_pillars, ws.pil_cnt, ws.pil_off,
-                  ws.pil_cell, ws.pil_mean, ws.list_s)));
+              k_emit_dense<4><<<egrid, 256, 0, st>>>(sw, P, N, d_mean, d_x, d_num_pillars, ws.pil_cnt,
+                                                     ws.pil_off, ws.feat_c));
   } else {
     PP_KERNEL("k_emit_dense", st,
-              (k_emit_dense<T, 1><<<(int)blocks, 256, 0, st>>>(
-                  pts, sp, sc, vec4, sw, g, P, N, d_mean, d_x, d_num_pillars, ws.pil_cnt, ws.pil_off,
-                  ws.pil_cell, ws.pil_mean, ws.list_s)));
+              k_emit_dense<1><<<egrid, 256, 0, st>>>(sw, P, N, d_mean, d_x, d_num_pillars, ws.pil_cnt,
+                                                     ws.pil_off, ws.feat_c));
   }
   return PP_OK;
 }

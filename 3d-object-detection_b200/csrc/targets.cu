@@ -17,7 +17,7 @@
 //   k_iou_pass<1>  same enumeration: candidates whose IoU equals best[a] -> atomicMin(arg[a], g);
 //                  positives (best > thresh) set a bit in posmask
 //   k_encode       dense, vectorised write of cls[A,K] and reg[A,9] (zeros + positives)
-//   k_forced       per sweep: the per-GT best-anchor overrides, in the reference's order
+//                  (forced per-GT best-anchor overrides are resolved inline, in the reference's order)
 #include <vector>
 
 #include "common.cuh"
@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(256) k_iou_pass(
     const unsigned char* __restrict__ index, long long A, const double* __restrict__ g_corners,
     const double* __restrict__ g_centers, GtParams gp, double pos_thresh,
     unsigned long long* __restrict__ best, int* __restrict__ arg, unsigned* __restrict__ posmask,
-    int* __restrict__ top_anchor, int* __restrict__ counts, int* __restrict__ status) {
+    unsigned* __restrict__ forcedmask, int* __restrict__ top_anchor, int* __restrict__ counts,
+    int* __restrict__ status) {
   const long long gg = blockIdx.x;  // global GT row
   const int b = find_gt_sweep(gp, gg);
   const int gl = (int)(gg - gp.off[b]);  // index of the GT inside its sweep
@@ -174,6 +175,14 @@ __global__ void __launch_bounds__(256) k_iou_pass(
   unsigned long long my_best = 0ull;
   int my_a = 0x7fffffff;
   unsigned long long* best_b = best + (size_t)b * A;
+  if (PASS == 1 && threadIdx.x == 0) {
+    // per-GT best anchor (computed by pass 0); 0 means "dropped" (utils/box_utils.py:204)
+    const int t = top_anchor[gg];
+    if (t != 0) {
+      atomicOr(&forcedmask[(size_t)b * ((A + 31) / 32) + (t >> 5)], 1u << (t & 31));
+      atomicAdd(&counts[b * 4 + 1], 1);
+    }
+  }
 
   for (int by = by0; by <= by1; ++by) {
     if (bx1 < bx0) break;
@@ -255,98 +264,87 @@ struct EncodeArgs {
   const int* g_cls;
   const int* arg;
   const unsigned* posmask;
+  const unsigned* forcedmask;
+  const int* top_anchor;
 };
 
-__device__ __forceinline__ bool is_pos(const EncodeArgs& ea, int b, long long A, long long a) {
-  return (ea.posmask[(size_t)b * ((A + 31) / 32) + (a >> 5)] >> (a & 31)) & 1u;
+// bit 0: positive by threshold, bit 1: forced (best anchor of some kept GT)
+__device__ __forceinline__ unsigned anchor_flags(const EncodeArgs& ea, int b, long long A, long long a) {
+  const size_t w = (size_t)b * ((A + 31) / 32) + (a >> 5);
+  return ((ea.posmask[w] >> (a & 31)) & 1u) | (((ea.forcedmask[w] >> (a & 31)) & 1u) << 1);
 }
 
 __device__ float encode_value(const EncodeArgs& ea, const GtParams& gp, int b, long long A, long long a,
-                              int col, bool is_reg) {
-  const long long gg = gp.off[b] + ea.arg[(size_t)b * A + a];
-  if (!is_reg) return ea.g_cls[gg] == col ? 1.f : 0.f;   // utils/box_utils.py:211
+                              int col, bool is_reg, unsigned flags) {
+  long long gg;
+  if (flags & 2u) {
+    // forced match (utils/box_utils.py:212-213,226-228): the row is cleared, every kept GT whose best
+    // anchor is `a` sets its class bit, the LAST such GT writes the regression row
+    gg = -1;
+    bool hit = false;
+    for (long long h = gp.off[b]; h < gp.off[b + 1]; ++h) {
+      if (ea.top_anchor[h] == (int)a) {
+        gg = h;
+        hit = hit || (ea.g_cls[h] == col);
+      }
+    }
+    if (!is_reg) return hit ? 1.f : 0.f;
+  } else {
+    gg = gp.off[b] + ea.arg[(size_t)b * A + a];
+    if (!is_reg) return ea.g_cls[gg] == col ? 1.f : 0.f;   // utils/box_utils.py:211
+  }
   double t[9];
   make_target(ea.a_centers + a * 3, ea.a_wlh + a * 3, ea.a_yaw[a], ea.g_centers + gg * 3,
               ea.g_wlh + gg * 3, ea.g_yaw[gg], t);
   return (float)t[col];                                   // utils/box_utils.py:219-221, then .float()
 }
 
-// dense write of one [A, ncol] float matrix per sweep (cls when !IS_REG, reg when IS_REG)
-template <bool IS_REG>
-__global__ void __launch_bounds__(256) k_encode(EncodeArgs ea, GtParams gp, long long A, int ncol,
+// dense write of one [A, ncol] float matrix per sweep (cls when !IS_REG, reg when IS_REG).
+// NCOL > 0 fixes the row width at compile time (9 for both outputs of the reference config) so the
+// element -> (anchor, column) split is a multiply-shift, not a 64-bit division.
+template <bool IS_REG, int NCOL>
+__global__ void __launch_bounds__(256) k_encode(EncodeArgs ea, GtParams gp, long long A, int ncol_rt,
                                                 bool vec_ok, float* __restrict__ out) {
+  const unsigned ncol = NCOL > 0 ? (unsigned)NCOL : (unsigned)ncol_rt;
   const int b = blockIdx.y;
-  const long long total = A * ncol;
+  const unsigned total = (unsigned)(A * ncol);        // host guarantees A*ncol < 2^31
   float* ob = out + (size_t)b * total;
+  const unsigned stride = gridDim.x * blockDim.x;
   if (vec_ok) {
-    const long long groups = total / 4;
-    for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups;
-         gi += (long long)gridDim.x * blockDim.x) {
-      const long long e0 = gi * 4;
-      const long long a0 = e0 / ncol, a1 = (e0 + 3) / ncol;
+    const unsigned groups = total / 4;
+    for (unsigned gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += stride) {
+      const unsigned e0 = gi * 4;
+      const unsigned a0 = e0 / ncol, a1 = (e0 + 3) / ncol;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      bool any = is_pos(ea, b, A, a0);
-      for (long long a = a0 + 1; a <= a1; ++a) any = any || is_pos(ea, b, A, a);
+      unsigned any = anchor_flags(ea, b, A, a0);
+      if (a1 != a0) any |= anchor_flags(ea, b, A, a1);
       if (any) {
         float* vf = reinterpret_cast<float*>(&v);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const long long a = (e0 + k) / ncol;
-          const int col = (int)((e0 + k) % ncol);
-          if (is_pos(ea, b, A, a)) vf[k] = encode_value(ea, gp, b, A, a, col, IS_REG);
+          const unsigned a = (e0 + k) / ncol;
+          const int col = (int)((e0 + k) - a * ncol);
+          const unsigned fl = anchor_flags(ea, b, A, a);
+          if (fl) vf[k] = encode_value(ea, gp, b, A, a, col, IS_REG, fl);
         }
       }
       __stcs(reinterpret_cast<float4*>(ob) + gi, v);
     }
   } else {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-      const long long a = e / ncol;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+      const unsigned a = e / ncol;
       float v = 0.f;
-      if (is_pos(ea, b, A, a)) v = encode_value(ea, gp, b, A, a, (int)(e % ncol), IS_REG);
+      const unsigned fl = anchor_flags(ea, b, A, a);
+      if (fl) v = encode_value(ea, gp, b, A, a, (int)(e - a * ncol), IS_REG, fl);
       ob[e] = v;
     }
   }
 }
 
-// utils/box_utils.py:212-213,226-228: per-GT best anchors override, later GT wins on reg.
-__global__ void __launch_bounds__(256) k_forced(EncodeArgs ea, GtParams gp, long long A, int ncls,
-                                                const int* __restrict__ top_anchor,
-                                                float* __restrict__ cls, float* __restrict__ reg,
-                                                int* __restrict__ counts) {
-  const int b = blockIdx.x;
-  const long long g0 = gp.off[b], g1 = gp.off[b + 1];
-  float* cb = cls + (size_t)b * A * ncls;
-  float* rb = reg + (size_t)b * A * 9;
-  int kept = 0;
-  for (long long g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
-    const int t = top_anchor[g];
-    if (t != 0) {
-      ++kept;
-      for (int c = 0; c < ncls; ++c) cb[(size_t)t * ncls + c] = 0.f;
-    }
-  }
-  __syncthreads();
-  for (long long g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
-    const int t = top_anchor[g];
-    if (t == 0) continue;
-    const int c = ea.g_cls[g];
-    if (c >= 0 && c < ncls) cb[(size_t)t * ncls + c] = 1.f;
-    bool last = true;
-    for (long long h = g + 1; h < g1; ++h) if (top_anchor[h] == t) { last = false; break; }
-    if (last) {
-      double tv[9];
-      make_target(ea.a_centers + (size_t)t * 3, ea.a_wlh + (size_t)t * 3, ea.a_yaw[t],
-                  ea.g_centers + g * 3, ea.g_wlh + g * 3, ea.g_yaw[g], tv);
-      for (int k = 0; k < 9; ++k) rb[(size_t)t * 9 + k] = (float)tv[k];
-    }
-  }
-  if (kept) atomicAdd(&counts[b * 4 + 1], kept);
-}
-
 struct TargetWs {
   unsigned long long* best;  // [B, A]   zero-init
   unsigned* posmask;         // [B, ceil(A/32)] zero-init
+  unsigned* forcedmask;      // [B, ceil(A/32)] zero-init
   int* arg;                  // [B, A]   0x7f-init
   size_t zero_bytes;
 };
@@ -356,9 +354,10 @@ static void targets_layout(AR& a, TargetWs* ws, int B, long long A) {
   size_t z0 = a.used;
   auto p0 = a.template take<unsigned long long>((size_t)B * A);
   auto p1 = a.template take<unsigned>((size_t)B * ((A + 31) / 32));
+  auto p3 = a.template take<unsigned>((size_t)B * ((A + 31) / 32));
   size_t z1 = a.used;
   auto p2 = a.template take<int>((size_t)B * A);
-  if (ws) { ws->best = p0; ws->posmask = p1; ws->arg = p2; ws->zero_bytes = z1 - z0; }
+  if (ws) { ws->best = p0; ws->posmask = p1; ws->forcedmask = p3; ws->arg = p2; ws->zero_bytes = z1 - z0; }
 }
 
 struct SizeArena3 {
@@ -484,7 +483,8 @@ int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (!d_a_corners || !d_a_centers || !d_a_wlh || !d_a_yaw || !d_anchor_index || A < 1 ||
       A > 0x7fffffffll || !h_gt_offsets || n_sweeps < 1 || n_sweeps > PP_MAX_SWEEPS ||
-      num_classes < 1 || !d_cls || !d_reg || !d_counts || !d_status)
+      num_classes < 1 || !d_cls || !d_reg || !d_counts || !d_status ||
+      (long long)A * (num_classes > 9 ? num_classes : 9) > 0x7fffffffll)
     return PP_ERR_INVALID_ARG;
   GtParams gp;
   gp.n_sweeps = n_sweeps;
@@ -509,32 +509,34 @@ int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, cons
   if (Gt > 0) {
     PP_KERNEL("k_iou_pass", st, k_iou_pass<0><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
                                            d_g_centers, gp, pos_thresh, ws.best, ws.arg, ws.posmask,
-                                           d_top_anchor, d_counts, d_status));
+                                           ws.forcedmask, d_top_anchor, d_counts, d_status));
     PP_KERNEL("k_iou_pass", st, k_iou_pass<1><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
                                            d_g_centers, gp, pos_thresh, ws.best, ws.arg, ws.posmask,
-                                           d_top_anchor, d_counts, d_status));
+                                           ws.forcedmask, d_top_anchor, d_counts, d_status));
   }
-  EncodeArgs ea{d_a_centers, d_a_wlh, d_a_yaw, d_g_centers, d_g_wlh, d_g_yaw, d_g_cls, ws.arg, ws.posmask};
+  EncodeArgs ea{d_a_centers, d_a_wlh, d_a_yaw, d_g_centers, d_g_wlh, d_g_yaw, d_g_cls, ws.arg,
+                ws.posmask, ws.forcedmask, d_top_anchor};
   {
     const long long total = (long long)A * num_classes;
     const bool vec_ok = (total % 4 == 0) && ((uintptr_t)d_cls % 16 == 0);
     long long blocks = ((vec_ok ? total / 4 : total) + 255) / 256;
-    const long long cap = (long long)sm_count() * 16;
+    const long long cap = (long long)sm_count() * 32;
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)n_sweeps);
-    PP_KERNEL("k_encode", st, k_encode<false><<<grid, 256, 0, st>>>(ea, gp, A, num_classes, vec_ok, d_cls));
+    if (num_classes == 9) {
+      PP_KERNEL("k_encode", st, (k_encode<false, 9><<<grid, 256, 0, st>>>(ea, gp, A, 9, vec_ok, d_cls)));
+    } else {
+      PP_KERNEL("k_encode", st, (k_encode<false, 0><<<grid, 256, 0, st>>>(ea, gp, A, num_classes, vec_ok, d_cls)));
+    }
   }
   {
     const long long total = (long long)A * 9;
     const bool vec_ok = (total % 4 == 0) && ((uintptr_t)d_reg % 16 == 0);
     long long blocks = ((vec_ok ? total / 4 : total) + 255) / 256;
-    const long long cap = (long long)sm_count() * 16;
+    const long long cap = (long long)sm_count() * 32;
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)n_sweeps);
-    PP_KERNEL("k_encode", st, k_encode<true><<<grid, 256, 0, st>>>(ea, gp, A, 9, vec_ok, d_reg));
-  }
-  if (Gt > 0) {
-    PP_KERNEL("k_forced", st, k_forced<<<n_sweeps, 256, 0, st>>>(ea, gp, A, num_classes, d_top_anchor, d_cls, d_reg, d_counts));
+    PP_KERNEL("k_encode", st, (k_encode<true, 9><<<grid, 256, 0, st>>>(ea, gp, A, 9, vec_ok, d_reg)));
   }
   return PP_OK;
 }
