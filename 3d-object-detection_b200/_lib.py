@@ -35,6 +35,7 @@ _SIGNATURES = {
     "pp_error_string": (_c.c_char_p, [_c.c_int]),
     "pp_last_cuda_error": (_c.c_int, []),
     "pp_launch_count": (_i64, []),
+    "pp_set_option": (_c.c_int, [_c.c_char_p, _c.c_int]),
     "pp_profile_enable": (_c.c_int, [_c.c_int]),
     "pp_profile_report": (_i64, [_c.c_char_p, _i64]),
     "pp_pillarize_workspace_bytes": (_sz, [_i32, _i64, _gridp, _i32]),

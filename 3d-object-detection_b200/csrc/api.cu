@@ -11,6 +11,7 @@
 
 namespace pp {
 thread_local int g_last_cuda_error = 0;
+int g_opt_pfn_tensor_cores = 1;
 
 // ---- launch counter + optional per-kernel CUDA-event timing -----------------------------------
 static std::atomic<long long> g_launches{0};
@@ -43,6 +44,12 @@ extern "C" {
 int pp_version(void) { return PP_B200_VERSION; }
 
 int pp_last_cuda_error(void) { return pp::g_last_cuda_error; }
+
+int pp_set_option(const char* key, int value) {
+  if (key == nullptr) return PP_ERR_INVALID_ARG;
+  if (strcmp(key, "pfn_tensor_cores") == 0) { pp::g_opt_pfn_tensor_cores = value ? 1 : 0; return PP_OK; }
+  return PP_ERR_INVALID_ARG;
+}
 
 int64_t pp_launch_count(void) { return (int64_t)pp::g_launches.load(); }
 

@@ -456,8 +456,20 @@ static int stats_blocks(long long rows) {
   return (int)nb;
 }
 
+// tensor-core (tcgen05) variant, pfn_tc.cu
+bool pfn_tc_supported(int D, int N, int C, const void* x);
+int launch_stats_tc(const float* d_x, int B, int P, int N, const float* w, const float* bias,
+                    const float* bn_w, int training, float* ext, double* partials, int nblocks,
+                    cudaStream_t st);
+extern int g_opt_pfn_tensor_cores;
+
 static int launch_stats(const float* d_x, int B, int P, int N, int C, const float* w, const float* bias,
-                        int training, PfnWs& ws, int nblocks, cudaStream_t st) {
+                        const float* bn_w, int training, PfnWs& ws, int& nblocks, cudaStream_t st) {
+  if (g_opt_pfn_tensor_cores && pfn_tc_supported(kD, N, C, d_x)) {
+    const long long pairs = ((long long)B * P + 1) / 2;
+    nblocks = (int)(pairs < sm_count() ? pairs : sm_count());
+    return launch_stats_tc(d_x, B, P, N, w, bias, bn_w, training, ws.ext, ws.partials, nblocks, st);
+  }
   int chunk = N < kMaxChunk ? N : kMaxChunk;
   chunk = (chunk + 3) & ~3;
   const int nchunks = (N + chunk - 1) / chunk;
@@ -484,7 +496,7 @@ static int pfn_common(const float* d_x, int B, int D, int P, int N, int C, const
                       const float* bias, const float* bn_w, const float* bn_b, float* rm, float* rv,
                       int64_t* nbt, int training, float momentum, float eps, PfnWs& ws, int nblocks,
                       cudaStream_t st) {
-  int rc = launch_stats(d_x, B, P, N, C, w, bias, training, ws, nblocks, st);
+  int rc = launch_stats(d_x, B, P, N, C, w, bias, bn_w, training, ws, nblocks, st);
   if (rc != PP_OK) return rc;
   PP_KERNEL("k_bn_finalize", st,
             k_bn_finalize<<<1, 512, 0, st>>>(C, nblocks, (double)B * P * N, training, momentum, eps,

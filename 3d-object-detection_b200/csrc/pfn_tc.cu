@@ -1,0 +1,408 @@
+// pfn_tc.cu -- K2 statistics pass on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Why tensor cores: on CUDA cores the 9->64 contraction of PPFeatureNet is FP32-issue-bound, not
+// HBM-bound (ncu r1a: 856 M warp instructions per batch-4 launch, DRAM 7 % of peak), which is the
+// case BASELINE.json:north_star reserves tensor cores for.
+//
+// Per pillar row (b,p) the kernel computes  Y^T[c, n] = sum_k A'[c,k] * B'[k,n]  with
+//   M = 64 channels, N = the N point slots of the pillar (one UMMA tile, N % 8 == 0, N <= 256),
+//   K = 4 k-steps of 8 (kind::tf32), fp32 accumulation in TMEM.
+// 1e-5 parity rules out plain TF32, so x and W are split  v = v_hi + v_lo  (both exactly
+// representable in tf32) and the three significant products are laid out along K:
+//   B' k     0.. 8  x_hi[0..8]      k     9..17  x_lo[0..8]    k   18  x_hi[8] (copy)
+//            19, 20  1.0 (bias rows) k    21..23  0
+//   k-step 0: rows 0-7   x A cols  W_hi[0..7]
+//   k-step 1: rows 8-15  x A cols [W_hi[8], W_hi[0..6]]             (x_hi[8], x_lo[0..6])
+//   k-step 2: rows 16-23 x A cols [W_hi[7], W_hi[8], W_lo[8], b_hi, b_lo, 0, 0, 0]
+//   k-step 3: rows 0-7   x A cols  W_lo[0..7]                        (re-reads the x_hi rows)
+// => y = W_hi x_hi + W_hi x_lo + W_lo x_hi + b  (dropped term W_lo x_lo ~ 2^-22 |w||x|).
+// A' rows are pre-multiplied by s_c = sign(gamma_c): BN(relu(.)) is monotone increasing in y when
+// gamma >= 0 and decreasing otherwise, so only max_n(s_c * y) has to be tracked per channel.
+//
+// Orientation: channels on the M axis (TMEM lanes), point slots on the N axis (TMEM columns), so
+// the max / sum over the N slots is an in-thread reduction over registers filled by tcgen05.ld
+// -- no shuffles.  M = 64 in cta_group::1 occupies lanes 0-15 of each 32-lane sub-partition; a
+// second pillar's accumulator is interleaved at lane offset 16, so a 32x32b TMEM load hands every
+// thread of the four epilogue warps one (pillar, channel) row.
+//
+// Warp roles (384 threads, one CTA per SM, persistent over pillar pairs):
+//   warp 0      TMA producer: 1-D bulk copies of the 2 x 9 raw rows into a 3-stage ring
+//   warp 1      TMEM allocation + MMA issuer (one elected lane issues 8 tcgen05.mma per pair)
+//   warps 4-7   epilogue: tcgen05.ld -> max / sum relu / sum relu^2 -> ext + fp64 partial sums
+//   warps 8-11  converters: raw fp32 rows -> per-slot (x_hi, x_lo) k-vectors in the UMMA K-major
+//               no-swizzle layout (a register-level transpose; kind::tf32 was measured to return
+//               zeros for an MN-major B operand on this part, so B' is stored K-major)
+// Pipelines (mbarriers): raw ring full/empty, B' tile full/empty (x2), TMEM accumulator full/empty (x2).
+#include "common.cuh"
+
+namespace pp {
+
+namespace tc {
+
+constexpr int kThreads = 384;
+constexpr int kRawStages = 3;
+constexpr int kABytes = 4 * 2048;      // 4 k-steps x (64 rows x 8 k) tf32
+constexpr int kSboB = 784;             // bytes between 8-slot groups of B' (6 core matrices of 128 B + 16 pad: conflict-free STS.128)
+constexpr int kLboB = 128;             // bytes between the two 4-wide k chunks of one k-step
+constexpr unsigned long long kSpinLimit = 4000000000ull;   // ~2 s at 1.9 GHz: trap instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kSpinLimit) __trap();   // a protocol bug must not wedge the device
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// shared-memory matrix descriptor, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= 1ull << 46;   // descriptor version 1 (Blackwell)
+  return d;
+}
+
+#define PP_TMEM_LD32(taddr, v)                                                                        \
+  asm volatile(                                                                                       \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                       \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"   \
+      "%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                          \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),          \
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),     \
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),  \
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),  \
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                            \
+      : "r"(taddr))
+#define PP_TMEM_LD8(taddr, v)                                                       \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
+               : "r"(taddr))
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Smem {
+  // byte offsets inside the dynamic shared memory block
+  int a_off, raw_off, b_off, bar_off, total;
+  int raw_stage_bytes, b_pillar_bytes, lbo_b;
+};
+
+__host__ __device__ inline Smem smem_plan(int N) {
+  Smem s;
+  s.a_off = 0;
+  s.raw_off = kABytes;
+  s.raw_stage_bytes = 2 * 9 * N * 4;
+  s.b_off = s.raw_off + kRawStages * s.raw_stage_bytes;
+  s.lbo_b = kLboB;
+  s.b_pillar_bytes = (N / 8) * kSboB;
+  s.bar_off = s.b_off + 2 * 2 * s.b_pillar_bytes;
+  s.bar_off = (s.bar_off + 15) & ~15;
+  s.total = s.bar_off + 16 * 8 + 16;
+  return s;
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kThreads, 1)
+k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __restrict__ conv_w,
+               const float* __restrict__ conv_b, const float* __restrict__ bn_w,
+               float* __restrict__ ext, double* __restrict__ partials) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const Smem sp = smem_plan(N);
+  const int warp = threadIdx.x >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
+  uint64_t* raw_full = bars;              // [3]
+  uint64_t* raw_empty = bars + 3;         // [3]
+  uint64_t* b_full = bars + 6;            // [2]
+  uint64_t* b_empty = bars + 8;           // [2]
+  uint64_t* acc_full = bars + 10;         // [2]
+  uint64_t* acc_empty = bars + 12;        // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const long long rows = (long long)B * P;
+  const long long pairs = (rows + 1) / 2;
+  const long long my_pairs = (long long)blockIdx.x < pairs ? (pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const size_t PN = (size_t)P * N;
+  const int G4 = N / 4;
+
+  // ---- one-time setup -------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRawStages; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&b_full[i], 4); mbar_init(&b_empty[i], 1);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  // A' tile: 64 x 32 tf32, K-major, no swizzle: core matrix = 8 rows x 16 B, k-chunk stride 128 B,
+  // row-group stride 256 B, k-step stride 2048 B
+  for (int idx = threadIdx.x; idx < 64 * 32; idx += kThreads) {
+    const int m = idx >> 5, kk = idx & 31, j = kk >> 3, k = kk & 7;
+    const float sgn = bn_w[m] < 0.f ? -1.f : 1.f;
+    auto whi = [&](int d) { return to_tf32(conv_w[m * 9 + d]); };
+    auto wlo = [&](int d) { const float w = conv_w[m * 9 + d]; return to_tf32(w - to_tf32(w)); };
+    float v = 0.f;
+    if (j == 0) v = whi(k);
+    else if (j == 1) v = (k == 0) ? whi(8) : whi(k - 1);
+    else if (j == 2) {
+      const float bb = conv_b[m];
+      if (k == 0) v = whi(7);
+      else if (k == 1) v = whi(8);
+      else if (k == 2) v = wlo(8);
+      else if (k == 3) v = to_tf32(bb);
+      else if (k == 4) v = to_tf32(bb - to_tf32(bb));
+    } else v = wlo(k);
+    *reinterpret_cast<float*>(smem + sp.a_off + j * 2048 + (m >> 3) * 256 + (k >> 2) * 128 + (m & 7) * 16 + (k & 3) * 4) = sgn * v;
+  }
+  fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  // ---- roles ----------------------------------------------------------------------------------
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (long long it = 0; it < my_pairs; ++it) {
+        const int s = (int)(it % kRawStages);
+        const uint32_t n = (uint32_t)(it / kRawStages);
+        mbar_wait(&raw_empty[s], (n & 1u) ^ 1u);
+        const long long pair = blockIdx.x + it * gridDim.x;
+        mbar_expect_tx(&raw_full[s], (uint32_t)sp.raw_stage_bytes);
+        for (int h = 0; h < 2; ++h) {
+          long long r = 2 * pair + h;
+          if (r >= rows) r = rows - 1;
+          const int b = (int)(r / P), p = (int)(r % P);
+          const float* src = x + (size_t)b * 9 * PN + (size_t)p * N;
+          unsigned char* dst = smem + sp.raw_off + s * sp.raw_stage_bytes + h * 9 * N * 4;
+#pragma unroll
+          for (int d = 0; d < 9; ++d) bulk_g2s(dst + d * N * 4, src + d * PN, (uint32_t)(N * 4), &raw_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): fp32 accumulate,
+      // A = B = tf32, both K-major, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) |
+                             ((uint32_t)(N >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+      const uint32_t a_addr = smem_u32(smem + sp.a_off);
+      for (long long it = 0; it < my_pairs; ++it) {
+        const int t = (int)(it & 1);
+        const uint32_t n = (uint32_t)(it >> 1);
+        mbar_wait(&b_full[t], n & 1u);
+        mbar_wait(&acc_empty[t], (n & 1u) ^ 1u);
+        tc_fence_after();
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t b_addr = smem_u32(smem + sp.b_off + (t * 2 + h) * sp.b_pillar_bytes);
+          const uint32_t d_tmem = tmem_base + ((uint32_t)(h * 16) << 16) + (uint32_t)(t * 256);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int kg = (j == 3) ? 0 : j;
+            const uint64_t ad = smem_desc(a_addr + j * 2048, 128, 256);
+            const uint64_t bd = smem_desc(b_addr + kg * 2 * kLboB, kLboB, kSboB);
+            umma_tf32(d_tmem, ad, bd, idesc, j > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&b_empty[t]);     // B' tile free once these MMAs have read it
+        umma_commit(&acc_full[t]);    // accumulators ready for the epilogue
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== epilogue: one (pillar-of-pair, channel) row per thread =====
+    const int q = warp & 3;
+    const int h = lane >> 4;
+    const int c = 16 * q + (int)(lane & 15u);
+    const float sgn = bn_w[c] < 0.f ? -1.f : 1.f;
+    double accS = 0.0, accQ = 0.0;
+    for (long long it = 0; it < my_pairs; ++it) {
+      const int t = (int)(it & 1);
+      const uint32_t n = (uint32_t)(it >> 1);
+      mbar_wait(&acc_full[t], n & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
+      float mx = -INFINITY, s2 = 0.f, q4 = 0.f;
+      int col = 0;
+      for (; col + 32 <= N; col += 32) {
+        uint32_t v[32];
+        PP_TMEM_LD32(taddr + col, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float y = __uint_as_float(v[i]);
+          mx = fmaxf(mx, y);
+          if (TRAIN) {
+            const float tt = fmaf(sgn, y, fabsf(y));   // 2*relu(s*y)
+            s2 += tt;
+            q4 = fmaf(tt, tt, q4);
+          }
+        }
+      }
+      for (; col + 8 <= N; col += 8) {
+        uint32_t v[8];
+        PP_TMEM_LD8(taddr + col, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float y = __uint_as_float(v[i]);
+          mx = fmaxf(mx, y);
+          if (TRAIN) {
+            const float tt = fmaf(sgn, y, fabsf(y));
+            s2 += tt;
+            q4 = fmaf(tt, tt, q4);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[t]);
+      const long long r = 2 * (blockIdx.x + it * gridDim.x) + h;
+      if (r < rows) {
+        const float val = sgn * mx;              // max_n y when gamma >= 0, min_n y otherwise
+        float* e = ext + (size_t)r * 128 + c;
+        e[0] = val;
+        e[64] = val;
+        if (TRAIN) {
+          accS += 0.5 * (double)s2;
+          accQ += 0.25 * (double)q4;
+        }
+      }
+    }
+    if (TRAIN) {
+      accS += __shfl_xor_sync(0xffffffffu, accS, 16);
+      accQ += __shfl_xor_sync(0xffffffffu, accQ, 16);
+      if (lane < 16) {
+        partials[((size_t)blockIdx.x * 2 + 0) * 64 + c] = accS;
+        partials[((size_t)blockIdx.x * 2 + 1) * 64 + c] = accQ;
+      }
+    }
+  } else if (warp >= 8) {
+    // ===== converters: raw fp32 rows -> x_hi / x_lo rows in the UMMA MN-major layout =====
+    const int ct = threadIdx.x - 8 * 32;    // 0..127
+    const int h = ct >> 6;                  // pillar of the pair
+    const int g = ct & 63;                  // 4-slot group
+    for (long long it = 0; it < my_pairs; ++it) {
+      const int s = (int)(it % kRawStages);
+      const uint32_t ns = (uint32_t)(it / kRawStages);
+      const int t = (int)(it & 1);
+      const uint32_t nb = (uint32_t)(it >> 1);
+      mbar_wait(&raw_full[s], ns & 1u);
+      mbar_wait(&b_empty[t], (nb & 1u) ^ 1u);
+      if (g < G4) {
+        const unsigned char* raw = smem + sp.raw_off + s * sp.raw_stage_bytes + h * 9 * N * 4 + g * 16;
+        float hi[9][4], lo[9][4];
+#pragma unroll
+        for (int d = 0; d < 9; ++d) {
+          const float4 v = *reinterpret_cast<const float4*>(raw + d * N * 4);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            hi[d][i] = to_tf32(vv[i]);
+            lo[d][i] = to_tf32(vv[i] - hi[d][i]);
+          }
+        }
+        unsigned char* bt = smem + sp.b_off + (t * 2 + h) * sp.b_pillar_bytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = 4 * g + i;
+          unsigned char* row = bt + (n >> 3) * kSboB + (n & 7) * 16;      // + kc*128 per 4-wide k chunk
+          *reinterpret_cast<float4*>(row + 0 * kLboB) = make_float4(hi[0][i], hi[1][i], hi[2][i], hi[3][i]);
+          *reinterpret_cast<float4*>(row + 1 * kLboB) = make_float4(hi[4][i], hi[5][i], hi[6][i], hi[7][i]);
+          *reinterpret_cast<float4*>(row + 2 * kLboB) = make_float4(hi[8][i], lo[0][i], lo[1][i], lo[2][i]);
+          *reinterpret_cast<float4*>(row + 3 * kLboB) = make_float4(lo[3][i], lo[4][i], lo[5][i], lo[6][i]);
+          *reinterpret_cast<float4*>(row + 4 * kLboB) = make_float4(lo[7][i], lo[8][i], hi[8][i], 1.f);
+          *reinterpret_cast<float4*>(row + 5 * kLboB) = make_float4(1.f, 0.f, 0.f, 0.f);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&b_full[t]);
+        mbar_arrive(&raw_empty[s]);
+      }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tc
+
+bool pfn_tc_supported(int D, int N, int C, const void* x) {
+  return D == 9 && C == 64 && N >= 8 && N <= 256 && (N % 8) == 0 && ((uintptr_t)x % 16) == 0;
+}
+
+int launch_stats_tc(const float* d_x, int B, int P, int N, const float* w, const float* bias,
+                    const float* bn_w, int training, float* ext, double* partials, int nblocks,
+                    cudaStream_t st) {
+  const tc::Smem sp = tc::smem_plan(N);
+  if (training) {
+    PP_CUDA(cudaFuncSetAttribute(tc::k_pfn_stats_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+    PP_KERNEL("k_pfn_stats_tc", st,
+              tc::k_pfn_stats_tc<true><<<nblocks, tc::kThreads, sp.total, st>>>(d_x, B, P, N, w, bias, bn_w, ext, partials));
+  } else {
+    PP_CUDA(cudaFuncSetAttribute(tc::k_pfn_stats_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+    PP_KERNEL("k_pfn_stats_tc", st,
+              tc::k_pfn_stats_tc<false><<<nblocks, tc::kThreads, sp.total, st>>>(d_x, B, P, N, w, bias, bn_w, ext, partials));
+  }
+  return PP_OK;
+}
+
+}  // namespace pp

@@ -252,6 +252,7 @@ def algorithmic_bytes(B, P, N, C, H, W, A, K, total_points, has_mean):
     return {
         "k_emit_dense": B * x_bytes + (x_bytes if has_mean else 0) + total_points * 16 + B * P * 24,
         "k_pfn_stats": B * x_bytes + B * P * 2 * C * 4,
+        "k_pfn_stats_tc": B * x_bytes + B * P * 2 * C * 4,
         "k_canvas": B * C * H * W * 4 + B * H * W * 4,
         "k_encode": B * A * 9 * 4,          # one launch each for cls [A,K=9] and reg [A,9]
     }

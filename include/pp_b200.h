@@ -78,6 +78,9 @@ int pp_last_cuda_error(void);
  * pp_profile_report: synchronise the device, write one "name launches total_ms" line per kernel
  * into buf, clear the records, return the bytes needed. */
 int64_t pp_launch_count(void);
+/* Process-wide options.  "pfn_tensor_cores": 1 (default) runs the PFN statistics pass on tcgen05
+ * tensor cores (TF32 3-term split) whenever D=9, C=64, N%8==0, N<=256; 0 forces the CUDA-core kernel. */
+int pp_set_option(const char* key, int value);
 int pp_profile_enable(int on);
 int64_t pp_profile_report(char* buf, int64_t buf_bytes);
 
