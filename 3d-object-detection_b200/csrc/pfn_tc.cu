@@ -25,10 +25,11 @@
 // second pillar's accumulator is interleaved at lane offset 16, so a 32x32b TMEM load hands every
 // thread of the four epilogue warps one (pillar, channel) row.
 //
-// Warp roles (384 threads, one CTA per SM, persistent over pillar pairs):
-//   warp 0      TMA producer: 1-D bulk copies of the 2 x 9 raw rows into a 3-stage ring
+// Warp roles (512 threads, one CTA per SM, persistent over pillar pairs):
+//   warp 0      TMA producer: 9 bulk copies (one per feature, both pillars of the pair) into a 3-stage ring
 //   warp 1      TMEM allocation + MMA issuer (one elected lane issues 8 tcgen05.mma per pair)
-//   warps 4-7   epilogue: tcgen05.ld -> max / sum relu / sum relu^2 -> ext + fp64 partial sums
+//   warps 4-7   epilogue group 0 (even pairs, accumulator buffer 0): tcgen05.ld -> max / sum relu /
+//               sum relu^2 -> ext + fp64 partial sums;  warps 12-15: group 1 (odd pairs, buffer 1)
 //   warps 8-11  converters: raw fp32 rows -> per-slot (x_hi, x_lo) k-vectors in the UMMA K-major
 //               no-swizzle layout (a register-level transpose; kind::tf32 was measured to return
 //               zeros for an MN-major B operand on this part, so B' is stored K-major)
@@ -39,7 +40,7 @@ namespace pp {
 
 namespace tc {
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 512;
 constexpr int kRawStages = 3;
 constexpr int kABytes = 4 * 2048;      // 4 k-steps x (64 rows x 8 k) tf32
 constexpr int kSboB = 784;             // bytes between 8-slot groups of B' (6 core matrices of 128 B + 16 pad: conflict-free STS.128)
@@ -166,10 +167,13 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
   uint64_t* acc_full = bars + 10;         // [2]
   uint64_t* acc_empty = bars + 12;        // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
+  __shared__ double s_stat[2][2][64];      // [epilogue group][sum, sum of squares][channel]
 
-  const long long rows = (long long)B * P;
-  const long long pairs = (rows + 1) / 2;
-  const long long my_pairs = (long long)blockIdx.x < pairs ? (pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // all loop counters are 32-bit and advance incrementally: the producer and issuer are single
+  // threads, 64-bit divisions there would sit on the critical path (host guarantees B*P < 2^31)
+  const int rows = B * P;
+  const int pairs = (rows + 1) / 2;
+  const int my_pairs = (int)blockIdx.x < pairs ? (pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const size_t PN = (size_t)P * N;
   const int G4 = N / 4;
 
@@ -212,22 +216,37 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
   // ---- roles ----------------------------------------------------------------------------------
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      for (long long it = 0; it < my_pairs; ++it) {
-        const int s = (int)(it % kRawStages);
-        const uint32_t n = (uint32_t)(it / kRawStages);
-        mbar_wait(&raw_empty[s], (n & 1u) ^ 1u);
-        const long long pair = blockIdx.x + it * gridDim.x;
-        mbar_expect_tx(&raw_full[s], (uint32_t)sp.raw_stage_bytes);
-        for (int h = 0; h < 2; ++h) {
-          long long r = 2 * pair + h;
-          if (r >= rows) r = rows - 1;
-          const int b = (int)(r / P), p = (int)(r % P);
-          const float* src = x + (size_t)b * 9 * PN + (size_t)p * N;
-          unsigned char* dst = smem + sp.raw_off + s * sp.raw_stage_bytes + h * 9 * N * 4;
-#pragma unroll
-          for (int d = 0; d < 9; ++d) bulk_g2s(dst + d * N * 4, src + d * PN, (uint32_t)(N * 4), &raw_full[s]);
+    // The two pillars of a pair are adjacent in memory (rows p and p+1 of the same feature plane), so
+    // one bulk copy per feature moves both: 9 copies of 2*N*4 bytes, issued by 9 lanes at once.
+    // Raw stage layout: [d][h][N].
+    {
+      int s = 0;
+      uint32_t ph = 1;                                  // parity to wait on raw_empty (first pass falls through)
+      int r0 = 2 * (int)blockIdx.x;                     // first row of the current pair
+      int b0 = r0 / P, p0 = r0 - b0 * P;                // (sweep, pillar) of that row, advanced incrementally
+      const int step = 2 * (int)gridDim.x;
+      for (int it = 0; it < my_pairs; ++it) {
+        mbar_wait(&raw_empty[s], ph);
+        if (lane == 0) mbar_expect_tx(&raw_full[s], (uint32_t)sp.raw_stage_bytes);
+        __syncwarp();
+        unsigned char* dst = smem + sp.raw_off + s * sp.raw_stage_bytes;
+        const bool contiguous = (p0 + 1 < P) && (r0 + 1 < rows);
+        if (contiguous) {
+          if (lane < 9) {
+            const float* src = x + ((size_t)b0 * 9 + lane) * PN + (size_t)p0 * N;
+            bulk_g2s(dst + lane * 2 * N * 4, src, (uint32_t)(2 * N * 4), &raw_full[s]);
+          }
+        } else if (lane < 18) {
+          const int d = (int)lane >> 1, h = (int)lane & 1;
+          int bb = b0, pp = p0 + h;
+          if (pp >= P) { pp -= P; ++bb; }
+          if (r0 + h >= rows) { bb = b0; pp = p0; }     // odd row count: duplicate the last row
+          const float* src = x + ((size_t)bb * 9 + d) * PN + (size_t)pp * N;
+          bulk_g2s(dst + (d * 2 + h) * N * 4, src, (uint32_t)(N * 4), &raw_full[s]);
         }
+        r0 += step; p0 += step;
+        while (p0 >= P) { p0 -= P; ++b0; }
+        if (++s == kRawStages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -238,8 +257,8 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) |
                              ((uint32_t)(N >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
       const uint32_t a_addr = smem_u32(smem + sp.a_off);
-      for (long long it = 0; it < my_pairs; ++it) {
-        const int t = (int)(it & 1);
+      for (int it = 0; it < my_pairs; ++it) {
+        const int t = it & 1;
         const uint32_t n = (uint32_t)(it >> 1);
         mbar_wait(&b_full[t], n & 1u);
         mbar_wait(&acc_empty[t], (n & 1u) ^ 1u);
@@ -259,63 +278,79 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
         umma_commit(&acc_full[t]);    // accumulators ready for the epilogue
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===== epilogue: one (pillar-of-pair, channel) row per thread =====
+  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+    // ===== epilogue: one (pillar-of-pair, channel) row per thread; group e owns accumulator buffer e =====
+    const int e = warp >= 12 ? 1 : 0;
     const int q = warp & 3;
     const int h = lane >> 4;
     const int c = 16 * q + (int)(lane & 15u);
     const float sgn = bn_w[c] < 0.f ? -1.f : 1.f;
     double accS = 0.0, accQ = 0.0;
-    for (long long it = 0; it < my_pairs; ++it) {
-      const int t = (int)(it & 1);
+    const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(e * 256);
+    const int nfull = N >> 5;              // 32-column chunks
+    for (int it = e; it < my_pairs; it += 2) {
       const uint32_t n = (uint32_t)(it >> 1);
-      mbar_wait(&acc_full[t], n & 1u);
+      mbar_wait(&acc_full[e], n & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
-      float mx = -INFINITY, s2 = 0.f, q4 = 0.f;
-      int col = 0;
-      for (; col + 32 <= N; col += 32) {
-        uint32_t v[32];
-        PP_TMEM_LD32(taddr + col, v);
-        tmem_ld_wait();
+      // four independent accumulator sets break the 4-cycle dependent chains
+      float mx[4], s2[4], q4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { mx[k] = -INFINITY; s2[k] = 0.f; q4[k] = 0.f; }
+      auto consume = [&](const uint32_t* v, int cnt) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float y = __uint_as_float(v[i]);
-          mx = fmaxf(mx, y);
-          if (TRAIN) {
-            const float tt = fmaf(sgn, y, fabsf(y));   // 2*relu(s*y)
-            s2 += tt;
-            q4 = fmaf(tt, tt, q4);
+          if (i < cnt) {
+            const float y = __uint_as_float(v[i]);
+            mx[i & 3] = fmaxf(mx[i & 3], y);
+            if (TRAIN) {
+              const float tt = fmaf(sgn, y, fabsf(y));   // 2*relu(s*y)
+              s2[i & 3] += tt;
+              q4[i & 3] = fmaf(tt, tt, q4[i & 3]);
+            }
           }
         }
+      };
+      // software-pipelined TMEM reads: chunk k+1 is in flight while chunk k is reduced
+      uint32_t va[32], vb[32];
+      if (nfull > 0) { PP_TMEM_LD32(taddr, va); }
+      for (int k = 0; k < nfull; k += 2) {
+        tmem_ld_wait();
+        if (k + 1 < nfull) { PP_TMEM_LD32(taddr + 32 * (k + 1), vb); }
+        consume(va, 32);
+        if (k + 1 < nfull) {
+          tmem_ld_wait();
+          if (k + 2 < nfull) { PP_TMEM_LD32(taddr + 32 * (k + 2), va); }
+          consume(vb, 32);
+        }
       }
-      for (; col + 8 <= N; col += 8) {
-        uint32_t v[8];
-        PP_TMEM_LD8(taddr + col, v);
+      for (int col = nfull * 32; col + 8 <= N; col += 8) {
+        uint32_t v8[8];
+        PP_TMEM_LD8(taddr + col, v8);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float y = __uint_as_float(v[i]);
-          mx = fmaxf(mx, y);
+          const float y = __uint_as_float(v8[i]);
+          mx[i & 3] = fmaxf(mx[i & 3], y);
           if (TRAIN) {
             const float tt = fmaf(sgn, y, fabsf(y));
-            s2 += tt;
-            q4 = fmaf(tt, tt, q4);
+            s2[i & 3] += tt;
+            q4[i & 3] = fmaf(tt, tt, q4[i & 3]);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[t]);
-      const long long r = 2 * (blockIdx.x + it * gridDim.x) + h;
+      if (lane == 0) mbar_arrive(&acc_empty[e]);
+      const int r = 2 * ((int)blockIdx.x + it * (int)gridDim.x) + h;
       if (r < rows) {
-        const float val = sgn * mx;              // max_n y when gamma >= 0, min_n y otherwise
-        float* e = ext + (size_t)r * 128 + c;
-        e[0] = val;
-        e[64] = val;
+        const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        const float val = sgn * m;               // max_n y when gamma >= 0, min_n y otherwise
+        float* eo = ext + (size_t)r * 128 + c;
+        eo[0] = val;
+        eo[64] = val;
         if (TRAIN) {
-          accS += 0.5 * (double)s2;
-          accQ += 0.25 * (double)q4;
+          accS += 0.5 * ((double)s2[0] + (double)s2[1] + (double)s2[2] + (double)s2[3]);
+          accQ += 0.25 * ((double)q4[0] + (double)q4[1] + (double)q4[2] + (double)q4[3]);
         }
       }
     }
@@ -323,28 +358,28 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
       accS += __shfl_xor_sync(0xffffffffu, accS, 16);
       accQ += __shfl_xor_sync(0xffffffffu, accQ, 16);
       if (lane < 16) {
-        partials[((size_t)blockIdx.x * 2 + 0) * 64 + c] = accS;
-        partials[((size_t)blockIdx.x * 2 + 1) * 64 + c] = accQ;
+        s_stat[e][0][c] = accS;
+        s_stat[e][1][c] = accQ;
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ===== converters: raw fp32 rows -> x_hi / x_lo rows in the UMMA MN-major layout =====
     const int ct = threadIdx.x - 8 * 32;    // 0..127
     const int h = ct >> 6;                  // pillar of the pair
     const int g = ct & 63;                  // 4-slot group
-    for (long long it = 0; it < my_pairs; ++it) {
-      const int s = (int)(it % kRawStages);
-      const uint32_t ns = (uint32_t)(it / kRawStages);
-      const int t = (int)(it & 1);
+    int s = 0;
+    uint32_t ph_raw = 0;
+    for (int it = 0; it < my_pairs; ++it) {
+      const int t = it & 1;
       const uint32_t nb = (uint32_t)(it >> 1);
-      mbar_wait(&raw_full[s], ns & 1u);
+      mbar_wait(&raw_full[s], ph_raw);
       mbar_wait(&b_empty[t], (nb & 1u) ^ 1u);
       if (g < G4) {
-        const unsigned char* raw = smem + sp.raw_off + s * sp.raw_stage_bytes + h * 9 * N * 4 + g * 16;
+        const unsigned char* raw = smem + sp.raw_off + s * sp.raw_stage_bytes + h * N * 4 + g * 16;
         float hi[9][4], lo[9][4];
 #pragma unroll
         for (int d = 0; d < 9; ++d) {
-          const float4 v = *reinterpret_cast<const float4*>(raw + d * N * 4);
+          const float4 v = *reinterpret_cast<const float4*>(raw + d * 2 * N * 4);
           const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -371,6 +406,7 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
         mbar_arrive(&b_full[t]);
         mbar_arrive(&raw_empty[s]);
       }
+      if (++s == kRawStages) { s = 0; ph_raw ^= 1u; }
     }
   }
 
@@ -380,6 +416,11 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+  if (TRAIN && threadIdx.x < 128) {
+    // fixed-order combination of the two epilogue groups -> deterministic per-CTA partials
+    const int qq = threadIdx.x >> 6, cc = threadIdx.x & 63;
+    partials[((size_t)blockIdx.x * 2 + qq) * 64 + cc] = s_stat[0][qq][cc] + s_stat[1][qq][cc];
   }
 }
 
