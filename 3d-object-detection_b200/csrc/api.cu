@@ -12,6 +12,7 @@
 namespace pp {
 thread_local int g_last_cuda_error = 0;
 int g_opt_pfn_tensor_cores = 1;
+int g_opt_pfn_tc_debug = 0;   // development knob: bit0 skip conversion, bit1 skip MMA, bit2 skip epilogue reads
 
 // ---- launch counter + optional per-kernel CUDA-event timing -----------------------------------
 static std::atomic<long long> g_launches{0};
@@ -48,6 +49,7 @@ int pp_last_cuda_error(void) { return pp::g_last_cuda_error; }
 int pp_set_option(const char* key, int value) {
   if (key == nullptr) return PP_ERR_INVALID_ARG;
   if (strcmp(key, "pfn_tensor_cores") == 0) { pp::g_opt_pfn_tensor_cores = value ? 1 : 0; return PP_OK; }
+  if (strcmp(key, "pfn_tc_debug") == 0) { pp::g_opt_pfn_tc_debug = value; return PP_OK; }
   return PP_ERR_INVALID_ARG;
 }
 

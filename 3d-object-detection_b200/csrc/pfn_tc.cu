@@ -41,7 +41,8 @@ namespace pp {
 namespace tc {
 
 constexpr int kThreads = 512;
-constexpr int kRawStages = 3;
+constexpr int kRawStages = 4;
+constexpr int kBStages = 3;            // B' operand tiles (one pillar pair each) in flight between converters and MMA
 constexpr int kABytes = 4 * 2048;      // 4 k-steps x (64 rows x 8 k) tf32
 constexpr int kSboB = 784;             // bytes between 8-slot groups of B' (6 core matrices of 128 B + 16 pad: conflict-free STS.128)
 constexpr int kLboB = 128;             // bytes between the two 4-wide k chunks of one k-step
@@ -103,6 +104,15 @@ __device__ __forceinline__ float to_tf32(float v) {
   return __uint_as_float(r);
 }
 
+// Blackwell packed fp32 pairs (add/fma .f32x2): S += (t0,t1), Q += (t0*t0, t1*t1) in two instructions
+__device__ __forceinline__ void acc_pair(unsigned long long& S, unsigned long long& Q, float t0, float t1) {
+  asm("{\n.reg .b64 tp;\nmov.b64 tp, {%2, %3};\nadd.rn.f32x2 %0, %0, tp;\nfma.rn.f32x2 %1, tp, tp, %1;\n}\n"
+      : "+l"(S), "+l"(Q) : "f"(t0), "f"(t1));
+}
+__device__ __forceinline__ float pair_sum(unsigned long long v) {
+  return __uint_as_float((unsigned)(v & 0xffffffffull)) + __uint_as_float((unsigned)(v >> 32));
+}
+
 // shared-memory matrix descriptor, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -144,9 +154,9 @@ __host__ __device__ inline Smem smem_plan(int N) {
   s.b_off = s.raw_off + kRawStages * s.raw_stage_bytes;
   s.lbo_b = kLboB;
   s.b_pillar_bytes = (N / 8) * kSboB;
-  s.bar_off = s.b_off + 2 * 2 * s.b_pillar_bytes;
+  s.bar_off = s.b_off + kBStages * 2 * s.b_pillar_bytes;
   s.bar_off = (s.bar_off + 15) & ~15;
-  s.total = s.bar_off + 16 * 8 + 16;
+  s.total = s.bar_off + (2 * kRawStages + 2 * kBStages + 4) * 8 + 16;
   return s;
 }
 
@@ -154,19 +164,19 @@ template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __restrict__ conv_w,
                const float* __restrict__ conv_b, const float* __restrict__ bn_w,
-               float* __restrict__ ext, double* __restrict__ partials) {
+               float* __restrict__ ext, double* __restrict__ partials, int dbg) {
   extern __shared__ __align__(128) unsigned char smem[];
   const Smem sp = smem_plan(N);
   const int warp = threadIdx.x >> 5;
   const unsigned lane = threadIdx.x & 31u;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
-  uint64_t* raw_full = bars;              // [3]
-  uint64_t* raw_empty = bars + 3;         // [3]
-  uint64_t* b_full = bars + 6;            // [2]
-  uint64_t* b_empty = bars + 8;           // [2]
-  uint64_t* acc_full = bars + 10;         // [2]
-  uint64_t* acc_empty = bars + 12;        // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* raw_full = bars;
+  uint64_t* raw_empty = bars + kRawStages;
+  uint64_t* b_full = bars + 2 * kRawStages;       // [kBStages]
+  uint64_t* b_empty = b_full + kBStages;           // [kBStages]
+  uint64_t* acc_full = b_empty + kBStages;         // [2]
+  uint64_t* acc_empty = acc_full + 2;              // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
   __shared__ double s_stat[2][2][64];      // [epilogue group][sum, sum of squares][channel]
 
   // all loop counters are 32-bit and advance incrementally: the producer and issuer are single
@@ -180,10 +190,8 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
   // ---- one-time setup -------------------------------------------------------------------------
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRawStages; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&b_full[i], 4); mbar_init(&b_empty[i], 1);
-      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
-    }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(&b_full[i], 4); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_barrier_init();
   }
   // A' tile: 64 x 32 tf32, K-major, no swizzle: core matrix = 8 rows x 16 B, k-chunk stride 128 B,
@@ -257,14 +265,16 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) |
                              ((uint32_t)(N >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
       const uint32_t a_addr = smem_u32(smem + sp.a_off);
+      int bs = 0;
+      uint32_t bph = 0;
       for (int it = 0; it < my_pairs; ++it) {
-        const int t = it & 1;
+        const int t = it & 1;                          // accumulator buffer
         const uint32_t n = (uint32_t)(it >> 1);
-        mbar_wait(&b_full[t], n & 1u);
+        mbar_wait(&b_full[bs], bph);
         mbar_wait(&acc_empty[t], (n & 1u) ^ 1u);
         tc_fence_after();
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t b_addr = smem_u32(smem + sp.b_off + (t * 2 + h) * sp.b_pillar_bytes);
+        for (int h = 0; h < 2 && !(dbg & 2); ++h) {
+          const uint32_t b_addr = smem_u32(smem + sp.b_off + (bs * 2 + h) * sp.b_pillar_bytes);
           const uint32_t d_tmem = tmem_base + ((uint32_t)(h * 16) << 16) + (uint32_t)(t * 256);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -274,8 +284,9 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
             umma_tf32(d_tmem, ad, bd, idesc, j > 0 ? 1u : 0u);
           }
         }
-        umma_commit(&b_empty[t]);     // B' tile free once these MMAs have read it
+        umma_commit(&b_empty[bs]);    // B' tile free once these MMAs have read it
         umma_commit(&acc_full[t]);    // accumulators ready for the epilogue
+        if (++bs == kBStages) { bs = 0; bph ^= 1u; }
       }
     }
   } else if ((warp >= 4 && warp < 8) || warp >= 12) {
@@ -292,20 +303,21 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
       const uint32_t n = (uint32_t)(it >> 1);
       mbar_wait(&acc_full[e], n & 1u);
       tc_fence_after();
-      // four independent accumulator sets break the 4-cycle dependent chains
-      float mx[4], s2[4], q4[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { mx[k] = -INFINITY; s2[k] = 0.f; q4[k] = 0.f; }
+      // independent accumulator sets break the dependent chains; sums are kept as packed fp32 pairs
+      float mx[2] = {-INFINITY, -INFINITY};
+      unsigned long long S[2] = {0ull, 0ull}, Q[2] = {0ull, 0ull};
+      // 2*relu(s*y) = s*y + |y| is one FFMA (FMA pipe; the ALU pipe that FMNMX runs on is half rate:
+      // doing the relu with FMNMX measured 434 us vs 307 us), sums are packed FADD2 / FFMA2
       auto consume = [&](const uint32_t* v, int cnt) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 32; i += 2) {
           if (i < cnt) {
-            const float y = __uint_as_float(v[i]);
-            mx[i & 3] = fmaxf(mx[i & 3], y);
+            const float y0 = __uint_as_float(v[i]), y1 = __uint_as_float(v[i + 1]);
+            mx[(i >> 1) & 1] = fmaxf(mx[(i >> 1) & 1], fmaxf(y0, y1));
             if (TRAIN) {
-              const float tt = fmaf(sgn, y, fabsf(y));   // 2*relu(s*y)
-              s2[i & 3] += tt;
-              q4[i & 3] = fmaf(tt, tt, q4[i & 3]);
+              const float t0 = fmaf(sgn, y0, fabsf(y0));
+              const float t1 = fmaf(sgn, y1, fabsf(y1));
+              acc_pair(S[(i >> 1) & 1], Q[(i >> 1) & 1], t0, t1);
             }
           }
         }
@@ -313,7 +325,7 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
       // software-pipelined TMEM reads: chunk k+1 is in flight while chunk k is reduced
       uint32_t va[32], vb[32];
       if (nfull > 0) { PP_TMEM_LD32(taddr, va); }
-      for (int k = 0; k < nfull; k += 2) {
+      for (int k = 0; k < ((dbg & 4) ? 0 : nfull); k += 2) {
         tmem_ld_wait();
         if (k + 1 < nfull) { PP_TMEM_LD32(taddr + 32 * (k + 1), vb); }
         consume(va, 32);
@@ -327,30 +339,21 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
         uint32_t v8[8];
         PP_TMEM_LD8(taddr + col, v8);
         tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float y = __uint_as_float(v8[i]);
-          mx[i & 3] = fmaxf(mx[i & 3], y);
-          if (TRAIN) {
-            const float tt = fmaf(sgn, y, fabsf(y));
-            s2[i & 3] += tt;
-            q4[i & 3] = fmaf(tt, tt, q4[i & 3]);
-          }
-        }
+        consume(v8, 8);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[e]);
       const int r = 2 * ((int)blockIdx.x + it * (int)gridDim.x) + h;
       if (r < rows) {
-        const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        const float m = fmaxf(mx[0], mx[1]);
         const float val = sgn * m;               // max_n y when gamma >= 0, min_n y otherwise
         float* eo = ext + (size_t)r * 128 + c;
         eo[0] = val;
         eo[64] = val;
         if (TRAIN) {
-          accS += 0.5 * ((double)s2[0] + (double)s2[1] + (double)s2[2] + (double)s2[3]);
-          accQ += 0.25 * ((double)q4[0] + (double)q4[1] + (double)q4[2] + (double)q4[3]);
+          accS += 0.5 * ((double)pair_sum(S[0]) + (double)pair_sum(S[1]));
+          accQ += 0.25 * ((double)pair_sum(Q[0]) + (double)pair_sum(Q[1]));
         }
       }
     }
@@ -367,14 +370,12 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
     const int ct = threadIdx.x - 8 * 32;    // 0..127
     const int h = ct >> 6;                  // pillar of the pair
     const int g = ct & 63;                  // 4-slot group
-    int s = 0;
-    uint32_t ph_raw = 0;
+    int s = 0, t = 0;
+    uint32_t ph_raw = 0, ph_b = 1;
     for (int it = 0; it < my_pairs; ++it) {
-      const int t = it & 1;
-      const uint32_t nb = (uint32_t)(it >> 1);
       mbar_wait(&raw_full[s], ph_raw);
-      mbar_wait(&b_empty[t], (nb & 1u) ^ 1u);
-      if (g < G4) {
+      mbar_wait(&b_empty[t], ph_b);
+      if (g < G4 && !(dbg & 1)) {
         const unsigned char* raw = smem + sp.raw_off + s * sp.raw_stage_bytes + h * N * 4 + g * 16;
         float hi[9][4], lo[9][4];
 #pragma unroll
@@ -383,8 +384,10 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
           const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            hi[d][i] = to_tf32(vv[i]);
-            lo[d][i] = to_tf32(vv[i] - hi[d][i]);
+            // hi = x truncated to tf32 (what the tensor core would do with the raw word); lo = x - hi is
+            // exact in fp32 (<= 13 significant bits) and is truncated to tf32 by the hardware on read
+            hi[d][i] = __uint_as_float(__float_as_uint(vv[i]) & 0xffffe000u);
+            lo[d][i] = vv[i] - hi[d][i];
           }
         }
         unsigned char* bt = smem + sp.b_off + (t * 2 + h) * sp.b_pillar_bytes;
@@ -407,6 +410,7 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
         mbar_arrive(&raw_empty[s]);
       }
       if (++s == kRawStages) { s = 0; ph_raw ^= 1u; }
+      if (++t == kBStages) { t = 0; ph_b ^= 1u; }
     }
   }
 
@@ -426,6 +430,8 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
 
 }  // namespace tc
 
+extern int g_opt_pfn_tc_debug;
+
 bool pfn_tc_supported(int D, int N, int C, const void* x) {
   return D == 9 && C == 64 && N >= 8 && N <= 256 && (N % 8) == 0 && ((uintptr_t)x % 16) == 0;
 }
@@ -437,11 +443,11 @@ int launch_stats_tc(const float* d_x, int B, int P, int N, const float* w, const
   if (training) {
     PP_CUDA(cudaFuncSetAttribute(tc::k_pfn_stats_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
     PP_KERNEL("k_pfn_stats_tc", st,
-              tc::k_pfn_stats_tc<true><<<nblocks, tc::kThreads, sp.total, st>>>(d_x, B, P, N, w, bias, bn_w, ext, partials));
+              tc::k_pfn_stats_tc<true><<<nblocks, tc::kThreads, sp.total, st>>>(d_x, B, P, N, w, bias, bn_w, ext, partials, g_opt_pfn_tc_debug));
   } else {
     PP_CUDA(cudaFuncSetAttribute(tc::k_pfn_stats_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
     PP_KERNEL("k_pfn_stats_tc", st,
-              tc::k_pfn_stats_tc<false><<<nblocks, tc::kThreads, sp.total, st>>>(d_x, B, P, N, w, bias, bn_w, ext, partials));
+              tc::k_pfn_stats_tc<false><<<nblocks, tc::kThreads, sp.total, st>>>(d_x, B, P, N, w, bias, bn_w, ext, partials, g_opt_pfn_tc_debug));
   }
   return PP_OK;
 }

@@ -351,31 +351,54 @@ __global__ void __launch_bounds__(256) k_mean(const T* __restrict__ pts, long lo
   for (int o = 16; o >= kMeanGroup; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
   const int* seg = live ? list_s + sw.off[b] + pil_off[grp] : nullptr;
   double m0 = 0, m1 = 0, m2 = 0;
-  for (int s = 0; s < cmax; s += kMeanGroup) {
+  // one chunk = kMeanGroup points: loads + four divisions per lane (independent of m), then the
+  // serial multiply-add chain on registers.  Pillars with many points take kMeanUnroll chunks per
+  // round so that the dependent index->point loads of several chunks are in flight together.
+  auto chunk_prepare = [&](int s, double& a, double& ex, double& ey, double& ez) {
     const int k = s + (int)li;
     double x = 0, y = 0, z = 0, r = 0;
     if (k < c) load_xyz(pts, sw.off[b] + seg[k], sp, sc, vec4, x, y, z, r);
-    const double n = (double)k;
-    const double n1 = __dadd_rn(n, 1.0);
-    const double a = __ddiv_rn(n, n1);
-    const double dx = __ddiv_rn(x, n1), dy = __ddiv_rn(y, n1), dz = __ddiv_rn(z, n1);
-    const int lim = min(kMeanGroup, cmax - s);
-    for (int j = 0; j < lim; ++j) {
-      const bool first = (s + j == 0);
-      const double aj = __shfl_sync(0xffffffffu, a, gbase + j);
-      const double xj = __shfl_sync(0xffffffffu, first ? x : dx, gbase + j);
-      const double yj = __shfl_sync(0xffffffffu, first ? y : dy, gbase + j);
-      const double zj = __shfl_sync(0xffffffffu, first ? z : dz, gbase + j);
+    const double n1 = __dadd_rn((double)k, 1.0);
+    a = __ddiv_rn((double)k, n1);
+    if (k == 0) { ex = x; ey = y; ez = z; }          // data/pillars.cpp:313-317: the first point initialises the mean
+    else { ex = __ddiv_rn(x, n1); ey = __ddiv_rn(y, n1); ez = __ddiv_rn(z, n1); }
+  };
+  auto chunk_chain = [&](int s, double a, double ex, double ey, double ez) {
+    double aj[kMeanGroup], xj[kMeanGroup], yj[kMeanGroup], zj[kMeanGroup];
+#pragma unroll
+    for (int j = 0; j < kMeanGroup; ++j) {
+      aj[j] = __shfl_sync(0xffffffffu, a, gbase + j);
+      xj[j] = __shfl_sync(0xffffffffu, ex, gbase + j);
+      yj[j] = __shfl_sync(0xffffffffu, ey, gbase + j);
+      zj[j] = __shfl_sync(0xffffffffu, ez, gbase + j);
+    }
+#pragma unroll
+    for (int j = 0; j < kMeanGroup; ++j) {
       if (s + j < c) {
-        if (first) {
-          m0 = xj; m1 = yj; m2 = zj;  // data/pillars.cpp:313-317
+        if (s + j == 0) {
+          m0 = xj[j]; m1 = yj[j]; m2 = zj[j];
         } else {
-          m0 = __dadd_rn(__dmul_rn(m0, aj), xj);  // data/pillars.cpp:324-326
-          m1 = __dadd_rn(__dmul_rn(m1, aj), yj);
-          m2 = __dadd_rn(__dmul_rn(m2, aj), zj);
+          m0 = __dadd_rn(__dmul_rn(m0, aj[j]), xj[j]);  // data/pillars.cpp:324-326
+          m1 = __dadd_rn(__dmul_rn(m1, aj[j]), yj[j]);
+          m2 = __dadd_rn(__dmul_rn(m2, aj[j]), zj[j]);
         }
       }
     }
+  };
+  constexpr int kMeanUnroll = 4;
+  int s = 0;
+  if (cmax > kMeanGroup) {
+    for (; s < cmax; s += kMeanGroup * kMeanUnroll) {
+      double a[kMeanUnroll], ex[kMeanUnroll], ey[kMeanUnroll], ez[kMeanUnroll];
+#pragma unroll
+      for (int u = 0; u < kMeanUnroll; ++u) chunk_prepare(s + u * kMeanGroup, a[u], ex[u], ey[u], ez[u]);
+#pragma unroll
+      for (int u = 0; u < kMeanUnroll; ++u) chunk_chain(s + u * kMeanGroup, a[u], ex[u], ey[u], ez[u]);
+    }
+  } else if (cmax > 0) {
+    double a, ex, ey, ez;
+    chunk_prepare(0, a, ex, ey, ez);
+    chunk_chain(0, a, ex, ey, ez);
   }
   if (live && li == 0) {
     pil_mean[grp * 3 + 0] = m0;

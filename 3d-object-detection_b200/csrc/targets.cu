@@ -25,6 +25,7 @@
 namespace pp {
 
 constexpr double kRadius = 10.0;  // data/pillars.cpp:418-419, hard-coded in the reference
+constexpr int kCandCap = 2048;    // per-GT IoU cache entries handed from pass 0 to pass 1 (overflow is recomputed)
 
 struct IndexHeader {  // first 64 bytes of the anchor index
   double x0, y0, cell;
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) k_iou_pass(
     const double* __restrict__ g_centers, GtParams gp, double pos_thresh,
     unsigned long long* __restrict__ best, int* __restrict__ arg, unsigned* __restrict__ posmask,
     unsigned* __restrict__ forcedmask, int* __restrict__ top_anchor, int* __restrict__ counts,
-    int* __restrict__ status) {
+    double* __restrict__ cand_iou, int* __restrict__ status) {
   const long long gg = blockIdx.x;  // global GT row
   const int b = find_gt_sweep(gp, gg);
   const int gl = (int)(gg - gp.off[b]);  // index of the GT inside its sweep
@@ -184,18 +185,29 @@ __global__ void __launch_bounds__(256) k_iou_pass(
     }
   }
 
+  double* cache = cand_iou + (size_t)gg * kCandCap;
+  int rowbase = 0;                                   // enumeration index of the first candidate of this bucket row
   for (int by = by0; by <= by1; ++by) {
     if (bx1 < bx0) break;
     const int s = bucket_start[by * hdr->nbx + bx0];
     const int e = bucket_start[by * hdr->nbx + bx1 + 1];
     for (int k = s + (int)threadIdx.x; k < e; k += blockDim.x) {
       const int a = ids[k];
-      if (prefilter_far(a_centers + (size_t)a * 3, gc)) continue;
-      double ar[8];
+      const int slot = rowbase + (k - s);
+      double v;
+      if (PASS == 1 && slot < kCandCap) {
+        v = cache[slot];                             // computed by pass 0
+      } else {
+        v = 0.0;
+        if (!prefilter_far(a_centers + (size_t)a * 3, gc)) {
+          double ar[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) ar[q] = a_corners[(size_t)a * 8 + q];
-      const double v = quad_iou(ar, g);
-      if (v < 0.0) { atomicOr(status, PP_STATUS_NEG_IOU); continue; }
+          for (int q = 0; q < 8; ++q) ar[q] = a_corners[(size_t)a * 8 + q];
+          v = quad_iou(ar, g);
+          if (v < 0.0) { atomicOr(status, PP_STATUS_NEG_IOU); v = 0.0; }
+        }
+        if (PASS == 0 && slot < kCandCap) cache[slot] = v;
+      }
       if (!(v > 0.0)) continue;
       const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
       if (PASS == 0) {
@@ -213,6 +225,7 @@ __global__ void __launch_bounds__(256) k_iou_pass(
         }
       }
     }
+    rowbase += e - s;
   }
 
   if (PASS == 0) {
@@ -300,48 +313,52 @@ __device__ float encode_value(const EncodeArgs& ea, const GtParams& gp, int b, l
 }
 
 // dense write of one [A, ncol] float matrix per sweep (cls when !IS_REG, reg when IS_REG).
+// A CTA owns tiles of 1024 anchors.  The positive / forced bitmasks say whether the tile holds any
+// non-zero row: >95 % of tiles do not and are pure 16-byte zero stores with no per-element logic.
 // NCOL > 0 fixes the row width at compile time (9 for both outputs of the reference config) so the
-// element -> (anchor, column) split is a multiply-shift, not a 64-bit division.
+// element -> (anchor, column) split in the rare path is a multiply-shift, not a 64-bit division.
+constexpr int kEncTile = 1024;   // anchors per tile (32 mask words)
 template <bool IS_REG, int NCOL>
 __global__ void __launch_bounds__(256) k_encode(EncodeArgs ea, GtParams gp, long long A, int ncol_rt,
                                                 bool vec_ok, float* __restrict__ out) {
   const unsigned ncol = NCOL > 0 ? (unsigned)NCOL : (unsigned)ncol_rt;
   const int b = blockIdx.y;
-  const unsigned total = (unsigned)(A * ncol);        // host guarantees A*ncol < 2^31
+  const unsigned nA = (unsigned)A;
+  const unsigned total = nA * ncol;                   // host guarantees A*ncol < 2^31
   float* ob = out + (size_t)b * total;
-  const unsigned stride = gridDim.x * blockDim.x;
-  if (vec_ok) {
-    const unsigned groups = total / 4;
-    for (unsigned gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += stride) {
-      const unsigned e0 = gi * 4;
-      const unsigned a0 = e0 / ncol, a1 = (e0 + 3) / ncol;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      unsigned any = anchor_flags(ea, b, A, a0);
-      if (a1 != a0) any |= anchor_flags(ea, b, A, a1);
-      if (any) {
-        float* vf = reinterpret_cast<float*>(&v);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const unsigned a = (e0 + k) / ncol;
-          const int col = (int)((e0 + k) - a * ncol);
-          const unsigned fl = anchor_flags(ea, b, A, a);
-          if (fl) vf[k] = encode_value(ea, gp, b, A, a, col, IS_REG, fl);
-        }
-      }
-      __stcs(reinterpret_cast<float4*>(ob) + gi, v);
+  const unsigned ntiles = (nA + kEncTile - 1) / kEncTile;
+  const size_t mw = (size_t)b * ((A + 31) / 32);
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const unsigned a0 = tile * kEncTile;
+    const unsigned a1 = min(a0 + kEncTile, nA);
+    // any flagged anchor in this tile?  (32 mask words, read by the first warp's lanes)
+    unsigned w = 0;
+    if (threadIdx.x < 32) {
+      const unsigned wi = (a0 >> 5) + threadIdx.x;
+      if (wi * 32 < a1) w = ea.posmask[mw + wi] | ea.forcedmask[mw + wi];
     }
-  } else {
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-      const unsigned a = e / ncol;
-      float v = 0.f;
-      const unsigned fl = anchor_flags(ea, b, A, a);
-      if (fl) v = encode_value(ea, gp, b, A, a, (int)(e - a * ncol), IS_REG, fl);
-      ob[e] = v;
+    const int any = __syncthreads_or(w != 0u);
+    const unsigned e0 = a0 * ncol, e1 = a1 * ncol;    // element range of the tile
+    if (!any && vec_ok && (e0 & 3u) == 0u) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4* o4 = reinterpret_cast<float4*>(ob + e0);
+      const unsigned n4 = (e1 - e0) >> 2;
+      for (unsigned i = threadIdx.x; i < n4; i += blockDim.x) __stcs(o4 + i, z);
+      for (unsigned e = e0 + (n4 << 2) + threadIdx.x; e < e1; e += blockDim.x) ob[e] = 0.f;
+    } else {
+      for (unsigned e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const unsigned a = e / ncol;
+        float v = 0.f;
+        const unsigned fl = any ? anchor_flags(ea, b, A, a) : 0u;
+        if (fl) v = encode_value(ea, gp, b, A, a, (int)(e - a * ncol), IS_REG, fl);
+        ob[e] = v;
+      }
     }
   }
 }
 
 struct TargetWs {
+  double* cand_iou;          // [Gt, kCandCap] pass-0 -> pass-1 IoU cache
   unsigned long long* best;  // [B, A]   zero-init
   unsigned* posmask;         // [B, ceil(A/32)] zero-init
   unsigned* forcedmask;      // [B, ceil(A/32)] zero-init
@@ -350,7 +367,9 @@ struct TargetWs {
 };
 
 template <class AR>
-static void targets_layout(AR& a, TargetWs* ws, int B, long long A) {
+static void targets_layout(AR& a, TargetWs* ws, int B, long long A, long long Gt) {
+  auto pc = a.template take<double>((size_t)(Gt > 0 ? Gt : 1) * kCandCap);
+  if (ws) ws->cand_iou = pc;
   size_t z0 = a.used;
   auto p0 = a.template take<unsigned long long>((size_t)B * A);
   auto p1 = a.template take<unsigned>((size_t)B * ((A + 31) / 32));
@@ -465,10 +484,10 @@ int pp_anchor_index_build(const double* h_a_centers, int64_t A, void* d_index, s
 
 size_t pp_assign_targets_workspace_bytes(int32_t n_sweeps, int64_t A, int64_t total_gt,
                                          const void* h_index_header) {
-  (void)total_gt; (void)h_index_header;
+  (void)h_index_header;
   if (n_sweeps < 1 || n_sweeps > PP_MAX_SWEEPS || A < 1) return 0;
   pp::SizeArena3 a;
-  pp::targets_layout(a, (pp::TargetWs*)nullptr, n_sweeps, A);
+  pp::targets_layout(a, (pp::TargetWs*)nullptr, n_sweeps, A, total_gt);
   return a.used + pp::kAlign;
 }
 
@@ -499,7 +518,7 @@ int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, cons
   if (Gt > 0x7fffffffll) return PP_ERR_INVALID_ARG;
   Arena arena(d_workspace, workspace_bytes);
   TargetWs ws{};
-  targets_layout(arena, &ws, n_sweeps, A);
+  targets_layout(arena, &ws, n_sweeps, A, Gt);
   if (!arena.ok) return PP_ERR_WORKSPACE;
 
   PP_CUDA(cudaMemsetAsync(ws.best, 0, ws.zero_bytes, st));
@@ -509,18 +528,18 @@ int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, cons
   if (Gt > 0) {
     PP_KERNEL("k_iou_pass", st, k_iou_pass<0><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
                                            d_g_centers, gp, pos_thresh, ws.best, ws.arg, ws.posmask,
-                                           ws.forcedmask, d_top_anchor, d_counts, d_status));
+                                           ws.forcedmask, d_top_anchor, d_counts, ws.cand_iou, d_status));
     PP_KERNEL("k_iou_pass", st, k_iou_pass<1><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
                                            d_g_centers, gp, pos_thresh, ws.best, ws.arg, ws.posmask,
-                                           ws.forcedmask, d_top_anchor, d_counts, d_status));
+                                           ws.forcedmask, d_top_anchor, d_counts, ws.cand_iou, d_status));
   }
   EncodeArgs ea{d_a_centers, d_a_wlh, d_a_yaw, d_g_centers, d_g_wlh, d_g_yaw, d_g_cls, ws.arg,
                 ws.posmask, ws.forcedmask, d_top_anchor};
   {
     const long long total = (long long)A * num_classes;
     const bool vec_ok = (total % 4 == 0) && ((uintptr_t)d_cls % 16 == 0);
-    long long blocks = ((vec_ok ? total / 4 : total) + 255) / 256;
-    const long long cap = (long long)sm_count() * 32;
+    long long blocks = (A + kEncTile - 1) / kEncTile;
+    const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)n_sweeps);
     if (num_classes == 9) {
@@ -532,8 +551,8 @@ int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, cons
   {
     const long long total = (long long)A * 9;
     const bool vec_ok = (total % 4 == 0) && ((uintptr_t)d_reg % 16 == 0);
-    long long blocks = ((vec_ok ? total / 4 : total) + 255) / 256;
-    const long long cap = (long long)sm_count() * 32;
+    long long blocks = (A + kEncTile - 1) / kEncTile;
+    const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)n_sweeps);
     PP_KERNEL("k_encode", st, (k_encode<true, 9><<<grid, 256, 0, st>>>(ea, gp, A, 9, vec_ok, d_reg)));

@@ -49,6 +49,10 @@ class InputPath:
         self.net.train(training)
         self.anchors = anchors
         self._pinned = {}
+        # target assignment (K3) does not depend on K1/K2: it runs on a side stream and overlaps the
+        # latency-bound binning kernels
+        self._side = torch.cuda.Stream(device=self.device)
+        self.overlap_targets = True
 
     # -- parameters ---------------------------------------------------------------------------
     def load_pfn_params(self, p):
@@ -146,6 +150,24 @@ class InputPath:
             gpack[lo:hi, 15] = torch.from_numpy(np.asarray(g["cls"], dtype=np.float64))
         return {"points": pts, "offsets": offs, "gt": gpack, "gt_offsets": goffs}
 
+    def _run(self, d_pts, offsets, gt_dev, gt_offsets, o):
+        main = torch.cuda.current_stream(self.device)
+        if self.overlap_targets:
+            self.ensure_anchors()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                cls, reg, top, counts = self.targets(gt_dev, gt_offsets, out=o.get("targets"))
+            x, inds, npil = self.pillarize(d_pts, offsets, out=o.get("pillars"))
+            canvas = self.encode(x, inds, out=o.get("canvas"))
+            main.wait_stream(self._side)
+            for t in (cls, reg, top, counts):
+                t.record_stream(main)
+        else:
+            x, inds, npil = self.pillarize(d_pts, offsets, out=o.get("pillars"))
+            canvas = self.encode(x, inds, out=o.get("canvas"))
+            cls, reg, top, counts = self.targets(gt_dev, gt_offsets, out=o.get("targets"))
+        return canvas, cls, reg, npil, counts
+
     def step_host(self, batch, out=None):
         """One pass of the whole path from pinned HOST buffers (``pack_host_batch``): H2D copy,
         pillarize, PFN + scatter, target assignment.  Outputs stay on the device, where the
@@ -159,16 +181,8 @@ class InputPath:
             "wlh": d_gt[:, 11:14].contiguous(), "yaw": d_gt[:, 14].contiguous(),
             "cls": d_gt[:, 15].to(torch.int32),
         }
-        o = out or {}
-        x, inds, npil = self.pillarize(d_pts, batch["offsets"], out=o.get("pillars"))
-        canvas = self.encode(x, inds, out=o.get("canvas"))
-        cls, reg, top, counts = self.targets(gt_dev, batch["gt_offsets"], out=o.get("targets"))
-        return canvas, cls, reg, npil, counts
+        return self._run(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out or {})
 
     def step_device(self, d_pts, offsets, gt_dev, gt_offsets, out=None):
         """Same pass with inputs already resident in HBM."""
-        o = out or {}
-        x, inds, npil = self.pillarize(d_pts, offsets, out=o.get("pillars"))
-        canvas = self.encode(x, inds, out=o.get("canvas"))
-        cls, reg, top, counts = self.targets(gt_dev, gt_offsets, out=o.get("targets"))
-        return canvas, cls, reg, npil, counts
+        return self._run(d_pts, offsets, gt_dev, gt_offsets, out or {})

@@ -340,12 +340,15 @@ def run_ours(args):
     d2h = int(BATCH * 4 + BATCH * 4 * 4)
 
     # per-kernel durations, live, CUDA events on the launching stream (separate instrumented pass)
+    # (stream overlap off here, so that each kernel is timed running alone)
+    path.overlap_targets = False
     L.pp_profile_enable(1)
     barrier()
     for _ in range(args.steps):
         step_dev()
     rep = _lib.profile_report()
     L.pp_profile_enable(0)
+    path.overlap_targets = True
     alg = algorithmic_bytes(BATCH, P, N, C, H, W, A, cfg.num_classes, T, True)
     peak, peak_src = measured_peak()
     kernels = []
