@@ -37,6 +37,7 @@ _SIGNATURES = {
     "pp_launch_count": (_i64, []),
     "pp_set_option": (_c.c_int, [_c.c_char_p, _c.c_int]),
     "pp_profile_enable": (_c.c_int, [_c.c_int]),
+    "pp_debug_tc_timing": (_c.c_int, [_i64p]),
     "pp_profile_report": (_i64, [_c.c_char_p, _i64]),
     "pp_pillarize_workspace_bytes": (_sz, [_i32, _i64, _gridp, _i32]),
     "pp_pillarize": (_c.c_int, [_vp, _i32, _i64, _i64, _i64p, _i32, _gridp, _i32, _i32, _vp, _vp,

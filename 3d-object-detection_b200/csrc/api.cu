@@ -12,6 +12,8 @@
 namespace pp {
 thread_local int g_last_cuda_error = 0;
 int g_opt_pfn_tensor_cores = 1;
+int g_opt_pfn_tc_timing = 0;
+int read_tc_prof(long long* out64);
 int g_opt_pfn_tc_debug = 0;   // development knob: bit0 skip conversion, bit1 skip MMA, bit2 skip epilogue reads
 
 // ---- launch counter + optional per-kernel CUDA-event timing -----------------------------------
@@ -48,10 +50,14 @@ int pp_last_cuda_error(void) { return pp::g_last_cuda_error; }
 
 int pp_set_option(const char* key, int value) {
   if (key == nullptr) return PP_ERR_INVALID_ARG;
-  if (strcmp(key, "pfn_tensor_cores") == 0) { pp::g_opt_pfn_tensor_cores = value ? 1 : 0; return PP_OK; }
+  if (strcmp(key, "pfn_tensor_cores") == 0) { pp::g_opt_pfn_tensor_cores = value; return PP_OK; }   // 0 CUDA cores, 1 fp16 split (+TF32 fallback), 2 TF32 split
+  if (strcmp(key, "pfn_tc_timing") == 0) { pp::g_opt_pfn_tc_timing = value; return PP_OK; }
   if (strcmp(key, "pfn_tc_debug") == 0) { pp::g_opt_pfn_tc_debug = value; return PP_OK; }
   return PP_ERR_INVALID_ARG;
 }
+
+/* development: per-role wait cycles of CTA 0 of the last k_pfn_stats_tc launch (64 int64) */
+int pp_debug_tc_timing(int64_t* out64) { return out64 ? pp::read_tc_prof((long long*)out64) : PP_ERR_INVALID_ARG; }
 
 int64_t pp_launch_count(void) { return (int64_t)pp::g_launches.load(); }
 

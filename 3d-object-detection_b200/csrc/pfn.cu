@@ -278,11 +278,22 @@ __global__ void __launch_bounds__(512) k_bn_finalize(int C, int nparts, double c
   if (training && c < C) {
     const int per = (nparts + 7) / 8;
     const int k0 = seg * per, k1 = min(nparts, k0 + per);
-    double S = 0.0, Q = 0.0;
-    for (int k = k0; k < k1; ++k) {
-      S += partials[((size_t)k * 2 + 0) * C + c];
-      Q += partials[((size_t)k * 2 + 1) * C + c];
+    // four independent accumulators (fixed combination order => still deterministic): the loads of a
+    // segment are in flight together instead of one L2 round trip per partial
+    double S4[4] = {0.0, 0.0, 0.0, 0.0}, Q4[4] = {0.0, 0.0, 0.0, 0.0};
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        S4[j] += partials[((size_t)(k + j) * 2 + 0) * C + c];
+        Q4[j] += partials[((size_t)(k + j) * 2 + 1) * C + c];
+      }
     }
+    for (int j = 0; k < k1; ++k, ++j) {
+      S4[j] += partials[((size_t)k * 2 + 0) * C + c];
+      Q4[j] += partials[((size_t)k * 2 + 1) * C + c];
+    }
+    const double S = (S4[0] + S4[1]) + (S4[2] + S4[3]), Q = (Q4[0] + Q4[1]) + (Q4[2] + Q4[3]);
     s_part[0][seg][c] = S;
     s_part[1][seg][c] = Q;
   }
@@ -313,8 +324,12 @@ __global__ void __launch_bounds__(512) k_bn_finalize(int C, int nparts, double c
   affine[c] = a;
 }
 
-__device__ __forceinline__ float apply_affine(const Affine& a, float vmax, float vmin) {
-  const float v = fmaxf(a.use_min != 0.f ? vmin : vmax, 0.f);   // relu of the extreme pre-activation
+// ext holds two fields per (row, channel): {max_n y, min_n y} from the CUDA-core kernel, or the partial
+// extremes of the two column halves from the tensor-core kernels (already sign-selected); in both
+// cases the pre-activation that survives BN(relu(.)) + max_n is max(e0,e1) for gamma*invstd >= 0 and
+// min(e0,e1) otherwise.
+__device__ __forceinline__ float apply_affine(const Affine& a, float e0, float e1) {
+  const float v = fmaxf(a.use_min != 0.f ? fminf(e0, e1) : fmaxf(e0, e1), 0.f);   // relu of the extreme pre-activation
   return fmaf(v - a.mean, a.scale, a.beta);
 }
 
@@ -358,53 +373,108 @@ __global__ void __launch_bounds__(256) k_build_map(const long long* __restrict__
   atomicMax(&map[(size_t)b * H * W + cy * W + cx], (int)(i % P));
 }
 
-// Dense canvas write, warp-centric: a warp owns 128 consecutive cells (4 per lane) for all channels,
-// so every store is a coalesced 512-byte row segment and no block-level synchronisation is needed.
-// ~95 % of the cells are empty: a group with no occupied cell streams zeros; occupied cells gather
-// their 64 channel values straight from the channel-contiguous ext rows (L1-resident lines).
+// Dense canvas write, warp-centric.  Work unit = (128 consecutive cells, kChanPerUnit channels): 4 cells
+// per lane, so every store is a coalesced 512-byte row segment and no block-level synchronisation is
+// needed.  ~95 % of the cells are empty but ~99.8 % of the 128-cell groups hold a pillar (~6 on
+// average).  Per unit the occupied cells are listed, their channel values (ext row slice + BN affine)
+// are staged into a small per-warp shared-memory tile by a flattened (cell, channel) loop, and the
+// store stream splices them in with one LDS per occupied component; lanes that own no pillar only
+// store zeros.  Gathering per (lane, channel) from global memory inside the store loop cost ~45
+// instructions per channel per warp and was issue-bound (ncu r1h).  Units with more than kStage
+// occupied cells take that gather path.
+// Units are dealt round-robin to a grid that is exactly one resident wave (occupancy x SM count CTAs):
+// with one unit of 64 channels per warp the 11264 units of the reference shape ran as 1.19 waves of
+// the 9472 resident warps, i.e. two passes with the second almost empty (96 us for 369 MB); 16-channel
+// units (45056) leave a 5 % imbalance.  A pure store stream with this access pattern reaches 6.2 TB/s
+// (scripts/ubench/wr.cu).
 //   FROM_EXT: source is ext[b*P+p][2][C] + affine (fused path); else feat[b][c][p] (PPScatter).
+constexpr int kChanPerUnit = 16;
+constexpr int kStage = 20;      // occupied cells staged per unit
 template <bool FROM_EXT>
 __global__ void __launch_bounds__(256) k_canvas(const float* __restrict__ src,
                                                 const Affine* __restrict__ affine,
-                                                const int* __restrict__ map, int P, int C, int HW,
+                                                const int* __restrict__ map, int B, int P, int C, int HW,
                                                 bool vec_ok, float* __restrict__ canvas) {
   constexpr int kCells = 128;
   __shared__ Affine s_aff[64];
-  const int b = blockIdx.y;
+  __shared__ float s_tile[8][kStage][kChanPerUnit + 1];   // [warp][occupied cell][channel of the slice], padded
+  __shared__ int s_slot[8][kStage];
   const int warp = threadIdx.x >> 5;
   const unsigned lane = lane_id();
   if (FROM_EXT) {
     if (threadIdx.x < C) s_aff[threadIdx.x] = affine[threadIdx.x];
     __syncthreads();
   }
-  const int* mb = map + (size_t)b * HW;
-  float* cb = canvas + (size_t)b * C * HW;
   const int ngroups = (HW + kCells - 1) / kCells;
-  auto value = [&](int slot, int c) -> float {
-    if (FROM_EXT) {
-      const float* e = src + ((size_t)b * P + slot) * 2 * C;
-      const Affine a = s_aff[c];
-      const float v = fmaxf(e[(a.use_min != 0.f ? C : 0) + c], 0.f);   // relu of the extreme pre-activation
-      return fmaf(v - a.mean, a.scale, a.beta);
-    }
-    return src[((size_t)b * C + c) * P + slot];
-  };
-  for (int grp = blockIdx.x * 8 + warp; grp < ngroups; grp += gridDim.x * 8) {
+  const int nq = (C + kChanPerUnit - 1) / kChanPerUnit;       // channel slices per group
+  const long long units = (long long)B * ngroups * nq;
+  const long long nwarps = (long long)gridDim.x * 8;
+  for (long long u = (long long)blockIdx.x * 8 + warp; u < units; u += nwarps) {
+    const int cq = (int)(u % nq);
+    const long long t = u / nq;
+    const int grp = (int)(t % ngroups);
+    const int b = (int)(t / ngroups);
+    const int c0 = cq * kChanPerUnit, c1 = min(C, c0 + kChanPerUnit);
+    const int* mb = map + (size_t)b * HW;
+    float* cb = canvas + (size_t)b * C * HW;
+    auto value = [&](int slot, int c) -> float {
+      if (FROM_EXT) {
+        const float* e = src + ((size_t)b * P + slot) * 2 * C;
+        return apply_affine(s_aff[c], e[c], e[C + c]);
+      }
+      return src[((size_t)b * C + c) * P + slot];
+    };
     const int cell0 = grp * kCells;
     if (vec_ok && cell0 + kCells <= HW) {
       const int4 sl = __ldg(reinterpret_cast<const int4*>(mb + cell0) + lane);
-      const bool occ = (sl.x >= 0) | (sl.y >= 0) | (sl.z >= 0) | (sl.w >= 0);
       float4* o = reinterpret_cast<float4*>(cb + cell0) + lane;
       const size_t cs = (size_t)HW / 4;                 // float4 stride between channels
-      if (!__any_sync(0xffffffffu, occ)) {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int mine = (sl.x >= 0) + (sl.y >= 0) + (sl.z >= 0) + (sl.w >= 0);
+      int incl = mine;                                  // inclusive warp scan of the occupied counts
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (total == 0) {
 #pragma unroll 8
-        for (int c = 0; c < C; ++c) __stcs(o + c * cs, z);
+        for (int c = c0; c < c1; ++c) __stcs(o + c * cs, z);
+      } else if (total <= kStage) {
+        int k0 = incl - mine;                           // first tile row of this lane's cells
+        const int kx = k0; if (sl.x >= 0) s_slot[warp][k0++] = sl.x;
+        const int ky = k0; if (sl.y >= 0) s_slot[warp][k0++] = sl.y;
+        const int kz = k0; if (sl.z >= 0) s_slot[warp][k0++] = sl.z;
+        const int kw = k0; if (sl.w >= 0) s_slot[warp][k0++] = sl.w;
+        __syncwarp();
+        const int nc = c1 - c0;
+#pragma unroll 2
+        for (int idx = (int)lane; idx < total * nc; idx += 32) {
+          const int k = idx / nc, cc = idx - k * nc;
+          s_tile[warp][k][cc] = value(s_slot[warp][k], c0 + cc);
+        }
+        __syncwarp();
+        if (mine == 0) {
+#pragma unroll 8
+          for (int c = c0; c < c1; ++c) __stcs(o + c * cs, z);
+        } else {
+#pragma unroll 4
+          for (int c = c0; c < c1; ++c) {
+            float4 v = z;
+            if (sl.x >= 0) v.x = s_tile[warp][kx][c - c0];
+            if (sl.y >= 0) v.y = s_tile[warp][ky][c - c0];
+            if (sl.z >= 0) v.z = s_tile[warp][kz][c - c0];
+            if (sl.w >= 0) v.w = s_tile[warp][kw][c - c0];
+            __stcs(o + c * cs, v);
+          }
+        }
+        __syncwarp();                                   // the tile is reused by the next unit
       } else {
 #pragma unroll 4
-        for (int c = 0; c < C; ++c) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (occ) {
+        for (int c = c0; c < c1; ++c) {
+          float4 v = z;
+          if (mine) {
             if (sl.x >= 0) v.x = value(sl.x, c);
             if (sl.y >= 0) v.y = value(sl.y, c);
             if (sl.z >= 0) v.z = value(sl.z, c);
@@ -416,7 +486,7 @@ __global__ void __launch_bounds__(256) k_canvas(const float* __restrict__ src,
     } else {
       for (int j = lane; j < kCells && cell0 + j < HW; j += 32) {
         const int slot = mb[cell0 + j];
-        for (int c = 0; c < C; ++c) cb[(size_t)c * HW + cell0 + j] = slot >= 0 ? value(slot, c) : 0.f;
+        for (int c = c0; c < c1; ++c) cb[(size_t)c * HW + cell0 + j] = slot >= 0 ? value(slot, c) : 0.f;
       }
     }
   }
@@ -428,6 +498,7 @@ struct PfnWs {
   double* partials;  // [nblocks, 2, C]
   Affine* affine;    // [C]
   int* map;          // [B, H*W]
+  int* flags;        // [0]: fp16 range guard of the tensor-core statistics kernel
 };
 
 template <class A>
@@ -436,7 +507,8 @@ static void pfn_layout(A& a, PfnWs* ws, int B, int P, int C, int H, int W, int n
   auto p1 = a.template take<double>((size_t)nblocks * 2 * C);
   auto p2 = a.template take<Affine>(64);
   auto p3 = a.template take<int>((size_t)B * H * W + 1);
-  if (ws) { ws->ext = p0; ws->partials = p1; ws->affine = p2; ws->map = p3; }
+  auto p4 = a.template take<int>(64);
+  if (ws) { ws->ext = p0; ws->partials = p1; ws->affine = p2; ws->map = p3; ws->flags = p4; }
 }
 
 struct SizeArena2 {
@@ -457,7 +529,12 @@ static int stats_blocks(long long rows) {
 bool pfn_tc_supported(int D, int N, int C, const void* x);
 int launch_stats_tc(const float* d_x, int B, int P, int N, const float* w, const float* bias,
                     const float* bn_w, int training, float* ext, double* partials, int nblocks,
-                    cudaStream_t st);
+                    const int* run_flag, cudaStream_t st);
+// fp16 compensated-split variant, pfn_tc16.cu (raises *range_flag when an input leaves the fp16 range)
+bool pfn_tc16_supported(int D, int N, int C, int P, const void* x);
+int launch_stats_tc16(const float* d_x, int B, int P, int N, const float* w, const float* bias,
+                      const float* bn_w, int training, float* ext, double* partials, int nblocks,
+                      int* range_flag, cudaStream_t st);
 extern int g_opt_pfn_tensor_cores;
 
 static int launch_stats(const float* d_x, int B, int P, int N, int C, const float* w, const float* bias,
@@ -465,7 +542,14 @@ static int launch_stats(const float* d_x, int B, int P, int N, int C, const floa
   if (g_opt_pfn_tensor_cores && pfn_tc_supported(kD, N, C, d_x)) {
     const long long pairs = ((long long)B * P + 1) / 2;
     nblocks = (int)(pairs < sm_count() ? pairs : sm_count());
-    return launch_stats_tc(d_x, B, P, N, w, bias, bn_w, training, ws.ext, ws.partials, nblocks, st);
+    if (g_opt_pfn_tensor_cores == 1 && pfn_tc16_supported(kD, N, C, P, d_x)) {
+      // fp16 fast path, then the TF32 kernel as a guarded fallback: it returns at once unless the
+      // fast path found a value outside the fp16 range, in which case it recomputes every output
+      const int rc = launch_stats_tc16(d_x, B, P, N, w, bias, bn_w, training, ws.ext, ws.partials, nblocks, ws.flags, st);
+      if (rc != PP_OK) return rc;
+      return launch_stats_tc(d_x, B, P, N, w, bias, bn_w, training, ws.ext, ws.partials, nblocks, ws.flags, st);
+    }
+    return launch_stats_tc(d_x, B, P, N, w, bias, bn_w, training, ws.ext, ws.partials, nblocks, nullptr, st);
   }
   int chunk = N < kMaxChunk ? N : kMaxChunk;
   chunk = (chunk + 3) & ~3;
@@ -513,14 +597,18 @@ static int canvas_launch(bool from_ext, const float* src, const Affine* aff, con
                          int P, int C, int H, int W, float* d_canvas, cudaStream_t st) {
   const int HW = H * W;
   const bool vec_ok = (HW % 4 == 0) && ((uintptr_t)d_canvas % 16 == 0);
-  int gx = ((HW + 127) / 128 + 7) / 8;                 // 8 warps (cell groups) per CTA
-  const int cap = sm_count() * 8;
+  // exactly one resident wave (8 CTAs of 8 warps per SM), fewer when there is less work than that
+  const long long units = (long long)B * ((HW + 127) / 128) * ((C + kChanPerUnit - 1) / kChanPerUnit);
+  long long gx = (units + 7) / 8;
+  int per_sm = 0;
+  if (from_ext) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canvas<true>, 256, 0));
+  else PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canvas<false>, 256, 0));
+  const long long cap = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
   if (gx > cap) gx = cap;
-  dim3 grid(gx, B);
   if (from_ext) {
-    PP_KERNEL("k_canvas", st, k_canvas<true><<<grid, 256, 0, st>>>(src, aff, map, P, C, HW, vec_ok, d_canvas));
+    PP_KERNEL("k_canvas", st, k_canvas<true><<<(int)gx, 256, 0, st>>>(src, aff, map, B, P, C, HW, vec_ok, d_canvas));
   } else {
-    PP_KERNEL("k_canvas", st, k_canvas<false><<<grid, 256, 0, st>>>(src, aff, map, P, C, HW, vec_ok, d_canvas));
+    PP_KERNEL("k_canvas", st, k_canvas<false><<<(int)gx, 256, 0, st>>>(src, aff, map, B, P, C, HW, vec_ok, d_canvas));
   }
   return PP_OK;
 }

@@ -34,7 +34,7 @@
 //               no-swizzle layout (a register-level transpose; kind::tf32 was measured to return
 //               zeros for an MN-major B operand on this part, so B' is stored K-major)
 // Pipelines (mbarriers): raw ring full/empty, B' tile full/empty (x2), TMEM accumulator full/empty (x2).
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace pp {
 
@@ -46,99 +46,8 @@ constexpr int kBStages = 3;            // B' operand tiles (one pillar pair each
 constexpr int kABytes = 4 * 2048;      // 4 k-steps x (64 rows x 8 k) tf32
 constexpr int kSboB = 784;             // bytes between 8-slot groups of B' (6 core matrices of 128 B + 16 pad: conflict-free STS.128)
 constexpr int kLboB = 128;             // bytes between the two 4-wide k chunks of one k-step
-constexpr unsigned long long kSpinLimit = 4000000000ull;   // ~2 s at 1.9 GHz: trap instead of hanging the GPU
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > kSpinLimit) __trap();   // a protocol bug must not wedge the device
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ float to_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
-}
-
-// Blackwell packed fp32 pairs (add/fma .f32x2): S += (t0,t1), Q += (t0*t0, t1*t1) in two instructions
-__device__ __forceinline__ void acc_pair(unsigned long long& S, unsigned long long& Q, float t0, float t1) {
-  asm("{\n.reg .b64 tp;\nmov.b64 tp, {%2, %3};\nadd.rn.f32x2 %0, %0, tp;\nfma.rn.f32x2 %1, tp, tp, %1;\n}\n"
-      : "+l"(S), "+l"(Q) : "f"(t0), "f"(t1));
-}
-__device__ __forceinline__ float pair_sum(unsigned long long v) {
-  return __uint_as_float((unsigned)(v & 0xffffffffull)) + __uint_as_float((unsigned)(v >> 32));
-}
-
-// shared-memory matrix descriptor, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3fff);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-  d |= 1ull << 46;   // descriptor version 1 (Blackwell)
-  return d;
-}
-
-#define PP_TMEM_LD32(taddr, v)                                                                        \
-  asm volatile(                                                                                       \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                       \
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"   \
-      "%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                          \
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),          \
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),     \
-        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),  \
-        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),  \
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                            \
-      : "r"(taddr))
-#define PP_TMEM_LD8(taddr, v)                                                       \
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" \
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
-               : "r"(taddr))
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+using namespace tcx;
 
 struct Smem {
   // byte offsets inside the dynamic shared memory block
@@ -164,7 +73,10 @@ template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __restrict__ conv_w,
                const float* __restrict__ conv_b, const float* __restrict__ bn_w,
-               float* __restrict__ ext, double* __restrict__ partials, int dbg) {
+               float* __restrict__ ext, double* __restrict__ partials, int dbg, long long* __restrict__ prof,
+               const int* __restrict__ run_flag) {
+  // fallback use: the fp16 kernel (pfn_tc16.cu) raises *run_flag when an input is outside the fp16 range
+  if (run_flag != nullptr && *run_flag == 0) return;
   extern __shared__ __align__(128) unsigned char smem[];
   const Smem sp = smem_plan(N);
   const int warp = threadIdx.x >> 5;
@@ -220,6 +132,9 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  const bool pon = prof != nullptr && blockIdx.x == 0;
+  long long pacc[4] = {0, 0, 0, 0};
+  const long long prole0 = pon ? clock64() : 0;
 
   // ---- roles ----------------------------------------------------------------------------------
   if (warp == 0) {
@@ -234,7 +149,7 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
       int b0 = r0 / P, p0 = r0 - b0 * P;                // (sweep, pillar) of that row, advanced incrementally
       const int step = 2 * (int)gridDim.x;
       for (int it = 0; it < my_pairs; ++it) {
-        mbar_wait(&raw_empty[s], ph);
+        mbar_wait_t(&raw_empty[s], ph, pon, pacc[0]);
         if (lane == 0) mbar_expect_tx(&raw_full[s], (uint32_t)sp.raw_stage_bytes);
         __syncwarp();
         unsigned char* dst = smem + sp.raw_off + s * sp.raw_stage_bytes;
@@ -270,8 +185,8 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
       for (int it = 0; it < my_pairs; ++it) {
         const int t = it & 1;                          // accumulator buffer
         const uint32_t n = (uint32_t)(it >> 1);
-        mbar_wait(&b_full[bs], bph);
-        mbar_wait(&acc_empty[t], (n & 1u) ^ 1u);
+        mbar_wait_t(&b_full[bs], bph, pon, pacc[0]);
+        mbar_wait_t(&acc_empty[t], (n & 1u) ^ 1u, pon, pacc[1]);
         tc_fence_after();
         for (int h = 0; h < 2 && !(dbg & 2); ++h) {
           const uint32_t b_addr = smem_u32(smem + sp.b_off + (bs * 2 + h) * sp.b_pillar_bytes);
@@ -301,7 +216,7 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
     const int nfull = N >> 5;              // 32-column chunks
     for (int it = e; it < my_pairs; it += 2) {
       const uint32_t n = (uint32_t)(it >> 1);
-      mbar_wait(&acc_full[e], n & 1u);
+      mbar_wait_t(&acc_full[e], n & 1u, pon, pacc[0]);
       tc_fence_after();
       // independent accumulator sets break the dependent chains; sums are kept as packed fp32 pairs
       float mx[2] = {-INFINITY, -INFINITY};
@@ -373,8 +288,8 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
     int s = 0, t = 0;
     uint32_t ph_raw = 0, ph_b = 1;
     for (int it = 0; it < my_pairs; ++it) {
-      mbar_wait(&raw_full[s], ph_raw);
-      mbar_wait(&b_empty[t], ph_b);
+      mbar_wait_t(&raw_full[s], ph_raw, pon, pacc[0]);
+      mbar_wait_t(&b_empty[t], ph_b, pon, pacc[1]);
       if (g < G4 && !(dbg & 1)) {
         const unsigned char* raw = smem + sp.raw_off + s * sp.raw_stage_bytes + h * N * 4 + g * 16;
         float hi[9][4], lo[9][4];
@@ -414,6 +329,10 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
     }
   }
 
+  if (pon && lane == 0) {
+    pacc[3] = clock64() - prole0;
+    for (int k = 0; k < 4; ++k) prof[warp * 4 + k] = pacc[k];
+  }
   // ---- teardown ---------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
@@ -431,6 +350,8 @@ k_pfn_stats_tc(const float* __restrict__ x, int B, int P, int N, const float* __
 }  // namespace tc
 
 extern int g_opt_pfn_tc_debug;
+extern int g_opt_pfn_tc_timing;
+__device__ long long g_tc_prof[128];
 
 bool pfn_tc_supported(int D, int N, int C, const void* x) {
   return D == 9 && C == 64 && N >= 8 && N <= 256 && (N % 8) == 0 && ((uintptr_t)x % 16) == 0;
@@ -438,17 +359,30 @@ bool pfn_tc_supported(int D, int N, int C, const void* x) {
 
 int launch_stats_tc(const float* d_x, int B, int P, int N, const float* w, const float* bias,
                     const float* bn_w, int training, float* ext, double* partials, int nblocks,
-                    cudaStream_t st) {
+                    const int* run_flag, cudaStream_t st) {
   const tc::Smem sp = tc::smem_plan(N);
+  long long* prof = nullptr;
+  if (g_opt_pfn_tc_timing) PP_CUDA(cudaGetSymbolAddress((void**)&prof, g_tc_prof));
   if (training) {
     PP_CUDA(cudaFuncSetAttribute(tc::k_pfn_stats_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-    PP_KERNEL("k_pfn_stats_tc", st,
-              tc::k_pfn_stats_tc<true><<<nblocks, tc::kThreads, sp.total, st>>>(d_x, B, P, N, w, bias, bn_w, ext, partials, g_opt_pfn_tc_debug));
+    PP_KERNEL("k_pfn_stats_tf32", st,
+              tc::k_pfn_stats_tc<true><<<nblocks, tc::kThreads, sp.total, st>>>(d_x, B, P, N, w, bias, bn_w, ext, partials, g_opt_pfn_tc_debug, prof, run_flag));
   } else {
     PP_CUDA(cudaFuncSetAttribute(tc::k_pfn_stats_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-    PP_KERNEL("k_pfn_stats_tc", st,
-              tc::k_pfn_stats_tc<false><<<nblocks, tc::kThreads, sp.total, st>>>(d_x, B, P, N, w, bias, bn_w, ext, partials, g_opt_pfn_tc_debug));
+    PP_KERNEL("k_pfn_stats_tf32", st,
+              tc::k_pfn_stats_tc<false><<<nblocks, tc::kThreads, sp.total, st>>>(d_x, B, P, N, w, bias, bn_w, ext, partials, g_opt_pfn_tc_debug, prof, run_flag));
   }
+  return PP_OK;
+}
+
+long long* tc_prof_ptr() {
+  long long* p = nullptr;
+  return cudaGetSymbolAddress((void**)&p, g_tc_prof) == cudaSuccess ? p : nullptr;
+}
+
+int read_tc_prof(long long* out64) {
+  PP_CUDA(cudaDeviceSynchronize());
+  PP_CUDA(cudaMemcpyFromSymbol(out64, g_tc_prof, sizeof(long long) * 128));
   return PP_OK;
 }
 

@@ -15,9 +15,10 @@
 //   k_assign     per tile: exclusive scan of first-touch flags -> pillar slot of each cell,
 //                list segment of each kept pillar
 //   k_scatter    per point: append its index to its pillar's segment (unordered)
-//   k_rank       per point: rank = number of smaller indices in the segment -> ordered segment
+//   k_rank       per point: rank = number of smaller indices in the segment; the point's running-mean
+//                terms (four IEEE divisions) go to its place in the ordered segment
 //   k_rank_big   pillars with more than kBig points: ordered compaction by a block scan instead
-//   k_mean       per pillar (one warp): sequential running mean, indices row
+//   k_mean       per pillar (one thread): sequential multiply-add chain of the running mean, indices row
 //   k_emit_*     dense [B,9,P,N] float with fused "- data_mean", or compact fp64 rows
 #include <type_traits>
 
@@ -242,13 +243,35 @@ __global__ void __launch_bounds__(256) k_scatter(SweepParams sw, GridDev g, int 
   }
 }
 
-__global__ void __launch_bounds__(256) k_rank(SweepParams sw, GridDev g, int P,
+// Per-point terms of the reference's running mean (data/pillars.cpp:311-328)
+//   m <- m*(n/(n+1)) + x/(n+1)
+// for the point of rank n: {a = n/(n+1), x/(n+1), y/(n+1), z/(n+1)} (the first point initialises the
+// mean: a = 0, terms = x, y, z).  The four IEEE divisions do not depend on m, so they are done here,
+// one point per thread with every lane busy, and k_mean is left with the bare multiply-add chain.
+template <typename T>
+__device__ __forceinline__ void mean_terms(const T* __restrict__ pts, long long gi, long long sp, long long sc,
+                                           bool vec4, int rank, double4* __restrict__ out) {
+  double x, y, z, r;
+  load_xyz(pts, gi, sp, sc, vec4, x, y, z, r);
+  double4 t;
+  if (rank == 0) {
+    t = make_double4(0.0, x, y, z);
+  } else {
+    const double n1 = __dadd_rn((double)rank, 1.0);
+    t = make_double4(__ddiv_rn((double)rank, n1), __ddiv_rn(x, n1), __ddiv_rn(y, n1), __ddiv_rn(z, n1));
+  }
+  *out = t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_rank(const T* __restrict__ pts, long long sp, long long sc, bool vec4,
+                                              SweepParams sw, GridDev g, int P,
                                               const int* __restrict__ cell_of_point,
                                               const int* __restrict__ cell_slot,
                                               const int* __restrict__ pil_cnt,
                                               const int* __restrict__ pil_off,
                                               const int* __restrict__ list_u,
-                                              int* __restrict__ list_s,
+                                              double4* __restrict__ terms,
                                               int* __restrict__ rank_of_point) {
   const long long total = sw.off[sw.n_sweeps];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -266,7 +289,7 @@ __global__ void __launch_bounds__(256) k_rank(SweepParams sw, GridDev g, int P,
           const int* seg = list_u + sw.off[b] + pil_off[pi];
           rank = 0;
           for (int k = 0; k < c; ++k) rank += (seg[k] < il) ? 1 : 0;
-          list_s[sw.off[b] + pil_off[pi] + rank] = il;
+          mean_terms(pts, i, sp, sc, vec4, rank, terms + sw.off[b] + pil_off[pi] + rank);
         } else {
           rank = -2;  // filled by k_rank_big
         }
@@ -277,13 +300,15 @@ __global__ void __launch_bounds__(256) k_rank(SweepParams sw, GridDev g, int P,
 }
 
 // One block per big pillar: ordered stream compaction of the sweep's points that fall in its cell.
-__global__ void __launch_bounds__(kTile) k_rank_big(SweepParams sw, int P,
+template <typename T>
+__global__ void __launch_bounds__(kTile) k_rank_big(const T* __restrict__ pts, long long sp, long long sc, bool vec4,
+                                                    SweepParams sw, int P,
                                                     const int* __restrict__ cell_of_point,
                                                     const int* __restrict__ pil_off,
                                                     const int* __restrict__ pil_cell,
                                                     const int* __restrict__ big_count,
                                                     const int* __restrict__ big_list,
-                                                    int* __restrict__ list_s,
+                                                    double4* __restrict__ terms,
                                                     int* __restrict__ rank_of_point) {
   __shared__ int warp_sum[kTile / 32];
   const int nbig = *big_count;
@@ -292,7 +317,7 @@ __global__ void __launch_bounds__(kTile) k_rank_big(SweepParams sw, int P,
     const int b = pi / P;
     const int cell = pil_cell[pi];
     const long long n_b = sw.off[b + 1] - sw.off[b];
-    int* out = list_s + sw.off[b] + pil_off[pi];
+    double4* out = terms + sw.off[b] + pil_off[pi];
     int running = 0;
     for (long long s = 0; s < n_b; s += kTile) {
       const long long il = s + threadIdx.x;
@@ -310,7 +335,7 @@ __global__ void __launch_bounds__(kTile) k_rank_big(SweepParams sw, int P,
       }
       if (flag) {
         const int rank = running + before + in_warp;
-        out[rank] = (int)il;
+        mean_terms(pts, sw.off[b] + il, sp, sc, vec4, rank, out + rank);
         rank_of_point[sw.off[b] + il] = rank;
       }
       running += total;
@@ -319,99 +344,80 @@ __global__ void __launch_bounds__(kTile) k_rank_big(SweepParams sw, int P,
   }
 }
 
-// Eight lanes per pillar slot (four pillars per warp): the reference's sequential running mean
-// (data/pillars.cpp:311-328)
-//   m <- m*(n/(n+1)) + x/(n+1)
-// evaluated in input order with separately rounded IEEE operations.  The divisions do not depend
-// on m, so the lanes of a group compute them 8 at a time and only the multiply-add chain is
-// sequential (median pillar: 2 points, p90: 7).
-constexpr int kMeanGroup = 8;
-template <typename T>
-__global__ void __launch_bounds__(256) k_mean(const T* __restrict__ pts, long long sp, long long sc,
-                                              bool vec4, SweepParams sw, GridDev g, int P,
+__device__ __forceinline__ double4 ld_terms(const double4* __restrict__ p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// One thread per pillar slot: the sequential multiply-add chain of the reference's running mean over
+// the terms k_rank prepared (32-byte records, contiguous per pillar, L2-resident), evaluated in input
+// order with separately rounded IEEE operations.  The records of the next steps are loaded ahead of
+// the chain (4-deep), so a pillar costs ~2 dependent fp64 operations per point (median pillar: 2
+// points, longest of a Lyft-shaped sweep: ~300).
+__global__ void __launch_bounds__(128) k_mean(SweepParams sw, GridDev g, int P,
                                               const int* __restrict__ num_pillars,
                                               const int* __restrict__ pil_cnt,
                                               const int* __restrict__ pil_off,
                                               const int* __restrict__ pil_cell,
-                                              const int* __restrict__ list_s,
+                                              const double4* __restrict__ terms,
                                               double* __restrict__ pil_mean,
                                               long long* __restrict__ indices) {
-  const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kMeanGroup;
-  const long long ngrp = (long long)sw.n_sweeps * P;
-  const unsigned lane = lane_id();
-  const unsigned li = lane % kMeanGroup;            // lane inside the group
-  const unsigned gbase = lane - li;                 // first lane of the group
-  const bool in_range = grp < ngrp;
-  const int b = in_range ? (int)(grp / P) : 0;
-  const int slot = in_range ? (int)(grp % P) : 0;
-  const bool live = in_range && slot < num_pillars[b];
-  if (in_range && !live && indices != nullptr && li < 3) indices[grp * 3 + li] = 0;
-  const int c = live ? pil_cnt[grp] : 0;
-  int cmax = c;
-  for (int o = 16; o >= kMeanGroup; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-  const int* seg = live ? list_s + sw.off[b] + pil_off[grp] : nullptr;
-  double m0 = 0, m1 = 0, m2 = 0;
-  // one chunk = kMeanGroup points: loads + four divisions per lane (independent of m), then the
-  // serial multiply-add chain on registers.  Pillars with many points take kMeanUnroll chunks per
-  // round so that the dependent index->point loads of several chunks are in flight together.
-  auto chunk_prepare = [&](int s, double& a, double& ex, double& ey, double& ez) {
-    const int k = s + (int)li;
-    double x = 0, y = 0, z = 0, r = 0;
-    if (k < c) load_xyz(pts, sw.off[b] + seg[k], sp, sc, vec4, x, y, z, r);
-    const double n1 = __dadd_rn((double)k, 1.0);
-    a = __ddiv_rn((double)k, n1);
-    if (k == 0) { ex = x; ey = y; ez = z; }          // data/pillars.cpp:313-317: the first point initialises the mean
-    else { ex = __ddiv_rn(x, n1); ey = __ddiv_rn(y, n1); ez = __ddiv_rn(z, n1); }
-  };
-  auto chunk_chain = [&](int s, double a, double ex, double ey, double ez) {
-    double aj[kMeanGroup], xj[kMeanGroup], yj[kMeanGroup], zj[kMeanGroup];
+  const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (grp >= (long long)sw.n_sweeps * P) return;
+  const int b = (int)(grp / P);
+  const int slot = (int)(grp - (long long)b * P);
+  if (slot >= num_pillars[b]) {
+    if (indices != nullptr) { indices[grp * 3 + 0] = 0; indices[grp * 3 + 1] = 0; indices[grp * 3 + 2] = 0; }
+    return;
+  }
+  const int c = pil_cnt[grp];
+  const double4* seg = terms + sw.off[b] + pil_off[grp];
+  double4 t = ld_terms(seg);                          // rank 0: a = 0, terms = the point itself
+  double m0 = t.y, m1 = t.z, m2 = t.w;             // data/pillars.cpp:313-317
+  constexpr int kAhead = 4;
+  int k = 1;
+  if (k + kAhead <= c) {
+    double4 u[kAhead], v[kAhead];
 #pragma unroll
-    for (int j = 0; j < kMeanGroup; ++j) {
-      aj[j] = __shfl_sync(0xffffffffu, a, gbase + j);
-      xj[j] = __shfl_sync(0xffffffffu, ex, gbase + j);
-      yj[j] = __shfl_sync(0xffffffffu, ey, gbase + j);
-      zj[j] = __shfl_sync(0xffffffffu, ez, gbase + j);
-    }
+    for (int j = 0; j < kAhead; ++j) u[j] = ld_terms(seg + k + j);
+    for (; k + kAhead <= c; k += kAhead) {
+      const bool more = k + 2 * kAhead <= c;
+      // long pillars are bound by the L2 round trip of their record stream, not by the arithmetic
+      // chain: pull the 128-byte line eight batches ahead into L1
+      if (k + 9 * kAhead <= c) asm volatile("prefetch.global.L1 [%0];" ::"l"(seg + k + 8 * kAhead));
+      if (more) {
 #pragma unroll
-    for (int j = 0; j < kMeanGroup; ++j) {
-      if (s + j < c) {
-        if (s + j == 0) {
-          m0 = xj[j]; m1 = yj[j]; m2 = zj[j];
-        } else {
-          m0 = __dadd_rn(__dmul_rn(m0, aj[j]), xj[j]);  // data/pillars.cpp:324-326
-          m1 = __dadd_rn(__dmul_rn(m1, aj[j]), yj[j]);
-          m2 = __dadd_rn(__dmul_rn(m2, aj[j]), zj[j]);
-        }
+        for (int j = 0; j < kAhead; ++j) v[j] = ld_terms(seg + k + kAhead + j);   // in flight during the chain below
+      }
+#pragma unroll
+      for (int j = 0; j < kAhead; ++j) {
+        m0 = __dadd_rn(__dmul_rn(m0, u[j].x), u[j].y);   // data/pillars.cpp:324-326
+        m1 = __dadd_rn(__dmul_rn(m1, u[j].x), u[j].z);
+        m2 = __dadd_rn(__dmul_rn(m2, u[j].x), u[j].w);
+      }
+      if (more) {
+#pragma unroll
+        for (int j = 0; j < kAhead; ++j) u[j] = v[j];
       }
     }
-  };
-  constexpr int kMeanUnroll = 4;
-  int s = 0;
-  if (cmax > kMeanGroup) {
-    for (; s < cmax; s += kMeanGroup * kMeanUnroll) {
-      double a[kMeanUnroll], ex[kMeanUnroll], ey[kMeanUnroll], ez[kMeanUnroll];
-#pragma unroll
-      for (int u = 0; u < kMeanUnroll; ++u) chunk_prepare(s + u * kMeanGroup, a[u], ex[u], ey[u], ez[u]);
-#pragma unroll
-      for (int u = 0; u < kMeanUnroll; ++u) chunk_chain(s + u * kMeanGroup, a[u], ex[u], ey[u], ez[u]);
-    }
-  } else if (cmax > 0) {
-    double a, ex, ey, ez;
-    chunk_prepare(0, a, ex, ey, ez);
-    chunk_chain(0, a, ex, ey, ez);
   }
-  if (live && li == 0) {
-    pil_mean[grp * 3 + 0] = m0;
-    pil_mean[grp * 3 + 1] = m1;
-    pil_mean[grp * 3 + 2] = m2;
-    if (indices != nullptr) {
-      const int cell = pil_cell[grp];
-      const double cx = (double)(cell % g.nx);
-      const double cy = __dsub_rn(__dsub_rn(g.canvas_height, 1.0), (double)(cell / g.nx));
-      indices[grp * 3 + 0] = 1;                 // data/pillars.cpp:390-392, then .long()
-      indices[grp * 3 + 1] = (long long)cx;
-      indices[grp * 3 + 2] = (long long)cy;
-    }
+  for (; k < c; ++k) {
+    const double4 u = ld_terms(seg + k);
+    m0 = __dadd_rn(__dmul_rn(m0, u.x), u.y);
+    m1 = __dadd_rn(__dmul_rn(m1, u.x), u.z);
+    m2 = __dadd_rn(__dmul_rn(m2, u.x), u.w);
+  }
+  pil_mean[grp * 3 + 0] = m0;
+  pil_mean[grp * 3 + 1] = m1;
+  pil_mean[grp * 3 + 2] = m2;
+  if (indices != nullptr) {
+    const int cell = pil_cell[grp];
+    const double cx = (double)(cell % g.nx);
+    const double cy = __dsub_rn(__dsub_rn(g.canvas_height, 1.0), (double)(cell / g.nx));
+    indices[grp * 3 + 0] = 1;                 // data/pillars.cpp:390-392, then .long()
+    indices[grp * 3 + 1] = (long long)cx;
+    indices[grp * 3 + 2] = (long long)cy;
   }
 }
 
@@ -562,7 +568,8 @@ __global__ void k_pillar_xy(GridDev g, int P, const int* __restrict__ num_pillar
 
 // ------------------------------------------------------------------------------------------
 struct PillarWs {
-  int *cell_first, *cell_slot, *cell_of_point, *rank_of_point, *tile_count, *list_u, *list_s;
+  int *cell_first, *cell_slot, *cell_of_point, *rank_of_point, *tile_count, *list_u;
+  double4* terms;   // per point, in its pillar's ordered segment: {n/(n+1), x/(n+1), y/(n+1), z/(n+1)}
   int *pil_cnt, *pil_off, *pil_cell, *big_list, *num_pillars_scratch;
   double* pil_mean;
   float* feat_c;
@@ -614,7 +621,7 @@ static void layout(A& a, PillarWs* ws, int B, long long T, long long ntiles, int
   TAKE(rank_of_point, int, t);
   TAKE(tile_count, int, (size_t)ntiles + 1);
   TAKE(list_u, int, t);
-  TAKE(list_s, int, t);
+  TAKE(terms, double4, t);
   TAKE(pil_cnt, int, np);
   TAKE(pil_off, int, np);
   TAKE(pil_cell, int, np);
@@ -651,16 +658,14 @@ static int run_stages(const T* pts, long long sp, long long sc, bool vec4, const
                                        d_num_pillars));
     PP_KERNEL("k_scatter", st, k_scatter<<<pt_blocks, 256, 0, st>>>(sw, g, P, ws.cell_of_point, ws.cell_slot, ws.pil_off,
                                          ws.pil_cursor, ws.list_u));
-    PP_KERNEL("k_rank", st, k_rank<<<pt_blocks, 256, 0, st>>>(sw, g, P, ws.cell_of_point, ws.cell_slot, ws.pil_cnt,
-                                      ws.pil_off, ws.list_u, ws.list_s, ws.rank_of_point));
-    PP_KERNEL("k_rank_big", st, k_rank_big<<<64, kTile, 0, st>>>(sw, P, ws.cell_of_point, ws.pil_off, ws.pil_cell,
-                                     ws.big_count, ws.big_list, ws.list_s, ws.rank_of_point));
+    PP_KERNEL("k_rank", st, k_rank<T><<<pt_blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, P, ws.cell_of_point, ws.cell_slot,
+                                         ws.pil_cnt, ws.pil_off, ws.list_u, ws.terms, ws.rank_of_point));
+    PP_KERNEL("k_rank_big", st, k_rank_big<T><<<64, kTile, 0, st>>>(pts, sp, sc, vec4, sw, P, ws.cell_of_point, ws.pil_off,
+                                        ws.pil_cell, ws.big_count, ws.big_list, ws.terms, ws.rank_of_point));
   }
   const long long groups = (long long)B * P;
-  const int mean_blocks = (int)((groups * kMeanGroup + 255) / 256);
-  PP_KERNEL("k_mean", st, k_mean<T><<<mean_blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, P, d_num_pillars, ws.pil_cnt,
-                                         ws.pil_off, ws.pil_cell, ws.list_s, ws.pil_mean,
-                                         d_indices));
+  PP_KERNEL("k_mean", st, k_mean<<<(int)((groups + 127) / 128), 128, 0, st>>>(sw, g, P, d_num_pillars, ws.pil_cnt, ws.pil_off,
+                                         ws.pil_cell, ws.terms, ws.pil_mean, d_indices));
   return PP_OK;
 }
 

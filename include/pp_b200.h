@@ -82,6 +82,9 @@ int64_t pp_launch_count(void);
  * tensor cores (TF32 3-term split) whenever D=9, C=64, N%8==0, N<=256; 0 forces the CUDA-core kernel. */
 int pp_set_option(const char* key, int value);
 int pp_profile_enable(int on);
+/* Development aid: with option "pfn_tc_timing"=1, CTA 0 of k_pfn_stats_tc records per-warp wait
+ * cycles; this reads them back (128 int64: [warp][wait0, wait1, -, role total]). */
+int pp_debug_tc_timing(int64_t* out64);
 int64_t pp_profile_report(char* buf, int64_t buf_bytes);
 
 /* ------------------------------------------------------------------------------------------

@@ -183,3 +183,68 @@ def test_scatter_edge_cases():
     sc(feat.cuda(), bad.cuda())
     with pytest.raises(_lib.PPError):
         _runtime.check_status(torch.device("cuda"), "scatter")
+
+
+def _set_tc(mode):
+    from pp_b200 import _lib
+    _lib.load().pp_set_option(b"pfn_tensor_cores", mode)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 0])
+def test_kernel_variants_agree_with_oracle(mode):
+    """pfn_tensor_cores = 1: fp16 compensated split (+ guarded TF32 fallback), 2: TF32 split, 0: CUDA cores."""
+    import pp_b200.model as M
+    from oracle import pfn
+    from pp_b200 import synth
+    x = _random_case(2, 200, 200, 64, 5, 6.0, 0.05)
+    prm = synth.make_pfn_params(3, 9, 64, flip_gamma=True)
+    t = lambda a: torch.from_numpy(a)
+    try:
+        _set_tc(mode)
+        net = M.PPFeatureNet(9, 64).cuda().train()
+        with torch.no_grad():
+            net.conv1.weight.copy_(t(prm["conv_w"]).reshape(64, 9, 1, 1)); net.conv1.bias.copy_(t(prm["conv_b"]))
+            net.bn1.weight.copy_(t(prm["bn_w"])); net.bn1.bias.copy_(t(prm["bn_b"]))
+            net.bn1.running_mean.copy_(t(prm["running_mean"])); net.bn1.running_var.copy_(t(prm["running_var"]))
+            got = net(t(x).cuda())
+    finally:
+        _set_tc(1)
+    want, rm, rv = pfn.pfn_forward(t(x), t(prm["conv_w"]), t(prm["conv_b"]), t(prm["bn_w"]), t(prm["bn_b"]),
+                                   t(prm["running_mean"]), t(prm["running_var"]), True)
+    y = torch.relu(torch.einsum('cd,bdpn->bcpn', t(prm["conv_w"]).double(), t(x).double())
+                   + t(prm["conv_b"]).double().view(1, -1, 1, 1))
+    amp = amplification(x, prm["conv_w"], prm["conv_b"], prm["bn_w"], y.var(dim=(0, 2, 3), unbiased=False))
+    close(got.cpu().numpy(), want.numpy(), amp=amp)
+    close(net.bn1.running_var.cpu().numpy(), rv.numpy())
+
+
+@pytest.mark.parametrize("what", ["x", "weight"])
+def test_fp16_range_guard_falls_back_to_tf32(what):
+    """Values outside the fp16 range (|x| >= 2^15 or |256 w| >= 2^15) must not reach the fp16 kernel's
+    result: the guarded TF32 kernel recomputes everything and parity still holds."""
+    import pp_b200.model as M
+    from oracle import pfn
+    from pp_b200 import synth, _lib
+    x = _random_case(1, 64, 200, 64, 7, 4.0, 0.02)
+    prm = synth.make_pfn_params(4, 9, 64, flip_gamma=False)
+    if what == "x":
+        x[0, 3, 5, 0] = 1.0e6            # an intensity far outside fp16
+        x[0, 0, 9, 2] = -70000.0
+    else:
+        prm["conv_w"][7, 2] = 300.0
+    t = lambda a: torch.from_numpy(a)
+    net = M.PPFeatureNet(9, 64).cuda().eval()
+    L = _lib.load()
+    with torch.no_grad():
+        net.conv1.weight.copy_(t(prm["conv_w"]).reshape(64, 9, 1, 1)); net.conv1.bias.copy_(t(prm["conv_b"]))
+        net.bn1.weight.copy_(t(prm["bn_w"])); net.bn1.bias.copy_(t(prm["bn_b"]))
+        net.bn1.running_mean.copy_(t(prm["running_mean"])); net.bn1.running_var.copy_(t(prm["running_var"]))
+        L.pp_profile_enable(1)
+        got = net(t(x).cuda())
+        rep = _lib.profile_report(); L.pp_profile_enable(0)
+    assert "k_pfn_stats_tc" in rep and "k_pfn_stats_tf32" in rep
+    want, _, _ = pfn.pfn_forward(t(x), t(prm["conv_w"]), t(prm["conv_b"]), t(prm["bn_w"]), t(prm["bn_b"]),
+                                 t(prm["running_mean"]), t(prm["running_var"]), False)
+    amp = amplification(x, prm["conv_w"], prm["conv_b"], prm["bn_w"], t(prm["running_var"]))
+    close(got.cpu().numpy(), want.numpy(), amp=amp)
+    assert np.isfinite(got.cpu().numpy()).all()
