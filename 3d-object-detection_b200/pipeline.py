@@ -27,6 +27,21 @@ def shard_range(n_items, rank, world_size):
     return lo, min(lo + per, n_items)
 
 
+class StepHandle:
+    """Result of ``InputPath.step_host_async``: device outputs + the step's counters on their way to
+    pinned host memory."""
+
+    def __init__(self, outputs, pinned, n_sweeps, done):
+        self.canvas, self.cls, self.reg, self.n_pillars, self.counts = outputs
+        self._pin, self._B, self._done = pinned, n_sweeps, done
+
+    def counters(self):
+        """(n_pillars [B], counts [B,4]) as host int32 tensors; waits for this step's D2H copy."""
+        self._done.synchronize()
+        B = self._B
+        return self._pin[:B].clone(), self._pin[B:5 * B].view(B, 4).clone()
+
+
 class InputPath:
     def __init__(self, cfg=None, device=None, data_mean=None, pfn_params=None, anchors=None,
                  training=True):
@@ -53,6 +68,12 @@ class InputPath:
         # latency-bound binning kernels
         self._side = torch.cuda.Stream(device=self.device)
         self.overlap_targets = True
+        # host-facing pipeline: copy stream, two device staging buffers, pinned result slots
+        self._copy = torch.cuda.Stream(device=self.device)
+        self._stage = [None, None]
+        self._slot_free = [None, None]
+        self._result_pin = [None, None]
+        self._step_no = 0
 
     # -- parameters ---------------------------------------------------------------------------
     def load_pfn_params(self, p):
@@ -124,31 +145,73 @@ class InputPath:
                               self.cfg.iou_pos_thresh, out=out)
 
     # -- host-facing step -----------------------------------------------------------------------
+    @staticmethod
+    def _blob_layout(T, ncol, Gt):
+        """Byte offsets of the sections of one packed batch (each 256-byte aligned)."""
+        al = lambda v: (v + 255) // 256 * 256
+        sizes = [("points", max(T, 1) * ncol * 4), ("corners", max(Gt, 1) * 8 * 8), ("centers", max(Gt, 1) * 3 * 8),
+                 ("wlh", max(Gt, 1) * 3 * 8), ("yaw", max(Gt, 1) * 8), ("cls", max(Gt, 1) * 4)]
+        off, o = {}, 0
+        for name, n in sizes:
+            off[name] = (o, n)
+            o = al(o + n)
+        return off, o
+
+    @staticmethod
+    def _blob_views(blob, off, T, ncol, Gt):
+        v = lambda name, dt: blob[off[name][0]:off[name][0] + off[name][1]].view(dt)
+        return {"points": v("points", torch.float32).view(max(T, 1), ncol),
+                "corners": v("corners", torch.float64).view(max(Gt, 1), 8),
+                "centers": v("centers", torch.float64).view(max(Gt, 1), 3),
+                "wlh": v("wlh", torch.float64).view(max(Gt, 1), 3),
+                "yaw": v("yaw", torch.float64), "cls": v("cls", torch.int32)}
+
     def pack_host_batch(self, sweeps, gts):
         """Pack a list of float32 [n_i, >=4] sweeps and a list of GT dicts (centers/wlh/yaw/cls in
-        canvas space, as the reference's box pickles hold them) into pinned host buffers."""
+        canvas space, as the reference's box pickles hold them) into ONE pinned host buffer
+        (points | GT corners | centres | wlh | yaw | class ids), so that a step needs a single
+        host-to-device copy and no device-side repacking."""
         offs = [0]
         for s in sweeps:
             offs.append(offs[-1] + int(s.shape[0]))
         ncol = int(sweeps[0].shape[1])
-        pts = torch.empty((max(offs[-1], 1), ncol), dtype=torch.float32).pin_memory()
-        for s, lo, hi in zip(sweeps, offs[:-1], offs[1:]):
-            pts[lo:hi] = torch.as_tensor(s, dtype=torch.float32)
         goffs = [0]
         for g in gts:
             goffs.append(goffs[-1] + int(len(g["yaw"])))
-        Gt = goffs[-1]
-        gpack = torch.zeros((max(Gt, 1), 16), dtype=torch.float64).pin_memory()   # corners 8 | centers 3 | wlh 3 | yaw 1 | cls 1
+        T, Gt = offs[-1], goffs[-1]
+        layout, nbytes = self._blob_layout(T, ncol, Gt)
+        blob = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+        hv = self._blob_views(blob, layout, T, ncol, Gt)
+        for s, lo, hi in zip(sweeps, offs[:-1], offs[1:]):
+            hv["points"][lo:hi] = torch.as_tensor(s, dtype=torch.float32)
         for g, lo, hi in zip(gts, goffs[:-1], goffs[1:]):
             if hi == lo:
                 continue
             cen, cor = gt_to_image_space(g, self.cfg.canvas_height)
-            gpack[lo:hi, 0:8] = torch.from_numpy(cor.reshape(-1, 8))
-            gpack[lo:hi, 8:11] = torch.from_numpy(cen)
-            gpack[lo:hi, 11:14] = torch.from_numpy(np.asarray(g["wlh"], dtype=np.float64))
-            gpack[lo:hi, 14] = torch.from_numpy(np.asarray(g["yaw"], dtype=np.float64))
-            gpack[lo:hi, 15] = torch.from_numpy(np.asarray(g["cls"], dtype=np.float64))
-        return {"points": pts, "offsets": offs, "gt": gpack, "gt_offsets": goffs}
+            hv["corners"][lo:hi] = torch.from_numpy(cor.reshape(-1, 8))
+            hv["centers"][lo:hi] = torch.from_numpy(cen)
+            hv["wlh"][lo:hi] = torch.from_numpy(np.asarray(g["wlh"], dtype=np.float64))
+            hv["yaw"][lo:hi] = torch.from_numpy(np.asarray(g["yaw"], dtype=np.float64))
+            hv["cls"][lo:hi] = torch.from_numpy(np.asarray(g["cls"], dtype=np.int32))
+        return {"blob": blob, "layout": layout, "ncol": ncol, "offsets": offs, "gt_offsets": goffs,
+                "points": hv["points"], "host": hv}
+
+    def upload(self, batch, slot=None):
+        """One host-to-device copy of a packed batch; returns (d_points, gt_dev) views of the device
+        copy.  ``slot`` selects one of the two resident staging buffers (step_host_async alternates)."""
+        dev = self.device
+        T, Gt = batch["offsets"][-1], batch["gt_offsets"][-1]
+        n = batch["blob"].numel()
+        if slot is None:
+            dblob = torch.empty(n, dtype=torch.uint8, device=dev)
+        else:
+            dblob = self._stage[slot]
+            if dblob is None or dblob.numel() < n:
+                dblob = self._stage[slot] = torch.empty(n, dtype=torch.uint8, device=dev)
+        dblob[:n].copy_(batch["blob"], non_blocking=True)
+        dv = self._blob_views(dblob, batch["layout"], T, batch["ncol"], Gt)
+        gt_dev = {k: dv[k] for k in ("corners", "centers", "wlh", "yaw", "cls")}
+        return dv["points"][:max(T, 1)], gt_dev
 
     def _run(self, d_pts, offsets, gt_dev, gt_offsets, o):
         main = torch.cuda.current_stream(self.device)
@@ -169,19 +232,40 @@ class InputPath:
         return canvas, cls, reg, npil, counts
 
     def step_host(self, batch, out=None):
-        """One pass of the whole path from pinned HOST buffers (``pack_host_batch``): H2D copy,
+        """One pass of the whole path from a pinned HOST batch (``pack_host_batch``): H2D copy,
         pillarize, PFN + scatter, target assignment.  Outputs stay on the device, where the
         backbone and the loss consume them; returns (canvas, cls, reg, n_pillars, counts)."""
-        dev = self.device
-        T, Gt = batch["offsets"][-1], batch["gt_offsets"][-1]
-        d_pts = batch["points"][:max(T, 1)].to(dev, non_blocking=True)
-        d_gt = batch["gt"][:max(Gt, 1)].to(dev, non_blocking=True)
-        gt_dev = {
-            "corners": d_gt[:, 0:8].contiguous(), "centers": d_gt[:, 8:11].contiguous(),
-            "wlh": d_gt[:, 11:14].contiguous(), "yaw": d_gt[:, 14].contiguous(),
-            "cls": d_gt[:, 15].to(torch.int32),
-        }
+        d_pts, gt_dev = self.upload(batch)
         return self._run(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out or {})
+
+    def step_host_async(self, batch, out=None):
+        """Pipelined form of ``step_host`` for a streaming loop: the H2D copy goes to a copy stream
+        into one of two staging buffers (so the copy of step k+1 overlaps the kernels of step k), the
+        step's counters come back through a pinned buffer, and nothing blocks the host.  Returns a
+        ``StepHandle``; ``handle.counters()`` waits for this step only."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        slot = self._step_no & 1
+        self._step_no += 1
+        if self._slot_free[slot] is not None:
+            self._copy.wait_event(self._slot_free[slot])     # kernels that read this staging buffer two steps ago
+        with torch.cuda.stream(self._copy):
+            d_pts, gt_dev = self.upload(batch, slot)
+            ready = torch.cuda.Event()
+            ready.record(self._copy)
+        main.wait_event(ready)
+        res = self._run(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out or {})
+        self._slot_free[slot] = torch.cuda.Event()
+        self._slot_free[slot].record(main)
+        B = len(batch["offsets"]) - 1
+        pin = self._result_pin[slot]
+        if pin is None or pin.numel() < 5 * B:
+            pin = self._result_pin[slot] = torch.empty(5 * B, dtype=torch.int32).pin_memory()
+        pin[:B].copy_(res[3], non_blocking=True)
+        pin[B:5 * B].view(B, 4).copy_(res[4], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        return StepHandle(res, pin, B, done)
 
     def step_device(self, d_pts, offsets, gt_dev, gt_offsets, out=None):
         """Same pass with inputs already resident in HBM."""

@@ -79,3 +79,33 @@ def test_full_size_batch_properties():
         nz = (c1[b] != 0).any(0).cpu()
         assert not (nz & ~support).any()
     assert int(k1[:, 0].sum()) > 50
+
+
+def test_async_streaming_steps_equal_the_blocking_call():
+    """step_host_async (copy stream, two staging buffers, pinned counters) over alternating batches
+    gives exactly what step_host gives for each of them, also with two steps in flight."""
+    from pp_b200 import pipeline, synth
+    path = pipeline.InputPath(data_mean=synth.make_data_mean(24000, 200, dense=False),
+                              pfn_params=synth.make_pfn_params(0), training=False)
+    batches = []
+    for k in range(3):
+        sweeps = [synth.make_sweep(10 * k + s) for s in range(2)]
+        gts = [synth.make_gt(10 * k + s, 20 + 7 * k) for s in range(2)]
+        batches.append(path.pack_host_batch(sweeps, gts))
+    want = []
+    for b in batches:
+        c, cls, reg, n, k = path.step_host(b)
+        want.append((c.clone(), cls.clone(), reg.clone(), n.cpu(), k.cpu()))
+    handles, got = [], []
+    for i in [0, 1, 2, 0, 2, 1]:
+        h = path.step_host_async(batches[i])            # fresh outputs per step (no shared `out`)
+        handles.append((i, h))
+        if len(handles) > 2:
+            j, hj = handles.pop(0)
+            got.append((j, hj.canvas, hj.cls, hj.reg) + hj.counters())
+    for j, hj in handles:
+        got.append((j, hj.canvas, hj.cls, hj.reg) + hj.counters())
+    assert len(got) == 6
+    for j, c, cls, reg, n, k in got:
+        assert torch.equal(c, want[j][0]) and torch.equal(cls, want[j][1]) and torch.equal(reg, want[j][2])
+        assert torch.equal(n, want[j][3]) and torch.equal(k, want[j][4])
