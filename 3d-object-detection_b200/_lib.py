@@ -11,7 +11,7 @@ from . import build as _build
 PP_OK = 0
 PP_F32, PP_F64, PP_I64 = 0, 1, 2
 PP_MAX_SWEEPS = 64
-STATUS_NEG_IOU, STATUS_BAD_POINT, STATUS_BAD_INDEX, STATUS_CAND_OVERFLOW = 1, 2, 4, 8
+STATUS_NEG_IOU, STATUS_BAD_POINT, STATUS_BAD_INDEX, STATUS_CAND_OVERFLOW, STATUS_RANGE = 1, 2, 4, 8, 16
 
 
 class PPGrid(ctypes.Structure):
@@ -51,6 +51,10 @@ _SIGNATURES = {
     "pp_pfn_scatter": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _i32, _f32, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _sz,
                                   _vp]),
+    "pp_input_path_workspace_bytes": (_sz, [_i32, _i64, _gridp, _i32, _i32, _i32, _i32]),
+    "pp_input_path": (_c.c_int, [_vp, _i32, _i64, _i64, _i64p, _i32, _gridp, _i32, _i32, _vp, _i32,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _i32, _i32,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pp_make_ious": (_c.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "pp_anchor_index_bytes": (_sz, [_vp, _i64]),
     "pp_anchor_index_build": (_c.c_int, [_vp, _i64, _vp, _sz, _vp]),

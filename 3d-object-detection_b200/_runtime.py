@@ -56,4 +56,7 @@ def check_status(device, what):
             msgs.append("scatter index outside the canvas")
         if v & _lib.STATUS_CAND_OVERFLOW:
             msgs.append("candidate overflow")
+        if v & _lib.STATUS_RANGE:
+            msgs.append("fused input path: data_mean / conv weight outside the fp16 range of the padding "
+                        "pass; use pillarize + encode")
         raise _lib.PPError("%s: %s" % (what, "; ".join(msgs)))

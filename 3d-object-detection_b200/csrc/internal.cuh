@@ -1,0 +1,51 @@
+// internal.cuh -- types shared between the K1 (pillarize.cu) and K2 (pfn*.cu) translation units for the
+// fused input path (pp_input_path): K1's compact per-point state is consumed directly, the dense
+// [B,9,P,N] network input is never materialised.
+#pragma once
+#include "common.cuh"
+
+namespace pp {
+
+struct SweepParams {
+  int n_sweeps;
+  int tile_start[PP_MAX_SWEEPS + 1];
+  long long off[PP_MAX_SWEEPS + 1];
+};
+
+// K1 state handed to the sparse PFN (all device pointers, valid until the workspace is reused)
+struct CompactPillars {
+  SweepParams sw;            // point offsets of the sweeps (host copy, passed by value to kernels)
+  int P, N;
+  const float* feat_c;       // [T, 9] float: decorated features of the kept points, before "- data_mean",
+                             //   at sw.off[b] + pil_off[b*P+p] + rank
+  const int* pil_cnt;        // [B*P] in-range points of the pillar (may exceed N)
+  const int* pil_off;        // [B*P] first entry of the pillar's segment (relative to the sweep)
+  const int* num_pillars;    // [B]
+  const float* data_mean;    // [9*P*N] or nullptr
+};
+
+constexpr int kSparseMaxSweeps = 8;   // sweeps per call of the sparse PFN (per-sweep suffix maxima live in registers)
+
+struct PfnParams {
+  const float *conv_w, *conv_b, *bn_w, *bn_b;
+  float *running_mean, *running_var;
+  int64_t* num_batches_tracked;
+  int training;
+  float momentum, eps;
+};
+
+namespace tch {
+// arguments of the padding pass (k_pfn_stats_tc<.., PAD = true>, pfn_tc16.cu)
+struct PadArgs {
+  int nb;                                   // real sweeps (<= kSparseMaxSweeps)
+  const unsigned long long* packed;         // [P]: byte b = min(count of pillar p in sweep b, N), 0xff = not a live pillar there
+};
+}  // namespace tch
+
+size_t pfn_sparse_workspace_bytes(int B, int P, int C, int H, int W);
+// canvas [B,C,H,W] from K1's compact state; d_inds is K1's [B,P,3] indices output
+int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, const PfnParams& prm, int H, int W,
+                       float* d_canvas, int32_t* d_status, void* d_ws, size_t ws_bytes, cudaStream_t st);
+bool pfn_sparse_supported(int B, int P, int N, int C, const void* data_mean);
+
+}  // namespace pp

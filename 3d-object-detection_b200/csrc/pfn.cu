@@ -24,7 +24,7 @@
 //                 (zeros + gathered pillars), from ext (+affine) or from a [B,C,P] feature tensor.
 #include <type_traits>
 
-#include "common.cuh"
+#include "internal.cuh"
 
 namespace pp {
 
@@ -264,8 +264,22 @@ k_pfn_stats(const float* __restrict__ x, int B, int P, int N, int chunk, int nch
 
 // 64 channels x 8 segments: each thread sums a contiguous run of per-CTA partials, the eight
 // segment sums are combined in fixed order => deterministic, ~8x shorter dependency chain.
+// Sparse path: sum = mult * (sum of partials) + (sum of partials2) + base, where partials come from
+// the padding pass (every padding value occurs once per sweep: mult = B), partials2 from k_pfn_real
+// (real slot minus the padding value it replaces) and base = pad_count * relu(bias) when there is no
+// data_mean (all padding slots are exactly zero, y == bias).
+struct SparseFinalize {
+  double mult;
+  const double* partials2;
+  int nparts2;
+  const float* conv_b;     // non-null: analytic padding base
+  double pad_count;
+  const int* range_flag;   // non-null: raise PP_STATUS_RANGE in *status when set
+  int* status;
+};
+
 __global__ void __launch_bounds__(512) k_bn_finalize(int C, int nparts, double count, int training,
-                                                     float momentum, float eps,
+                                                     float momentum, float eps, SparseFinalize sf,
                                                      const double* __restrict__ partials,
                                                      const float* __restrict__ bn_w,
                                                      const float* __restrict__ bn_b,
@@ -275,25 +289,57 @@ __global__ void __launch_bounds__(512) k_bn_finalize(int C, int nparts, double c
                                                      Affine* __restrict__ affine) {
   __shared__ double s_part[2][8][64];
   const int c = threadIdx.x & 63, seg = threadIdx.x >> 6;
+  if (threadIdx.x == 0 && sf.range_flag != nullptr && *sf.range_flag != 0) atomicOr(sf.status, PP_STATUS_RANGE);
   if (training && c < C) {
     const int per = (nparts + 7) / 8;
     const int k0 = seg * per, k1 = min(nparts, k0 + per);
     // four independent accumulators (fixed combination order => still deterministic): the loads of a
     // segment are in flight together instead of one L2 round trip per partial
-    double S4[4] = {0.0, 0.0, 0.0, 0.0}, Q4[4] = {0.0, 0.0, 0.0, 0.0};
+    double S4[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, Q4[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     int k = k0;
-    for (; k + 4 <= k1; k += 4) {
+    for (; k + 8 <= k1; k += 8) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         S4[j] += partials[((size_t)(k + j) * 2 + 0) * C + c];
         Q4[j] += partials[((size_t)(k + j) * 2 + 1) * C + c];
       }
     }
-    for (int j = 0; k < k1; ++k, ++j) {
-      S4[j] += partials[((size_t)k * 2 + 0) * C + c];
-      Q4[j] += partials[((size_t)k * 2 + 1) * C + c];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (k + j < k1) {
+        S4[j] += partials[((size_t)(k + j) * 2 + 0) * C + c];
+        Q4[j] += partials[((size_t)(k + j) * 2 + 1) * C + c];
+      }
     }
-    const double S = (S4[0] + S4[1]) + (S4[2] + S4[3]), Q = (Q4[0] + Q4[1]) + (Q4[2] + Q4[3]);
+    double S = (((S4[0] + S4[1]) + (S4[2] + S4[3])) + ((S4[4] + S4[5]) + (S4[6] + S4[7]))) * sf.mult;
+    double Q = (((Q4[0] + Q4[1]) + (Q4[2] + Q4[3])) + ((Q4[4] + Q4[5]) + (Q4[6] + Q4[7]))) * sf.mult;
+    if (sf.partials2 != nullptr) {
+      const int per2 = (sf.nparts2 + 7) / 8;
+      const int j0 = seg * per2, j1 = min(sf.nparts2, j0 + per2);
+      double S2[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, Q2[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      int j = j0;
+      for (; j + 8 <= j1; j += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          S2[u] += sf.partials2[((size_t)(j + u) * 2 + 0) * C + c];
+          Q2[u] += sf.partials2[((size_t)(j + u) * 2 + 1) * C + c];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (j + u < j1) {
+          S2[u] += sf.partials2[((size_t)(j + u) * 2 + 0) * C + c];
+          Q2[u] += sf.partials2[((size_t)(j + u) * 2 + 1) * C + c];
+        }
+      }
+      S += ((S2[0] + S2[1]) + (S2[2] + S2[3])) + ((S2[4] + S2[5]) + (S2[6] + S2[7]));
+      Q += ((Q2[0] + Q2[1]) + (Q2[2] + Q2[3])) + ((Q2[4] + Q2[5]) + (Q2[6] + Q2[7]));
+    }
+    if (sf.conv_b != nullptr && seg == 0) {
+      const double rb = (double)fmaxf(sf.conv_b[c], 0.f);
+      S += sf.pad_count * rb;
+      Q += sf.pad_count * rb * rb;
+    }
     s_part[0][seg][c] = S;
     s_part[1][seg][c] = Q;
   }
@@ -328,6 +374,10 @@ __global__ void __launch_bounds__(512) k_bn_finalize(int C, int nparts, double c
 // extremes of the two column halves from the tensor-core kernels (already sign-selected); in both
 // cases the pre-activation that survives BN(relu(.)) + max_n is max(e0,e1) for gamma*invstd >= 0 and
 // min(e0,e1) otherwise.
+__device__ __forceinline__ float apply_affine(const Affine& a, float e0, float e1, float e2) {
+  const float v = fmaxf(a.use_min != 0.f ? fminf(fminf(e0, e1), e2) : fmaxf(fmaxf(e0, e1), e2), 0.f);
+  return fmaf(v - a.mean, a.scale, a.beta);
+}
 __device__ __forceinline__ float apply_affine(const Affine& a, float e0, float e1) {
   const float v = fmaxf(a.use_min != 0.f ? fminf(e0, e1) : fmaxf(e0, e1), 0.f);   // relu of the extreme pre-activation
   return fmaf(v - a.mean, a.scale, a.beta);
@@ -390,7 +440,8 @@ __global__ void __launch_bounds__(256) k_build_map(const long long* __restrict__
 //   FROM_EXT: source is ext[b*P+p][2][C] + affine (fused path); else feat[b][c][p] (PPScatter).
 constexpr int kChanPerUnit = 16;
 constexpr int kStage = 20;      // occupied cells staged per unit
-template <bool FROM_EXT>
+// FROM_EXT: 0 = feature tensor, 2 / 3 = ext rows with that many fields per (pillar, channel)
+template <int FROM_EXT>
 __global__ void __launch_bounds__(256) k_canvas(const float* __restrict__ src,
                                                 const Affine* __restrict__ affine,
                                                 const int* __restrict__ map, int B, int P, int C, int HW,
@@ -418,9 +469,13 @@ __global__ void __launch_bounds__(256) k_canvas(const float* __restrict__ src,
     const int* mb = map + (size_t)b * HW;
     float* cb = canvas + (size_t)b * C * HW;
     auto value = [&](int slot, int c) -> float {
-      if (FROM_EXT) {
+      if (FROM_EXT == 2) {
         const float* e = src + ((size_t)b * P + slot) * 2 * C;
         return apply_affine(s_aff[c], e[c], e[C + c]);
+      }
+      if (FROM_EXT == 3) {
+        const float* e = src + ((size_t)b * P + slot) * 3 * C;
+        return apply_affine(s_aff[c], e[c], e[C + c], e[2 * C + c]);
       }
       return src[((size_t)b * C + c) * P + slot];
     };
@@ -534,7 +589,7 @@ int launch_stats_tc(const float* d_x, int B, int P, int N, const float* w, const
 bool pfn_tc16_supported(int D, int N, int C, int P, const void* x);
 int launch_stats_tc16(const float* d_x, int B, int P, int N, const float* w, const float* bias,
                       const float* bn_w, int training, float* ext, double* partials, int nblocks,
-                      int* range_flag, cudaStream_t st);
+                      int* range_flag, const tch::PadArgs* pad, cudaStream_t st);
 extern int g_opt_pfn_tensor_cores;
 
 static int launch_stats(const float* d_x, int B, int P, int N, int C, const float* w, const float* bias,
@@ -545,7 +600,7 @@ static int launch_stats(const float* d_x, int B, int P, int N, int C, const floa
     if (g_opt_pfn_tensor_cores == 1 && pfn_tc16_supported(kD, N, C, P, d_x)) {
       // fp16 fast path, then the TF32 kernel as a guarded fallback: it returns at once unless the
       // fast path found a value outside the fp16 range, in which case it recomputes every output
-      const int rc = launch_stats_tc16(d_x, B, P, N, w, bias, bn_w, training, ws.ext, ws.partials, nblocks, ws.flags, st);
+      const int rc = launch_stats_tc16(d_x, B, P, N, w, bias, bn_w, training, ws.ext, ws.partials, nblocks, ws.flags, nullptr, st);
       if (rc != PP_OK) return rc;
       return launch_stats_tc(d_x, B, P, N, w, bias, bn_w, training, ws.ext, ws.partials, nblocks, ws.flags, st);
     }
@@ -581,8 +636,8 @@ static int pfn_common(const float* d_x, int B, int D, int P, int N, int C, const
   if (rc != PP_OK) return rc;
   PP_KERNEL("k_bn_finalize", st,
             k_bn_finalize<<<1, 512, 0, st>>>(C, nblocks, (double)B * P * N, training, momentum, eps,
-                                            ws.partials, bn_w, bn_b, rm, rv, (long long*)nbt,
-                                            ws.affine));
+                                            SparseFinalize{1.0, nullptr, 0, nullptr, 0.0, nullptr, nullptr}, ws.partials, bn_w, bn_b,
+                                            rm, rv, (long long*)nbt, ws.affine));
   return PP_OK;
 }
 
@@ -593,7 +648,7 @@ static bool pfn_args_ok(const void* x, int B, int D, int P, int N, int C, const 
          (C == 32 || C == 64) && (long long)B * P < 0x7fffffffll;
 }
 
-static int canvas_launch(bool from_ext, const float* src, const Affine* aff, const int* map, int B,
+static int canvas_launch(int from_ext, const float* src, const Affine* aff, const int* map, int B,
                          int P, int C, int H, int W, float* d_canvas, cudaStream_t st) {
   const int HW = H * W;
   const bool vec_ok = (HW % 4 == 0) && ((uintptr_t)d_canvas % 16 == 0);
@@ -601,16 +656,23 @@ static int canvas_launch(bool from_ext, const float* src, const Affine* aff, con
   const long long units = (long long)B * ((HW + 127) / 128) * ((C + kChanPerUnit - 1) / kChanPerUnit);
   long long gx = (units + 7) / 8;
   int per_sm = 0;
-  if (from_ext) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canvas<true>, 256, 0));
-  else PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canvas<false>, 256, 0));
+  if (from_ext == 2) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canvas<2>, 256, 0));
+  else if (from_ext == 3) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canvas<3>, 256, 0));
+  else PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canvas<0>, 256, 0));
   const long long cap = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
   if (gx > cap) gx = cap;
-  if (from_ext) {
-    PP_KERNEL("k_canvas", st, k_canvas<true><<<(int)gx, 256, 0, st>>>(src, aff, map, B, P, C, HW, vec_ok, d_canvas));
+  if (from_ext == 2) {
+    PP_KERNEL("k_canvas", st, k_canvas<2><<<(int)gx, 256, 0, st>>>(src, aff, map, B, P, C, HW, vec_ok, d_canvas));
+  } else if (from_ext == 3) {
+    PP_KERNEL("k_canvas", st, k_canvas<3><<<(int)gx, 256, 0, st>>>(src, aff, map, B, P, C, HW, vec_ok, d_canvas));
   } else {
-    PP_KERNEL("k_canvas", st, k_canvas<false><<<(int)gx, 256, 0, st>>>(src, aff, map, B, P, C, HW, vec_ok, d_canvas));
+    PP_KERNEL("k_canvas", st, k_canvas<0><<<(int)gx, 256, 0, st>>>(src, aff, map, B, P, C, HW, vec_ok, d_canvas));
   }
   return PP_OK;
+}
+
+__global__ void k_flag_status(const int* __restrict__ flag, int* __restrict__ status, int bit) {
+  if (threadIdx.x == 0 && *flag != 0) atomicOr(status, bit);
 }
 
 static int build_map(const int64_t* d_inds, int B, int P, int H, int W, int* map, int32_t* d_status,
@@ -620,6 +682,211 @@ static int build_map(const int64_t* d_inds, int B, int P, int H, int W, int* map
   PP_KERNEL("k_build_map", st, k_build_map<<<(int)((n + 255) / 256), 256, 0, st>>>((const long long*)d_inds, B, P, H, W, map,
                                                       d_status));
   return PP_OK;
+}
+
+// ---- sparse path (pp_input_path): K1's compact state in, canvas out, x never materialised --------
+// For slot (b,p,n) the network input is x = f - mean[:,p,n] with f = the point's decorated features,
+// or f = 0 for a padding slot.  A padding slot therefore holds the same value in every sweep, and
+//   sum_{b,p,n} g(y)            = B * sum_{p,n} g(y_pad[p,n]) + sum_{real} (g(y_real) - g(y_pad[p,n]))
+//   max_n y[b,p,n]              = max( max_{n < cnt} y_real , max_{n >= cnt} y_pad[p,n] )
+// for g = relu, relu^2.  The padding pass (k_pfn_pad_tc, tensor cores) evaluates y_pad once per (p,n)
+// instead of once per sweep and keeps one suffix maximum per sweep; k_pfn_real below handles the
+// ~1.3 % of slots that hold a point.  Results equal the dense path's up to summation order.
+
+__global__ void __launch_bounds__(256) k_pack_counts(int B, int P, int N, const int* __restrict__ num_pillars,
+                                                     const int* __restrict__ pil_cnt,
+                                                     unsigned long long* __restrict__ packed) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  unsigned long long v = 0ull;
+  for (int b = 0; b < kSparseMaxSweeps; ++b) {
+    unsigned long long cb = 0xffull;
+    if (b < B && p < num_pillars[b]) cb = (unsigned long long)min(pil_cnt[(size_t)b * P + p], N);
+    v |= cb << (8 * b);
+  }
+  packed[p] = v;
+}
+
+// One warp per live pillar, CPL channels per lane; conv weights in registers.  The points of the
+// pillar are fetched 32 at a time with lanes = points (features and per-slot means, 18 loads per
+// lane, all in flight together), staged in a per-warp shared-memory tile as {x_real[9], x_pad[9]}
+// records and read back as warp-uniform LDS.128 broadcasts, so the per-point loop has neither
+// global latency nor shuffles in it.  ext_s[b*P+p][0][c] = extreme of y over the pillar's points.
+constexpr int kRealWarps = 8;
+constexpr int kRealRec = 20;       // floats per staged point: 9 real + 9 padding + 2 pad (16-byte multiples)
+template <int CPL>
+__global__ void __launch_bounds__(kRealWarps * 32, 3) k_pfn_real(CompactPillars cp, int C,
+                                                  const float* __restrict__ conv_w,
+                                                  const float* __restrict__ conv_b,
+                                                  const float* __restrict__ bn_w,
+                                                  float* __restrict__ ext_s,
+                                                  double* __restrict__ partials2) {
+  const int warp = threadIdx.x >> 5;
+  const unsigned lane = lane_id();
+  __shared__ double s_red[kRealWarps][2][64];
+  __shared__ __align__(16) float s_pts[kRealWarps][32][kRealRec];
+  float w[CPL][kD], bias[CPL], sgn[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = CPL * lane + j;
+    bias[j] = conv_b[c];
+    sgn[j] = bn_w[c] < 0.f ? -1.f : 1.f;
+#pragma unroll
+    for (int d = 0; d < kD; ++d) w[j][d] = conv_w[c * kD + d];
+  }
+  double accS[CPL], accQ[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { accS[j] = 0.0; accQ[j] = 0.0; }
+  const int P = cp.P, N = cp.N;
+  const unsigned PN = (unsigned)P * (unsigned)N;          // host guarantees P*N < 2^31
+  const bool has_mean = cp.data_mean != nullptr;
+  const long long rows = (long long)cp.sw.n_sweeps * P;
+  const long long nw = (long long)gridDim.x * kRealWarps;
+  float* tile = &s_pts[warp][0][0];
+  for (long long r = (long long)blockIdx.x * kRealWarps + warp; r < rows; r += nw) {
+    const int b = (int)(r / P), p = (int)(r - (long long)b * P);
+    if (p >= cp.num_pillars[b]) continue;
+    const int cnt = min(cp.pil_cnt[r], N);
+    const float* f = cp.feat_c + (size_t)(cp.sw.off[b] + cp.pil_off[r]) * kD;
+    const float* m = has_mean ? cp.data_mean + (size_t)p * N : nullptr;
+    float mx[CPL], mn[CPL], ds[CPL], dq[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { mx[j] = -INFINITY; mn[j] = INFINITY; ds[j] = 0.f; dq[j] = 0.f; }
+    for (int n0 = 0; n0 < cnt; n0 += 32) {
+      const int n = n0 + (int)lane;
+      if (n < cnt) {
+        float fv[kD], mv[kD];
+#pragma unroll
+        for (int d = 0; d < kD; ++d) {
+          fv[d] = __ldg(f + (unsigned)n * kD + d);
+          mv[d] = has_mean ? __ldg(m + (unsigned)d * PN + (unsigned)n) : 0.f;
+        }
+        float* rec = tile + lane * kRealRec;
+#pragma unroll
+        for (int d = 0; d < kD; ++d) {
+          rec[d] = __fsub_rn(fv[d], mv[d]);                // data/dataset.py:105
+          rec[kD + d] = __fsub_rn(0.f, mv[d]);             // what the slot holds when it is padding
+        }
+      }
+      __syncwarp();
+      const int steps = min(32, cnt - n0);
+      for (int k = 0; k < steps; ++k) {
+        const float4* rec = reinterpret_cast<const float4*>(tile + k * kRealRec);
+        const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4];
+        const float a[kD] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
+        const float q[kD] = {r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w, r4.x, r4.y};
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          float y = bias[j], yp = bias[j];
+#pragma unroll
+          for (int d = 0; d < kD; ++d) { y = fmaf(w[j][d], a[d], y); yp = fmaf(w[j][d], q[d], yp); }
+          mx[j] = fmaxf(mx[j], y);
+          mn[j] = fminf(mn[j], y);
+          const float ry = fmaxf(y, 0.f), rp = fmaxf(yp, 0.f);
+          ds[j] += ry - rp;                                // the padding pass counted this slot as padding
+          dq[j] += fmaf(ry, ry, -rp * rp);
+        }
+      }
+      __syncwarp();                                        // the tile is refilled by the next chunk / pillar
+    }
+    float* e = ext_s + (size_t)r * 3 * C + CPL * lane;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      e[j] = sgn[j] > 0.f ? mx[j] : mn[j];
+      if (!has_mean) {
+        // no padding pass: every padding slot is exactly zero, y == bias; neutral when the pillar is full
+        const float neutral = sgn[j] > 0.f ? -INFINITY : INFINITY;
+        e[C + j] = cnt < N ? bias[j] : neutral;
+        e[2 * C + j] = neutral;
+      }
+      accS[j] += (double)ds[j];
+      accQ[j] += (double)dq[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    s_red[warp][0][CPL * lane + j] = accS[j];
+    s_red[warp][1][CPL * lane + j] = accQ[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * C) {
+    const int q = threadIdx.x / C, c = threadIdx.x % C;
+    double v = 0.0;
+    for (int wv = 0; wv < kRealWarps; ++wv) v += s_red[wv][q][c];
+    partials2[((size_t)blockIdx.x * 2 + q) * C + c] = v;
+  }
+}
+
+struct SparseWs {
+  float* ext_s;        // [B*P, 3, C]
+  double* partials;    // [nblocks, 2, C]   padding pass
+  double* partials2;   // [nblocks2, 2, C]  k_pfn_real
+  Affine* affine;
+  int* map;
+  int* flags;
+  unsigned long long* packed;   // [P] per-sweep counts of pillar p, one byte each
+};
+
+static int real_blocks() { return sm_count() * 3; }
+
+template <class A>
+static void sparse_layout(A& a, SparseWs* ws, int B, int P, int C, int H, int W) {
+  auto p0 = a.template take<float>((size_t)B * P * 3 * C);
+  auto p1 = a.template take<double>((size_t)sm_count() * 2 * C);
+  auto p2 = a.template take<double>((size_t)real_blocks() * 2 * C);
+  auto p3 = a.template take<Affine>(64);
+  auto p4 = a.template take<int>((size_t)B * H * W + 1);
+  auto p5 = a.template take<int>(64);
+  auto p6 = a.template take<unsigned long long>((size_t)P);
+  if (ws) { ws->ext_s = p0; ws->partials = p1; ws->partials2 = p2; ws->affine = p3; ws->map = p4; ws->flags = p5; ws->packed = p6; }
+}
+
+size_t pfn_sparse_workspace_bytes(int B, int P, int C, int H, int W) {
+  SizeArena2 a;
+  sparse_layout(a, (SparseWs*)nullptr, B, P, C, H, W);
+  return a.used + kAlign;
+}
+
+bool pfn_sparse_supported(int B, int P, int N, int C, const void* data_mean) {
+  if (!g_opt_pfn_tensor_cores) return false;
+  if (B < 1 || B > kSparseMaxSweeps || C != 64 || N > 255) return false;
+  return data_mean == nullptr || pfn_tc16_supported(kD, N, C, P, data_mean);
+}
+
+int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, const PfnParams& prm, int H, int W,
+                       float* d_canvas, int32_t* d_status, void* d_ws, size_t ws_bytes, cudaStream_t st) {
+  const int B = cp.sw.n_sweeps, P = cp.P, N = cp.N;
+  if (!pfn_sparse_supported(B, P, N, C, cp.data_mean)) return PP_ERR_UNSUPPORTED;
+  Arena arena(d_ws, ws_bytes);
+  SparseWs ws{};
+  sparse_layout(arena, &ws, B, P, C, H, W);
+  if (!arena.ok) return PP_ERR_WORKSPACE;
+  int rc = build_map(d_inds, B, P, H, W, ws.map, d_status, st);
+  if (rc != PP_OK) return rc;
+  int nblocks = 0;
+  if (cp.data_mean != nullptr) {
+    const long long pairs = P / 2;
+    nblocks = (int)(pairs < sm_count() ? pairs : sm_count());
+    PP_KERNEL("k_pack_counts", st,
+              k_pack_counts<<<(P + 255) / 256, 256, 0, st>>>(B, P, N, cp.num_pillars, cp.pil_cnt, ws.packed));
+    tch::PadArgs pad{B, ws.packed};
+    rc = launch_stats_tc16(cp.data_mean, 1, P, N, prm.conv_w, prm.conv_b, prm.bn_w, prm.training, ws.ext_s,
+                           ws.partials, nblocks, ws.flags, &pad, st);
+    if (rc != PP_OK) return rc;
+  }
+  const int nb2 = real_blocks();
+  PP_KERNEL("k_pfn_real", st,
+            k_pfn_real<2><<<nb2, kRealWarps * 32, 0, st>>>(cp, C, prm.conv_w, prm.conv_b, prm.bn_w, ws.ext_s, ws.partials2));
+  // the padding pass has no TF32 fallback: a mean or weight outside the fp16 range is reported through
+  // the status word (by the finalize kernel, which runs anyway)
+  SparseFinalize sf{(double)B, prm.training ? ws.partials2 : nullptr, nb2,
+                    cp.data_mean == nullptr ? prm.conv_b : nullptr, (double)B * P * N,
+                    cp.data_mean != nullptr ? ws.flags : nullptr, d_status};
+  PP_KERNEL("k_bn_finalize", st,
+            k_bn_finalize<<<1, 512, 0, st>>>(C, nblocks, (double)B * P * N, prm.training, prm.momentum, prm.eps, sf,
+                                            ws.partials, prm.bn_w, prm.bn_b, prm.running_mean, prm.running_var,
+                                            (long long*)prm.num_batches_tracked, ws.affine));
+  return canvas_launch(3, ws.ext_s, ws.affine, ws.map, B, P, C, H, W, d_canvas, st);
 }
 
 }  // namespace pp
@@ -670,7 +937,7 @@ int pp_scatter(const float* d_feat, const int64_t* d_inds, int32_t B, int32_t C,
   if (!arena.ok) return PP_ERR_WORKSPACE;
   int rc = build_map(d_inds, B, P, canvas_h, canvas_w, map, d_status, st);
   if (rc != PP_OK) return rc;
-  return canvas_launch(false, d_feat, nullptr, map, B, P, C, canvas_h, canvas_w, d_canvas, st);
+  return canvas_launch(0, d_feat, nullptr, map, B, P, C, canvas_h, canvas_w, d_canvas, st);
 }
 
 int pp_pfn_scatter(const float* d_x, const int64_t* d_inds, int32_t B, int32_t D, int32_t P,
@@ -698,7 +965,7 @@ int pp_pfn_scatter(const float* d_x, const int64_t* d_inds, int32_t B, int32_t D
   rc = pfn_common(d_x, B, D, P, N, C, d_conv_w, d_conv_b, d_bn_w, d_bn_b, d_running_mean,
                   d_running_var, d_num_batches_tracked, training, momentum, eps, ws, nblocks, st);
   if (rc != PP_OK) return rc;
-  rc = canvas_launch(true, ws.ext, ws.affine, ws.map, B, P, C, canvas_h, canvas_w, d_canvas, st);
+  rc = canvas_launch(2, ws.ext, ws.affine, ws.map, B, P, C, canvas_h, canvas_w, d_canvas, st);
   if (rc != PP_OK) return rc;
   if (d_out != nullptr) {
     dim3 grid((P + 31) / 32, B);

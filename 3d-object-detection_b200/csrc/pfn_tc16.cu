@@ -42,6 +42,7 @@
 #include <cuda.h>
 
 #include "tc_common.cuh"
+#include "internal.cuh"
 
 namespace pp {
 
@@ -122,12 +123,17 @@ __device__ __forceinline__ float h_value(unsigned short h) {
         "=r"(v[14]), "=r"(v[15])                                                                    \
       : "r"(taddr))
 
-template <bool TRAIN>
+// PAD = true is the padding pass of the sparse path (pfn.cu: pfn_sparse_scatter): the input tensor is
+// data_mean viewed as one sweep [9,P,N], the weights are negated (a padding slot holds x = 0 - mean),
+// and instead of one maximum per pillar the epilogue keeps, for each of the `pad.nb` real sweeps, the
+// maximum over the slots n >= cnt[b][p] that are padding in THAT sweep; the statistics are summed
+// unweighted over all (p, n) (the caller multiplies by the number of sweeps).
+template <bool TRAIN, bool PAD, int NBMAX>
 __global__ void __launch_bounds__(kThreads, 1)
 k_pfn_stats_tc(const __grid_constant__ CUtensorMap tmap, int B, int P, int N,
                const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                const float* __restrict__ bn_w, float* __restrict__ ext, double* __restrict__ partials,
-               int* __restrict__ range_flag, int dbg, long long* __restrict__ prof) {
+               int* __restrict__ range_flag, int dbg, long long* __restrict__ prof, PadArgs pad) {
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((128u - (smem_u32(smem_unaligned) & 127u)) & 127u);
   const Smem sp = smem_plan(N);
@@ -178,6 +184,7 @@ k_pfn_stats_tc(const __grid_constant__ CUtensorMap tmap, int B, int P, int N,
         v = K == 27 ? bh : (bb - bh);
       }
       const int j = K >> 4, kk = K & 15;
+      if (PAD && K < 27) v = -v;             // x = 0 - mean
       *reinterpret_cast<unsigned short*>(smem + sp.a_off + j * 2048 + (m >> 3) * 256 + (kk >> 3) * 128 + (m & 7) * 16 + (kk & 7) * 2) =
           h_bits(sgn * v);
     }
@@ -260,59 +267,120 @@ k_pfn_stats_tc(const __grid_constant__ CUtensorMap tmap, int B, int P, int N,
     const int ncols = n1 - n0;             // multiple of 8
     for (int it = e; it < my_pairs; it += 2) {
       const uint32_t n = (uint32_t)(it >> 1);
+      const int r = 2 * ((int)blockIdx.x + it * (int)gridDim.x) + h;      // row: pillar (b,p); PAD: pillar p
+      unsigned long long pk = 0ull;
+      if (PAD) pk = __ldg(pad.packed + r);             // in flight while waiting for the accumulator
       mbar_wait_t(&acc_full[e], n & 1u, pon, pacc[0]);
       tc_fence_after();
       const long long tq0 = pon ? clock64() : 0;
       // four independent accumulator sets break the dependent chains; sums are packed fp32 pairs.
       // 2*relu(s*y) = s*y + |y| is one FFMA (the ALU pipe that FMNMX runs on is half rate).
       float mx[2] = {-INFINITY, -INFINITY};
+      constexpr int NCH = PAD ? 2 : 4;       // accumulator chains (the padding pass is short of registers)
       unsigned long long S[4] = {0ull, 0ull, 0ull, 0ull}, Q[4] = {0ull, 0ull, 0ull, 0ull};
+      // PAD: per real sweep, first padding slot of this pillar (one byte each; 0xff = not live there)
+      // sm[b]: chunks below the largest count; common: chunks that are padding in every sweep (most)
+      float sm[NBMAX], common = -INFINITY;
+      int cmaxcnt = 0;
+      if (PAD) {
+#pragma unroll
+        for (int b = 0; b < NBMAX; ++b) {
+          sm[b] = -INFINITY;
+          if (b < pad.nb) {
+            const int cb = (int)((pk >> (8 * b)) & 0xffull);
+            if (cb != 0xff) cmaxcnt = max(cmaxcnt, cb);
+          }
+        }
+      }
       // three passes over the chunk keep every instruction independent of its neighbours (the t values
       // replace the y values in place).  One 32-column tcgen05.ld per chunk, no register double buffer:
       // the four epilogue warps of a scheduler hide each other's TMEM latency, and ptxas sinks a
       // prefetching tcgen05.ld below the arithmetic anyway (measured: x32 single 4.2 cycles per
       // warp-value per scheduler, x16 double-buffered 5.1; scripts/ubench/epi3.cu)
-      auto consume = [&](uint32_t* v, const int cnt) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          if (i < cnt) mx[(i >> 1) & 1] = fmaxf(mx[(i >> 1) & 1], fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-        if (TRAIN) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < cnt) { const float y = __uint_as_float(v[i]); v[i] = __float_as_uint(fmaf(sgn, y, fabsf(y))); }
+      auto consume = [&](uint32_t* v, const int cnt, const int col0) {
+        if (PAD) {
+          // maximum of the chunk, folded into the suffix maximum of every sweep whose padding range
+          // covers it; a chunk that straddles a sweep's first padding slot is masked per column
+          float c0 = -INFINITY, c1 = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 32; i += 2)
-            if (i < cnt) acc_pair(S[(i >> 1) & 3], Q[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            if (i < cnt) { if (i & 2) c1 = fmaxf(c1, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1]))); else c0 = fmaxf(c0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1]))); }
+          const float cm = fmaxf(c0, c1);
+          if (col0 >= cmaxcnt) {
+            common = fmaxf(common, cm);
+          } else {
+#pragma unroll
+          for (int b = 0; b < NBMAX; ++b) {
+            if (b < pad.nb) {
+              int cb = (int)((pk >> (8 * b)) & 0xffull);
+              if (cb == 0xff) cb = 0;                 // not live: never written, treat as all padding
+              if (cb <= col0) {
+                sm[b] = fmaxf(sm[b], cm);
+              } else if (cb < col0 + cnt) {
+                float t = sm[b];
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < cnt && col0 + i >= cb) t = fmaxf(t, __uint_as_float(v[i]));
+                sm[b] = t;
+              }
+            }
+          }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            if (i < cnt) mx[(i >> 1) & 1] = fmaxf(mx[(i >> 1) & 1], fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+        }
+        if (TRAIN) {
+          {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < cnt) { const float y = __uint_as_float(v[i]); v[i] = __float_as_uint(fmaf(sgn, y, fabsf(y))); }
+#pragma unroll
+            for (int i = 0; i < 32; i += 2)
+              if (i < cnt) acc_pair(S[(i >> 1) & (NCH - 1)], Q[(i >> 1) & (NCH - 1)], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+          }
         }
       };
       if (!(dbg & 4)) {
         uint32_t v[32];
         int col = 0;
+        // the narrow chunks come first: most pillars hold < 8 points, so the chunk that straddles the
+        // first padding slot (PAD: masked per column) is the 8-column one
+        if (ncols & 8) {
+          PP_TMEM_LD8(taddr + col, v);
+          tmem_ld_wait();
+          consume(v, 8, n0 + col);
+          col += 8;
+        }
+        if (ncols & 16) {
+          PP_TMEM_LD16(taddr + col, v);
+          tmem_ld_wait();
+          consume(v, 16, n0 + col);
+          col += 16;
+        }
         for (; col + 32 <= ncols; col += 32) {
           PP_TMEM_LD32(taddr + col, v);
           tmem_ld_wait();
-          consume(v, 32);
-        }
-        if (ncols - col >= 16) {
-          PP_TMEM_LD16(taddr + col, v);
-          tmem_ld_wait();
-          consume(v, 16);
-          col += 16;
-        }
-        if (ncols - col >= 8) {
-          PP_TMEM_LD8(taddr + col, v);
-          tmem_ld_wait();
-          consume(v, 8);
+          consume(v, 32, n0 + col);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[e]);
       if (pon) pacc[1] += clock64() - tq0;
-      const int r = 2 * ((int)blockIdx.x + it * (int)gridDim.x) + h;
       // TMEM holds 256*s*y: the partial extreme of this column half goes to ext[r][j][c]; consumers
-      // combine the two halves (max when gamma >= 0, min otherwise)
-      ext[(size_t)r * 128 + j * 64 + c] = sgn * fmaxf(mx[0], mx[1]) * (1.f / 256.f);
+      // combine the fields (max when gamma >= 0, min otherwise)
+      if (PAD) {
+        // sparse layout ext[b*P+p][3][64]: field 0 = real points (k_pfn_real), fields 1, 2 = padding
+        // slots of the two column halves; an empty range stays -inf (+inf after the sign), neutral
+#pragma unroll
+        for (int b = 0; b < NBMAX; ++b)
+          if (b < pad.nb && ((pk >> (8 * b)) & 0xffull) != 0xffull)
+            ext[(((size_t)b * P + r) * 3 + 1 + j) * 64 + c] = sgn * fmaxf(sm[b], common) * (1.f / 256.f);
+      } else {
+        ext[(size_t)r * 128 + j * 64 + c] = sgn * fmaxf(mx[0], mx[1]) * (1.f / 256.f);
+      }
       if (TRAIN) {
         accS += (double)((pair_sum(S[0]) + pair_sum(S[1])) + (pair_sum(S[2]) + pair_sum(S[3])));
         accQ += (double)((pair_sum(Q[0]) + pair_sum(Q[1])) + (pair_sum(Q[2]) + pair_sum(Q[3])));
@@ -429,9 +497,11 @@ bool pfn_tc16_supported(int D, int N, int C, int P, const void* x) {
          tch::encode_fn() != nullptr;
 }
 
+// pad == nullptr: statistics + per-pillar extremes of x [B,9,P,N] -> ext [B*P][2][64].
+// pad != nullptr: padding pass of the sparse path over d_x = data_mean ([9,P,N], B must be 1).
 int launch_stats_tc16(const float* d_x, int B, int P, int N, const float* w, const float* bias,
                       const float* bn_w, int training, float* ext, double* partials, int nblocks,
-                      int* range_flag, cudaStream_t st) {
+                      int* range_flag, const tch::PadArgs* pad, cudaStream_t st) {
   const tch::Smem sp = tch::smem_plan(N);
   if (sp.raw_stages < 2) return PP_ERR_UNSUPPORTED;
   CUtensorMap tmap;
@@ -445,15 +515,25 @@ int launch_stats_tc16(const float* d_x, int B, int P, int N, const float* w, con
     return PP_ERR_UNSUPPORTED;
   long long* prof = g_opt_pfn_tc_timing ? tc_prof_ptr() : nullptr;
   PP_CUDA(cudaMemsetAsync(range_flag, 0, sizeof(int), st));
-  if (training) {
-    PP_CUDA(cudaFuncSetAttribute(tch::k_pfn_stats_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-    PP_KERNEL("k_pfn_stats_tc", st,
-              tch::k_pfn_stats_tc<true><<<nblocks, tch::kThreads, sp.total, st>>>(tmap, B, P, N, w, bias, bn_w, ext, partials, range_flag, g_opt_pfn_tc_debug, prof));
+  const tch::PadArgs pa = pad ? *pad : tch::PadArgs{0, nullptr};
+#define PP_TC16(TR, PD, NB, NAME)                                                                                 \
+  do {                                                                                                            \
+    PP_CUDA(cudaFuncSetAttribute(tch::k_pfn_stats_tc<TR, PD, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total)); \
+    PP_KERNEL(NAME, st,                                                                                           \
+              (tch::k_pfn_stats_tc<TR, PD, NB><<<nblocks, tch::kThreads, sp.total, st>>>(                         \
+                  tmap, B, P, N, w, bias, bn_w, ext, partials, range_flag, g_opt_pfn_tc_debug, prof, pa)));      \
+  } while (0)
+  if (pad) {
+    if (B != 1 || pad->nb < 1 || pad->nb > kSparseMaxSweeps) return PP_ERR_INVALID_ARG;
+    if (pad->nb <= 4) {
+      if (training) PP_TC16(true, true, 4, "k_pfn_pad_tc"); else PP_TC16(false, true, 4, "k_pfn_pad_tc");
+    } else {
+      if (training) PP_TC16(true, true, 8, "k_pfn_pad_tc"); else PP_TC16(false, true, 8, "k_pfn_pad_tc");
+    }
   } else {
-    PP_CUDA(cudaFuncSetAttribute(tch::k_pfn_stats_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-    PP_KERNEL("k_pfn_stats_tc", st,
-              tch::k_pfn_stats_tc<false><<<nblocks, tch::kThreads, sp.total, st>>>(tmap, B, P, N, w, bias, bn_w, ext, partials, range_flag, g_opt_pfn_tc_debug, prof));
+    if (training) PP_TC16(true, false, 1, "k_pfn_stats_tc"); else PP_TC16(false, false, 1, "k_pfn_stats_tc");
   }
+#undef PP_TC16
   return PP_OK;
 }
 

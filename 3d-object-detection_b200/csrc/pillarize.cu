@@ -22,18 +22,12 @@
 //   k_emit_*     dense [B,9,P,N] float with fused "- data_mean", or compact fp64 rows
 #include <type_traits>
 
-#include "common.cuh"
+#include "internal.cuh"
 
 namespace pp {
 
 constexpr int kTile = 1024;  // points per scan tile == threads per block of the scan kernels
 constexpr int kBig = 1024;   // pillars with more points than this take the block-scan rank path
-
-struct SweepParams {
-  int n_sweeps;
-  int tile_start[PP_MAX_SWEEPS + 1];
-  long long off[PP_MAX_SWEEPS + 1];
-};
 
 struct GridDev {
   double x_step, y_step, x_min, y_min, z_min, x_max, y_max, z_max, canvas_height;
@@ -687,6 +681,28 @@ static int make_sweeps(const int64_t* h_off, int n_sweeps, SweepParams& sw) {
   return PP_OK;
 }
 
+static int emit_dense(const SweepParams& sw, int P, int N, const float* d_mean, float* d_x,
+                      const int32_t* d_num_pillars, const PillarWs& ws, cudaStream_t st) {
+  const long long PN = (long long)P * N;
+  const bool v4 = (N % 4 == 0) && ((uintptr_t)d_x % 16) == 0 &&
+                  (d_mean == nullptr || ((uintptr_t)d_mean % 16) == 0);
+  const long long groups = v4 ? PN / 4 : PN;
+  long long blocks = (groups + 255) / 256;
+  const long long cap = (long long)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  const dim3 egrid((unsigned)blocks, 9 / kFeatGroup);
+  if (v4) {
+    PP_KERNEL("k_emit_dense", st,
+              k_emit_dense<4><<<egrid, 256, 0, st>>>(sw, P, N, d_mean, d_x, d_num_pillars, ws.pil_cnt,
+                                                     ws.pil_off, ws.feat_c));
+  } else {
+    PP_KERNEL("k_emit_dense", st,
+              k_emit_dense<1><<<egrid, 256, 0, st>>>(sw, P, N, d_mean, d_x, d_num_pillars, ws.pil_cnt,
+                                                     ws.pil_off, ws.feat_c));
+  }
+  return PP_OK;
+}
+
 template <typename T>
 static int pillarize_impl(const T* pts, long long sp, long long sc, const int64_t* h_off, int B,
                           const pp_grid* grid, int N, int P, const float* d_mean, float* d_x,
@@ -709,14 +725,6 @@ static int pillarize_impl(const T* pts, long long sp, long long sc, const int64_
   rc = run_stages<T>(pts, sp, sc, vec4, sw, g, P, ws, d_num_pillars, (long long*)d_indices,
                      d_status, st);
   if (rc != PP_OK) return rc;
-  const long long PN = (long long)P * N;
-  const bool v4 = (N % 4 == 0) && ((uintptr_t)d_x % 16) == 0 &&
-                  (d_mean == nullptr || ((uintptr_t)d_mean % 16) == 0);
-  const long long groups = v4 ? PN / 4 : PN;
-  long long blocks = (groups + 255) / 256;
-  const long long cap = (long long)sm_count() * 32;
-  if (blocks > cap) blocks = cap;
-  const dim3 egrid((unsigned)blocks, 9 / kFeatGroup);
   const long long total = sw.off[B];
   if (total > 0) {
     PP_KERNEL("k_feat", st,
@@ -724,16 +732,53 @@ static int pillarize_impl(const T* pts, long long sp, long long sc, const int64_
                   pts, sp, sc, vec4, sw, g, P, N, ws.cell_of_point, ws.cell_slot, ws.rank_of_point,
                   ws.pil_off, ws.pil_mean, ws.feat_c));
   }
-  if (v4) {
-    PP_KERNEL("k_emit_dense", st,
-              k_emit_dense<4><<<egrid, 256, 0, st>>>(sw, P, N, d_mean, d_x, d_num_pillars, ws.pil_cnt,
-                                                     ws.pil_off, ws.feat_c));
-  } else {
-    PP_KERNEL("k_emit_dense", st,
-              k_emit_dense<1><<<egrid, 256, 0, st>>>(sw, P, N, d_mean, d_x, d_num_pillars, ws.pil_cnt,
-                                                     ws.pil_off, ws.feat_c));
-  }
+  rc = emit_dense(sw, P, N, d_mean, d_x, d_num_pillars, ws, st);
+  if (rc != PP_OK) return rc;
   return PP_OK;
+}
+
+// pp_input_path: K1 stages + (optional) dense emit + sparse PFN + canvas
+template <typename T>
+static int input_path_impl(const T* pts, long long sp, long long sc, const int64_t* h_off, int B,
+                           const pp_grid* grid, int N, int P, const float* d_mean, int C, const PfnParams& prm,
+                           int H, int W, float* d_canvas, float* d_x, int64_t* d_indices,
+                           int32_t* d_num_pillars, int32_t* d_status, void* d_ws, size_t ws_bytes,
+                           cudaStream_t st) {
+  GridDev g;
+  SweepParams sw;
+  if (!make_grid(grid, g)) return PP_ERR_INVALID_ARG;
+  int rc = make_sweeps(h_off, B, sw);
+  if (rc != PP_OK) return rc;
+  if (N < 1 || P < 1 || d_canvas == nullptr || d_indices == nullptr || d_num_pillars == nullptr ||
+      d_status == nullptr || (pts == nullptr && sw.off[B] > 0) || (long long)P * N > 0x7fffffffll || H < 1 || W < 1)
+    return PP_ERR_INVALID_ARG;
+  if ((long long)B * g.ncell > 0x7fffffffll || (long long)B * P > 0x3fffffffll) return PP_ERR_INVALID_ARG;
+  if (!pfn_sparse_supported(B, P, N, C, d_mean)) return PP_ERR_UNSUPPORTED;
+  Arena arena(d_ws, ws_bytes);
+  PillarWs ws{};
+  layout(arena, &ws, B, sw.off[B], sw.tile_start[B], g.ncell, P);
+  if (!arena.ok) return PP_ERR_WORKSPACE;
+  const size_t k1_bytes = arena.used;
+  const bool vec4 = sizeof(T) == 4 && sp == 4 && sc == 1 && ((uintptr_t)pts % 16) == 0;
+  rc = run_stages<T>(pts, sp, sc, vec4, sw, g, P, ws, d_num_pillars, (long long*)d_indices, d_status, st);
+  if (rc != PP_OK) return rc;
+  const long long total = sw.off[B];
+  if (total > 0) {
+    PP_KERNEL("k_feat", st,
+              k_feat<T><<<(int)((total + 255) / 256), 256, 0, st>>>(
+                  pts, sp, sc, vec4, sw, g, P, N, ws.cell_of_point, ws.cell_slot, ws.rank_of_point,
+                  ws.pil_off, ws.pil_mean, ws.feat_c));
+  }
+  if (d_x != nullptr) {
+    rc = emit_dense(sw, P, N, d_mean, d_x, d_num_pillars, ws, st);
+    if (rc != PP_OK) return rc;
+  }
+  CompactPillars cp;
+  cp.sw = sw; cp.P = P; cp.N = N;
+  cp.feat_c = ws.feat_c; cp.pil_cnt = ws.pil_cnt; cp.pil_off = ws.pil_off;
+  cp.num_pillars = d_num_pillars; cp.data_mean = d_mean;
+  return pfn_sparse_scatter(cp, d_indices, C, prm, H, W, d_canvas, d_status, (char*)d_ws + k1_bytes,
+                            ws_bytes - k1_bytes, st);
 }
 
 template <typename T>
@@ -805,6 +850,39 @@ int pp_pillarize(const void* d_points, int32_t point_dtype, int64_t stride_point
                                       h_sweep_offsets, n_sweeps, grid, max_points_per_pillar,
                                       max_pillars, d_data_mean, d_x, d_indices, d_num_pillars,
                                       d_status, d_workspace, workspace_bytes, st);
+  return PP_ERR_INVALID_ARG;
+}
+
+size_t pp_input_path_workspace_bytes(int32_t n_sweeps, int64_t total_points, const pp_grid* grid,
+                                     int32_t max_pillars, int32_t C, int32_t canvas_h, int32_t canvas_w) {
+  const size_t k1 = pp_pillarize_workspace_bytes(n_sweeps, total_points, grid, max_pillars);
+  if (k1 == 0 || C < 1 || canvas_h < 1 || canvas_w < 1) return 0;
+  return k1 + pp::pfn_sparse_workspace_bytes(n_sweeps, max_pillars, C, canvas_h, canvas_w);
+}
+
+int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_point, int64_t stride_col,
+                  const int64_t* h_sweep_offsets, int32_t n_sweeps, const pp_grid* grid,
+                  int32_t max_points_per_pillar, int32_t max_pillars, const float* d_data_mean, int32_t C,
+                  const float* d_conv_w, const float* d_conv_b, const float* d_bn_w, const float* d_bn_b,
+                  float* d_running_mean, float* d_running_var, int64_t* d_num_batches_tracked,
+                  int32_t training, float momentum, float eps, int32_t canvas_h, int32_t canvas_w,
+                  float* d_canvas, float* d_x, int64_t* d_indices, int32_t* d_num_pillars,
+                  int32_t* d_status, void* d_workspace, size_t workspace_bytes, pp_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_conv_w || !d_conv_b || !d_bn_w || !d_bn_b || !d_running_mean || !d_running_var)
+    return PP_ERR_INVALID_ARG;
+  pp::PfnParams prm{d_conv_w, d_conv_b, d_bn_w, d_bn_b, d_running_mean, d_running_var,
+                    d_num_batches_tracked, training, momentum, eps};
+  if (point_dtype == PP_F32)
+    return pp::input_path_impl<float>((const float*)d_points, stride_point, stride_col, h_sweep_offsets,
+                                      n_sweeps, grid, max_points_per_pillar, max_pillars, d_data_mean, C, prm,
+                                      canvas_h, canvas_w, d_canvas, d_x, d_indices, d_num_pillars, d_status,
+                                      d_workspace, workspace_bytes, st);
+  if (point_dtype == PP_F64)
+    return pp::input_path_impl<double>((const double*)d_points, stride_point, stride_col, h_sweep_offsets,
+                                       n_sweeps, grid, max_points_per_pillar, max_pillars, d_data_mean, C, prm,
+                                       canvas_h, canvas_w, d_canvas, d_x, d_indices, d_num_pillars, d_status,
+                                       d_workspace, workspace_bytes, st);
   return PP_ERR_INVALID_ARG;
 }
 

@@ -87,6 +87,11 @@ __device__ __forceinline__ void acc_pair(unsigned long long& S, unsigned long lo
   asm("{\n.reg .b64 tp;\nmov.b64 tp, {%2, %3};\nadd.rn.f32x2 %0, %0, tp;\nfma.rn.f32x2 %1, tp, tp, %1;\n}\n"
       : "+l"(S), "+l"(Q) : "f"(t0), "f"(t1));
 }
+// weighted form: S += (u0,u1), Q += (u0*t0, u1*t1)
+__device__ __forceinline__ void acc_pair_w(unsigned long long& S, unsigned long long& Q, float u0, float u1, float t0, float t1) {
+  asm("{\n.reg .b64 up, tp;\nmov.b64 up, {%2, %3};\nmov.b64 tp, {%4, %5};\nadd.rn.f32x2 %0, %0, up;\nfma.rn.f32x2 %1, up, tp, %1;\n}\n"
+      : "+l"(S), "+l"(Q) : "f"(u0), "f"(u1), "f"(t0), "f"(t1));
+}
 __device__ __forceinline__ float pair_sum(unsigned long long v) {
   return __uint_as_float((unsigned)(v & 0xffffffffull)) + __uint_as_float((unsigned)(v >> 32));
 }

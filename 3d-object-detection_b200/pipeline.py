@@ -17,7 +17,7 @@ import torch
 from . import _lib, _runtime
 from .box_utils import AnchorSet, assign_targets, gt_to_image_space
 from .config import PPConfig
-from .model import PPFeatureScatter
+from .model import PPFeatureScatter, _bn_args
 
 
 def shard_range(n_items, rank, world_size):
@@ -44,7 +44,7 @@ class StepHandle:
 
 class InputPath:
     def __init__(self, cfg=None, device=None, data_mean=None, pfn_params=None, anchors=None,
-                 training=True):
+                 training=True, fused=False):
         if not torch.cuda.is_available():
             raise _lib.PPError("no CUDA device: the input path has no CPU fallback")
         _lib.load()
@@ -68,6 +68,9 @@ class InputPath:
         # latency-bound binning kernels
         self._side = torch.cuda.Stream(device=self.device)
         self.overlap_targets = True
+        # fused=True: the step goes through pp_input_path (x never materialised); False: the
+        # signature-preserving pp_pillarize -> x -> pp_pfn_scatter sequence
+        self.fused = fused
         # host-facing pipeline: copy stream, two device staging buffers, pinned result slots
         self._copy = torch.cuda.Stream(device=self.device)
         self._stage = [None, None]
@@ -134,6 +137,66 @@ class InputPath:
     # -- K2 -----------------------------------------------------------------------------------
     def encode(self, x, inds, out=None, return_features=False):
         return self.net(x, inds, return_features=return_features, out=out)
+
+    # -- K1 + K2 fused, x never materialised (pp_input_path) ------------------------------------
+    def fused_supported(self, n_sweeps):
+        c = self.cfg
+        return (1 <= n_sweeps <= 8 and c.feature_net_out == 64 and c.max_points_per_pillar <= 255
+                and c.max_points_per_pillar % 8 == 0 and c.max_pillars % 2 == 0)
+
+    def pillarize_encode(self, points, offsets, out=None, want_x=False):
+        """points/offsets as in ``pillarize``.  Returns (canvas, inds, n_pillars[, x]): the canvas of
+        ``encode(pillarize(...))`` without writing and re-reading the dense [B,9,P,N] tensor (it is
+        only produced when ``want_x``)."""
+        L = _lib.load()
+        c = self.cfg
+        _runtime.require_cuda(points, "points")
+        if points.dtype == torch.float32:
+            dt = _lib.PP_F32
+        elif points.dtype == torch.float64:
+            dt = _lib.PP_F64
+        else:
+            raise _lib.PPError("points must be float32 or float64")
+        B = len(offsets) - 1
+        if not self.fused_supported(B):
+            raise _lib.PPError("fused input path: 1..8 sweeps, C=64, N<=255 and N%8==0, P even")
+        T = int(offsets[-1])
+        P, N, C = c.max_pillars, c.max_points_per_pillar, c.feature_net_out
+        H, W = c.canvas_height, c.canvas_width
+        dev = self.device
+        o = out or {}
+        canvas = o.get("canvas")
+        if canvas is None:
+            canvas = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+        if o.get("pillars") is not None:
+            x, inds, npil = o["pillars"]
+        else:
+            x = torch.empty((B, 9, P, N), dtype=torch.float32, device=dev) if want_x else None
+            inds = torch.empty((B, P, 3), dtype=torch.int64, device=dev)
+            npil = torch.empty(B, dtype=torch.int32, device=dev)
+        if not want_x:
+            x = None
+        net = self.net
+        grid = c.grid()
+        nbytes = L.pp_input_path_workspace_bytes(B, T, grid, P, C, H, W)
+        ws = _runtime.workspace(nbytes, dev, "input_path")
+        status = _runtime.status_word(dev)
+        momentum, eps = _bn_args(net.bn1)
+        w = net.conv1.weight.detach().reshape(C, 9).contiguous()
+        nbt = net.bn1.num_batches_tracked
+        with torch.cuda.device(dev):
+            rc = L.pp_input_path(
+                points.data_ptr() if T > 0 else None, dt, points.stride(0), points.stride(1),
+                _lib.i64_array(offsets), B, grid, N, P,
+                self.data_mean.data_ptr() if self.data_mean is not None else None, C,
+                w.data_ptr(), net.conv1.bias.detach().data_ptr(), net.bn1.weight.detach().data_ptr(),
+                net.bn1.bias.detach().data_ptr(), net.bn1.running_mean.data_ptr(),
+                net.bn1.running_var.data_ptr(), nbt.data_ptr() if nbt is not None else None,
+                1 if net.training else 0, momentum, eps, H, W, canvas.data_ptr(),
+                x.data_ptr() if x is not None else None, inds.data_ptr(), npil.data_ptr(),
+                status.data_ptr(), ws.data_ptr(), ws.numel(), _runtime.stream_ptr(dev))
+        _lib.check(rc, "pp_input_path")
+        return (canvas, inds, npil, x) if want_x else (canvas, inds, npil)
 
     # -- K3 -----------------------------------------------------------------------------------
     def targets(self, gt_dev, gt_offsets, out=None):
@@ -220,16 +283,22 @@ class InputPath:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 cls, reg, top, counts = self.targets(gt_dev, gt_offsets, out=o.get("targets"))
-            x, inds, npil = self.pillarize(d_pts, offsets, out=o.get("pillars"))
-            canvas = self.encode(x, inds, out=o.get("canvas"))
+            canvas, npil = self._k12(d_pts, offsets, o)
             main.wait_stream(self._side)
             for t in (cls, reg, top, counts):
                 t.record_stream(main)
         else:
-            x, inds, npil = self.pillarize(d_pts, offsets, out=o.get("pillars"))
-            canvas = self.encode(x, inds, out=o.get("canvas"))
+            canvas, npil = self._k12(d_pts, offsets, o)
             cls, reg, top, counts = self.targets(gt_dev, gt_offsets, out=o.get("targets"))
         return canvas, cls, reg, npil, counts
+
+    def _k12(self, d_pts, offsets, o):
+        if self.fused and self.fused_supported(len(offsets) - 1):
+            canvas, inds, npil = self.pillarize_encode(d_pts, offsets, out=o)
+        else:
+            x, inds, npil = self.pillarize(d_pts, offsets, out=o.get("pillars"))
+            canvas = self.encode(x, inds, out=o.get("canvas"))
+        return canvas, npil
 
     def step_host(self, batch, out=None):
         """One pass of the whole path from a pinned HOST batch (``pack_host_batch``): H2D copy,

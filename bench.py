@@ -254,6 +254,8 @@ def algorithmic_bytes(B, P, N, C, H, W, A, K, total_points, has_mean):
         "k_pfn_stats": B * x_bytes + B * P * 2 * C * 4,
         "k_pfn_stats_tc": B * x_bytes + B * P * 2 * C * 4,
         "k_canvas": B * C * H * W * 4 + B * H * W * 4,
+        # fused path: data_mean read once + the ext rows of the live pillars (2 padding fields per sweep)
+        "k_pfn_pad_tc": (x_bytes if has_mean else 0) + B * 16500 * 2 * C * 4,
         "k_encode": B * A * 9 * 4,          # one launch each for cls [A,K=9] and reg [A,9]
     }
 
@@ -277,7 +279,9 @@ def run_ours(args):
     cfg = pp_b200.PPConfig()
     P, N, C, H, W = cfg.max_pillars, cfg.max_points_per_pillar, cfg.feature_net_out, cfg.canvas_height, cfg.canvas_width
     mean = synth.make_data_mean(P, N, seed=0, dense=True)
-    path = pipeline.InputPath(cfg, device=dev, data_mean=mean, pfn_params=synth.make_pfn_params(0), training=True)
+    fused = not args.dense_path
+    path = pipeline.InputPath(cfg, device=dev, data_mean=mean, pfn_params=synth.make_pfn_params(0), training=True,
+                              fused=fused)
     anchors = path.ensure_anchors()
     A = anchors.A
     # each rank owns its own batch of BATCH sweeps per step (weak scaling, no data-path collective)
@@ -287,7 +291,7 @@ def run_ours(args):
     T = batch["offsets"][-1]
     d_pts, gt_dev = path.upload(batch)
     out = {
-        "pillars": (torch.empty((BATCH, 9, P, N), dtype=torch.float32, device=dev),
+        "pillars": (torch.empty((BATCH, 9, P, N), dtype=torch.float32, device=dev) if not fused else None,
                     torch.empty((BATCH, P, 3), dtype=torch.int64, device=dev),
                     torch.empty(BATCH, dtype=torch.int32, device=dev)),
         "canvas": torch.empty((BATCH, C, H, W), dtype=torch.float32, device=dev),
@@ -340,16 +344,12 @@ def run_ours(args):
     for _ in range(3):
         step_e2e()
     drain_e2e()
-
-    def e2e_loop():
-        step_e2e()
-
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        e2e_loop()
+        step_e2e()
     drain_e2e()                                # the last step's counters are read before the clock stops
     e1.record()
     barrier()
@@ -360,40 +360,64 @@ def run_ours(args):
     h2d = int(batch["blob"].numel())
     d2h = int(BATCH * 4 + BATCH * 4 * 4)
 
-    # per-kernel durations, live, CUDA events on the launching stream (separate instrumented pass)
-    # (stream overlap off here, so that each kernel is timed running alone)
-    path.overlap_targets = False
-    L.pp_profile_enable(1)
-    barrier()
-    for _ in range(args.steps):
-        step_dev()
-    rep = _lib.profile_report()
-    L.pp_profile_enable(0)
-    path.overlap_targets = True
     alg = algorithmic_bytes(BATCH, P, N, C, H, W, A, cfg.num_classes, T, True)
     peak, peak_src = measured_peak()
-    kernels = []
-    tot_ms = sum(v[1] for v in rep.values()) or 1.0
-    for name, (n, total_ms) in rep.items():
-        k = {"name": name, "launches_per_step": n / args.steps, "ms_per_launch": total_ms / n,
-             "share_of_kernel_time": total_ms / tot_ms}
-        if name in alg:
-            k["alg_bytes_per_launch"] = alg[name]
-            k["GBps"] = alg[name] / (total_ms / n * 1e-3) / 1e9
-            k["frac_of_peak"] = k["GBps"] / peak
-        kernels.append(k)
-    kernels.sort(key=lambda k: -k["share_of_kernel_time"])
-    dom = next((k for k in kernels if "GBps" in k), None)
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom["name"])
-    except Exception:  # noqa: BLE001
-        pass
-    roofline = None
-    if dom is not None:
-        roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+
+    def kernel_table(pth, o):
+        """Per-kernel durations, live, CUDA events on the launching stream (separate instrumented pass,
+        stream overlap off so that each kernel is timed running alone)."""
+        pth.overlap_targets = False
+        L.pp_profile_enable(1)
+        barrier()
+        for _ in range(args.steps):
+            pth.step_device(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out=o)
+        rep = _lib.profile_report()
+        L.pp_profile_enable(0)
+        pth.overlap_targets = True
+        ks = []
+        tot_ms = sum(v[1] for v in rep.values()) or 1.0
+        for name, (n, total_ms) in rep.items():
+            k = {"name": name, "launches_per_step": n / args.steps, "ms_per_launch": total_ms / n,
+                 "share_of_kernel_time": total_ms / tot_ms}
+            if name in alg:
+                k["alg_bytes_per_launch"] = alg[name]
+                k["GBps"] = alg[name] / (total_ms / n * 1e-3) / 1e9
+                k["frac_of_peak"] = k["GBps"] / peak
+            ks.append(k)
+        ks.sort(key=lambda k: -k["share_of_kernel_time"])
+        dom = next((k for k in ks if "GBps" in k), None)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom["name"])
+        except Exception:  # noqa: BLE001
+            pass
+        roof = None
+        if dom is not None:
+            roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
                     "frac": dom["frac_of_peak"], "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": dom["alg_bytes_per_launch"], "ms_per_launch": dom["ms_per_launch"]}
+        return ks, roof
+
+    kernels, roofline = kernel_table(path, out)
+
+    # the other formulation of the same step, for reference (same inputs, same outputs)
+    other = None
+    if fused and not args.no_dense_reference:
+        path2 = pipeline.InputPath(cfg, device=dev, data_mean=mean, pfn_params=synth.make_pfn_params(0),
+                                   training=True, fused=False, anchors=anchors)
+        out2 = dict(out)
+        out2["pillars"] = (torch.empty((BATCH, 9, P, N), dtype=torch.float32, device=dev), out["pillars"][1],
+                           out["pillars"][2])
+        step2 = lambda: path2.step_device(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out=out2)
+        for _ in range(3):
+            step2()
+        ms2 = timed(step2, args.steps)
+        ms2_max, units2 = reduce_over_ranks(ms2, float(BATCH * args.steps), dev)
+        k2, roof2 = kernel_table(path2, out2)
+        other = {"what": "signature-preserving sequence pp_pillarize -> x [B,9,P,N] -> pp_pfn_scatter (x materialised)",
+                 "value": units2 / (ms2_max / 1e3), "unit": UNIT, "ms_per_step": ms2_max / args.steps,
+                 "roofline": roof2, "kernels": k2}
+        del out2, path2
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -413,11 +437,15 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (PFN, features) + f64 (binning, means, IoU)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "sweeps_per_gpu_per_step": BATCH, "points_per_step_per_gpu": int(T),
+                       "path": ("fused pp_input_path: pillarize stages -> PFN + scatter straight from the compact "
+                                "per-point state, x [B,9,P,N] never materialised (padding slots evaluated once per "
+                                "(p,n)); see dense_path for the signature-preserving sequence") if fused else
+                               "pp_pillarize -> x [B,9,P,N] -> pp_pfn_scatter",
                        "data_mean": "dense synthetic per-slot mean [9*P*N]", "bn": "training mode",
                        "l2": "no flush: per-step working set ~1.5 GB (x 691 MB, canvas 369 MB, targets 156 MB, "
                              "data_mean 173 MB) >> 126 MB L2",
                        "parallelism": "dp%d (one process per GPU, sweeps sharded, no collective)" % world},
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "kernels": kernels, "dense_path": other, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e_max / args.steps, "host_wall_ms_per_step": ms_e_host / args.steps,
                     "pipeline": "step_host_async: copy stream + 2 staging buffers, one step in flight; each step's "
@@ -438,6 +466,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dense-reference", action="store_true", help="skip the extra dense_path measurement")
+    ap.add_argument("--dense-path", action="store_true",
+                    help="time the signature-preserving sequence pp_pillarize -> x [B,9,P,N] -> pp_pfn_scatter "
+                         "instead of the fused pp_input_path (x never materialised)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

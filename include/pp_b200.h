@@ -51,7 +51,10 @@ enum {
   PP_STATUS_NEG_IOU = 1,       /* wrong corner winding: the reference would exit(1) */
   PP_STATUS_BAD_POINT = 2,     /* NaN/Inf coordinate met the reference's range filter (out of contract); point dropped */
   PP_STATUS_BAD_INDEX = 4,     /* scatter index outside the canvas; row skipped */
-  PP_STATUS_CAND_OVERFLOW = 8  /* more candidate anchors for one GT than the anchor index promised */
+  PP_STATUS_CAND_OVERFLOW = 8, /* more candidate anchors for one GT than the anchor index promised */
+  PP_STATUS_RANGE = 16         /* pp_input_path: a data_mean value or conv weight left the fp16 range of the
+                                  tensor-core padding pass (|v| >= 2^15, |256 w| >= 2^15); canvas invalid,
+                                  use pp_pillarize + pp_pfn_scatter */
 };
 
 enum { PP_F32 = 0, PP_F64 = 1, PP_I64 = 2 };
@@ -72,6 +75,28 @@ int pp_version(void);
 const char* pp_error_string(int code);
 /* cudaError_t of the most recent failing CUDA call made by this thread inside the library. */
 int pp_last_cuda_error(void);
+
+/* Fused input path: pp_pillarize's stages, then PPFeatureNet + PPScatter evaluated straight from the
+ * compact per-point state -- the dense network input x [B,9,P,N] (data/dataset.py:99-105) is never
+ * materialised unless d_x is non-NULL.  Same canvas as pp_pillarize + pp_pfn_scatter up to fp32
+ * summation order (model/model.py:31-40,53-62; BatchNorm statistics over all B*P*N slots, padding
+ * included).  It uses that a padding slot holds 0 - data_mean[d,p,n] in every sweep: the padding
+ * slots are evaluated once per (p,n) on the tensor cores (with one suffix maximum per sweep), the
+ * ~1.3 % of slots that hold a point are evaluated separately.  Supported: 1 <= n_sweeps <= 8, C = 64,
+ * max_points_per_pillar <= 255 and a multiple of 8, max_pillars even; otherwise PP_ERR_UNSUPPORTED
+ * (call pp_pillarize + pp_pfn_scatter).  d_indices [B,P,3] int64 and d_num_pillars [B] int32 are
+ * outputs as in pp_pillarize.  A data_mean value or weight outside the fp16 range of the padding
+ * pass raises PP_STATUS_RANGE in *d_status. */
+size_t pp_input_path_workspace_bytes(int32_t n_sweeps, int64_t total_points, const pp_grid* grid,
+                                     int32_t max_pillars, int32_t C, int32_t canvas_h, int32_t canvas_w);
+int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_point, int64_t stride_col,
+                  const int64_t* h_sweep_offsets, int32_t n_sweeps, const pp_grid* grid,
+                  int32_t max_points_per_pillar, int32_t max_pillars, const float* d_data_mean, int32_t C,
+                  const float* d_conv_w, const float* d_conv_b, const float* d_bn_w, const float* d_bn_b,
+                  float* d_running_mean, float* d_running_var, int64_t* d_num_batches_tracked,
+                  int32_t training, float momentum, float eps, int32_t canvas_h, int32_t canvas_w,
+                  float* d_canvas, float* d_x, int64_t* d_indices, int32_t* d_num_pillars,
+                  int32_t* d_status, void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
 
 /* Instrumentation.  pp_launch_count: kernels launched by this library since load (all threads).
  * pp_profile_enable(1): bracket every kernel launch with CUDA events on its stream;

@@ -1,0 +1,55 @@
+"""Print the fused-vs-dense canvas differences and time the fused step (development aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, numpy as np
+import pp_b200
+from pp_b200 import _lib, pipeline, synth
+L = _lib.load()
+P, N = 24000, 200
+for dense_mean in (True, False):
+    for training in (True, False):
+        mean = synth.make_data_mean(P, N, dense=dense_mean)
+        prm = synth.make_pfn_params(1, flip_gamma=True)
+        mk = lambda: pipeline.InputPath(data_mean=mean, pfn_params=prm, training=training)
+        pa, pb = mk(), mk()
+        sweeps = [synth.make_sweep(40 + s) for s in range(4)]
+        offs = np.cumsum([0] + [len(s) for s in sweeps]).tolist()
+        pts = torch.from_numpy(np.concatenate(sweeps)).cuda()
+        x, inds, npil = pa.pillarize(pts, offs)
+        want = pa.encode(x, inds)
+        canvas, inds2, npil2 = pb.pillarize_encode(pts, offs)
+        d = (canvas.double() - want.double()).abs()
+        nz = want != 0
+        print("mean=%s train=%s max|diff| %.3g  max|canvas| %.3g  mean|diff| on support %.3g  rm diff %.3g rv diff %.3g" % (
+            dense_mean, training, d.max().item(), want.abs().max().item(), d[nz].mean().item(),
+            (pa.net.bn1.running_mean - pb.net.bn1.running_mean).abs().max().item(),
+            (pa.net.bn1.running_var - pb.net.bn1.running_var).abs().max().item()))
+# timing
+mean = synth.make_data_mean(P, N, dense=True)
+path = pipeline.InputPath(data_mean=mean, pfn_params=synth.make_pfn_params(0), training=True)
+sweeps = [synth.make_sweep(s) for s in range(4)]
+offs = np.cumsum([0] + [len(s) for s in sweeps]).tolist()
+pts = torch.from_numpy(np.concatenate(sweeps)).cuda()
+out = {"canvas": torch.empty((4, 64, 600, 600), device="cuda")}
+for _ in range(3): path.pillarize_encode(pts, offs, out=out)
+L.pp_profile_enable(1)
+for _ in range(10): path.pillarize_encode(pts, offs, out=out)
+rep = _lib.profile_report(); L.pp_profile_enable(0)
+tot = 0
+for k, v in rep.items():
+    print("%-20s %7.1f us" % (k, v[1] / v[0] * 1e3)); tot += v[1] / v[0] * 1e3
+print("sum %.1f us" % tot)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20): path.pillarize_encode(pts, offs, out=out)
+e1.record(); torch.cuda.synchronize()
+print("fused K1+K2: %.1f us per batch-4" % (e0.elapsed_time(e1) / 20 * 1e3))
+for dbg in (0, 4, 5, 7):
+    L.pp_set_option(b"pfn_tc_debug", dbg)
+    for _ in range(2): path.pillarize_encode(pts, offs, out=out)
+    L.pp_profile_enable(1)
+    for _ in range(5): path.pillarize_encode(pts, offs, out=out)
+    rep = _lib.profile_report(); L.pp_profile_enable(0)
+    print("dbg=%d k_pfn_pad_tc %.1f us" % (dbg, rep["k_pfn_pad_tc"][1] / rep["k_pfn_pad_tc"][0] * 1e3))
+L.pp_set_option(b"pfn_tc_debug", 0)

@@ -109,3 +109,82 @@ def test_async_streaming_steps_equal_the_blocking_call():
     for j, c, cls, reg, n, k in got:
         assert torch.equal(c, want[j][0]) and torch.equal(cls, want[j][1]) and torch.equal(reg, want[j][2])
         assert torch.equal(n, want[j][3]) and torch.equal(k, want[j][4])
+
+
+def _canvas_close(a, b, amp_scale):
+    """PFN tolerance of test_gpu_pfn.py with a scalar bound on the conditioning magnitude."""
+    a = a.double().cpu().numpy(); b = b.double().cpu().numpy()
+    tol = 1e-5 * np.maximum(np.abs(a), np.abs(b)) + 2e-6 + 1e-6 * amp_scale
+    err = np.abs(a - b) - tol
+    assert err.max() <= 0, "max violation %g (max abs diff %g)" % (err.max(), np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("dense_mean", [True, False])
+@pytest.mark.parametrize("training", [True, False])
+def test_fused_input_path_equals_pillarize_then_encode(dense_mean, training):
+    """pp_input_path (x never materialised, padding slots evaluated once per (p,n)) vs the
+    signature-preserving pp_pillarize -> x -> pp_pfn_scatter sequence at the reference sizes:
+    identical indices / counts, canvas within the PFN tolerance, identical running statistics up to
+    that tolerance; and the optional x output is bit-identical to pillarize's."""
+    from pp_b200 import pipeline, synth
+    P, N = 24000, 200
+    mean = synth.make_data_mean(P, N, dense=dense_mean)
+    prm = synth.make_pfn_params(1, flip_gamma=True)
+    mk = lambda: pipeline.InputPath(data_mean=mean, pfn_params=prm, training=training)
+    pa, pb = mk(), mk()
+    sweeps = [synth.make_sweep(40 + s) for s in range(3)]
+    offs = np.cumsum([0] + [len(s) for s in sweeps]).tolist()
+    pts = torch.from_numpy(np.concatenate(sweeps)).cuda()
+    x, inds, npil = pa.pillarize(pts, offs)
+    want = pa.encode(x, inds)
+    canvas, inds2, npil2, x2 = pb.pillarize_encode(pts, offs, want_x=True)
+    assert torch.equal(inds, inds2) and torch.equal(npil, npil2) and torch.equal(x, x2)
+    # conditioning magnitude: |gamma|/sigma * max(sum_d |w x| + |b|) over the batch
+    w = torch.from_numpy(prm["conv_w"]).cuda().abs()
+    absdot = torch.einsum('cd,bdpn->bcpn', w, x[:, :, :2048].abs()).amax() + float(np.abs(prm["conv_b"]).max())
+    var = pa.net.bn1.running_var if not training else None
+    sigma = float(torch.sqrt(pa.net.bn1.running_var.min() + 1e-5)) if not training else 1.0
+    amp = float(absdot) * float(np.abs(prm["bn_w"]).max()) / min(sigma, 1.0) * 4.0
+    _canvas_close(canvas, want, amp)
+    assert torch.equal(canvas != 0, want != 0) or ((canvas != 0) ^ (want != 0)).sum() < 10
+    if training:
+        assert torch.allclose(pa.net.bn1.running_mean, pb.net.bn1.running_mean, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(pa.net.bn1.running_var, pb.net.bn1.running_var, rtol=1e-5, atol=1e-6)
+    from pp_b200 import _runtime
+    _runtime.check_status(torch.device("cuda"), "fused input path")
+
+
+def test_fused_input_path_against_fp64_oracle():
+    """Small grid, many points per pillar (some over the N cap), hand-checkable sizes: fused path vs the
+    fp64 oracle composition (oracle.glue + oracle.pfn)."""
+    import pp_b200
+    from oracle import glue, pfn
+    from pp_b200 import pipeline, synth
+    cfg = pp_b200.PPConfig(max_pillars=600, max_points_per_pillar=16)
+    P, N = 600, 16
+    mean = synth.make_data_mean(P, N, dense=True)
+    prm = synth.make_pfn_params(5, flip_gamma=True)
+    path = pipeline.InputPath(cfg, data_mean=mean, pfn_params=prm, training=True)
+    rng = np.random.default_rng(3)
+    sweeps = []
+    for s in range(2):
+        n = 6000
+        pts = np.zeros((n, 5), np.float32)
+        pts[:, 0] = rng.uniform(-6, 6, n); pts[:, 1] = rng.uniform(-6, 6, n)      # ~60x60 cells: > P pillars, some > N points
+        pts[:, 2] = rng.uniform(-2, 2, n); pts[:, 3] = 100.0
+        sweeps.append(pts)
+    offs = np.cumsum([0] + [len(s) for s in sweeps]).tolist()
+    canvas, inds, npil = path.pillarize_encode(torch.from_numpy(np.concatenate(sweeps)).cuda(), offs)
+    xs, iis = [], []
+    for s in sweeps:
+        x1, i1 = glue.pillarize(s[:, :4].astype(np.float64), torch.from_numpy(mean), max_pillars=P, max_points=N)
+        xs.append(x1); iis.append(i1)
+    x = torch.stack(xs); ii = torch.stack(iis)
+    t = lambda a: torch.from_numpy(a)
+    y, rm, rv = pfn.pfn_forward(x, t(prm["conv_w"]), t(prm["conv_b"]), t(prm["bn_w"]), t(prm["bn_b"]),
+                                t(prm["running_mean"]), t(prm["running_var"]), True)
+    want = pfn.scatter(y.float(), ii, cfg.canvas_height, cfg.canvas_width)
+    assert torch.equal(inds.cpu(), ii)
+    absdot = torch.einsum('cd,bdpn->bcpn', t(prm["conv_w"]).abs().double(), x.abs().double()).amax()
+    _canvas_close(canvas, want, float(absdot) * 4.0)
+    assert torch.allclose(path.net.bn1.running_var.cpu(), rv.float(), rtol=1e-5, atol=1e-6)
