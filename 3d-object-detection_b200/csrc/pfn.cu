@@ -374,10 +374,6 @@ __global__ void __launch_bounds__(512) k_bn_finalize(int C, int nparts, double c
 // extremes of the two column halves from the tensor-core kernels (already sign-selected); in both
 // cases the pre-activation that survives BN(relu(.)) + max_n is max(e0,e1) for gamma*invstd >= 0 and
 // min(e0,e1) otherwise.
-__device__ __forceinline__ float apply_affine(const Affine& a, float e0, float e1, float e2) {
-  const float v = fmaxf(a.use_min != 0.f ? fminf(fminf(e0, e1), e2) : fmaxf(fmaxf(e0, e1), e2), 0.f);
-  return fmaf(v - a.mean, a.scale, a.beta);
-}
 __device__ __forceinline__ float apply_affine(const Affine& a, float e0, float e1) {
   const float v = fmaxf(a.use_min != 0.f ? fminf(e0, e1) : fmaxf(e0, e1), 0.f);   // relu of the extreme pre-activation
   return fmaf(v - a.mean, a.scale, a.beta);
@@ -473,9 +469,9 @@ __global__ void __launch_bounds__(256) k_canvas(const float* __restrict__ src,
         const float* e = src + ((size_t)b * P + slot) * 2 * C;
         return apply_affine(s_aff[c], e[c], e[C + c]);
       }
-      if (FROM_EXT == 3) {
+      if (FROM_EXT == 3) {       // sparse path: field 0 of a 3-field row is already the pillar's extreme
         const float* e = src + ((size_t)b * P + slot) * 3 * C;
-        return apply_affine(s_aff[c], e[c], e[C + c], e[2 * C + c]);
+        return apply_affine(s_aff[c], e[c], e[c]);
       }
       return src[((size_t)b * C + c) * P + slot];
     };
@@ -789,16 +785,19 @@ __global__ void __launch_bounds__(kRealWarps * 32, 3) k_pfn_real(CompactPillars 
       }
       __syncwarp();                                        // the tile is refilled by the next chunk / pillar
     }
+    // field 0 <- extreme over the whole pillar: its points (here) and its padding slots (fields 1, 2,
+    // written by the padding pass, which ran before this kernel; y == bias without a data_mean)
     float* e = ext_s + (size_t)r * 3 * C + CPL * lane;
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
-      e[j] = sgn[j] > 0.f ? mx[j] : mn[j];
-      if (!has_mean) {
-        // no padding pass: every padding slot is exactly zero, y == bias; neutral when the pillar is full
-        const float neutral = sgn[j] > 0.f ? -INFINITY : INFINITY;
-        e[C + j] = cnt < N ? bias[j] : neutral;
-        e[2 * C + j] = neutral;
+      float p1, p2;
+      if (has_mean) {
+        p1 = e[C + j];
+        p2 = e[2 * C + j];
+      } else {
+        p1 = p2 = cnt < N ? bias[j] : (sgn[j] > 0.f ? -INFINITY : INFINITY);
       }
+      e[j] = sgn[j] > 0.f ? fmaxf(mx[j], fmaxf(p1, p2)) : fminf(mn[j], fminf(p1, p2));
       accS[j] += (double)ds[j];
       accQ[j] += (double)dq[j];
     }
