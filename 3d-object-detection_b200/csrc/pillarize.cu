@@ -743,12 +743,13 @@ static int input_path_impl(const T* pts, long long sp, long long sc, const int64
                            const pp_grid* grid, int N, int P, const float* d_mean, int C, const PfnParams& prm,
                            int H, int W, float* d_canvas, float* d_x, int64_t* d_indices,
                            int32_t* d_num_pillars, int32_t* d_status, void* d_ws, size_t ws_bytes,
-                           cudaStream_t st) {
+                           int stages, cudaStream_t st) {
   GridDev g;
   SweepParams sw;
   if (!make_grid(grid, g)) return PP_ERR_INVALID_ARG;
   int rc = make_sweeps(h_off, B, sw);
   if (rc != PP_OK) return rc;
+  if ((stages & 3) == 0) return PP_ERR_INVALID_ARG;
   if (N < 1 || P < 1 || d_canvas == nullptr || d_indices == nullptr || d_num_pillars == nullptr ||
       d_status == nullptr || (pts == nullptr && sw.off[B] > 0) || (long long)P * N > 0x7fffffffll || H < 1 || W < 1)
     return PP_ERR_INVALID_ARG;
@@ -759,20 +760,23 @@ static int input_path_impl(const T* pts, long long sp, long long sc, const int64
   layout(arena, &ws, B, sw.off[B], sw.tile_start[B], g.ncell, P);
   if (!arena.ok) return PP_ERR_WORKSPACE;
   const size_t k1_bytes = arena.used;
-  const bool vec4 = sizeof(T) == 4 && sp == 4 && sc == 1 && ((uintptr_t)pts % 16) == 0;
-  rc = run_stages<T>(pts, sp, sc, vec4, sw, g, P, ws, d_num_pillars, (long long*)d_indices, d_status, st);
-  if (rc != PP_OK) return rc;
-  const long long total = sw.off[B];
-  if (total > 0) {
-    PP_KERNEL("k_feat", st,
-              k_feat<T><<<(int)((total + 255) / 256), 256, 0, st>>>(
-                  pts, sp, sc, vec4, sw, g, P, N, ws.cell_of_point, ws.cell_slot, ws.rank_of_point,
-                  ws.pil_off, ws.pil_mean, ws.feat_c));
-  }
-  if (d_x != nullptr) {
-    rc = emit_dense(sw, P, N, d_mean, d_x, d_num_pillars, ws, st);
+  if (stages & 1) {
+    const bool vec4 = sizeof(T) == 4 && sp == 4 && sc == 1 && ((uintptr_t)pts % 16) == 0;
+    rc = run_stages<T>(pts, sp, sc, vec4, sw, g, P, ws, d_num_pillars, (long long*)d_indices, d_status, st);
     if (rc != PP_OK) return rc;
+    const long long total = sw.off[B];
+    if (total > 0) {
+      PP_KERNEL("k_feat", st,
+                k_feat<T><<<(int)((total + 255) / 256), 256, 0, st>>>(
+                    pts, sp, sc, vec4, sw, g, P, N, ws.cell_of_point, ws.cell_slot, ws.rank_of_point,
+                    ws.pil_off, ws.pil_mean, ws.feat_c));
+    }
+    if (d_x != nullptr) {
+      rc = emit_dense(sw, P, N, d_mean, d_x, d_num_pillars, ws, st);
+      if (rc != PP_OK) return rc;
+    }
   }
+  if (!(stages & 2)) return PP_OK;
   CompactPillars cp;
   cp.sw = sw; cp.P = P; cp.N = N;
   cp.feat_c = ws.feat_c; cp.pil_cnt = ws.pil_cnt; cp.pil_off = ws.pil_off;
@@ -867,7 +871,8 @@ int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_poin
                   float* d_running_mean, float* d_running_var, int64_t* d_num_batches_tracked,
                   int32_t training, float momentum, float eps, int32_t canvas_h, int32_t canvas_w,
                   float* d_canvas, float* d_x, int64_t* d_indices, int32_t* d_num_pillars,
-                  int32_t* d_status, void* d_workspace, size_t workspace_bytes, pp_stream_t stream) {
+                  int32_t* d_status, void* d_workspace, size_t workspace_bytes, int32_t stages,
+                  pp_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!d_conv_w || !d_conv_b || !d_bn_w || !d_bn_b || !d_running_mean || !d_running_var)
     return PP_ERR_INVALID_ARG;
@@ -877,12 +882,12 @@ int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_poin
     return pp::input_path_impl<float>((const float*)d_points, stride_point, stride_col, h_sweep_offsets,
                                       n_sweeps, grid, max_points_per_pillar, max_pillars, d_data_mean, C, prm,
                                       canvas_h, canvas_w, d_canvas, d_x, d_indices, d_num_pillars, d_status,
-                                      d_workspace, workspace_bytes, st);
+                                      d_workspace, workspace_bytes, stages, st);
   if (point_dtype == PP_F64)
     return pp::input_path_impl<double>((const double*)d_points, stride_point, stride_col, h_sweep_offsets,
                                        n_sweeps, grid, max_points_per_pillar, max_pillars, d_data_mean, C, prm,
                                        canvas_h, canvas_w, d_canvas, d_x, d_indices, d_num_pillars, d_status,
-                                       d_workspace, workspace_bytes, st);
+                                       d_workspace, workspace_bytes, stages, st);
   return PP_ERR_INVALID_ARG;
 }
 

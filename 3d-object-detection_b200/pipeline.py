@@ -35,10 +35,19 @@ class StepHandle:
         self.canvas, self.cls, self.reg, self.n_pillars, self.counts = outputs
         self._pin, self._B, self._done = pinned, n_sweeps, done
 
+    def wait(self, stream=None):
+        """Order ``stream`` (default: the current one) after this step; the outputs are then safe to use there."""
+        (stream or torch.cuda.current_stream()).wait_event(self._done)
+
+    def synchronize(self):
+        self._done.synchronize()
+
     def counters(self):
         """(n_pillars [B], counts [B,4]) as host int32 tensors; waits for this step's D2H copy."""
         self._done.synchronize()
         B = self._B
+        if self._pin is None:
+            return self.n_pillars.cpu(), self.counts.cpu()
         return self._pin[:B].clone(), self._pin[B:5 * B].view(B, 4).clone()
 
 
@@ -73,6 +82,12 @@ class InputPath:
         self.fused = fused
         # host-facing pipeline: copy stream, two device staging buffers, pinned result slots
         self._copy = torch.cuda.Stream(device=self.device)
+        # two lanes (main + side stream each) for the *_async calls: consecutive steps alternate lanes, so
+        # the latency-bound pillarize stage of step k+1 overlaps the encode stage of step k; the encode
+        # stages themselves are ordered (they update the BatchNorm running statistics)
+        self._lanes = [(torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)) for _ in range(2)]
+        self._lane_no = 0
+        self._last_encode = None
         self._stage = [None, None]
         self._slot_free = [None, None]
         self._result_pin = [None, None]
@@ -144,10 +159,12 @@ class InputPath:
         return (1 <= n_sweeps <= 8 and c.feature_net_out == 64 and c.max_points_per_pillar <= 255
                 and c.max_points_per_pillar % 8 == 0 and c.max_pillars % 2 == 0)
 
-    def pillarize_encode(self, points, offsets, out=None, want_x=False):
+    def pillarize_encode(self, points, offsets, out=None, want_x=False, stages=3):
         """points/offsets as in ``pillarize``.  Returns (canvas, inds, n_pillars[, x]): the canvas of
         ``encode(pillarize(...))`` without writing and re-reading the dense [B,9,P,N] tensor (it is
-        only produced when ``want_x``)."""
+        only produced when ``want_x``).  ``stages`` = 1 runs only the pillarize stage, 2 only the encode
+        stage on the state the pillarize stage left in the workspace of the current stream (same
+        ``points`` / ``offsets`` / ``out`` for both calls)."""
         L = _lib.load()
         c = self.cfg
         _runtime.require_cuda(points, "points")
@@ -194,7 +211,7 @@ class InputPath:
                 net.bn1.running_var.data_ptr(), nbt.data_ptr() if nbt is not None else None,
                 1 if net.training else 0, momentum, eps, H, W, canvas.data_ptr(),
                 x.data_ptr() if x is not None else None, inds.data_ptr(), npil.data_ptr(),
-                status.data_ptr(), ws.data_ptr(), ws.numel(), _runtime.stream_ptr(dev))
+                status.data_ptr(), ws.data_ptr(), ws.numel(), int(stages), _runtime.stream_ptr(dev))
         _lib.check(rc, "pp_input_path")
         return (canvas, inds, npil, x) if want_x else (canvas, inds, npil)
 
@@ -276,29 +293,59 @@ class InputPath:
         gt_dev = {k: dv[k] for k in ("corners", "centers", "wlh", "yaw", "cls")}
         return dv["points"][:max(T, 1)], gt_dev
 
-    def _run(self, d_pts, offsets, gt_dev, gt_offsets, o):
+    def _run(self, d_pts, offsets, gt_dev, gt_offsets, o, side=None, ordered=False):
         main = torch.cuda.current_stream(self.device)
+        side = self._side if side is None else side
         if self.overlap_targets:
             self.ensure_anchors()
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
                 cls, reg, top, counts = self.targets(gt_dev, gt_offsets, out=o.get("targets"))
-            canvas, npil = self._k12(d_pts, offsets, o)
-            main.wait_stream(self._side)
+            canvas, npil = self._k12(d_pts, offsets, o, main, ordered)
+            main.wait_stream(side)
             for t in (cls, reg, top, counts):
                 t.record_stream(main)
         else:
-            canvas, npil = self._k12(d_pts, offsets, o)
+            canvas, npil = self._k12(d_pts, offsets, o, main, ordered)
             cls, reg, top, counts = self.targets(gt_dev, gt_offsets, out=o.get("targets"))
         return canvas, cls, reg, npil, counts
 
-    def _k12(self, d_pts, offsets, o):
-        if self.fused and self.fused_supported(len(offsets) - 1):
-            canvas, inds, npil = self.pillarize_encode(d_pts, offsets, out=o)
+    def _k12(self, d_pts, offsets, o, main, ordered):
+        """Pillarize + encode on the current stream.  ``ordered``: called from a lane; the encode stage
+        waits for the encode stage of the previous step (running statistics are read-modify-write)."""
+        fused = self.fused and self.fused_supported(len(offsets) - 1)
+        if fused:
+            if o.get("pillars") is None or o.get("canvas") is None:
+                o = dict(o)
+                c = self.cfg
+                B = len(offsets) - 1
+                if o.get("canvas") is None:
+                    o["canvas"] = torch.empty((B, c.feature_net_out, c.canvas_height, c.canvas_width),
+                                              dtype=torch.float32, device=self.device)
+                if o.get("pillars") is None:
+                    o["pillars"] = (None, torch.empty((B, c.max_pillars, 3), dtype=torch.int64, device=self.device),
+                                    torch.empty(B, dtype=torch.int32, device=self.device))
+            if ordered:
+                self.pillarize_encode(d_pts, offsets, out=o, stages=1)
+                if self._last_encode is not None:
+                    main.wait_event(self._last_encode)
+                canvas, inds, npil = self.pillarize_encode(d_pts, offsets, out=o, stages=2)
+            else:
+                canvas, inds, npil = self.pillarize_encode(d_pts, offsets, out=o)
         else:
             x, inds, npil = self.pillarize(d_pts, offsets, out=o.get("pillars"))
+            if ordered and self._last_encode is not None:
+                main.wait_event(self._last_encode)
             canvas = self.encode(x, inds, out=o.get("canvas"))
+        if ordered:
+            self._last_encode = torch.cuda.Event()
+            self._last_encode.record(main)
         return canvas, npil
+
+    def _next_lane(self):
+        lane = self._lanes[self._lane_no & 1]
+        self._lane_no += 1
+        return lane
 
     def step_host(self, batch, out=None):
         """One pass of the whole path from a pinned HOST batch (``pack_host_batch``): H2D copy,
@@ -309,32 +356,47 @@ class InputPath:
 
     def step_host_async(self, batch, out=None):
         """Pipelined form of ``step_host`` for a streaming loop: the H2D copy goes to a copy stream
-        into one of two staging buffers (so the copy of step k+1 overlaps the kernels of step k), the
-        step's counters come back through a pinned buffer, and nothing blocks the host.  Returns a
-        ``StepHandle``; ``handle.counters()`` waits for this step only."""
+        into one of two staging buffers, the kernels to one of two lanes (so the copy and the
+        pillarize stage of step k+1 overlap the encode stage of step k), the step's counters come
+        back through a pinned buffer, and nothing blocks the host.  Consecutive calls must not share
+        ``out`` buffers.  Returns a ``StepHandle``; ``handle.counters()`` waits for this step only."""
         dev = self.device
-        main = torch.cuda.current_stream(dev)
         slot = self._step_no & 1
         self._step_no += 1
+        main, side = self._next_lane()
         if self._slot_free[slot] is not None:
             self._copy.wait_event(self._slot_free[slot])     # kernels that read this staging buffer two steps ago
+        self._copy.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(self._copy):
             d_pts, gt_dev = self.upload(batch, slot)
             ready = torch.cuda.Event()
             ready.record(self._copy)
-        main.wait_event(ready)
-        res = self._run(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out or {})
-        self._slot_free[slot] = torch.cuda.Event()
-        self._slot_free[slot].record(main)
-        B = len(batch["offsets"]) - 1
-        pin = self._result_pin[slot]
-        if pin is None or pin.numel() < 5 * B:
-            pin = self._result_pin[slot] = torch.empty(5 * B, dtype=torch.int32).pin_memory()
-        pin[:B].copy_(res[3], non_blocking=True)
-        pin[B:5 * B].view(B, 4).copy_(res[4], non_blocking=True)
-        done = torch.cuda.Event()
-        done.record(main)
+        with torch.cuda.stream(main):
+            main.wait_event(ready)
+            res = self._run(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out or {}, side=side, ordered=True)
+            self._slot_free[slot] = torch.cuda.Event()
+            self._slot_free[slot].record(main)
+            B = len(batch["offsets"]) - 1
+            pin = self._result_pin[slot]
+            if pin is None or pin.numel() < 5 * B:
+                pin = self._result_pin[slot] = torch.empty(5 * B, dtype=torch.int32).pin_memory()
+            pin[:B].copy_(res[3], non_blocking=True)
+            pin[B:5 * B].view(B, 4).copy_(res[4], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
         return StepHandle(res, pin, B, done)
+
+    def step_device_async(self, d_pts, offsets, gt_dev, gt_offsets, out=None):
+        """``step_device`` on one of the two lanes (see ``step_host_async``); inputs must be ready on the
+        current stream.  Returns a ``StepHandle`` (``wait()`` orders the current stream after the step)."""
+        dev = self.device
+        main, side = self._next_lane()
+        main.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(main):
+            res = self._run(d_pts, offsets, gt_dev, gt_offsets, out or {}, side=side, ordered=True)
+            done = torch.cuda.Event()
+            done.record(main)
+        return StepHandle(res, None, len(offsets) - 1, done)
 
     def step_device(self, d_pts, offsets, gt_dev, gt_offsets, out=None):
         """Same pass with inputs already resident in HBM."""

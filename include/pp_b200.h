@@ -86,7 +86,12 @@ int pp_last_cuda_error(void);
  * max_points_per_pillar <= 255 and a multiple of 8, max_pillars even; otherwise PP_ERR_UNSUPPORTED
  * (call pp_pillarize + pp_pfn_scatter).  d_indices [B,P,3] int64 and d_num_pillars [B] int32 are
  * outputs as in pp_pillarize.  A data_mean value or weight outside the fp16 range of the padding
- * pass raises PP_STATUS_RANGE in *d_status. */
+ * pass raises PP_STATUS_RANGE in *d_status.
+ * stages: PP_STAGE_PILLARIZE | PP_STAGE_ENCODE (3) runs everything.  A streaming caller may issue the
+ * two stages separately (same arguments, same workspace) -- e.g. the pillarize stage of batch k+1 on
+ * one stream while the encode stage of batch k runs on another; with training != 0 the encode stages
+ * of successive batches must be ordered by the caller (they update the running statistics). */
+enum { PP_STAGE_PILLARIZE = 1, PP_STAGE_ENCODE = 2 };
 size_t pp_input_path_workspace_bytes(int32_t n_sweeps, int64_t total_points, const pp_grid* grid,
                                      int32_t max_pillars, int32_t C, int32_t canvas_h, int32_t canvas_w);
 int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_point, int64_t stride_col,
@@ -96,7 +101,8 @@ int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_poin
                   float* d_running_mean, float* d_running_var, int64_t* d_num_batches_tracked,
                   int32_t training, float momentum, float eps, int32_t canvas_h, int32_t canvas_w,
                   float* d_canvas, float* d_x, int64_t* d_indices, int32_t* d_num_pillars,
-                  int32_t* d_status, void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
+                  int32_t* d_status, void* d_workspace, size_t workspace_bytes, int32_t stages,
+                  pp_stream_t stream);
 
 /* Instrumentation.  pp_launch_count: kernels launched by this library since load (all threads).
  * pp_profile_enable(1): bracket every kernel launch with CUDA events on its stream;

@@ -99,6 +99,7 @@ def test_async_streaming_steps_equal_the_blocking_call():
     handles, got = [], []
     for i in [0, 1, 2, 0, 2, 1]:
         h = path.step_host_async(batches[i])            # fresh outputs per step (no shared `out`)
+        assert h.canvas is not None
         handles.append((i, h))
         if len(handles) > 2:
             j, hj = handles.pop(0)
@@ -188,3 +189,28 @@ def test_fused_input_path_against_fp64_oracle():
     absdot = torch.einsum('cd,bdpn->bcpn', t(prm["conv_w"]).abs().double(), x.abs().double()).amax()
     _canvas_close(canvas, want, float(absdot) * 4.0)
     assert torch.allclose(path.net.bn1.running_var.cpu(), rv.float(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_two_lane_training_steps_equal_sequential_steps(fused):
+    """Training-mode BN updates the running statistics every step: the streaming lanes must give exactly
+    the sequence of canvases and statistics that blocking steps give (encode stages are ordered)."""
+    from pp_b200 import pipeline, synth
+    mean = synth.make_data_mean(24000, 200, dense=True)
+    mk = lambda: pipeline.InputPath(data_mean=mean, pfn_params=synth.make_pfn_params(2), training=True, fused=fused)
+    pa, pb = mk(), mk()
+    batches = []
+    for k in range(4):
+        sweeps = [synth.make_sweep(20 * k + s) for s in range(2)]
+        gts = [synth.make_gt(20 * k + s, 15) for s in range(2)]
+        batches.append(pa.pack_host_batch(sweeps, gts))
+    want = []
+    for b in batches:
+        c = pa.step_host(b)[0]
+        want.append((c.clone(), pa.net.bn1.running_var.clone()))
+    handles = [pb.step_host_async(b) for b in batches]      # all four in flight
+    for h, (c, rv) in zip(handles, want):
+        h.synchronize()
+        assert torch.equal(h.canvas, c)
+    assert torch.equal(pb.net.bn1.running_var, want[-1][1])
+    assert int(pb.net.bn1.num_batches_tracked) == 4
