@@ -587,6 +587,7 @@ int launch_stats_tc16(const float* d_x, int B, int P, int N, const float* w, con
                       const float* bn_w, int training, float* ext, double* partials, int nblocks,
                       int* range_flag, const tch::PadArgs* pad, cudaStream_t st);
 extern int g_opt_pfn_tensor_cores;
+extern int g_opt_pfn_tc_debug;
 
 static int launch_stats(const float* d_x, int B, int P, int N, int C, const float* w, const float* bias,
                         const float* bn_w, int training, PfnWs& ws, int& nblocks, cudaStream_t st) {
@@ -872,6 +873,11 @@ int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, c
     rc = launch_stats_tc16(cp.data_mean, 1, P, N, prm.conv_w, prm.conv_b, prm.bn_w, prm.training, ws.ext_s,
                            ws.partials, nblocks, ws.flags, &pad, st);
     if (rc != PP_OK) return rc;
+    if (g_opt_pfn_tc_debug & 16) {   // development: second back-to-back launch to expose per-launch fixed costs
+      rc = launch_stats_tc16(cp.data_mean, 1, P, N, prm.conv_w, prm.conv_b, prm.bn_w, prm.training, ws.ext_s,
+                             ws.partials, nblocks, ws.flags, &pad, st);
+      if (rc != PP_OK) return rc;
+    }
   }
   const int nb2 = real_blocks();
   PP_KERNEL("k_pfn_real", st,

@@ -261,15 +261,21 @@ k_pfn_stats_tc(const __grid_constant__ CUtensorMap tmap, int B, int P, int N,
     const int c = 16 * q + (int)(lane & 15u);
     const float sgn = bn_w[c] < 0.f ? -1.f : 1.f;
     double accS = 0.0, accQ = 0.0;
-    const int split = ((N / 8 + 1) / 2) * 8;
+    // PAD: the first half also carries the per-sweep masked maxima of the chunks that straddle a count
+    // (~1400 cycles per visit, measured), so it gets fewer columns
+    const int split = (PAD && N >= 136) ? 72 : ((N / 8 + 1) / 2) * 8;
     const int n0 = j ? split : 0, n1 = j ? N : split;
     const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(e * kAccCols + n0);
     const int ncols = n1 - n0;             // multiple of 8
+    // PAD: the packed per-sweep counts of a pillar are fetched one visit ahead (the epilogue is the
+    // bottleneck, so the accumulator is usually ready and a load issued at the wait would be exposed)
+    unsigned long long pk_next = 0ull;
+    if (PAD && e < my_pairs) pk_next = __ldg(pad.packed + 2 * ((int)blockIdx.x + e * (int)gridDim.x) + h);
     for (int it = e; it < my_pairs; it += 2) {
       const uint32_t n = (uint32_t)(it >> 1);
       const int r = 2 * ((int)blockIdx.x + it * (int)gridDim.x) + h;      // row: pillar (b,p); PAD: pillar p
-      unsigned long long pk = 0ull;
-      if (PAD) pk = __ldg(pad.packed + r);             // in flight while waiting for the accumulator
+      const unsigned long long pk = pk_next;
+      if (PAD && it + 2 < my_pairs) pk_next = __ldg(pad.packed + 2 * ((int)blockIdx.x + (it + 2) * (int)gridDim.x) + h);
       mbar_wait_t(&acc_full[e], n & 1u, pon, pacc[0]);
       tc_fence_after();
       const long long tq0 = pon ? clock64() : 0;
