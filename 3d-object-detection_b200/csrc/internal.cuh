@@ -24,7 +24,7 @@ struct CompactPillars {
   const float* data_mean;    // [9*P*N] or nullptr
 };
 
-constexpr int kSparseMaxSweeps = 8;   // sweeps per call of the sparse PFN (per-sweep suffix maxima live in registers)
+constexpr int kSparseMaxSweeps = 8;   // sweeps per padding pass (per-sweep suffix maxima live in registers); larger batches take several passes
 
 struct PfnParams {
   const float *conv_w, *conv_b, *bn_w, *bn_b;
@@ -37,7 +37,8 @@ struct PfnParams {
 namespace tch {
 // arguments of the padding pass (k_pfn_stats_tc<.., PAD = true>, pfn_tc16.cu)
 struct PadArgs {
-  int nb;                                   // real sweeps (<= kSparseMaxSweeps)
+  int nb;                                   // real sweeps of this pass (<= kSparseMaxSweeps)
+  int b0;                                   // first sweep of this pass (ext rows are indexed by b0 + b)
   const unsigned long long* packed;         // [P]: byte b = min(count of pillar p in sweep b, N), 0xff = not a live pillar there
 };
 }  // namespace tch

@@ -690,18 +690,20 @@ static int build_map(const int64_t* d_inds, int B, int P, int H, int W, int* map
 // instead of once per sweep and keeps one suffix maximum per sweep; k_pfn_real below handles the
 // ~1.3 % of slots that hold a point.  Results equal the dense path's up to summation order.
 
+// packed[chunk][p]: byte b = min(count of pillar p in sweep 8*chunk + b, N), 0xff = not a live pillar there
 __global__ void __launch_bounds__(256) k_pack_counts(int B, int P, int N, const int* __restrict__ num_pillars,
                                                      const int* __restrict__ pil_cnt,
                                                      unsigned long long* __restrict__ packed) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b0 = blockIdx.y * kSparseMaxSweeps;
   if (p >= P) return;
   unsigned long long v = 0ull;
   for (int b = 0; b < kSparseMaxSweeps; ++b) {
     unsigned long long cb = 0xffull;
-    if (b < B && p < num_pillars[b]) cb = (unsigned long long)min(pil_cnt[(size_t)b * P + p], N);
+    if (b0 + b < B && p < num_pillars[b0 + b]) cb = (unsigned long long)min(pil_cnt[(size_t)(b0 + b) * P + p], N);
     v |= cb << (8 * b);
   }
-  packed[p] = v;
+  packed[(size_t)blockIdx.y * P + p] = v;
 }
 
 // One warp per live pillar, CPL channels per lane; conv weights in registers.  The points of the
@@ -837,7 +839,7 @@ static void sparse_layout(A& a, SparseWs* ws, int B, int P, int C, int H, int W)
   auto p3 = a.template take<Affine>(64);
   auto p4 = a.template take<int>((size_t)B * H * W + 1);
   auto p5 = a.template take<int>(64);
-  auto p6 = a.template take<unsigned long long>((size_t)P);
+  auto p6 = a.template take<unsigned long long>((size_t)P * ((B + kSparseMaxSweeps - 1) / kSparseMaxSweeps));
   if (ws) { ws->ext_s = p0; ws->partials = p1; ws->partials2 = p2; ws->affine = p3; ws->map = p4; ws->flags = p5; ws->packed = p6; }
 }
 
@@ -849,7 +851,7 @@ size_t pfn_sparse_workspace_bytes(int B, int P, int C, int H, int W) {
 
 bool pfn_sparse_supported(int B, int P, int N, int C, const void* data_mean) {
   if (!g_opt_pfn_tensor_cores) return false;
-  if (B < 1 || B > kSparseMaxSweeps || C != 64 || N > 255) return false;
+  if (B < 1 || B > PP_MAX_SWEEPS || C != 64 || N > 255) return false;
   return data_mean == nullptr || pfn_tc16_supported(kD, N, C, P, data_mean);
 }
 
@@ -867,15 +869,15 @@ int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, c
   if (cp.data_mean != nullptr) {
     const long long pairs = P / 2;
     nblocks = (int)(pairs < sm_count() ? pairs : sm_count());
+    const int nchunks = (B + kSparseMaxSweeps - 1) / kSparseMaxSweeps;
     PP_KERNEL("k_pack_counts", st,
-              k_pack_counts<<<(P + 255) / 256, 256, 0, st>>>(B, P, N, cp.num_pillars, cp.pil_cnt, ws.packed));
-    tch::PadArgs pad{B, ws.packed};
-    rc = launch_stats_tc16(cp.data_mean, 1, P, N, prm.conv_w, prm.conv_b, prm.bn_w, prm.training, ws.ext_s,
-                           ws.partials, nblocks, ws.flags, &pad, st);
-    if (rc != PP_OK) return rc;
-    if (g_opt_pfn_tc_debug & 16) {   // development: second back-to-back launch to expose per-launch fixed costs
-      rc = launch_stats_tc16(cp.data_mean, 1, P, N, prm.conv_w, prm.conv_b, prm.bn_w, prm.training, ws.ext_s,
-                             ws.partials, nblocks, ws.flags, &pad, st);
+              k_pack_counts<<<dim3((P + 255) / 256, nchunks), 256, 0, st>>>(B, P, N, cp.num_pillars, cp.pil_cnt, ws.packed));
+    // one padding pass per 8 sweeps (their suffix maxima); the statistics come from the first pass only
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int b0 = ch * kSparseMaxSweeps;
+      tch::PadArgs pad{min(kSparseMaxSweeps, B - b0), b0, ws.packed + (size_t)ch * P};
+      rc = launch_stats_tc16(cp.data_mean, 1, P, N, prm.conv_w, prm.conv_b, prm.bn_w, (prm.training && ch == 0) ? 1 : 0,
+                             ws.ext_s, ws.partials, nblocks, ws.flags + ch, &pad, st);
       if (rc != PP_OK) return rc;
     }
   }

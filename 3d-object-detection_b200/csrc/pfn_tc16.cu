@@ -383,7 +383,7 @@ k_pfn_stats_tc(const __grid_constant__ CUtensorMap tmap, int B, int P, int N,
 #pragma unroll
         for (int b = 0; b < NBMAX; ++b)
           if (b < pad.nb && ((pk >> (8 * b)) & 0xffull) != 0xffull)
-            ext[(((size_t)b * P + r) * 3 + 1 + j) * 64 + c] = sgn * fmaxf(sm[b], common) * (1.f / 256.f);
+            ext[(((size_t)(pad.b0 + b) * P + r) * 3 + 1 + j) * 64 + c] = sgn * fmaxf(sm[b], common) * (1.f / 256.f);
       } else {
         ext[(size_t)r * 128 + j * 64 + c] = sgn * fmaxf(mx[0], mx[1]) * (1.f / 256.f);
       }
@@ -521,7 +521,7 @@ int launch_stats_tc16(const float* d_x, int B, int P, int N, const float* w, con
     return PP_ERR_UNSUPPORTED;
   long long* prof = g_opt_pfn_tc_timing ? tc_prof_ptr() : nullptr;
   PP_CUDA(cudaMemsetAsync(range_flag, 0, sizeof(int), st));
-  const tch::PadArgs pa = pad ? *pad : tch::PadArgs{0, nullptr};
+  const tch::PadArgs pa = pad ? *pad : tch::PadArgs{0, 0, nullptr};
 #define PP_TC16(TR, PD, NB, NAME)                                                                                 \
   do {                                                                                                            \
     PP_CUDA(cudaFuncSetAttribute(tch::k_pfn_stats_tc<TR, PD, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total)); \

@@ -186,6 +186,51 @@ __global__ void __launch_bounds__(256) k_iou_pass(
   }
 
   double* cache = cand_iou + (size_t)gg * kCandCap;
+  // GT bounding box: an anchor whose bounding box is strictly separated from it cannot intersect the
+  // GT polygon, the reference's bg::intersection output is empty and its IoU is exactly 0
+  // (data/pillars.cpp:161-163) -- no clipping needed for those
+  double gx0 = g[0], gx1 = g[0], gy0 = g[1], gy1 = g[1];
+#pragma unroll
+  for (int q = 1; q < 4; ++q) {
+    gx0 = fmin(gx0, g[2 * q]); gx1 = fmax(gx1, g[2 * q]);
+    gy0 = fmin(gy0, g[2 * q + 1]); gy1 = fmax(gy1, g[2 * q + 1]);
+  }
+  // PASS 0 runs in two phases so that every lane clips a polygon pair: phase 1 classifies the window's
+  // candidates (centre prefilter + bounding boxes; ~3 of 4 drop out) and queues the survivors in
+  // shared memory, phase 2 deals the queue round-robin to the threads.  Clipping inline left most
+  // lanes of a warp idle behind the few that passed (ncu r1h: 22 % issue utilisation, 82 us).
+  constexpr int kQueue = 2048;
+  __shared__ int q_a[PASS == 0 ? kQueue : 1];
+  __shared__ int q_slot[PASS == 0 ? kQueue : 1];
+  __shared__ int q_n;
+  if (PASS == 0) {
+    if (threadIdx.x == 0) q_n = 0;
+    __syncthreads();
+  }
+  auto survives = [&](int a) -> bool {
+    if (prefilter_far(a_centers + (size_t)a * 3, gc)) return false;
+    const double* ar = a_corners + (size_t)a * 8;
+    double ax0 = ar[0], ax1 = ar[0], ay0 = ar[1], ay1 = ar[1];
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      ax0 = fmin(ax0, ar[2 * q]); ax1 = fmax(ax1, ar[2 * q]);
+      ay0 = fmin(ay0, ar[2 * q + 1]); ay1 = fmax(ay1, ar[2 * q + 1]);
+    }
+    return !(ax1 < gx0 || gx1 < ax0 || ay1 < gy0 || gy1 < ay0);
+  };
+  auto clip = [&](int a) -> double {
+    double ar[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ar[q] = a_corners[(size_t)a * 8 + q];
+    double v = quad_iou(ar, g);
+    if (v < 0.0) { atomicOr(status, PP_STATUS_NEG_IOU); v = 0.0; }
+    return v;
+  };
+  auto account0 = [&](int a, double v) {        // PASS 0 bookkeeping of one positive IoU
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    atomicMax(&best_b[a], bits);
+    if (bits > my_best || (bits == my_best && a < my_a)) { my_best = bits; my_a = a; }
+  };
   int rowbase = 0;                                   // enumeration index of the first candidate of this bucket row
   for (int by = by0; by <= by1; ++by) {
     if (bx1 < bx0) break;
@@ -194,26 +239,26 @@ __global__ void __launch_bounds__(256) k_iou_pass(
     for (int k = s + (int)threadIdx.x; k < e; k += blockDim.x) {
       const int a = ids[k];
       const int slot = rowbase + (k - s);
-      double v;
-      if (PASS == 1 && slot < kCandCap) {
-        v = cache[slot];                             // computed by pass 0
-      } else {
-        v = 0.0;
-        if (!prefilter_far(a_centers + (size_t)a * 3, gc)) {
-          double ar[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) ar[q] = a_corners[(size_t)a * 8 + q];
-          v = quad_iou(ar, g);
-          if (v < 0.0) { atomicOr(status, PP_STATUS_NEG_IOU); v = 0.0; }
-        }
-        if (PASS == 0 && slot < kCandCap) cache[slot] = v;
-      }
-      if (!(v > 0.0)) continue;
-      const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
       if (PASS == 0) {
-        atomicMax(&best_b[a], bits);
-        if (bits > my_best || (bits == my_best && a < my_a)) { my_best = bits; my_a = a; }
+        if (survives(a)) {
+          const int pos = atomicAdd(&q_n, 1);
+          if (pos < kQueue) {
+            q_a[pos] = a;
+            q_slot[pos] = slot;
+          } else {                                   // queue full (cannot happen with the reference's anchor grid): inline
+            const double v = clip(a);
+            if (slot < kCandCap) cache[slot] = v;
+            if (v > 0.0) account0(a, v);
+          }
+        } else if (slot < kCandCap) {
+          cache[slot] = 0.0;
+        }
       } else {
+        double v;
+        if (slot < kCandCap) v = cache[slot];        // computed by pass 0
+        else v = survives(a) ? clip(a) : 0.0;
+        if (!(v > 0.0)) continue;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
         if (bits == best_b[a]) {
           atomicMin(&arg[(size_t)b * A + a], gl);
           if (v > pos_thresh) {
@@ -226,6 +271,16 @@ __global__ void __launch_bounds__(256) k_iou_pass(
       }
     }
     rowbase += e - s;
+  }
+  if (PASS == 0) {
+    __syncthreads();
+    const int nq = min(q_n, kQueue);
+    for (int i = (int)threadIdx.x; i < nq; i += blockDim.x) {
+      const int a = q_a[i];
+      const double v = clip(a);
+      if (q_slot[i] < kCandCap) cache[q_slot[i]] = v;
+      if (v > 0.0) account0(a, v);
+    }
   }
 
   if (PASS == 0) {

@@ -156,7 +156,7 @@ class InputPath:
     # -- K1 + K2 fused, x never materialised (pp_input_path) ------------------------------------
     def fused_supported(self, n_sweeps):
         c = self.cfg
-        return (1 <= n_sweeps <= 8 and c.feature_net_out == 64 and c.max_points_per_pillar <= 255
+        return (1 <= n_sweeps <= _lib.PP_MAX_SWEEPS and c.feature_net_out == 64 and c.max_points_per_pillar <= 255
                 and c.max_points_per_pillar % 8 == 0 and c.max_pillars % 2 == 0)
 
     def pillarize_encode(self, points, offsets, out=None, want_x=False, stages=3):
@@ -176,7 +176,7 @@ class InputPath:
             raise _lib.PPError("points must be float32 or float64")
         B = len(offsets) - 1
         if not self.fused_supported(B):
-            raise _lib.PPError("fused input path: 1..8 sweeps, C=64, N<=255 and N%8==0, P even")
+            raise _lib.PPError("fused input path: 1..%d sweeps, C=64, N<=255 and N%%8==0, P even" % _lib.PP_MAX_SWEEPS)
         T = int(offsets[-1])
         P, N, C = c.max_pillars, c.max_points_per_pillar, c.feature_net_out
         H, W = c.canvas_height, c.canvas_width

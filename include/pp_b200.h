@@ -82,7 +82,8 @@ int pp_last_cuda_error(void);
  * summation order (model/model.py:31-40,53-62; BatchNorm statistics over all B*P*N slots, padding
  * included).  It uses that a padding slot holds 0 - data_mean[d,p,n] in every sweep: the padding
  * slots are evaluated once per (p,n) on the tensor cores (with one suffix maximum per sweep), the
- * ~1.3 % of slots that hold a point are evaluated separately.  Supported: 1 <= n_sweeps <= 8, C = 64,
+ * ~1.3 % of slots that hold a point are evaluated separately (one padding pass per 8 sweeps).
+ * Supported: 1 <= n_sweeps <= PP_MAX_SWEEPS, C = 64,
  * max_points_per_pillar <= 255 and a multiple of 8, max_pillars even; otherwise PP_ERR_UNSUPPORTED
  * (call pp_pillarize + pp_pfn_scatter).  d_indices [B,P,3] int64 and d_num_pillars [B] int32 are
  * outputs as in pp_pillarize.  A data_mean value or weight outside the fp16 range of the padding

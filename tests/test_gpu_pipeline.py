@@ -214,3 +214,28 @@ def test_two_lane_training_steps_equal_sequential_steps(fused):
         assert torch.equal(h.canvas, c)
     assert torch.equal(pb.net.bn1.running_var, want[-1][1])
     assert int(pb.net.bn1.num_batches_tracked) == 4
+
+
+def test_fused_input_path_more_than_eight_sweeps():
+    """B = 11 (two padding passes: 8 + 3 sweeps, statistics from the first only) vs the dense sequence."""
+    import pp_b200
+    from pp_b200 import pipeline, synth
+    cfg = pp_b200.PPConfig(max_pillars=6000, max_points_per_pillar=64)
+    P, N = 6000, 64
+    mean = synth.make_data_mean(P, N, dense=True)
+    prm = synth.make_pfn_params(6, flip_gamma=True)
+    mk = lambda: pipeline.InputPath(cfg, data_mean=mean, pfn_params=prm, training=True)
+    pa, pb = mk(), mk()
+    sweeps = [synth.make_sweep(70 + s)[:30000] for s in range(11)]
+    offs = np.cumsum([0] + [len(s) for s in sweeps]).tolist()
+    pts = torch.from_numpy(np.concatenate(sweeps)).cuda()
+    x, inds, npil = pa.pillarize(pts, offs)
+    want = pa.encode(x, inds)
+    canvas, inds2, npil2 = pb.pillarize_encode(pts, offs)
+    assert torch.equal(inds, inds2) and torch.equal(npil, npil2)
+    w = torch.from_numpy(prm["conv_w"]).cuda().abs()
+    absdot = torch.einsum('cd,bdpn->bcpn', w, x[:, :, :1024].abs()).amax() + float(np.abs(prm["conv_b"]).max())
+    _canvas_close(canvas, want, float(absdot) * float(np.abs(prm["bn_w"]).max()) * 4.0)
+    assert torch.allclose(pa.net.bn1.running_var, pb.net.bn1.running_var, rtol=1e-5, atol=1e-6)
+    d = (canvas.double() - want.double()).abs().max().item()
+    assert d < 1e-3 * max(1.0, want.abs().max().item() * 1e-2), d
