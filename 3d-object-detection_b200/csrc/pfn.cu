@@ -278,7 +278,8 @@ struct SparseFinalize {
   int* status;
 };
 
-__global__ void __launch_bounds__(512) k_bn_finalize(int C, int nparts, double count, int training,
+constexpr int kFinSegs = 16;
+__global__ void __launch_bounds__(64 * kFinSegs) k_bn_finalize(int C, int nparts, double count, int training,
                                                      float momentum, float eps, SparseFinalize sf,
                                                      const double* __restrict__ partials,
                                                      const float* __restrict__ bn_w,
@@ -287,11 +288,11 @@ __global__ void __launch_bounds__(512) k_bn_finalize(int C, int nparts, double c
                                                      float* __restrict__ running_var,
                                                      long long* __restrict__ num_batches_tracked,
                                                      Affine* __restrict__ affine) {
-  __shared__ double s_part[2][8][64];
+  __shared__ double s_part[2][kFinSegs][64];
   const int c = threadIdx.x & 63, seg = threadIdx.x >> 6;
   if (threadIdx.x == 0 && sf.range_flag != nullptr && *sf.range_flag != 0) atomicOr(sf.status, PP_STATUS_RANGE);
   if (training && c < C) {
-    const int per = (nparts + 7) / 8;
+    const int per = (nparts + kFinSegs - 1) / kFinSegs;
     const int k0 = seg * per, k1 = min(nparts, k0 + per);
     // four independent accumulators (fixed combination order => still deterministic): the loads of a
     // segment are in flight together instead of one L2 round trip per partial
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(512) k_bn_finalize(int C, int nparts, double c
     double S = (((S4[0] + S4[1]) + (S4[2] + S4[3])) + ((S4[4] + S4[5]) + (S4[6] + S4[7]))) * sf.mult;
     double Q = (((Q4[0] + Q4[1]) + (Q4[2] + Q4[3])) + ((Q4[4] + Q4[5]) + (Q4[6] + Q4[7]))) * sf.mult;
     if (sf.partials2 != nullptr) {
-      const int per2 = (sf.nparts2 + 7) / 8;
+      const int per2 = (sf.nparts2 + kFinSegs - 1) / kFinSegs;
       const int j0 = seg * per2, j1 = min(sf.nparts2, j0 + per2);
       double S2[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, Q2[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       int j = j0;
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(512) k_bn_finalize(int C, int nparts, double c
   double mean, var;
   if (training) {
     double S = 0.0, Q = 0.0;
-    for (int k = 0; k < 8; ++k) { S += s_part[0][k][c]; Q += s_part[1][k][c]; }
+    for (int k = 0; k < kFinSegs; ++k) { S += s_part[0][k][c]; Q += s_part[1][k][c]; }
     mean = S / count;
     var = Q / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -632,7 +633,7 @@ static int pfn_common(const float* d_x, int B, int D, int P, int N, int C, const
   int rc = launch_stats(d_x, B, P, N, C, w, bias, bn_w, training, ws, nblocks, st);
   if (rc != PP_OK) return rc;
   PP_KERNEL("k_bn_finalize", st,
-            k_bn_finalize<<<1, 512, 0, st>>>(C, nblocks, (double)B * P * N, training, momentum, eps,
+            k_bn_finalize<<<1, 64 * kFinSegs, 0, st>>>(C, nblocks, (double)B * P * N, training, momentum, eps,
                                             SparseFinalize{1.0, nullptr, 0, nullptr, 0.0, nullptr, nullptr}, ws.partials, bn_w, bn_b,
                                             rm, rv, (long long*)nbt, ws.affine));
   return PP_OK;
@@ -890,7 +891,7 @@ int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, c
                     cp.data_mean == nullptr ? prm.conv_b : nullptr, (double)B * P * N,
                     cp.data_mean != nullptr ? ws.flags : nullptr, d_status};
   PP_KERNEL("k_bn_finalize", st,
-            k_bn_finalize<<<1, 512, 0, st>>>(C, nblocks, (double)B * P * N, prm.training, prm.momentum, prm.eps, sf,
+            k_bn_finalize<<<1, 64 * kFinSegs, 0, st>>>(C, nblocks, (double)B * P * N, prm.training, prm.momentum, prm.eps, sf,
                                             ws.partials, prm.bn_w, prm.bn_b, prm.running_mean, prm.running_var,
                                             (long long*)prm.num_batches_tracked, ws.affine));
   return canvas_launch(3, ws.ext_s, ws.affine, ws.map, B, P, C, H, W, d_canvas, st);

@@ -325,7 +325,7 @@ def run_ours(args):
         h = path.step_device_async(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out=outs[tick[0] & 1])
         tick[0] += 1
         inflight.append(h)
-        if len(inflight) > 1:
+        if len(inflight) > args.inflight - 1:
             inflight.pop(0).synchronize()
 
     def drain_dev():
@@ -340,7 +340,7 @@ def run_ours(args):
         # region
         pending.append(path.step_host_async(batch, out=outs[tick[0] & 1]))
         tick[0] += 1
-        if len(pending) > 1:
+        if len(pending) > args.inflight - 1:
             pending.pop(0).counters()
 
     def drain_e2e():
@@ -508,6 +508,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense-reference", action="store_true", help="skip the extra dense_path measurement")
+    ap.add_argument("--inflight", type=int, default=2, help="steps in flight in the streaming loops (>= 2)")
     ap.add_argument("--dense-path", action="store_true",
                     help="time the signature-preserving sequence pp_pillarize -> x [B,9,P,N] -> pp_pfn_scatter "
                          "instead of the fused pp_input_path (x never materialised)")
