@@ -77,3 +77,35 @@ def test_host_mirrors_fail_loudly_without_gpu():
         model.PPFeatureNet(9, 64)(torch.zeros(1, 9, 4, 4))
     with pytest.raises(_lib.PPError):
         pipeline.InputPath()
+
+
+def test_input_path_workspace_and_validation_without_gpu():
+    """pp_input_path: workspace query covers both stages; bad arguments are rejected before any CUDA call."""
+    L = _lib.load()
+    grid = pp_b200.PPConfig().grid()
+    k1 = L.pp_pillarize_workspace_bytes(4, 280000, grid, 24000)
+    n = L.pp_input_path_workspace_bytes(4, 280000, grid, 24000, 64, 600, 600)
+    assert n > k1 + 4 * 24000 * 3 * 64 * 4                     # K1 state + ext rows of the sparse PFN
+    assert L.pp_input_path_workspace_bytes(4, 280000, grid, 24000, 0, 600, 600) == 0
+    assert L.pp_input_path_workspace_bytes(0, 280000, grid, 24000, 64, 600, 600) == 0
+    args = [None, 0, 4, 1, _lib.i64_array([0, 0]), 1, grid, 200, 24000, None, 64,
+            None, None, None, None, None, None, None, 1, 0.1, 1e-5, 600, 600,
+            None, None, None, None, None, None, 0, 3, None]
+    assert L.pp_input_path(*args) == 1                           # NULL weights: PP_ERR_INVALID_ARG
+
+
+def test_packed_host_batch_layout_is_aligned_and_disjoint():
+    """One pinned blob per batch: every section 256-byte aligned, sections disjoint, sizes as declared."""
+    from pp_b200.pipeline import InputPath
+    off, total = InputPath._blob_layout(271631, 5, 400)
+    order = ["points", "corners", "centers", "wlh", "yaw", "cls"]
+    assert list(off) == order
+    end = 0
+    for name in order:
+        o, n = off[name]
+        assert o % 256 == 0 and o >= end
+        end = o + n
+    assert total >= end and total % 256 == 0
+    assert off["points"][1] == 271631 * 5 * 4 and off["corners"][1] == 400 * 8 * 8 and off["cls"][1] == 400 * 4
+    off0, total0 = InputPath._blob_layout(0, 5, 0)             # empty batch still has one row per section
+    assert off0["points"][1] == 5 * 4 and total0 > 0
