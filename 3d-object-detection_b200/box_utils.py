@@ -75,13 +75,14 @@ class AnchorSet:
         self.A = int(self.h_centers.shape[0])
         f = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
         self.corners, self.centers, self.wlh, self.yaw = f(corners), f(self.h_centers), f(wlh), f(yaw)
-        nbytes = L.pp_anchor_index_bytes(self.h_centers.ctypes.data, self.A)
+        h_corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(self.A, 8)
+        nbytes = L.pp_anchor_index_bytes(self.h_centers.ctypes.data, self.A, 1)
         if nbytes == 0:
             raise _lib.PPError("pp_anchor_index_bytes: invalid anchors")
         self.index = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            rc = L.pp_anchor_index_build(self.h_centers.ctypes.data, self.A, self.index.data_ptr(),
-                                         self.index.numel(), _runtime.stream_ptr(self.device))
+            rc = L.pp_anchor_index_build(self.h_centers.ctypes.data, h_corners.ctypes.data, self.A,
+                                         self.index.data_ptr(), self.index.numel(), _runtime.stream_ptr(self.device))
         _lib.check(rc, "pp_anchor_index_build")
 
     @classmethod

@@ -33,7 +33,8 @@ struct IndexHeader {  // first 64 bytes of the anchor index
   long long A;
   int max_bucket;
   int magic;
-  long long pad[2];
+  long long geom_off;   // byte offset of the bucket-ordered geometry copy (0: none): [A][10] doubles = centre x,y + 4 corners
+  long long pad;
 };
 static_assert(sizeof(IndexHeader) == 64, "index header must be 64 bytes");
 constexpr int kIndexMagic = 0x50504958;
@@ -157,6 +158,9 @@ __global__ void __launch_bounds__(256) k_iou_pass(
   const int* bucket_start = reinterpret_cast<const int*>(index + sizeof(IndexHeader));
   const int nb = hdr->nbx * hdr->nby;
   const int* ids = bucket_start + nb + 1;
+  // bucket-ordered copy of the anchor geometry (centre x,y + corners): candidate k of a bucket row reads
+  // 80 contiguous bytes next to its neighbours' instead of two dependent gathers from the [A,...] arrays
+  const double* geom = hdr->geom_off != 0 ? reinterpret_cast<const double*>(index + hdr->geom_off) : nullptr;
 
   double g[8], gc[2];
 #pragma unroll
@@ -202,14 +206,16 @@ __global__ void __launch_bounds__(256) k_iou_pass(
   constexpr int kQueue = 2048;
   __shared__ int q_a[PASS == 0 ? kQueue : 1];
   __shared__ int q_slot[PASS == 0 ? kQueue : 1];
+  __shared__ int q_k[PASS == 0 ? kQueue : 1];
   __shared__ int q_n;
   if (PASS == 0) {
     if (threadIdx.x == 0) q_n = 0;
     __syncthreads();
   }
-  auto survives = [&](int a) -> bool {
-    if (prefilter_far(a_centers + (size_t)a * 3, gc)) return false;
-    const double* ar = a_corners + (size_t)a * 8;
+  auto survives = [&](int a, int k) -> bool {
+    const double* ac = geom != nullptr ? geom + (size_t)k * 10 : a_centers + (size_t)a * 3;
+    if (prefilter_far(ac, gc)) return false;
+    const double* ar = geom != nullptr ? geom + (size_t)k * 10 + 2 : a_corners + (size_t)a * 8;
     double ax0 = ar[0], ax1 = ar[0], ay0 = ar[1], ay1 = ar[1];
 #pragma unroll
     for (int q = 1; q < 4; ++q) {
@@ -218,10 +224,11 @@ __global__ void __launch_bounds__(256) k_iou_pass(
     }
     return !(ax1 < gx0 || gx1 < ax0 || ay1 < gy0 || gy1 < ay0);
   };
-  auto clip = [&](int a) -> double {
+  auto clip = [&](int a, int k) -> double {
     double ar[8];
+    const double* src = geom != nullptr ? geom + (size_t)k * 10 + 2 : a_corners + (size_t)a * 8;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) ar[q] = a_corners[(size_t)a * 8 + q];
+    for (int q = 0; q < 8; ++q) ar[q] = src[q];
     double v = quad_iou(ar, g);
     if (v < 0.0) { atomicOr(status, PP_STATUS_NEG_IOU); v = 0.0; }
     return v;
@@ -240,13 +247,14 @@ __global__ void __launch_bounds__(256) k_iou_pass(
       const int a = ids[k];
       const int slot = rowbase + (k - s);
       if (PASS == 0) {
-        if (survives(a)) {
+        if (survives(a, k)) {
           const int pos = atomicAdd(&q_n, 1);
           if (pos < kQueue) {
             q_a[pos] = a;
             q_slot[pos] = slot;
+            q_k[pos] = k;
           } else {                                   // queue full (cannot happen with the reference's anchor grid): inline
-            const double v = clip(a);
+            const double v = clip(a, k);
             if (slot < kCandCap) cache[slot] = v;
             if (v > 0.0) account0(a, v);
           }
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(256) k_iou_pass(
       } else {
         double v;
         if (slot < kCandCap) v = cache[slot];        // computed by pass 0
-        else v = survives(a) ? clip(a) : 0.0;
+        else v = survives(a, k) ? clip(a, k) : 0.0;
         if (!(v > 0.0)) continue;
         const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
         if (bits == best_b[a]) {
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(256) k_iou_pass(
     const int nq = min(q_n, kQueue);
     for (int i = (int)threadIdx.x; i < nq; i += blockDim.x) {
       const int a = q_a[i];
-      const double v = clip(a);
+      const double v = clip(a, q_k[i]);
       if (q_slot[i] < kCandCap) cache[q_slot[i]] = v;
       if (v > 0.0) account0(a, v);
     }
@@ -445,6 +453,7 @@ struct HostIndex {
   std::vector<int> start, ids;
 };
 
+static size_t geom_offset(const HostIndex& hi);
 static bool build_host_index(const double* c, long long A, HostIndex& hi) {
   if (c == nullptr || A < 1 || A > 0x7fffffffll) return false;
   double x0 = 0, x1 = 0, y0 = 0, y1 = 0;
@@ -465,7 +474,7 @@ static bool build_host_index(const double* c, long long A, HostIndex& hi) {
   h.x0 = x0; h.y0 = y0; h.cell = cell;
   h.nbx = (int)floor((x1 - x0) / cell) + 1;
   h.nby = (int)floor((y1 - y0) / cell) + 1;
-  h.A = A; h.magic = kIndexMagic; h.pad[0] = h.pad[1] = 0;
+  h.A = A; h.magic = kIndexMagic; h.geom_off = 0; h.pad = 0;
   const int nb = h.nbx * h.nby;
   hi.start.assign((size_t)nb + 1, 0);
   std::vector<int> bucket((size_t)A);
@@ -493,6 +502,11 @@ static bool build_host_index(const double* c, long long A, HostIndex& hi) {
   return true;
 }
 
+static size_t geom_offset(const HostIndex& hi) {
+  const size_t ints = sizeof(IndexHeader) + (hi.start.size() + hi.ids.size()) * sizeof(int);
+  return (ints + 15) / 16 * 16;
+}
+
 }  // namespace pp
 
 extern "C" {
@@ -513,21 +527,34 @@ int pp_make_ious(const double* d_a_corners, const double* d_g_corners, const dou
   return PP_OK;
 }
 
-size_t pp_anchor_index_bytes(const double* h_a_centers, int64_t A) {
+size_t pp_anchor_index_bytes(const double* h_a_centers, int64_t A, int32_t with_geometry) {
   pp::HostIndex hi;
   if (!pp::build_host_index(h_a_centers, A, hi)) return 0;
-  return sizeof(pp::IndexHeader) + (hi.start.size() + hi.ids.size()) * sizeof(int) + pp::kAlign;
+  return pp::geom_offset(hi) + (with_geometry ? (size_t)A * 10 * sizeof(double) : 0) + pp::kAlign;
 }
 
-int pp_anchor_index_build(const double* h_a_centers, int64_t A, void* d_index, size_t index_bytes,
-                          pp_stream_t stream) {
+int pp_anchor_index_build(const double* h_a_centers, const double* h_a_corners, int64_t A, void* d_index,
+                          size_t index_bytes, pp_stream_t stream) {
   using namespace pp;
   HostIndex hi;
   if (d_index == nullptr || !build_host_index(h_a_centers, A, hi)) return PP_ERR_INVALID_ARG;
-  const size_t need = sizeof(IndexHeader) + (hi.start.size() + hi.ids.size()) * sizeof(int);
+  const size_t goff = geom_offset(hi);
+  const size_t need = goff + (h_a_corners != nullptr ? (size_t)A * 10 * sizeof(double) : 0);
   if (index_bytes < need) return PP_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* d = (unsigned char*)d_index;
+  std::vector<double> geom;
+  if (h_a_corners != nullptr) {
+    hi.hdr.geom_off = (long long)goff;
+    geom.resize((size_t)A * 10);
+    for (long long k = 0; k < A; ++k) {
+      const long long a = hi.ids[(size_t)k];
+      geom[(size_t)k * 10 + 0] = h_a_centers[a * 3];
+      geom[(size_t)k * 10 + 1] = h_a_centers[a * 3 + 1];
+      for (int q = 0; q < 8; ++q) geom[(size_t)k * 10 + 2 + q] = h_a_corners[a * 8 + q];
+    }
+    PP_CUDA(cudaMemcpyAsync(d + goff, geom.data(), geom.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
   PP_CUDA(cudaMemcpyAsync(d, &hi.hdr, sizeof(IndexHeader), cudaMemcpyHostToDevice, st));
   PP_CUDA(cudaMemcpyAsync(d + sizeof(IndexHeader), hi.start.data(), hi.start.size() * sizeof(int),
                           cudaMemcpyHostToDevice, st));

@@ -213,10 +213,12 @@ int pp_make_ious(const double* d_a_corners, const double* d_g_corners, const dou
 
 /* Anchors are batch-invariant (built once offline in the reference, train_prep.py:115-120).
  * The index buckets anchor centres on a uniform grid so that each GT visits only the anchors
- * that can pass the centre prefilter.  Built once per anchor set from HOST centres. */
-size_t pp_anchor_index_bytes(const double* h_a_centers, int64_t A);
-int pp_anchor_index_build(const double* h_a_centers, int64_t A, void* d_index, size_t index_bytes,
-                          pp_stream_t stream);
+ * that can pass the centre prefilter.  Built once per anchor set from HOST centres; with
+ * h_a_corners ([A,4,2], non-NULL / with_geometry != 0) the index also keeps a bucket-ordered copy of
+ * the centres and corners, which turns the kernels' per-candidate gathers into contiguous reads. */
+size_t pp_anchor_index_bytes(const double* h_a_centers, int64_t A, int32_t with_geometry);
+int pp_anchor_index_build(const double* h_a_centers, const double* h_a_corners, int64_t A, void* d_index,
+                          size_t index_bytes, pp_stream_t stream);
 
 size_t pp_assign_targets_workspace_bytes(int32_t n_sweeps, int64_t A, int64_t total_gt,
                                          const void* h_index_header /* first 64 bytes of the index, host copy; may be NULL for a safe upper bound */);
