@@ -90,7 +90,7 @@ class InputPath:
         self._last_encode = None
         self._stage = [None, None]
         self._slot_free = [None, None]
-        self._result_pin = [None, None]
+        self._result_pin = [None] * 8      # ring of pinned result buffers: a handle's counters stay valid for 8 more steps
         self._step_no = 0
 
     # -- parameters ---------------------------------------------------------------------------
@@ -359,7 +359,8 @@ class InputPath:
         into one of two staging buffers, the kernels to one of two lanes (so the copy and the
         pillarize stage of step k+1 overlap the encode stage of step k), the step's counters come
         back through a pinned buffer, and nothing blocks the host.  Consecutive calls must not share
-        ``out`` buffers.  Returns a ``StepHandle``; ``handle.counters()`` waits for this step only."""
+        ``out`` buffers.  Returns a ``StepHandle``; ``handle.counters()`` waits for this step only and must
+        be called before eight further steps have been issued (the pinned result buffers form a ring)."""
         dev = self.device
         slot = self._step_no & 1
         self._step_no += 1
@@ -377,9 +378,10 @@ class InputPath:
             self._slot_free[slot] = torch.cuda.Event()
             self._slot_free[slot].record(main)
             B = len(batch["offsets"]) - 1
-            pin = self._result_pin[slot]
+            ring = (self._step_no - 1) % len(self._result_pin)
+            pin = self._result_pin[ring]
             if pin is None or pin.numel() < 5 * B:
-                pin = self._result_pin[slot] = torch.empty(5 * B, dtype=torch.int32).pin_memory()
+                pin = self._result_pin[ring] = torch.empty(5 * B, dtype=torch.int32).pin_memory()
             pin[:B].copy_(res[3], non_blocking=True)
             pin[B:5 * B].view(B, 4).copy_(res[4], non_blocking=True)
             done = torch.cuda.Event()

@@ -256,7 +256,8 @@ def algorithmic_bytes(B, P, N, C, H, W, A, K, total_points, has_mean):
         "k_canvas": B * C * H * W * 4 + B * H * W * 4,
         # fused path: data_mean read once + the ext rows of the live pillars (2 padding fields per sweep)
         "k_pfn_pad_tc": (x_bytes if has_mean else 0) + B * 16500 * 2 * C * 4,
-        "k_encode": B * A * 9 * 4,          # one launch each for cls [A,K=9] and reg [A,9]
+        "k_encode_zero": 2 * B * A * 9 * 4,  # zero stream of cls [B,A,9] and reg [B,A,9] (flagged rows patched after)
+        "k_encode": B * A * 9 * 4,
     }
 
 
