@@ -239,3 +239,63 @@ def test_fused_input_path_more_than_eight_sweeps():
     assert torch.allclose(pa.net.bn1.running_var, pb.net.bn1.running_var, rtol=1e-5, atol=1e-6)
     d = (canvas.double() - want.double()).abs().max().item()
     assert d < 1e-3 * max(1.0, want.abs().max().item() * 1e-2), d
+
+
+def test_fused_input_path_edge_cases():
+    """Empty sweep, single-point sweep, everything out of range, one pillar holding more than N points:
+    fused path == dense sequence (indices, counts, canvas within the PFN tolerance)."""
+    import pp_b200
+    from pp_b200 import pipeline, synth
+    cfg = pp_b200.PPConfig(max_pillars=2000, max_points_per_pillar=24)
+    P, N = 2000, 24
+    mean = synth.make_data_mean(P, N, dense=True)
+    prm = synth.make_pfn_params(8, flip_gamma=True)
+    rng = np.random.default_rng(5)
+    full = synth.make_sweep(90)[:20000]
+    pile = np.zeros((100, 5), np.float32); pile[:, 0] = 3.03 + rng.uniform(0, .1, 100); pile[:, 1] = -7.01 - rng.uniform(0, .1, 100)
+    pile[:, 2] = rng.uniform(-1, 1, 100); pile[:, 3] = 100.0                  # 100 points in one or two cells (> N)
+    far = np.full((50, 5), 500.0, np.float32)                                 # all out of range
+    one = np.array([[1.0, 2.0, 0.5, 100.0, 0.0]], np.float32)
+    empty = np.zeros((0, 5), np.float32)
+    sweeps = [full, empty, pile, far, one]
+    offs = np.cumsum([0] + [len(s) for s in sweeps]).tolist()
+    pts = torch.from_numpy(np.concatenate(sweeps)).cuda()
+    for training in (True, False):
+        mk = lambda: pipeline.InputPath(cfg, data_mean=mean, pfn_params=prm, training=training)
+        pa, pb = mk(), mk()
+        x, inds, npil = pa.pillarize(pts, offs)
+        want = pa.encode(x, inds)
+        canvas, inds2, npil2 = pb.pillarize_encode(pts, offs)
+        assert torch.equal(inds, inds2) and torch.equal(npil, npil2)
+        assert npil.tolist()[1] == 0 and npil.tolist()[3] == 0 and npil.tolist()[4] == 1
+        assert not canvas[1].any() and not canvas[3].any() and not want[1].any()
+        w = torch.from_numpy(prm["conv_w"]).cuda().abs()
+        absdot = torch.einsum('cd,bdpn->bcpn', w, x.abs()).amax() + float(np.abs(prm["conv_b"]).max())
+        _canvas_close(canvas, want, float(absdot) * float(np.abs(prm["bn_w"]).max()) * 4.0)
+        assert torch.equal(canvas != 0, want != 0)
+        if training:
+            assert torch.allclose(pa.net.bn1.running_var, pb.net.bn1.running_var, rtol=1e-5, atol=1e-6)
+
+
+def test_fused_dense_stress_cloud():
+    """BASELINE config 5 shape through the fused path: 10-sweep cloud (~590k points), P = 30000 (the cap
+    binds), 200 GT boxes; equals the dense sequence, targets included."""
+    import pp_b200
+    from pp_b200 import pipeline, synth
+    cfg = pp_b200.PPConfig(max_pillars=30000)
+    P, N = 30000, 200
+    mean = synth.make_data_mean(P, N, dense=True)
+    prm = synth.make_pfn_params(9)
+    cloud = synth.make_dense_cloud(0) if hasattr(synth, "make_dense_cloud") else np.concatenate(
+        [synth.make_sweep(100 + k) + np.array([0.3 * k, 0, 0, 0, 0], np.float32) for k in range(10)])
+    gts = [synth.make_gt(3, 200)]
+    pa = pipeline.InputPath(cfg, data_mean=mean, pfn_params=prm, training=True, fused=False)
+    pb = pipeline.InputPath(cfg, data_mean=mean, pfn_params=prm, training=True, fused=True, anchors=pa.ensure_anchors())
+    ba = pa.pack_host_batch([cloud], gts)
+    ca, clsa, rega, na, ka = pa.step_host(ba)
+    cb, clsb, regb, nb, kb = pb.step_host(pb.pack_host_batch([cloud], gts))
+    assert int(na[0]) == 30000 and torch.equal(na, nb)
+    assert torch.equal(clsa, clsb) and torch.equal(rega, regb) and torch.equal(ka, kb)
+    d = (ca.double() - cb.double()).abs().max().item()
+    assert d <= 1e-5 * ca.abs().max().item() + 2e-4, d
+    assert torch.equal(ca != 0, cb != 0)
