@@ -105,6 +105,21 @@ int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_poin
                   int32_t* d_status, void* d_workspace, size_t workspace_bytes, int32_t stages,
                   pp_stream_t stream);
 
+/* Loss front-end: forward of the reference's PPLoss (model/loss.py:24-63) and the gradient
+ * of its total loss b_cls*cls + b_reg*reg + b_ort*ort with respect to both network outputs.
+ *   d_cls_out [B, Ad*K, H, W] float NCHW logits; d_reg_out [B, Ad*R, H, W] float, MODIFIED IN PLACE like
+ *   the reference does: tanh on network channel 6 (model/loss.py:50 indexes the permuted view's last axis);
+ *   d_cls_t [B, A, K], d_reg_t [B, A, 9] float targets (pp_assign_targets layout), A = H*W*Ad.
+ * Outputs: d_scores [B, A*K] = sigmoid(logits) in target order (may be NULL), d_grad_cls / d_grad_reg in the
+ * layout of the inputs (may be NULL), d_losses float[4] = {cls_loss, reg_loss, ort_loss, total}.
+ * focal weight (t == 1 ? alpha_pos : 1) * (1 - pt)^gamma is detached as in the reference (alpha_pos = 25 there).
+ * No positive anchor -> reg/ort/total are NaN (torch's mean over an empty tensor).  Ad*K <= 96, R >= 7. */
+size_t pp_loss_workspace_bytes(int32_t B, int32_t H, int32_t W);
+int pp_loss(const float* d_cls_out, float* d_reg_out, const float* d_cls_t, const float* d_reg_t, int32_t B,
+            int32_t H, int32_t W, int32_t anchors_per_cell, int32_t num_classes, int32_t reg_dims, float gamma,
+            float alpha_pos, float b_cls, float b_reg, float b_ort, float* d_scores, float* d_grad_cls,
+            float* d_grad_reg, float* d_losses, void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
+
 /* Instrumentation.  pp_launch_count: kernels launched by this library since load (all threads).
  * pp_profile_enable(1): bracket every kernel launch with CUDA events on its stream;
  * pp_profile_report: synchronise the device, write one "name launches total_ms" line per kernel
