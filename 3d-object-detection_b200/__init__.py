@@ -4,7 +4,8 @@ A from-scratch implementation of the per-sweep hot path of mr3543/3d-Object-Dete
 reference's own interfaces:
 
     pillars.create_pillars / pillars.make_ious   (data/pillars.cpp pybind11 module)
-    model.PPFeatureNet / model.PPScatter         (model/model.py)
+    model.PPFeatureNet / model.PPScatter         (model/model.py; forward and parameter gradients)
+    loss.PPLoss                                  (model/loss.py; losses + gradients in one fused pass)
     box_utils.create_target                      (utils/box_utils.py)
     pipeline.InputPath                           (device-native batch entry points)
 
@@ -17,12 +18,12 @@ The directory is named ``3d-object-detection_b200`` (not an identifier); import 
 from . import _lib, build, config, synth  # noqa: F401
 from .config import PPConfig, cfg  # noqa: F401
 
-__all__ = ["pillars", "model", "box_utils", "pipeline", "synth", "config", "PPConfig", "cfg"]
+__all__ = ["pillars", "model", "loss", "box_utils", "pipeline", "synth", "config", "PPConfig", "cfg"]
 
 
 def __getattr__(name):
     # torch-dependent sub-modules are imported lazily so that build / symbol checks stay light
-    if name in ("pillars", "model", "box_utils", "pipeline", "_runtime"):
+    if name in ("pillars", "model", "loss", "box_utils", "pipeline", "_runtime"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -1,0 +1,297 @@
+// pfn_bwd.cu -- backward of PPFeatureNet (and of PPScatter in front of it): the gradients torch autograd
+// produces through model/model.py:36-39 (conv1 1x1 -> relu -> bn1 -> max over N) for conv1.weight,
+// conv1.bias, bn1.weight, bn1.bias -- SURVEY 8(f) N1, the step train.py:147 needs.
+//
+// With z = W x + b, r = relu(z), batch statistics mu, var over M = B*P*N elements, s = sqrt(var + eps),
+// G[b,c,p] the incoming gradient routed to the arg-max element e* of every (b,c,p):
+//   d beta  = sum G                 d gamma = (sum G r* - mu sum G) / s
+//   d W[c,d] = gamma/s * ( T[c,d] - (d beta / M) S1[c,d] - (d gamma / (M s)) (S2[c,d] - mu S1[c,d]) )
+//   T = sum G 1[z*>0] x_d(e*),   S1 = sum_e 1[z>0] x_d,   S2 = sum_e relu(z) x_d          (x_9 == 1: the bias)
+// The two dense moment matrices come from training-mode BatchNorm (mean and variance depend on W); in eval
+// mode only T is needed.  mu = S2[c,9]/M and var = sum r^2/M - mu^2 fall out of the same pass, so the
+// backward needs nothing saved by the forward except its inputs.
+//
+// k_pfn_bwd: one warp per (pillar, channel half), lane = channel.  The pillar's x rows are staged in shared
+// memory with cp.async (double buffered over groups of 4 pillars), every lane walks the N slots reading x
+// as warp-uniform float4 broadcasts: 9 FMA for z, 21 for the moments, 4 for the running arg-max per slot and
+// channel.  Per-pillar fp32 sums are folded into fp64 registers; one fp64 partial row per warp is combined in
+// a fixed order by k_pfn_bwd_finalize (deterministic).
+#include "common.cuh"
+
+namespace pp {
+
+constexpr int kBwdPil = 4;                 // pillars per block iteration (8 warps = 4 pillars x 2 channel halves)
+constexpr int kBwdAcc = 33;                // S1[10], S2[10], sum r^2, T[10], sum G, sum G r*
+constexpr int kBwdD = 9, kBwdC = 64;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+struct BwdGrad {             // where G[b,c,p] lives: the [B,C,P] gradient, or the canvas gradient through inds
+  const float* g;
+  const long long* inds;     // null: dense [B,C,P]
+  int H, W;
+};
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(256, 1) k_pfn_bwd(const float* __restrict__ x, int B, int P, int N, int Np,
+                                                   const float* __restrict__ w, const float* __restrict__ bias,
+                                                   const float* __restrict__ bn_w, BwdGrad gr, int vec16,
+                                                   double* __restrict__ partials) {
+  extern __shared__ __align__(16) float s_tile[];            // [2][kBwdPil][9][Np]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pl = warp >> 1, c = (warp & 1) * 32 + lane;
+  const long long BP = (long long)B * P;
+  const long long ngroups = (BP + kBwdPil - 1) / kBwdPil;
+  const size_t stage_floats = (size_t)kBwdPil * kBwdD * Np;
+
+  float wr[kBwdD];
+#pragma unroll
+  for (int d = 0; d < kBwdD; ++d) wr[d] = __ldg(w + c * kBwdD + d);
+  const float bc = __ldg(bias + c);
+  const float gam = __ldg(bn_w + c);
+  const float sgn = gam > 0.f ? 1.f : (gam < 0.f ? -1.f : 0.f);
+
+  double acc[kBwdAcc];
+#pragma unroll
+  for (int k = 0; k < kBwdAcc; ++k) acc[k] = 0.0;
+
+  auto issue = [&](long long grp, int stage) {
+    float* dst0 = s_tile + (size_t)stage * stage_floats;
+    if (vec16) {
+      const int chunks = N >> 2;
+      for (int i = tid; i < kBwdPil * kBwdD * chunks; i += 256) {
+        const int row = i / chunks, ck = i - row * chunks;
+        const int q = row / kBwdD, d = row - q * kBwdD;
+        const long long task = grp * kBwdPil + q;
+        if (task < BP) {
+          const long long b = task / P, p = task - b * P;
+          cp_async16(dst0 + ((size_t)q * kBwdD + d) * Np + ck * 4, x + ((size_t)(b * kBwdD + d) * P + p) * N + ck * 4);
+        }
+      }
+    } else {
+      for (int i = tid; i < kBwdPil * kBwdD * N; i += 256) {
+        const int row = i / N, n = i - row * N;
+        const int q = row / kBwdD, d = row - q * kBwdD;
+        const long long task = grp * kBwdPil + q;
+        if (task < BP) {
+          const long long b = task / P, p = task - b * P;
+          cp_async4(dst0 + ((size_t)q * kBwdD + d) * Np + n, x + ((size_t)(b * kBwdD + d) * P + p) * N + n);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  int stage = 0;
+  long long grp = blockIdx.x;
+  if (grp < ngroups) issue(grp, 0);
+  for (; grp < ngroups; grp += gridDim.x) {
+    const long long nxt = grp + gridDim.x;
+    if (nxt < ngroups) {
+      issue(nxt, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const long long task = grp * kBwdPil + pl;
+    if (task < BP) {
+      const float* t = s_tile + (size_t)stage * stage_floats + (size_t)pl * kBwdD * Np;
+      float s1[10], s2[10], q2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 10; ++d) { s1[d] = 0.f; s2[d] = 0.f; }
+      float best = 0.f;
+      int nbest = 0;
+      for (int n0 = 0; n0 < N; n0 += 4) {
+        float4 xv[kBwdD];
+#pragma unroll
+        for (int d = 0; d < kBwdD; ++d) xv[d] = *reinterpret_cast<const float4*>(t + d * Np + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (n0 + j < N) {
+            float xs[kBwdD];
+#pragma unroll
+            for (int d = 0; d < kBwdD; ++d) xs[d] = j == 0 ? xv[d].x : (j == 1 ? xv[d].y : (j == 2 ? xv[d].z : xv[d].w));
+            float z = bc;
+#pragma unroll
+            for (int d = 0; d < kBwdD; ++d) z = fmaf(wr[d], xs[d], z);
+            const float r = fmaxf(z, 0.f);
+            if (TRAIN) {
+              const float on = z > 0.f ? 1.f : 0.f;
+#pragma unroll
+              for (int d = 0; d < kBwdD; ++d) {
+                s1[d] = fmaf(on, xs[d], s1[d]);
+                s2[d] = fmaf(r, xs[d], s2[d]);
+              }
+              s1[9] += on;
+              s2[9] += r;
+              q2 = fmaf(r, r, q2);
+            }
+            const float key = sgn * r;
+            if (n0 + j == 0) best = key;
+            if (key > best) { best = key; nbest = n0 + j; }        // strict: first index wins a tie
+          }
+        }
+      }
+      // the arg-max element takes the incoming gradient
+      const long long b = task / P, p = task - b * P;
+      float G;
+      if (gr.inds != nullptr) {
+        const long long* row = gr.inds + task * 3;
+        const long long fl = row[0], xi = row[1], yi = row[2];
+        const bool ok = fl != 0 && xi >= 0 && xi < gr.W && yi >= 0 && yi < gr.H;
+        G = ok ? __ldg(gr.g + ((size_t)(b * kBwdC + c) * gr.H + (size_t)yi) * gr.W + (size_t)xi) : 0.f;
+      } else {
+        G = __ldg(gr.g + (size_t)(b * kBwdC + c) * P + p);
+      }
+      const float rstar = sgn * best;                              // sgn == 0: slot 0, r recomputed below
+      float zs = bc;
+#pragma unroll
+      for (int d = 0; d < kBwdD; ++d) zs = fmaf(wr[d], t[d * Np + nbest], zs);
+      const float rs = sgn != 0.f ? rstar : fmaxf(zs, 0.f);
+      const float Gon = zs > 0.f ? G : 0.f;
+#pragma unroll
+      for (int d = 0; d < kBwdD; ++d) acc[21 + d] += (double)(Gon * t[d * Np + nbest]);
+      acc[30] += (double)Gon;
+      acc[31] += (double)G;
+      acc[32] += (double)G * (double)rs;
+      if (TRAIN) {
+#pragma unroll
+        for (int d = 0; d < 10; ++d) { acc[d] += (double)s1[d]; acc[10 + d] += (double)s2[d]; }
+        acc[20] += (double)q2;
+      }
+    }
+    __syncthreads();
+    stage ^= 1;
+  }
+  double* dst = partials + ((size_t)blockIdx.x * 8 + warp) * kBwdAcc * 32;
+#pragma unroll
+  for (int k = 0; k < kBwdAcc; ++k) dst[k * 32 + lane] = acc[k];
+}
+
+// sums[k][c] over blocks and the four warps of each channel half, then the closed forms above.
+__global__ void __launch_bounds__(1024) k_pfn_bwd_finalize(const double* __restrict__ partials, int nblocks, double M,
+                                                           const float* __restrict__ bn_w,
+                                                           const float* __restrict__ running_mean,
+                                                           const float* __restrict__ running_var, int training, float eps,
+                                                           float* __restrict__ g_w, float* __restrict__ g_b,
+                                                           float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+  __shared__ double sums[kBwdAcc][kBwdC];
+  const int c = threadIdx.x & 63, kq = threadIdx.x >> 6;
+  const int half = c >> 5, lane = c & 31;
+  for (int k = kq; k < kBwdAcc; k += 16) {
+    double s = 0.0;
+    for (int blk = 0; blk < nblocks; ++blk)
+      for (int q = 0; q < 4; ++q) s += partials[(((size_t)blk * 8 + q * 2 + half) * kBwdAcc + k) * 32 + lane];
+    sums[k][c] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kBwdC) {
+    const double gam = (double)bn_w[c];
+    double mu, var;
+    if (training) {
+      mu = sums[19][c] / M;
+      var = fmax(sums[20][c] / M - mu * mu, 0.0);
+    } else {
+      mu = (double)running_mean[c];
+      var = (double)running_var[c];
+    }
+    const double s = sqrt(var + (double)eps);
+    const double d_beta = sums[31][c];
+    const double d_gamma = (sums[32][c] - mu * d_beta) / s;
+    for (int d = 0; d < 10; ++d) {
+      double v = sums[21 + d][c];
+      if (training) v -= (d_beta / M) * sums[d][c] + (d_gamma / (M * s)) * (sums[10 + d][c] - mu * sums[d][c]);
+      v *= gam / s;
+      if (d < kBwdD) { if (g_w) g_w[c * kBwdD + d] = (float)v; }
+      else if (g_b) g_b[c] = (float)v;
+    }
+    if (g_gamma) g_gamma[c] = (float)d_gamma;
+    if (g_beta) g_beta[c] = (float)d_beta;
+  }
+}
+
+// PPScatter backward: g_feat[b,c,p] = g_canvas[b,c,y,x] for rows with inds[b,p,0] != 0, else 0.
+__global__ void __launch_bounds__(256) k_scatter_bwd(const float* __restrict__ g_canvas, const long long* __restrict__ inds,
+                                                     int B, int C, int P, int H, int W, float* __restrict__ g_feat) {
+  const size_t n = (size_t)B * C * P;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const size_t bc = i / P, p = i - bc * P, b = bc / C;
+    const long long* row = inds + (b * P + p) * 3;
+    const long long fl = row[0], xi = row[1], yi = row[2];
+    const bool ok = fl != 0 && xi >= 0 && xi < W && yi >= 0 && yi < H;
+    g_feat[i] = ok ? __ldg(g_canvas + (bc * H + (size_t)yi) * W + (size_t)xi) : 0.f;
+  }
+}
+
+static int bwd_blocks() { return sm_count(); }
+
+}  // namespace pp
+
+extern "C" {
+
+size_t pp_pfn_backward_workspace_bytes(int32_t B, int32_t P, int32_t C) {
+  if (B < 1 || P < 1 || C != pp::kBwdC) return 0;
+  return pp::align_up((size_t)pp::bwd_blocks() * 8 * pp::kBwdAcc * 32 * sizeof(double)) + pp::kAlign;
+}
+
+int pp_pfn_backward(const float* d_x, int32_t B, int32_t D, int32_t P, int32_t N, int32_t C, const float* d_conv_w,
+                    const float* d_conv_b, const float* d_bn_w, const float* d_running_mean,
+                    const float* d_running_var, int32_t training, float eps, const float* d_grad_out,
+                    const int64_t* d_inds, int32_t canvas_h, int32_t canvas_w, float* d_grad_conv_w,
+                    float* d_grad_conv_b, float* d_grad_bn_w, float* d_grad_bn_b, void* d_workspace,
+                    size_t workspace_bytes, pp_stream_t stream) {
+  using namespace pp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_x || !d_conv_w || !d_conv_b || !d_bn_w || !d_grad_out || B < 1 || P < 1 || N < 1) return PP_ERR_INVALID_ARG;
+  if (!training && (!d_running_mean || !d_running_var)) return PP_ERR_INVALID_ARG;
+  if (d_inds != nullptr && (canvas_h < 1 || canvas_w < 1)) return PP_ERR_INVALID_ARG;
+  if (D != kBwdD || C != kBwdC) return PP_ERR_UNSUPPORTED;
+  const int Np = (N + 3) & ~3;
+  const size_t smem = (size_t)2 * kBwdPil * kBwdD * Np * sizeof(float);
+  if (smem > 200 * 1024) return PP_ERR_UNSUPPORTED;
+  Arena arena(d_workspace, workspace_bytes);
+  const int nb = bwd_blocks();
+  double* partials = arena.take<double>((size_t)nb * 8 * kBwdAcc * 32);
+  if (!arena.ok) return PP_ERR_WORKSPACE;
+  const int vec16 = (N % 4 == 0 && ((uintptr_t)d_x % 16) == 0) ? 1 : 0;
+  BwdGrad gr{d_grad_out, (const long long*)d_inds, canvas_h, canvas_w};
+  if (training) {
+    PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PP_KERNEL("k_pfn_bwd", st,
+              (k_pfn_bwd<true><<<nb, 256, smem, st>>>(d_x, B, P, N, Np, d_conv_w, d_conv_b, d_bn_w, gr, vec16, partials)));
+  } else {
+    PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PP_KERNEL("k_pfn_bwd_eval", st,
+              (k_pfn_bwd<false><<<nb, 256, smem, st>>>(d_x, B, P, N, Np, d_conv_w, d_conv_b, d_bn_w, gr, vec16, partials)));
+  }
+  PP_KERNEL("k_pfn_bwd_finalize", st,
+            (k_pfn_bwd_finalize<<<1, 1024, 0, st>>>(partials, nb, (double)B * P * N, d_bn_w, d_running_mean, d_running_var,
+                                                    training ? 1 : 0, eps, d_grad_conv_w, d_grad_conv_b, d_grad_bn_w,
+                                                    d_grad_bn_b)));
+  return PP_OK;
+}
+
+int pp_scatter_backward(const float* d_grad_canvas, const int64_t* d_inds, int32_t B, int32_t C, int32_t P,
+                        int32_t canvas_h, int32_t canvas_w, float* d_grad_feat, pp_stream_t stream) {
+  using namespace pp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_grad_canvas || !d_inds || !d_grad_feat || B < 1 || C < 1 || P < 1 || canvas_h < 1 || canvas_w < 1)
+    return PP_ERR_INVALID_ARG;
+  const size_t n = (size_t)B * C * P;
+  const int blocks = (int)((n + 255) / 256 < (size_t)sm_count() * 16 ? (n + 255) / 256 : (size_t)sm_count() * 16);
+  PP_KERNEL("k_scatter_bwd", st,
+            (k_scatter_bwd<<<blocks, 256, 0, st>>>(d_grad_canvas, (const long long*)d_inds, B, C, P, canvas_h, canvas_w,
+                                                   d_grad_feat)));
+  return PP_OK;
+}
+
+}  // extern "C"

@@ -6,7 +6,9 @@ checkpoints written by the reference's train.py load unchanged and ``PPModel`` c
 is.  ``forward`` runs the sm_100a kernels of libpp_b200.so; there is no eager fallback: CPU
 tensors raise.  ``PPFeatureScatter`` is the fused module (x, inds) -> canvas.
 
-Forward only in this round: the custom autograd function raises in backward.
+Training: the three modules are differentiable with respect to conv1.weight/bias and bn1.weight/bias
+(pp_pfn_backward, csrc/pfn_bwd.cu -- SURVEY.md 8(f) N1), which is what train.py:147 needs; the gradient with
+respect to the input tensor x is not built (x is data in train.py) and asking for it raises.
 """
 import torch
 import torch.nn as nn
@@ -33,17 +35,94 @@ def _prep(x, conv, bn):
     return x.contiguous()
 
 
-class _PFNForward(torch.autograd.Function):
+def _pfn_backward(x, conv_w, conv_b, bn_w, running_mean, running_var, training, eps, grad, inds, H, W):
+    """pp_pfn_backward: (grad conv1.weight [C,D,1,1], grad conv1.bias, grad bn1.weight, grad bn1.bias).
+    ``grad`` is dL/d(features) [B,C,P] (inds None) or the canvas gradient [B,C,H,W] with inds [B,P,3]."""
+    L = _lib.load()
+    B, D, P, N = x.shape
+    C = conv_w.shape[0]
+    dev = x.device
+    grad = grad.contiguous()
+    if grad.dtype != torch.float32:
+        raise _lib.PPError("PPFeatureNet backward: the incoming gradient must be float32")
+    g_w = torch.empty((C, D), dtype=torch.float32, device=dev)
+    g_b = torch.empty(C, dtype=torch.float32, device=dev)
+    g_gamma = torch.empty(C, dtype=torch.float32, device=dev)
+    g_beta = torch.empty(C, dtype=torch.float32, device=dev)
+    nbytes = L.pp_pfn_backward_workspace_bytes(B, P, C)
+    if nbytes == 0:
+        raise _lib.PPError("PPFeatureNet backward supports in_channels 9, out_channels 64")
+    ws = _runtime.workspace(nbytes, dev, "pfn_bwd")
+    w2 = conv_w.reshape(C, D).contiguous()
+    with torch.cuda.device(dev):
+        rc = L.pp_pfn_backward(
+            x.data_ptr(), B, D, P, N, C, w2.data_ptr(), conv_b.data_ptr(), bn_w.data_ptr(),
+            running_mean.data_ptr() if running_mean is not None else None,
+            running_var.data_ptr() if running_var is not None else None, 1 if training else 0, eps,
+            grad.data_ptr(), inds.data_ptr() if inds is not None else None, H, W, g_w.data_ptr(), g_b.data_ptr(),
+            g_gamma.data_ptr(), g_beta.data_ptr(), ws.data_ptr(), ws.numel(), _runtime.stream_ptr(dev))
+    _lib.check(rc, "pp_pfn_backward")
+    return g_w.view(C, D, 1, 1), g_b, g_gamma, g_beta
+
+
+def _no_input_grad(x):
+    if x.requires_grad:
+        raise _lib.PPError("the gradient with respect to the pillar tensor x is not built (it is input data in the "
+                           "reference's train.py); detach x")
+
+
+class _PFNFunction(torch.autograd.Function):
+    """forward: module._run(x) (pp_pfn_forward / pp_pfn_scatter); backward: pp_pfn_backward.  The eval-mode
+    running statistics are copied at forward time because the backward normalises with them."""
+
     @staticmethod
-    def forward(ctx, x, conv_w, conv_b, bn_w, bn_b, module):
-        out = module._run(x)
+    def forward(ctx, x, conv_w, conv_b, bn_w, bn_b, module, inds):
+        _no_input_grad(x)
+        ctx.training = bool(module.training)
+        ctx.eps = float(module.bn1.eps)
+        ctx.canvas = inds is not None
+        if ctx.training:
+            rm = rv = None
+        else:
+            rm, rv = module.bn1.running_mean.clone(), module.bn1.running_var.clone()
+        out = module._run(x, inds) if ctx.canvas else module._run(x)
+        ctx.hw = (out.shape[2], out.shape[3]) if ctx.canvas else (0, 0)
+        ctx.stats = (rm, rv)
+        ctx.save_for_backward(x, conv_w, conv_b, bn_w, inds)
         return out
 
     @staticmethod
-    def backward(ctx, *grads):  # pragma: no cover
-        raise NotImplementedError(
-            "PPFeatureNet backward is not built yet (SURVEY.md 8(f) row N1); run under "
-            "torch.no_grad() or detach the input")
+    def backward(ctx, grad):
+        x, conv_w, conv_b, bn_w, inds = ctx.saved_tensors
+        rm, rv = ctx.stats
+        g_w, g_b, g_gamma, g_beta = _pfn_backward(x.contiguous(), conv_w, conv_b, bn_w, rm, rv, ctx.training, ctx.eps,
+                                                  grad, inds if ctx.canvas else None, ctx.hw[0], ctx.hw[1])
+        return None, g_w, g_b, g_gamma, g_beta, None, None
+
+
+class _ScatterFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, inds, module):
+        ctx.save_for_backward(inds)
+        ctx.P = x.shape[2]
+        return module._run(x, inds)
+
+    @staticmethod
+    def backward(ctx, grad):
+        L = _lib.load()
+        (inds,) = ctx.saved_tensors
+        grad = grad.contiguous()
+        B, C, H, W = grad.shape
+        out = torch.empty((B, C, ctx.P), dtype=torch.float32, device=grad.device)
+        with torch.cuda.device(grad.device):
+            rc = L.pp_scatter_backward(grad.data_ptr(), inds.data_ptr(), B, C, ctx.P, H, W, out.data_ptr(),
+                                       _runtime.stream_ptr(grad.device))
+        _lib.check(rc, "pp_scatter_backward")
+        return out, None, None
+
+
+def _wants_grad(x, module):
+    return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters()))
 
 
 class PPFeatureNet(nn.Module):
@@ -77,9 +156,8 @@ class PPFeatureNet(nn.Module):
         return out
 
     def forward(self, x):
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            return _PFNForward.apply(x, self.conv1.weight, self.conv1.bias, self.bn1.weight,
-                                     self.bn1.bias, self)
+        if _wants_grad(x, self):
+            return _PFNFunction.apply(x, self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, self, None)
         return self._run(x)
 
 
@@ -93,6 +171,11 @@ class PPScatter(nn.Module):
         self.canvas_width = int(_cfg.canvas_width if canvas_width is None else canvas_width)
 
     def forward(self, x, inds):
+        if torch.is_grad_enabled() and isinstance(x, torch.Tensor) and x.requires_grad:
+            return _ScatterFunction.apply(x, inds.contiguous(), self)
+        return self._run(x, inds)
+
+    def _run(self, x, inds):
         L = _lib.load()
         _runtime.require_cuda(x, "x")
         _runtime.require_cuda(inds, "inds")
@@ -124,8 +207,17 @@ class PPFeatureScatter(nn.Module):
         self.canvas_height = int(_cfg.canvas_height if canvas_height is None else canvas_height)
         self.canvas_width = int(_cfg.canvas_width if canvas_width is None else canvas_width)
 
-    @torch.no_grad()
     def forward(self, x, inds, return_features=False, out=None):
+        if _wants_grad(x, self):
+            if return_features or out is not None:
+                raise _lib.PPError("PPFeatureScatter: return_features / out are inference-only arguments")
+            _runtime.require_cuda(inds, "inds")
+            return _PFNFunction.apply(x, self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, self,
+                                      inds.contiguous())
+        return self._run(x, inds, return_features, out)
+
+    @torch.no_grad()
+    def _run(self, x, inds, return_features=False, out=None):
         L = _lib.load()
         x = _prep(x, self.conv1, self.bn1)
         _runtime.require_cuda(inds, "inds")

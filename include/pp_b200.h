@@ -105,6 +105,29 @@ int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_poin
                   int32_t* d_status, void* d_workspace, size_t workspace_bytes, int32_t stages,
                   pp_stream_t stream);
 
+/* Backward of PPFeatureNet: the gradients torch autograd computes through
+ * model/model.py:36-39 (conv1 -> relu -> bn1 -> max over N) for the four parameter tensors, from the same
+ * inputs the forward took; nothing saved by the forward is needed (batch statistics are recomputed).
+ *   d_grad_out: dL/d(output) [B, C, P] when d_inds is NULL; otherwise the CANVAS gradient [B, C, H, W] and
+ *   d_inds [B, P, 3] int64 -- the PPScatter backward (model/model.py:61) is folded in: rows with
+ *   inds[b,p,0] != 0 read the gradient at (inds[b,p,2], inds[b,p,1]), the others get zero.
+ *   training != 0: BatchNorm batch statistics (the mean/variance terms of the BN backward are included);
+ *   training == 0: d_running_mean / d_running_var normalise, as in the forward.
+ * Outputs (any may be NULL): d_grad_conv_w [C, D], d_grad_conv_b [C], d_grad_bn_w [C], d_grad_bn_b [C].
+ * The gradient with respect to x is not produced (x is input data in train.py).  D == 9, C == 64. */
+size_t pp_pfn_backward_workspace_bytes(int32_t B, int32_t P, int32_t C);
+int pp_pfn_backward(const float* d_x, int32_t B, int32_t D, int32_t P, int32_t N, int32_t C, const float* d_conv_w,
+                    const float* d_conv_b, const float* d_bn_w, const float* d_running_mean,
+                    const float* d_running_var, int32_t training, float eps, const float* d_grad_out,
+                    const int64_t* d_inds, int32_t canvas_h, int32_t canvas_w, float* d_grad_conv_w,
+                    float* d_grad_conv_b, float* d_grad_bn_w, float* d_grad_bn_b, void* d_workspace,
+                    size_t workspace_bytes, pp_stream_t stream);
+
+/* Backward of PPScatter alone (model/model.py:61): d_grad_feat [B, C, P] = canvas gradient at each non-empty
+ * row's cell (torch's index_put derivative: every indexed row reads its cell), zero for rows with flag 0. */
+int pp_scatter_backward(const float* d_grad_canvas, const int64_t* d_inds, int32_t B, int32_t C, int32_t P,
+                        int32_t canvas_h, int32_t canvas_w, float* d_grad_feat, pp_stream_t stream);
+
 /* Loss front-end: forward of the reference's PPLoss (model/loss.py:24-63) and the gradient
  * of its total loss b_cls*cls + b_reg*reg + b_ort*ort with respect to both network outputs.
  *   d_cls_out [B, Ad*K, H, W] float NCHW logits; d_reg_out [B, Ad*R, H, W] float, MODIFIED IN PLACE like
