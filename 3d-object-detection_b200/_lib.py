@@ -59,7 +59,8 @@ _SIGNATURES = {
     "pp_pfn_backward": (_c.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp,
                                    _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pp_scatter_backward": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "pp_loss_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "pp_loss_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "pp_loss_scale_grads": (_c.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _vp]),
     "pp_loss": (_c.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _f32,
                            _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pp_make_ious": (_c.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),

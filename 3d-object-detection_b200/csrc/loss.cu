@@ -18,9 +18,20 @@
 //   ort_loss       bce_with_logits(element 7, target element 8) over the positives, mean   (:59-61)
 // Sums are fp64 per-block partials combined in fixed order (deterministic).  With no positive anchor the
 // reference's means over an empty tensor are NaN; so are ours.
-#include "common.cuh"
+//
+// k_loss_cls_tma is the production kernel for aligned shapes (H*W % 4 == 0, 16-byte aligned tensors): a
+// persistent block per SM streams [channels][128 cells] tiles through a three-stage shared-memory ring
+// with bulk TMA copies (one producer warp: loads complete on an mbarrier, results leave through
+// cp.async.bulk stores), 16 compute warps transform each tile in place, so two tiles (110 KB) are always
+// in flight per SM.  It also applies the in-place tanh.  k_loss_cls + k_loss_tanh remain for other shapes.
+// k_loss_reg reads the target rows fully coalesced, appends the positives to a list and writes unscaled
+// gradient rows; k_loss_finalize knows the positive count and scales the listed rows (this replaced a
+// separate counting pass over the 78 MB target tensor).
+#include "tc_common.cuh"
 
 namespace pp {
+
+extern int g_opt_loss_tma;
 
 constexpr int kLossCells = 32;      // cells (w positions) per tile
 constexpr int kLossMaxCh = 96;      // Ad*K supported by the shared-memory tile
@@ -81,6 +92,141 @@ __global__ void __launch_bounds__(256) k_loss_cls(const float* __restrict__ cls,
   if (threadIdx.x == 0) partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
 }
 
+constexpr int kTmaCells = 128;      // cells per tile of the TMA kernel
+constexpr int kTmaStages = 3;
+constexpr int kTmaComputeWarps = 16;
+
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tcx::smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float focal_term(float x, float t, float gamma, bool g2, float alpha, float grad_scale, float& p_out,
+                                            float& g_out) {
+  const float e = __expf(-fabsf(x));                             // in (0, 1]
+  const float inv = __frcp_rn(1.f + e);
+  const float p = x >= 0.f ? inv : e * inv;                      // torch.sigmoid (:39)
+  const bool pos = t == 1.f;
+  const float om = pos ? 1.f - p : p;                            // 1 - pt (:40)
+  const float wgt = (pos ? alpha : 1.f) * (g2 ? om * om : powf(om, gamma));   // (:41-43)
+  const float bce = fmaxf(x, 0.f) - x * t + log1pf(e);           // F.binary_cross_entropy_with_logits
+  p_out = p;
+  g_out = grad_scale * wgt * (p - t);                            // d(b_cls * cls_loss)/dx, weight detached
+  return wgt * bce;
+}
+
+__global__ void __launch_bounds__((kTmaComputeWarps + 1) * 32, 1)
+k_loss_cls_tma(const float* __restrict__ cls, const float* __restrict__ cls_t, int B, int plane, int CK, float gamma,
+               float alpha, float grad_scale, float* __restrict__ scores, float* __restrict__ grad,
+               float* __restrict__ reg, int CR, double* __restrict__ partials) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ uint64_t full[kTmaStages], done[kTmaStages];
+  __shared__ double s_red[kTmaComputeWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int stage_floats = 2 * CK * kTmaCells;                  // X [CK][128] then T [128*CK]
+  float* s_f = reinterpret_cast<float*>(s_raw);
+  const int tiles_per_plane = (plane + kTmaCells - 1) / kTmaCells;
+  const int ntiles = B * tiles_per_plane;
+  if (tid == 0) {
+    for (int i = 0; i < kTmaStages; ++i) {
+      tcx::mbar_init(&full[i], 32);                              // every producer lane arrives with its byte count
+      tcx::mbar_init(&done[i], kTmaComputeWarps);
+    }
+    tcx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == kTmaComputeWarps) {
+    // ---------------- producer warp: lane l moves channel rows l, l+32, ...; lane 0 also the target run
+    auto load = [&](int it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b = tile / tiles_per_plane, c0 = (tile - b * tiles_per_plane) * kTmaCells;
+      const int nc = min(kTmaCells, plane - c0);
+      const int st = it % kTmaStages;
+      float* X = s_f + (size_t)st * stage_floats;
+      float* T = X + CK * kTmaCells;
+      uint32_t bytes = 0;
+      for (int ch = lane; ch < CK; ch += 32) bytes += (uint32_t)nc * 4u;
+      if (lane == 0) bytes += (uint32_t)nc * CK * 4u;
+      if (bytes) tcx::mbar_expect_tx(&full[st], bytes); else tcx::mbar_arrive(&full[st]);
+      for (int ch = lane; ch < CK; ch += 32)
+        tcx::bulk_g2s(X + ch * kTmaCells, cls + ((size_t)b * CK + ch) * plane + c0, (uint32_t)nc * 4u, &full[st]);
+      if (lane == 0) tcx::bulk_g2s(T, cls_t + ((size_t)b * plane + c0) * CK, (uint32_t)nc * CK * 4u, &full[st]);
+    };
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    for (int it = 0; it < min(my_tiles, kTmaStages); ++it) load(it);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int st = it % kTmaStages;
+      tcx::mbar_wait(&done[st], (it / kTmaStages) & 1);
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b = tile / tiles_per_plane, c0 = (tile - b * tiles_per_plane) * kTmaCells;
+      const int nc = min(kTmaCells, plane - c0);
+      float* X = s_f + (size_t)st * stage_floats;
+      float* T = X + CK * kTmaCells;
+      if (grad != nullptr)
+        for (int ch = lane; ch < CK; ch += 32)
+          bulk_s2g(grad + ((size_t)b * CK + ch) * plane + c0, X + ch * kTmaCells, (uint32_t)nc * 4u);
+      if (lane == 0 && scores != nullptr) bulk_s2g(scores + ((size_t)b * plane + c0) * CK, T, (uint32_t)nc * CK * 4u);
+      bulk_commit();
+      if (it + kTmaStages < my_tiles) {
+        bulk_wait_read<0>();                                     // this lane's stores have left shared memory
+        load(it + kTmaStages);
+      }
+    }
+    bulk_wait<0>();
+    return;
+  }
+
+  // ---------------- compute warps
+  const bool g2 = gamma == 2.f;
+  double acc = 0.0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int b = tile / tiles_per_plane, c0 = (tile - b * tiles_per_plane) * kTmaCells;
+    const int nc = min(kTmaCells, plane - c0);
+    const int st = it % kTmaStages;
+    float* X = s_f + (size_t)st * stage_floats;
+    float* T = X + CK * kTmaCells;
+    tcx::mbar_wait(&full[st], (it / kTmaStages) & 1);
+    float part = 0.f;
+    for (int idx = tid; idx < CK * kTmaCells; idx += kTmaComputeWarps * 32) {
+      const int ch = idx >> 7, cell = idx & (kTmaCells - 1);
+      if (cell < nc) {
+        float p, g;
+        part += focal_term(X[idx], T[cell * CK + ch], gamma, g2, alpha, grad_scale, p, g);
+        T[cell * CK + ch] = p;
+        X[idx] = g;
+      }
+    }
+    acc += (double)part;
+    tcx::fence_proxy_async();                                    // generic-proxy writes -> visible to the bulk stores
+    __syncwarp();
+    if (lane == 0) tcx::mbar_arrive(&done[st]);
+  }
+  // in-place tanh on network channel 6 of reg_out (model/loss.py:50)
+  if (reg != nullptr) {
+    const size_t n = (size_t)B * plane;
+    for (size_t i = (size_t)blockIdx.x * (kTmaComputeWarps * 32) + tid; i < n; i += (size_t)gridDim.x * kTmaComputeWarps * 32) {
+      const size_t b = i / plane, c = i - b * plane;
+      float* q = reg + (b * CR + 6) * plane + c;
+      *q = tanhf(*q);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) s_red[warp] = acc;
+  asm volatile("bar.sync 1, %0;" ::"n"(kTmaComputeWarps * 32));  // compute warps only (the producer has left)
+  if (tid == 0) {
+    double r = 0.0;
+    for (int w = 0; w < kTmaComputeWarps; ++w) r += s_red[w];
+    partials[blockIdx.x] = r;
+  }
+}
+
 // in-place tanh on network channel 6 of reg_out (model/loss.py:50)
 __global__ void __launch_bounds__(256) k_loss_tanh(float* __restrict__ reg, int B, size_t plane, int CR) {
   const size_t n = (size_t)B * plane;
@@ -91,47 +237,68 @@ __global__ void __launch_bounds__(256) k_loss_tanh(float* __restrict__ reg, int 
   }
 }
 
-__global__ void __launch_bounds__(256) k_loss_count(const float* __restrict__ reg_t, size_t n_anchors, int* __restrict__ n_pos) {
-  int c = 0;
-  for (size_t a = (size_t)blockIdx.x * 256 + threadIdx.x; a < n_anchors; a += (size_t)gridDim.x * 256)
-    c += __ldg(reg_t + a * 9) == 1.f ? 1 : 0;
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if (lane_id() == 0 && c) atomicAdd(n_pos, c);                  // integer: exact and order-independent
+// one positive anchor row: smooth-L1 / orientation terms and its unscaled gradient row.  Kept out of line so
+// the streaming loop of k_loss_reg stays small (positives are a few hundred per sweep).
+__device__ __noinline__ void loss_reg_row(const float* __restrict__ reg, const float* __restrict__ tr, size_t i, size_t A,
+                                          size_t plane, int Ad, int R, float* __restrict__ grad, double& sr, double& so) {
+  const size_t b = i / A, a = i - b * A;
+  const size_t cell = a / Ad;
+  const int d = (int)(a - cell * Ad);
+  const float* src = reg + (b * (size_t)Ad * R + (size_t)d * R) * plane + cell;
+  float* dst = grad != nullptr ? grad + (b * (size_t)Ad * R + (size_t)d * R) * plane + cell : nullptr;
+  for (int c = 0; c < 7; ++c) {
+    const float x = src[(size_t)c * plane];
+    const float df = x - __ldg(tr + 1 + c);
+    const float ad = fabsf(df);
+    sr += (double)(ad < 1.f ? 0.5f * df * df : ad - 0.5f);         // F.smooth_l1_loss, beta = 1 (:57)
+    float g = ad < 1.f ? df : (df > 0.f ? 1.f : -1.f);
+    if (d == 0 && c == 6) g *= 1.f - x * x;                        // x is already tanh(.): chain rule of (:50)
+    if (dst != nullptr) dst[(size_t)c * plane] = g;
+  }
+  if (R > 7) {
+    const float o = src[(size_t)7 * plane], ot = __ldg(tr + 8);
+    so += (double)(fmaxf(o, 0.f) - o * ot + log1pf(expf(-fabsf(o))));                 // (:59-61)
+    if (dst != nullptr) dst[(size_t)7 * plane] = 1.f / (1.f + expf(-o)) - ot;
+  }
 }
 
-// positives: smooth-L1 / orientation terms and the gradient rows (grad_reg is zeroed by the caller)
+// positives: loss terms, UNSCALED gradient rows (grad_reg is zeroed by the caller) and the list of positive
+// anchors.  A warp reads 32 consecutive target rows (288 floats) as nine coalesced loads; the lane that holds
+// a row's flag word handles that row.
 __global__ void __launch_bounds__(256) k_loss_reg(const float* __restrict__ reg, const float* __restrict__ reg_t,
-                                                  int B, int H, int W, int Ad, int R, const int* __restrict__ n_pos,
-                                                  float b_reg, float b_ort, float* __restrict__ grad,
+                                                  int B, int H, int W, int Ad, int R, float* __restrict__ grad,
+                                                  unsigned* __restrict__ n_pos, unsigned* __restrict__ list,
                                                   double* __restrict__ partials) {
   __shared__ double s_red[8];
   const size_t plane = (size_t)H * W;
   const size_t A = plane * Ad, n = A * B;
-  const int np = *n_pos;
-  const float inv_r = np > 0 ? b_reg / (7.f * (float)np) : 0.f;
-  const float inv_o = np > 0 ? b_ort / (float)np : 0.f;
+  const int lane = lane_id();
+  const size_t nchunks = (n + 31) / 32, e_end = n * 9;
   double sr = 0.0, so = 0.0;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-    const float* tr = reg_t + i * 9;
-    if (__ldg(tr) != 1.f) continue;                              // (:54) pos_anchors
-    const size_t b = i / A, a = i - b * A;
-    const size_t cell = a / Ad;
-    const int d = (int)(a - cell * Ad);
-    const float* src = reg + (b * (size_t)Ad * R + (size_t)d * R) * plane + cell;
-    float* dst = grad != nullptr ? grad + (b * (size_t)Ad * R + (size_t)d * R) * plane + cell : nullptr;
-    for (int c = 0; c < 7; ++c) {
-      const float v = src[(size_t)c * plane];
-      const float df = v - __ldg(tr + 1 + c);
-      const float ad = fabsf(df);
-      sr += (double)(ad < 1.f ? 0.5f * df * df : ad - 0.5f);     // F.smooth_l1_loss, beta = 1
-      float g = (ad < 1.f ? df : (df > 0.f ? 1.f : -1.f)) * inv_r;
-      if (d == 0 && c == 6) g *= 1.f - v * v;                    // v is already tanh(.): chain rule of (:50)
-      if (dst != nullptr) dst[(size_t)c * plane] = g;
+  for (size_t ck = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); ck < nchunks; ck += (size_t)gridDim.x * 8) {
+    const size_t e0 = ck * 288;
+    float v[9];
+    if (e0 + 288 <= e_end) {                                       // nine independent loads in flight per lane
+#pragma unroll
+      for (int j = 0; j < 9; ++j) v[j] = __ldg(reg_t + e0 + lane + 32 * j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const size_t e = e0 + lane + 32 * j;
+        v[j] = e < e_end ? __ldg(reg_t + e) : 0.f;
+      }
     }
-    if (R > 7) {
-      const float o = src[(size_t)7 * plane], ot = __ldg(tr + 8);
-      so += (double)(fmaxf(o, 0.f) - o * ot + log1pf(expf(-fabsf(o))));
-      if (dst != nullptr) dst[(size_t)7 * plane] = (1.f / (1.f + expf(-o)) - ot) * inv_o;
+    unsigned hit = 0;                                              // bit j: word lane + 32 j is a flag word equal to 1
+#pragma unroll
+    for (int j = 0; j < 9; ++j)
+      hit |= (v[j] == 1.f && (lane + 32 * j) % 9 == 0) ? 1u << j : 0u;   // (:54) where(reg_targets[...,0] == 1)
+    while (hit) {
+      const int j = __ffs(hit) - 1;
+      hit &= hit - 1;
+      const size_t i = ck * 32 + (lane + 32 * j) / 9;
+      const unsigned slot = atomicAdd(n_pos, 1u);
+      if (list != nullptr) list[slot] = (unsigned)i;
+      loss_reg_row(reg, reg_t + i * 9, i, A, plane, Ad, R, grad, sr, so);
     }
   }
   const double a0 = block_sum(sr, s_red);
@@ -142,42 +309,63 @@ __global__ void __launch_bounds__(256) k_loss_reg(const float* __restrict__ reg,
   }
 }
 
+// Every block re-derives the three sums (a few thousand doubles, fixed order), block 0 writes the losses, and
+// all blocks scale the listed gradient rows by b_reg / (7 n_pos) and b_ort / n_pos.
 __global__ void __launch_bounds__(256) k_loss_finalize(const double* __restrict__ pc, int nc, const double* __restrict__ pr,
-                                                       int nr, const int* __restrict__ n_pos, double n_cls, float b_cls,
-                                                       float b_reg, float b_ort, float* __restrict__ losses) {
+                                                       int nr, const unsigned* __restrict__ n_pos,
+                                                       const unsigned* __restrict__ list, double n_cls, float b_cls,
+                                                       float b_reg, float b_ort, int B, int H, int W, int Ad, int R,
+                                                       float* __restrict__ grad, float* __restrict__ losses) {
   __shared__ double s_red[8];
-  double c = 0.0, r = 0.0, o = 0.0;
-  for (int i = threadIdx.x; i < nc; i += 256) c += pc[i];
-  for (int i = threadIdx.x; i < nr; i += 256) { r += pr[2 * i]; o += pr[2 * i + 1]; }
-  const double C = block_sum(c, s_red), Rr = block_sum(r, s_red), O = block_sum(o, s_red);
-  if (threadIdx.x == 0) {
-    const int np = *n_pos;
-    const double nan = __longlong_as_double(0x7ff8000000000000ll);
-    const double cls_loss = C / n_cls;
-    const double reg_loss = np > 0 ? Rr / (7.0 * np) : nan;     // torch: mean over an empty tensor
-    const double ort_loss = np > 0 ? O / np : nan;
-    losses[0] = (float)cls_loss;
-    losses[1] = (float)reg_loss;
-    losses[2] = (float)ort_loss;
-    losses[3] = (float)((double)b_cls * cls_loss + (double)b_reg * reg_loss + (double)b_ort * ort_loss);   // (:63)
+  const unsigned np = *n_pos;
+  if (blockIdx.x == 0) {
+    double c = 0.0, r = 0.0, o = 0.0;
+    for (int i = threadIdx.x; i < nc; i += 256) c += pc[i];
+    for (int i = threadIdx.x; i < nr; i += 256) { r += pr[2 * i]; o += pr[2 * i + 1]; }
+    const double C = block_sum(c, s_red), Rr = block_sum(r, s_red), O = block_sum(o, s_red);
+    if (threadIdx.x == 0) {
+      const double nan = __longlong_as_double(0x7ff8000000000000ll);
+      const double cls_loss = C / n_cls;
+      const double reg_loss = np > 0 ? Rr / (7.0 * np) : nan;     // torch: mean over an empty tensor
+      const double ort_loss = np > 0 ? O / np : nan;
+      losses[0] = (float)cls_loss;
+      losses[1] = (float)reg_loss;
+      losses[2] = (float)ort_loss;
+      losses[3] = (float)((double)b_cls * cls_loss + (double)b_reg * reg_loss + (double)b_ort * ort_loss);   // (:63)
+    }
+  }
+  if (grad == nullptr || list == nullptr || np == 0) return;
+  const float inv_r = b_reg / (7.f * (float)np), inv_o = b_ort / (float)np;
+  const size_t plane = (size_t)H * W, A = plane * Ad;
+  const int rows = R > 7 ? 8 : 7;
+  for (size_t q = (size_t)blockIdx.x * 256 + threadIdx.x; q < (size_t)np * rows; q += (size_t)gridDim.x * 256) {
+    const size_t i = list[q / rows];
+    const int c = (int)(q % rows);
+    const size_t b = i / A, a = i - b * A, cell = a / Ad;
+    const int d = (int)(a - cell * Ad);
+    float* g = grad + (b * (size_t)Ad * R + (size_t)d * R + c) * plane + cell;
+    *g *= c < 7 ? inv_r : inv_o;
   }
 }
 
 struct LossWs {
   double* pc;
   double* pr;
-  int* n_pos;
+  unsigned* n_pos;
+  unsigned* list;
 };
 
 static int loss_reg_blocks() { return sm_count() * 8; }
+constexpr int kLossFinBlocks = 64;
 
 template <class A>
-static void loss_layout(A& a, LossWs* ws, int B, int H, int W) {
-  const size_t nc = (size_t)B * H * ((W + kLossCells - 1) / kLossCells);
-  auto p0 = a.template take<double>(nc);
+static void loss_layout(A& a, LossWs* ws, int B, int H, int W, int Ad) {
+  const size_t nc = (size_t)B * H * ((W + kLossCells - 1) / kLossCells);       // generic kernel's grid; >= #SMs
+  auto p0 = a.template take<double>(nc > 1024 ? nc : 1024);
   auto p1 = a.template take<double>((size_t)loss_reg_blocks() * 2);
-  auto p2 = a.template take<int>(64);
-  if (ws) { ws->pc = p0; ws->pr = p1; ws->n_pos = p2; }
+  auto p2 = a.template take<unsigned>(64);
+  auto p3 = a.template take<unsigned>((size_t)B * H * W * Ad);
+  if (ws) { ws->pc = p0; ws->pr = p1; ws->n_pos = p2; ws->list = p3; }
 }
 
 struct SizeArena4 {
@@ -186,14 +374,23 @@ struct SizeArena4 {
   T* take(size_t count) { used += align_up(count * sizeof(T)); return nullptr; }
 };
 
+__global__ void __launch_bounds__(256) k_loss_scale(float* __restrict__ a, size_t na, float* __restrict__ b, size_t nb,
+                                                    const float* __restrict__ scale, const float* __restrict__ applied) {
+  const float r = applied != nullptr ? *scale / *applied : *scale;
+  if (r == 1.f) return;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < na + nb; i += (size_t)gridDim.x * 256) {
+    if (i < na) a[i] *= r; else b[i - na] *= r;
+  }
+}
+
 }  // namespace pp
 
 extern "C" {
 
-size_t pp_loss_workspace_bytes(int32_t B, int32_t H, int32_t W) {
-  if (B < 1 || H < 1 || W < 1) return 0;
+size_t pp_loss_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t anchors_per_cell) {
+  if (B < 1 || H < 1 || W < 1 || anchors_per_cell < 1) return 0;
   pp::SizeArena4 a;
-  pp::loss_layout(a, (pp::LossWs*)nullptr, B, H, W);
+  pp::loss_layout(a, (pp::LossWs*)nullptr, B, H, W, anchors_per_cell);
   return a.used + pp::kAlign;
 }
 
@@ -207,29 +404,58 @@ int pp_loss(const float* d_cls_out, float* d_reg_out, const float* d_cls_t, cons
       anchors_per_cell < 1 || num_classes < 1 || reg_dims < 7)
     return PP_ERR_INVALID_ARG;
   const int CK = anchors_per_cell * num_classes, CR = anchors_per_cell * reg_dims;
-  if (CK > kLossMaxCh || CR <= 6 || B > 65535 || H > 65535) return PP_ERR_UNSUPPORTED;
-  Arena arena(d_workspace, workspace_bytes);
-  LossWs ws{};
-  loss_layout(arena, &ws, B, H, W);
-  if (!arena.ok) return PP_ERR_WORKSPACE;
   const size_t plane = (size_t)H * W;
   const size_t n_anchors = plane * anchors_per_cell * B;
+  if (CK > kLossMaxCh || CR <= 6 || B > 65535 || H > 65535 || n_anchors >= (1ull << 32) ||
+      plane * B >= (1ull << 31))
+    return PP_ERR_UNSUPPORTED;
+  Arena arena(d_workspace, workspace_bytes);
+  LossWs ws{};
+  loss_layout(arena, &ws, B, H, W, anchors_per_cell);
+  if (!arena.ok) return PP_ERR_WORKSPACE;
   const double n_cls = (double)n_anchors * num_classes;
-  PP_CUDA(cudaMemsetAsync(ws.n_pos, 0, sizeof(int), st));
-  const dim3 gc((W + kLossCells - 1) / kLossCells, H, B);
-  PP_KERNEL("k_loss_cls", st,
-            (k_loss_cls<<<gc, 256, 0, st>>>(d_cls_out, d_cls_t, H, W, CK, gamma, alpha_pos, (float)((double)b_cls / n_cls),
-                                            d_scores, d_grad_cls, ws.pc)));
-  PP_KERNEL("k_loss_tanh", st, (k_loss_tanh<<<(int)((B * plane + 255) / 256), 256, 0, st>>>(d_reg_out, B, plane, CR)));
+  const float gscale = (float)((double)b_cls / n_cls);
+  PP_CUDA(cudaMemsetAsync(ws.n_pos, 0, sizeof(unsigned), st));
+  auto aligned16 = [](const void* q) { return q == nullptr || ((uintptr_t)q % 16) == 0; };
+  const size_t smem = (size_t)kTmaStages * 2 * CK * kTmaCells * sizeof(float);
+  const bool tma = g_opt_loss_tma && plane % 4 == 0 && CK % 2 == 0 && aligned16(d_cls_out) && aligned16(d_cls_t) &&
+                   aligned16(d_scores) && aligned16(d_grad_cls) && smem <= 200 * 1024;
+  int nparts;
+  if (tma) {
+    const int tiles = B * (int)((plane + kTmaCells - 1) / kTmaCells);
+    nparts = tiles < sm_count() ? tiles : sm_count();
+    PP_CUDA(cudaFuncSetAttribute(k_loss_cls_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PP_KERNEL("k_loss_cls_tma", st,
+              (k_loss_cls_tma<<<nparts, (kTmaComputeWarps + 1) * 32, smem, st>>>(d_cls_out, d_cls_t, B, (int)plane, CK, gamma,
+                                                                                alpha_pos, gscale, d_scores, d_grad_cls,
+                                                                                d_reg_out, CR, ws.pc)));
+  } else {
+    const dim3 gc((W + kLossCells - 1) / kLossCells, H, B);
+    nparts = (int)((size_t)gc.x * gc.y * gc.z);
+    PP_KERNEL("k_loss_cls", st,
+              (k_loss_cls<<<gc, 256, 0, st>>>(d_cls_out, d_cls_t, H, W, CK, gamma, alpha_pos, gscale, d_scores, d_grad_cls, ws.pc)));
+    PP_KERNEL("k_loss_tanh", st, (k_loss_tanh<<<(int)((B * plane + 255) / 256), 256, 0, st>>>(d_reg_out, B, plane, CR)));
+  }
   const int nb = loss_reg_blocks();
-  PP_KERNEL("k_loss_count", st, (k_loss_count<<<nb, 256, 0, st>>>(d_reg_t, n_anchors, ws.n_pos)));
   if (d_grad_reg != nullptr) PP_CUDA(cudaMemsetAsync(d_grad_reg, 0, (size_t)B * CR * plane * sizeof(float), st));
   PP_KERNEL("k_loss_reg", st,
-            (k_loss_reg<<<nb, 256, 0, st>>>(d_reg_out, d_reg_t, B, H, W, anchors_per_cell, reg_dims, ws.n_pos, b_reg, b_ort,
-                                            d_grad_reg, ws.pr)));
+            (k_loss_reg<<<nb, 256, 0, st>>>(d_reg_out, d_reg_t, B, H, W, anchors_per_cell, reg_dims, d_grad_reg, ws.n_pos,
+                                            d_grad_reg != nullptr ? ws.list : nullptr, ws.pr)));
   PP_KERNEL("k_loss_finalize", st,
-            (k_loss_finalize<<<1, 256, 0, st>>>(ws.pc, (int)((size_t)gc.x * gc.y * gc.z), ws.pr, nb, ws.n_pos, n_cls, b_cls,
-                                                b_reg, b_ort, d_losses)));
+            (k_loss_finalize<<<kLossFinBlocks, 256, 0, st>>>(ws.pc, nparts, ws.pr, nb, ws.n_pos, ws.list, n_cls, b_cls, b_reg,
+                                                             b_ort, B, H, W, anchors_per_cell, reg_dims, d_grad_reg,
+                                                             d_losses)));
+  return PP_OK;
+}
+
+int pp_loss_scale_grads(float* d_grad_cls, size_t n_cls, float* d_grad_reg, size_t n_reg, const float* d_scale,
+                        const float* d_applied, pp_stream_t stream) {
+  using namespace pp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_scale || (!d_grad_cls && n_cls) || (!d_grad_reg && n_reg)) return PP_ERR_INVALID_ARG;
+  if (n_cls + n_reg == 0) return PP_OK;
+  PP_KERNEL("k_loss_scale", st,
+            (k_loss_scale<<<sm_count() * 8, 256, 0, st>>>(d_grad_cls, n_cls, d_grad_reg, n_reg, d_scale, d_applied)));
   return PP_OK;
 }
 

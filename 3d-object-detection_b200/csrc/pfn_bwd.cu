@@ -14,8 +14,9 @@
 // k_pfn_bwd: one warp per (pillar, channel half), lane = channel.  The pillar's x rows are staged in shared
 // memory with cp.async (double buffered over groups of 4 pillars), every lane walks the N slots reading x
 // as warp-uniform float4 broadcasts: 9 FMA for z, 21 for the moments, 4 for the running arg-max per slot and
-// channel.  Per-pillar fp32 sums are folded into fp64 registers; one fp64 partial row per warp is combined in
-// a fixed order by k_pfn_bwd_finalize (deterministic).
+// channel.  Per-pillar fp32 sums go through a shared staging tile into fp64 accumulators that are spread
+// over the block's threads ((row, channel) pairs), so the inner loop keeps 125 registers and two blocks fit
+// an SM; one fp64 partial tile per block is combined in a fixed order by k_pfn_bwd_finalize (deterministic).
 #include "common.cuh"
 
 namespace pp {
@@ -40,17 +41,43 @@ struct BwdGrad {             // where G[b,c,p] lives: the [B,C,P] gradient, or t
   int H, W;
 };
 
+constexpr int kBwdRows = 34;               // staged per pillar and channel: the 33 sums (+1 pad row)
+constexpr int kBwdOwn = (kBwdAcc * kBwdC + 255) / 256;     // (k, c) pairs owned by each thread of the block
+
 template <bool TRAIN>
-__global__ void __launch_bounds__(256, 1) k_pfn_bwd(const float* __restrict__ x, int B, int P, int N, int Np,
+__device__ __forceinline__ void bwd_slot(const float (&wr)[kBwdD], float bc, float sgn, const float (&xs)[kBwdD], int n,
+                                         float (&s1)[10], float (&s2)[10], float& q2, float& best, int& nbest) {
+  float z = bc;
+#pragma unroll
+  for (int d = 0; d < kBwdD; ++d) z = fmaf(wr[d], xs[d], z);
+  const float r = fmaxf(z, 0.f);
+  if (TRAIN) {
+    const float on = z > 0.f ? 1.f : 0.f;
+#pragma unroll
+    for (int d = 0; d < kBwdD; ++d) {
+      s1[d] = fmaf(on, xs[d], s1[d]);
+      s2[d] = fmaf(r, xs[d], s2[d]);
+    }
+    s1[9] += on;
+    s2[9] += r;
+    q2 = fmaf(r, r, q2);
+  }
+  const float key = sgn * r;
+  if (key > best) { best = key; nbest = n; }                       // strict: the first index wins a tie
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(256, 2) k_pfn_bwd(const float* __restrict__ x, int B, int P, int N, int Np,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                    const float* __restrict__ bn_w, BwdGrad gr, int vec16,
                                                    double* __restrict__ partials) {
-  extern __shared__ __align__(16) float s_tile[];            // [2][kBwdPil][9][Np]
+  extern __shared__ __align__(16) float s_tile[];            // [2][kBwdPil][9][Np] | staging [kBwdPil][kBwdRows][64]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pl = warp >> 1, c = (warp & 1) * 32 + lane;
   const long long BP = (long long)B * P;
   const long long ngroups = (BP + kBwdPil - 1) / kBwdPil;
   const size_t stage_floats = (size_t)kBwdPil * kBwdD * Np;
+  float* s_sum = s_tile + 2 * stage_floats;
 
   float wr[kBwdD];
 #pragma unroll
@@ -59,9 +86,10 @@ __global__ void __launch_bounds__(256, 1) k_pfn_bwd(const float* __restrict__ x,
   const float gam = __ldg(bn_w + c);
   const float sgn = gam > 0.f ? 1.f : (gam < 0.f ? -1.f : 0.f);
 
-  double acc[kBwdAcc];
+  // fp64 accumulators are spread over the block: thread t owns the (k, c) pairs t, t+256, ...
+  double acc[kBwdOwn];
 #pragma unroll
-  for (int k = 0; k < kBwdAcc; ++k) acc[k] = 0.0;
+  for (int k = 0; k < kBwdOwn; ++k) acc[k] = 0.0;
 
   auto issue = [&](long long grp, int stage) {
     float* dst0 = s_tile + (size_t)stage * stage_floats;
@@ -72,7 +100,7 @@ __global__ void __launch_bounds__(256, 1) k_pfn_bwd(const float* __restrict__ x,
         const int q = row / kBwdD, d = row - q * kBwdD;
         const long long task = grp * kBwdPil + q;
         if (task < BP) {
-          const long long b = task / P, p = task - b * P;
+          const int b = (int)((unsigned)task / (unsigned)P), p = (int)task - b * P;
           cp_async16(dst0 + ((size_t)q * kBwdD + d) * Np + ck * 4, x + ((size_t)(b * kBwdD + d) * P + p) * N + ck * 4);
         }
       }
@@ -82,7 +110,7 @@ __global__ void __launch_bounds__(256, 1) k_pfn_bwd(const float* __restrict__ x,
         const int q = row / kBwdD, d = row - q * kBwdD;
         const long long task = grp * kBwdPil + q;
         if (task < BP) {
-          const long long b = task / P, p = task - b * P;
+          const int b = (int)((unsigned)task / (unsigned)P), p = (int)task - b * P;
           cp_async4(dst0 + ((size_t)q * kBwdD + d) * Np + n, x + ((size_t)(b * kBwdD + d) * P + p) * N + n);
         }
       }
@@ -101,45 +129,34 @@ __global__ void __launch_bounds__(256, 1) k_pfn_bwd(const float* __restrict__ x,
     } else {
       cp_async_wait<0>();
     }
-    __syncthreads();
+    __syncthreads();                                             // tile landed; previous staging rows consumed
     const long long task = grp * kBwdPil + pl;
+    float* srow = s_sum + (size_t)pl * kBwdRows * kBwdC + c;
     if (task < BP) {
       const float* t = s_tile + (size_t)stage * stage_floats + (size_t)pl * kBwdD * Np;
       float s1[10], s2[10], q2 = 0.f;
 #pragma unroll
       for (int d = 0; d < 10; ++d) { s1[d] = 0.f; s2[d] = 0.f; }
-      float best = 0.f;
+      float best = -INFINITY;
       int nbest = 0;
-      for (int n0 = 0; n0 < N; n0 += 4) {
+      const int N4 = N & ~3;
+      for (int n0 = 0; n0 < N4; n0 += 4) {
         float4 xv[kBwdD];
 #pragma unroll
         for (int d = 0; d < kBwdD; ++d) xv[d] = *reinterpret_cast<const float4*>(t + d * Np + n0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (n0 + j < N) {
-            float xs[kBwdD];
+          float xs[kBwdD];
 #pragma unroll
-            for (int d = 0; d < kBwdD; ++d) xs[d] = j == 0 ? xv[d].x : (j == 1 ? xv[d].y : (j == 2 ? xv[d].z : xv[d].w));
-            float z = bc;
-#pragma unroll
-            for (int d = 0; d < kBwdD; ++d) z = fmaf(wr[d], xs[d], z);
-            const float r = fmaxf(z, 0.f);
-            if (TRAIN) {
-              const float on = z > 0.f ? 1.f : 0.f;
-#pragma unroll
-              for (int d = 0; d < kBwdD; ++d) {
-                s1[d] = fmaf(on, xs[d], s1[d]);
-                s2[d] = fmaf(r, xs[d], s2[d]);
-              }
-              s1[9] += on;
-              s2[9] += r;
-              q2 = fmaf(r, r, q2);
-            }
-            const float key = sgn * r;
-            if (n0 + j == 0) best = key;
-            if (key > best) { best = key; nbest = n0 + j; }        // strict: first index wins a tie
-          }
+          for (int d = 0; d < kBwdD; ++d) xs[d] = j == 0 ? xv[d].x : (j == 1 ? xv[d].y : (j == 2 ? xv[d].z : xv[d].w));
+          bwd_slot<TRAIN>(wr, bc, sgn, xs, n0 + j, s1, s2, q2, best, nbest);
         }
+      }
+      for (int n = N4; n < N; ++n) {
+        float xs[kBwdD];
+#pragma unroll
+        for (int d = 0; d < kBwdD; ++d) xs[d] = t[d * Np + n];
+        bwd_slot<TRAIN>(wr, bc, sgn, xs, n, s1, s2, q2, best, nbest);
       }
       // the arg-max element takes the incoming gradient
       const long long b = task / P, p = task - b * P;
@@ -152,48 +169,85 @@ __global__ void __launch_bounds__(256, 1) k_pfn_bwd(const float* __restrict__ x,
       } else {
         G = __ldg(gr.g + (size_t)(b * kBwdC + c) * P + p);
       }
-      const float rstar = sgn * best;                              // sgn == 0: slot 0, r recomputed below
       float zs = bc;
 #pragma unroll
       for (int d = 0; d < kBwdD; ++d) zs = fmaf(wr[d], t[d * Np + nbest], zs);
-      const float rs = sgn != 0.f ? rstar : fmaxf(zs, 0.f);
       const float Gon = zs > 0.f ? G : 0.f;
 #pragma unroll
-      for (int d = 0; d < kBwdD; ++d) acc[21 + d] += (double)(Gon * t[d * Np + nbest]);
-      acc[30] += (double)Gon;
-      acc[31] += (double)G;
-      acc[32] += (double)G * (double)rs;
-      if (TRAIN) {
+      for (int d = 0; d < 10; ++d) {
+        srow[d * kBwdC] = s1[d];
+        srow[(10 + d) * kBwdC] = s2[d];
+      }
+      srow[20 * kBwdC] = q2;
 #pragma unroll
-        for (int d = 0; d < 10; ++d) { acc[d] += (double)s1[d]; acc[10 + d] += (double)s2[d]; }
-        acc[20] += (double)q2;
+      for (int d = 0; d < kBwdD; ++d) srow[(21 + d) * kBwdC] = Gon * t[d * Np + nbest];
+      srow[30 * kBwdC] = Gon;
+      srow[31 * kBwdC] = G;
+      srow[32 * kBwdC] = G * fmaxf(zs, 0.f);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kBwdAcc; ++k) srow[k * kBwdC] = 0.f;
+    }
+    __syncthreads();                                             // staging rows complete; tile stage free
+#pragma unroll
+    for (int k = 0; k < kBwdOwn; ++k) {
+      const int idx = tid + k * 256;                             // = row * 64 + channel
+      if (idx < kBwdAcc * kBwdC) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < kBwdPil; ++q) v += (double)s_sum[(size_t)q * kBwdRows * kBwdC + idx];
+        acc[k] += v;
       }
     }
-    __syncthreads();
     stage ^= 1;
   }
-  double* dst = partials + ((size_t)blockIdx.x * 8 + warp) * kBwdAcc * 32;
+  double* dst = partials + (size_t)blockIdx.x * kBwdAcc * kBwdC;
 #pragma unroll
-  for (int k = 0; k < kBwdAcc; ++k) dst[k * 32 + lane] = acc[k];
+  for (int k = 0; k < kBwdOwn; ++k) {
+    const int idx = tid + k * 256;
+    if (idx < kBwdAcc * kBwdC) dst[idx] = acc[k];
+  }
 }
 
-// sums[k][c] over blocks and the four warps of each channel half, then the closed forms above.
+// One block per sum row k: sums[k][c] over the per-block partial tiles in a fixed order; the last block to
+// finish (a ticket counter) evaluates the closed forms above.
 __global__ void __launch_bounds__(1024) k_pfn_bwd_finalize(const double* __restrict__ partials, int nblocks, double M,
                                                            const float* __restrict__ bn_w,
                                                            const float* __restrict__ running_mean,
                                                            const float* __restrict__ running_var, int training, float eps,
+                                                           double* __restrict__ sums_g, unsigned* __restrict__ ticket,
                                                            float* __restrict__ g_w, float* __restrict__ g_b,
                                                            float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+  __shared__ double part[16][kBwdC];
   __shared__ double sums[kBwdAcc][kBwdC];
-  const int c = threadIdx.x & 63, kq = threadIdx.x >> 6;
-  const int half = c >> 5, lane = c & 31;
-  for (int k = kq; k < kBwdAcc; k += 16) {
-    double s = 0.0;
-    for (int blk = 0; blk < nblocks; ++blk)
-      for (int q = 0; q < 4; ++q) s += partials[(((size_t)blk * 8 + q * 2 + half) * kBwdAcc + k) * 32 + lane];
-    sums[k][c] = s;
+  __shared__ bool last;
+  const int c = threadIdx.x & 63, seg = threadIdx.x >> 6, k = blockIdx.x;
+  {
+    double s0 = 0.0, s1 = 0.0;
+    int blk = seg;
+    for (; blk + 16 < nblocks; blk += 32) {
+      s0 += partials[((size_t)blk * kBwdAcc + k) * kBwdC + c];
+      s1 += partials[((size_t)(blk + 16) * kBwdAcc + k) * kBwdC + c];
+    }
+    if (blk < nblocks) s0 += partials[((size_t)blk * kBwdAcc + k) * kBwdC + c];
+    part[seg][c] = s0 + s1;
   }
   __syncthreads();
+  if (seg == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) tot += part[q][c];
+    sums_g[k * kBwdC + c] = tot;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < kBwdAcc * kBwdC; i += 1024) sums[i / kBwdC][i % kBwdC] = __ldcg(sums_g + i);
+  __syncthreads();
+  if (threadIdx.x == 0) *ticket = 0;                                // ready for the next call
   if (threadIdx.x < kBwdC) {
     const double gam = (double)bn_w[c];
     double mu, var;
@@ -232,7 +286,7 @@ __global__ void __launch_bounds__(256) k_scatter_bwd(const float* __restrict__ g
   }
 }
 
-static int bwd_blocks() { return sm_count(); }
+static int bwd_blocks() { return sm_count() * 2; }
 
 }  // namespace pp
 
@@ -240,7 +294,8 @@ extern "C" {
 
 size_t pp_pfn_backward_workspace_bytes(int32_t B, int32_t P, int32_t C) {
   if (B < 1 || P < 1 || C != pp::kBwdC) return 0;
-  return pp::align_up((size_t)pp::bwd_blocks() * 8 * pp::kBwdAcc * 32 * sizeof(double)) + pp::kAlign;
+  return pp::align_up((size_t)pp::bwd_blocks() * pp::kBwdAcc * pp::kBwdC * sizeof(double)) +
+         pp::align_up((size_t)pp::kBwdAcc * pp::kBwdC * sizeof(double)) + 2 * pp::kAlign;
 }
 
 int pp_pfn_backward(const float* d_x, int32_t B, int32_t D, int32_t P, int32_t N, int32_t C, const float* d_conv_w,
@@ -254,14 +309,17 @@ int pp_pfn_backward(const float* d_x, int32_t B, int32_t D, int32_t P, int32_t N
   if (!d_x || !d_conv_w || !d_conv_b || !d_bn_w || !d_grad_out || B < 1 || P < 1 || N < 1) return PP_ERR_INVALID_ARG;
   if (!training && (!d_running_mean || !d_running_var)) return PP_ERR_INVALID_ARG;
   if (d_inds != nullptr && (canvas_h < 1 || canvas_w < 1)) return PP_ERR_INVALID_ARG;
-  if (D != kBwdD || C != kBwdC) return PP_ERR_UNSUPPORTED;
+  if (D != kBwdD || C != kBwdC || (long long)B * P >= (1ll << 31)) return PP_ERR_UNSUPPORTED;
   const int Np = (N + 3) & ~3;
-  const size_t smem = (size_t)2 * kBwdPil * kBwdD * Np * sizeof(float);
-  if (smem > 200 * 1024) return PP_ERR_UNSUPPORTED;
+  const size_t smem = ((size_t)2 * kBwdPil * kBwdD * Np + (size_t)kBwdPil * kBwdRows * kBwdC) * sizeof(float);
+  if (smem > 110 * 1024) return PP_ERR_UNSUPPORTED;
   Arena arena(d_workspace, workspace_bytes);
   const int nb = bwd_blocks();
-  double* partials = arena.take<double>((size_t)nb * 8 * kBwdAcc * 32);
+  double* partials = arena.take<double>((size_t)nb * kBwdAcc * kBwdC);
+  double* sums_g = arena.take<double>((size_t)kBwdAcc * kBwdC);
+  unsigned* ticket = arena.take<unsigned>(1);
   if (!arena.ok) return PP_ERR_WORKSPACE;
+  PP_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   const int vec16 = (N % 4 == 0 && ((uintptr_t)d_x % 16) == 0) ? 1 : 0;
   BwdGrad gr{d_grad_out, (const long long*)d_inds, canvas_h, canvas_w};
   if (training) {
@@ -274,8 +332,8 @@ int pp_pfn_backward(const float* d_x, int32_t B, int32_t D, int32_t P, int32_t N
               (k_pfn_bwd<false><<<nb, 256, smem, st>>>(d_x, B, P, N, Np, d_conv_w, d_conv_b, d_bn_w, gr, vec16, partials)));
   }
   PP_KERNEL("k_pfn_bwd_finalize", st,
-            (k_pfn_bwd_finalize<<<1, 1024, 0, st>>>(partials, nb, (double)B * P * N, d_bn_w, d_running_mean, d_running_var,
-                                                    training ? 1 : 0, eps, d_grad_conv_w, d_grad_conv_b, d_grad_bn_w,
+            (k_pfn_bwd_finalize<<<kBwdAcc, 1024, 0, st>>>(partials, nb, (double)B * P * N, d_bn_w, d_running_mean,
+                                                          d_running_var, training ? 1 : 0, eps, sums_g, ticket, d_grad_conv_w, d_grad_conv_b, d_grad_bn_w,
                                                     d_grad_bn_b)));
   return PP_OK;
 }

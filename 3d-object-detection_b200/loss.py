@@ -38,7 +38,7 @@ class _PPLossFn(torch.autograd.Function):
         g_cls = torch.empty_like(cls_c)
         g_reg = torch.empty_like(reg_tensor)
         losses = torch.empty(4, dtype=torch.float32, device=dev)
-        ws = _runtime.workspace(L.pp_loss_workspace_bytes(B, H, W), dev, "loss")
+        ws = _runtime.workspace(L.pp_loss_workspace_bytes(B, H, W, Ad), dev, "loss")
         with torch.cuda.device(dev):
             rc = L.pp_loss(cls_c.data_ptr(), reg_tensor.data_ptr(), ct.data_ptr(), rt.data_ptr(), B, H, W, Ad, K, R,
                            float(gamma), float(alpha_pos), float(b_cls), float(b_reg), float(b_ort),
@@ -46,6 +46,7 @@ class _PPLossFn(torch.autograd.Function):
                            ws.data_ptr(), ws.numel(), _runtime.stream_ptr(dev))
         _lib.check(rc, "pp_loss")
         ctx.mark_dirty(reg_tensor)
+        ctx.applied = None
         ctx.save_for_backward(g_cls, g_reg)
         ctx.mark_non_differentiable(scores)
         return losses[3], scores, losses[0].detach(), losses[1].detach(), losses[2].detach(), reg_tensor
@@ -53,7 +54,18 @@ class _PPLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_total, g_scores, g_c, g_r, g_o, g_regout):
         g_cls, g_reg = ctx.saved_tensors
-        return g_cls * g_total, g_reg * g_total, None, None, None, None, None, None, None, None
+        if ctx.applied is not None:
+            # a second backward through the same graph: out of place, the first result may be in use
+            r = g_total.to(torch.float32) / ctx.applied
+            return g_cls * r, g_reg * r, None, None, None, None, None, None, None, None
+        # first (normally only) backward: scale in place; the kernel exits at once for an upstream gradient of 1
+        g = g_total.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(g_cls.device):
+            rc = _lib.load().pp_loss_scale_grads(g_cls.data_ptr(), g_cls.numel(), g_reg.data_ptr(), g_reg.numel(),
+                                                 g.data_ptr(), None, _runtime.stream_ptr(g_cls.device))
+        _lib.check(rc, "pp_loss_scale_grads")
+        ctx.applied = g
+        return g_cls, g_reg, None, None, None, None, None, None, None, None
 
 
 class PPLoss(nn.Module):

@@ -137,11 +137,17 @@ int pp_scatter_backward(const float* d_grad_canvas, const int64_t* d_inds, int32
  * layout of the inputs (may be NULL), d_losses float[4] = {cls_loss, reg_loss, ort_loss, total}.
  * focal weight (t == 1 ? alpha_pos : 1) * (1 - pt)^gamma is detached as in the reference (alpha_pos = 25 there).
  * No positive anchor -> reg/ort/total are NaN (torch's mean over an empty tensor).  Ad*K <= 96, R >= 7. */
-size_t pp_loss_workspace_bytes(int32_t B, int32_t H, int32_t W);
+size_t pp_loss_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t anchors_per_cell);
 int pp_loss(const float* d_cls_out, float* d_reg_out, const float* d_cls_t, const float* d_reg_t, int32_t B,
             int32_t H, int32_t W, int32_t anchors_per_cell, int32_t num_classes, int32_t reg_dims, float gamma,
             float alpha_pos, float b_cls, float b_reg, float b_ort, float* d_scores, float* d_grad_cls,
             float* d_grad_reg, float* d_losses, void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
+
+/* Chain rule for a non-unit upstream gradient of the total loss: both gradient tensors are multiplied in place
+ * by *d_scale / *d_applied (d_applied NULL = 1).  The kernel returns at once when the factor is exactly 1, the
+ * usual total_loss.backward() case, so no pass over the 147 MB of gradients is spent on it. */
+int pp_loss_scale_grads(float* d_grad_cls, size_t n_cls, float* d_grad_reg, size_t n_reg, const float* d_scale,
+                        const float* d_applied, pp_stream_t stream);
 
 /* Instrumentation.  pp_launch_count: kernels launched by this library since load (all threads).
  * pp_profile_enable(1): bracket every kernel launch with CUDA events on its stream;
