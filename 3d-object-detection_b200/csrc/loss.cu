@@ -21,17 +21,20 @@
 //
 // k_loss_cls_tma is the production kernel for aligned shapes (H*W % 4 == 0, 16-byte aligned tensors): a
 // persistent block per SM streams [channels][128 cells] tiles through a three-stage shared-memory ring
-// with bulk TMA copies (one producer warp: loads complete on an mbarrier, results leave through
-// cp.async.bulk stores), 16 compute warps transform each tile in place, so two tiles (110 KB) are always
+// with TMA (one producer thread: a 2-D tensor-map box for the logit tile and a bulk copy for the target run
+// complete on an mbarrier, results leave through the matching TMA stores), 16 compute warps transform each tile in place, so two tiles (110 KB) are always
 // in flight per SM.  It also applies the in-place tanh.  k_loss_cls + k_loss_tanh remain for other shapes.
 // k_loss_reg reads the target rows fully coalesced, appends the positives to a list and writes unscaled
 // gradient rows; k_loss_finalize knows the positive count and scales the listed rows (this replaced a
 // separate counting pass over the 78 MB target tensor).
+#include <cuda.h>
+
 #include "tc_common.cuh"
 
 namespace pp {
 
 extern int g_opt_loss_tma;
+void* tensor_map_encode_fn();        // pfn_tc16.cu: cuTensorMapEncodeTiled through the runtime's entry-point query
 
 constexpr int kLossCells = 32;      // cells (w positions) per tile
 constexpr int kLossMaxCh = 96;      // Ad*K supported by the shared-memory tile
@@ -100,30 +103,55 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tcx::smem_u32(src)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(tcx::smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(tcx::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(tmap), "r"(c0), "r"(c1), "r"(tcx::smem_u32(src)) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
+// One logit: returns w * bce, writes sigmoid and d(b_cls * cls_loss)/dx.  All terms derive from e = exp(-|x|):
+//   sigmoid(x) and 1 - sigmoid(x) are {1, e} / (1 + e) (no cancellation on either side),
+//   log1p(e) = 2 atanh(e / (2 + e)) as an odd series in s <= 1/3 (eight terms: below 2e-8 relative).
 __device__ __forceinline__ float focal_term(float x, float t, float gamma, bool g2, float alpha, float grad_scale, float& p_out,
                                             float& g_out) {
   const float e = __expf(-fabsf(x));                             // in (0, 1]
-  const float inv = __frcp_rn(1.f + e);
-  const float p = x >= 0.f ? inv : e * inv;                      // torch.sigmoid (:39)
+  float inv, inv2;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f + e));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv2) : "f"(2.f + e));
+  const float q = e * inv;
+  const bool nonneg = x >= 0.f;
+  const float p = nonneg ? inv : q;                              // torch.sigmoid (:39)
+  const float np1 = nonneg ? q : inv;                            // 1 - p
   const bool pos = t == 1.f;
-  const float om = pos ? 1.f - p : p;                            // 1 - pt (:40)
+  const float om = pos ? np1 : p;                                // 1 - pt (:40)
   const float wgt = (pos ? alpha : 1.f) * (g2 ? om * om : powf(om, gamma));   // (:41-43)
-  const float bce = fmaxf(x, 0.f) - x * t + log1pf(e);           // F.binary_cross_entropy_with_logits
+  const float sv = e * inv2, z = sv * sv;
+  float poly = fmaf(z, 1.f / 15.f, 1.f / 13.f);
+  poly = fmaf(poly, z, 1.f / 11.f);
+  poly = fmaf(poly, z, 1.f / 9.f);
+  poly = fmaf(poly, z, 1.f / 7.f);
+  poly = fmaf(poly, z, 1.f / 5.f);
+  poly = fmaf(poly, z, 1.f / 3.f);
+  poly = fmaf(poly, z, 1.f);
+  const float l1p = 2.f * sv * poly;                             // log1p(exp(-|x|))
+  const float bce = fmaxf(x, 0.f) - x * t + l1p;                 // F.binary_cross_entropy_with_logits (:46)
   p_out = p;
   g_out = grad_scale * wgt * (p - t);                            // d(b_cls * cls_loss)/dx, weight detached
   return wgt * bce;
 }
 
 __global__ void __launch_bounds__((kTmaComputeWarps + 1) * 32, 1)
-k_loss_cls_tma(const float* __restrict__ cls, const float* __restrict__ cls_t, int B, int plane, int CK, float gamma,
-               float alpha, float grad_scale, float* __restrict__ scores, float* __restrict__ grad,
-               float* __restrict__ reg, int CR, double* __restrict__ partials) {
+k_loss_cls_tma(const __grid_constant__ CUtensorMap tm_cls, const __grid_constant__ CUtensorMap tm_grad,
+               const float* __restrict__ cls_t, int B, int plane, int CK, float gamma, float alpha, float grad_scale,
+               float* __restrict__ scores, int want_grad, float* __restrict__ reg, int CR, double* __restrict__ partials) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ uint64_t full[kTmaStages], done[kTmaStages];
   __shared__ double s_red[kTmaComputeWarps];
@@ -134,7 +162,7 @@ k_loss_cls_tma(const float* __restrict__ cls, const float* __restrict__ cls_t, i
   const int ntiles = B * tiles_per_plane;
   if (tid == 0) {
     for (int i = 0; i < kTmaStages; ++i) {
-      tcx::mbar_init(&full[i], 32);                              // every producer lane arrives with its byte count
+      tcx::mbar_init(&full[i], 1);
       tcx::mbar_init(&done[i], kTmaComputeWarps);
     }
     tcx::fence_barrier_init();
@@ -142,7 +170,8 @@ k_loss_cls_tma(const float* __restrict__ cls, const float* __restrict__ cls_t, i
   __syncthreads();
 
   if (warp == kTmaComputeWarps) {
-    // ---------------- producer warp: lane l moves channel rows l, l+32, ...; lane 0 also the target run
+    // ---------------- producer: one thread issues two TMA loads and two TMA stores per tile
+    if (lane != 0) return;
     auto load = [&](int it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int b = tile / tiles_per_plane, c0 = (tile - b * tiles_per_plane) * kTmaCells;
@@ -150,13 +179,9 @@ k_loss_cls_tma(const float* __restrict__ cls, const float* __restrict__ cls_t, i
       const int st = it % kTmaStages;
       float* X = s_f + (size_t)st * stage_floats;
       float* T = X + CK * kTmaCells;
-      uint32_t bytes = 0;
-      for (int ch = lane; ch < CK; ch += 32) bytes += (uint32_t)nc * 4u;
-      if (lane == 0) bytes += (uint32_t)nc * CK * 4u;
-      if (bytes) tcx::mbar_expect_tx(&full[st], bytes); else tcx::mbar_arrive(&full[st]);
-      for (int ch = lane; ch < CK; ch += 32)
-        tcx::bulk_g2s(X + ch * kTmaCells, cls + ((size_t)b * CK + ch) * plane + c0, (uint32_t)nc * 4u, &full[st]);
-      if (lane == 0) tcx::bulk_g2s(T, cls_t + ((size_t)b * plane + c0) * CK, (uint32_t)nc * CK * 4u, &full[st]);
+      tcx::mbar_expect_tx(&full[st], (uint32_t)(CK * kTmaCells + nc * CK) * 4u);     // the box always lands whole (zero fill)
+      tma_load_2d(X, &tm_cls, c0, b * CK, &full[st]);
+      tcx::bulk_g2s(T, cls_t + ((size_t)b * plane + c0) * CK, (uint32_t)nc * CK * 4u, &full[st]);
     };
     const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     for (int it = 0; it < min(my_tiles, kTmaStages); ++it) load(it);
@@ -168,13 +193,11 @@ k_loss_cls_tma(const float* __restrict__ cls, const float* __restrict__ cls_t, i
       const int nc = min(kTmaCells, plane - c0);
       float* X = s_f + (size_t)st * stage_floats;
       float* T = X + CK * kTmaCells;
-      if (grad != nullptr)
-        for (int ch = lane; ch < CK; ch += 32)
-          bulk_s2g(grad + ((size_t)b * CK + ch) * plane + c0, X + ch * kTmaCells, (uint32_t)nc * 4u);
-      if (lane == 0 && scores != nullptr) bulk_s2g(scores + ((size_t)b * plane + c0) * CK, T, (uint32_t)nc * CK * 4u);
+      if (want_grad) tma_store_2d(&tm_grad, X, c0, b * CK);       // columns past the plane are clipped
+      if (scores != nullptr) bulk_s2g(scores + ((size_t)b * plane + c0) * CK, T, (uint32_t)nc * CK * 4u);
       bulk_commit();
       if (it + kTmaStages < my_tiles) {
-        bulk_wait_read<0>();                                     // this lane's stores have left shared memory
+        bulk_wait_read<0>();                                     // the stores have left shared memory
         load(it + kTmaStages);
       }
     }
@@ -193,17 +216,28 @@ k_loss_cls_tma(const float* __restrict__ cls, const float* __restrict__ cls_t, i
     float* X = s_f + (size_t)st * stage_floats;
     float* T = X + CK * kTmaCells;
     tcx::mbar_wait(&full[st], (it / kTmaStages) & 1);
-    float part = 0.f;
-    for (int idx = tid; idx < CK * kTmaCells; idx += kTmaComputeWarps * 32) {
-      const int ch = idx >> 7, cell = idx & (kTmaCells - 1);
-      if (cell < nc) {
-        float p, g;
-        part += focal_term(X[idx], T[cell * CK + ch], gamma, g2, alpha, grad_scale, p, g);
-        T[cell * CK + ch] = p;
-        X[idx] = g;
+    float part = 0.f, part2 = 0.f;
+    constexpr int kStep = kTmaComputeWarps * 32;
+    const int cell = tid & (kTmaCells - 1);                      // fixed per thread: kStep is a multiple of the tile width
+    if (cell < nc) {
+      const int total = CK * kTmaCells;
+      int idx = tid;
+      for (; idx + kStep < total; idx += 2 * kStep) {             // two independent elements per trip
+        const int ta = cell * CK + (idx >> 7), tb = ta + kStep / kTmaCells;
+        float pa, ga, pb, gb;
+        part += focal_term(X[idx], T[ta], gamma, g2, alpha, grad_scale, pa, ga);
+        part2 += focal_term(X[idx + kStep], T[tb], gamma, g2, alpha, grad_scale, pb, gb);
+        T[ta] = pa; X[idx] = ga;
+        T[tb] = pb; X[idx + kStep] = gb;
+      }
+      if (idx < total) {
+        const int ta = cell * CK + (idx >> 7);
+        float pa, ga;
+        part += focal_term(X[idx], T[ta], gamma, g2, alpha, grad_scale, pa, ga);
+        T[ta] = pa; X[idx] = ga;
       }
     }
-    acc += (double)part;
+    acc += (double)(part + part2);
     tcx::fence_proxy_async();                                    // generic-proxy writes -> visible to the bulk stores
     __syncwarp();
     if (lane == 0) tcx::mbar_arrive(&done[st]);
@@ -263,9 +297,9 @@ __device__ __noinline__ void loss_reg_row(const float* __restrict__ reg, const f
 }
 
 // positives: loss terms, UNSCALED gradient rows (grad_reg is zeroed by the caller) and the list of positive
-// anchors.  A warp reads 32 consecutive target rows (288 floats) as nine coalesced loads; the lane that holds
-// a row's flag word handles that row.
-__global__ void __launch_bounds__(256) k_loss_reg(const float* __restrict__ reg, const float* __restrict__ reg_t,
+// anchors.  A warp reads 128 consecutive target rows (1152 floats) as nine coalesced 16-byte loads per lane; the
+// lane that holds a row's flag word handles that row.
+__global__ void __launch_bounds__(256, 3) k_loss_reg(const float* __restrict__ reg, const float* __restrict__ reg_t,
                                                   int B, int H, int W, int Ad, int R, float* __restrict__ grad,
                                                   unsigned* __restrict__ n_pos, unsigned* __restrict__ list,
                                                   double* __restrict__ partials) {
@@ -273,29 +307,38 @@ __global__ void __launch_bounds__(256) k_loss_reg(const float* __restrict__ reg,
   const size_t plane = (size_t)H * W;
   const size_t A = plane * Ad, n = A * B;
   const int lane = lane_id();
-  const size_t nchunks = (n + 31) / 32, e_end = n * 9;
+  const size_t nchunks = (n + 127) / 128, e_end = n * 9;          // 128 rows = 1152 floats = 9 float4 per lane
+  const bool vec = ((uintptr_t)reg_t % 16) == 0;
   double sr = 0.0, so = 0.0;
   for (size_t ck = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); ck < nchunks; ck += (size_t)gridDim.x * 8) {
-    const size_t e0 = ck * 288;
-    float v[9];
-    if (e0 + 288 <= e_end) {                                       // nine independent loads in flight per lane
+    const size_t e0 = ck * 1152;
+    float4 v[9];
+    if (vec && e0 + 1152 <= e_end) {                               // nine independent 16-byte loads in flight per lane
 #pragma unroll
-      for (int j = 0; j < 9; ++j) v[j] = __ldg(reg_t + e0 + lane + 32 * j);
+      for (int j = 0; j < 9; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(reg_t + e0) + lane + 32 * j);
     } else {
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
-        const size_t e = e0 + lane + 32 * j;
-        v[j] = e < e_end ? __ldg(reg_t + e) : 0.f;
+        const size_t e = e0 + 4 * (size_t)(lane + 32 * j);
+        v[j].x = e < e_end ? __ldg(reg_t + e) : 0.f;
+        v[j].y = e + 1 < e_end ? __ldg(reg_t + e + 1) : 0.f;
+        v[j].z = e + 2 < e_end ? __ldg(reg_t + e + 2) : 0.f;
+        v[j].w = e + 3 < e_end ? __ldg(reg_t + e + 3) : 0.f;
       }
     }
-    unsigned hit = 0;                                              // bit j: word lane + 32 j is a flag word equal to 1
+    unsigned long long hit = 0;                                    // bit 4j+k: word 4(lane+32j)+k is a flag word equal to 1
 #pragma unroll
-    for (int j = 0; j < 9; ++j)
-      hit |= (v[j] == 1.f && (lane + 32 * j) % 9 == 0) ? 1u << j : 0u;   // (:54) where(reg_targets[...,0] == 1)
+    for (int j = 0; j < 9; ++j) {
+      const int w = 4 * (lane + 32 * j), m = w % 9;                // (:54) where(reg_targets[...,0] == 1)
+      const float f[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (f[k] == 1.f && (m + k == 0 || m + k == 9)) hit |= 1ull << (4 * j + k);
+    }
     while (hit) {
-      const int j = __ffs(hit) - 1;
+      const int bit = __ffsll((long long)hit) - 1;
       hit &= hit - 1;
-      const size_t i = ck * 32 + (lane + 32 * j) / 9;
+      const size_t i = ck * 128 + (4 * (lane + 32 * (bit >> 2)) + (bit & 3)) / 9;
       const unsigned slot = atomicAdd(n_pos, 1u);
       if (list != nullptr) list[slot] = (unsigned)i;
       loss_reg_row(reg, reg_t + i * 9, i, A, plane, Ad, R, grad, sr, so);
@@ -355,7 +398,7 @@ struct LossWs {
   unsigned* list;
 };
 
-static int loss_reg_blocks() { return sm_count() * 8; }
+static int loss_reg_blocks() { return sm_count() * 3; }
 constexpr int kLossFinBlocks = 64;
 
 template <class A>
@@ -418,17 +461,34 @@ int pp_loss(const float* d_cls_out, float* d_reg_out, const float* d_cls_t, cons
   PP_CUDA(cudaMemsetAsync(ws.n_pos, 0, sizeof(unsigned), st));
   auto aligned16 = [](const void* q) { return q == nullptr || ((uintptr_t)q % 16) == 0; };
   const size_t smem = (size_t)kTmaStages * 2 * CK * kTmaCells * sizeof(float);
-  const bool tma = g_opt_loss_tma && plane % 4 == 0 && CK % 2 == 0 && aligned16(d_cls_out) && aligned16(d_cls_t) &&
+  const bool tma = g_opt_loss_tma && tensor_map_encode_fn() != nullptr && plane % 4 == 0 && CK % 2 == 0 && aligned16(d_cls_out) && aligned16(d_cls_t) &&
                    aligned16(d_scores) && aligned16(d_grad_cls) && smem <= 200 * 1024;
   int nparts;
   if (tma) {
     const int tiles = B * (int)((plane + kTmaCells - 1) / kTmaCells);
     nparts = tiles < sm_count() ? tiles : sm_count();
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeFn enc = (EncodeFn)tensor_map_encode_fn();
+    CUtensorMap tm_cls, tm_grad;
+    const cuuint64_t gdim[2] = {(cuuint64_t)plane, (cuuint64_t)B * CK};
+    const cuuint64_t gstride[1] = {(cuuint64_t)plane * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kTmaCells, (cuuint32_t)CK};
+    const cuuint32_t estr[2] = {1u, 1u};
+    auto encode = [&](CUtensorMap* m, const float* base) {
+      return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    if (!encode(&tm_cls, d_cls_out) || !encode(&tm_grad, d_grad_cls != nullptr ? d_grad_cls : d_cls_out))
+      return PP_ERR_UNSUPPORTED;
     PP_CUDA(cudaFuncSetAttribute(k_loss_cls_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PP_KERNEL("k_loss_cls_tma", st,
-              (k_loss_cls_tma<<<nparts, (kTmaComputeWarps + 1) * 32, smem, st>>>(d_cls_out, d_cls_t, B, (int)plane, CK, gamma,
-                                                                                alpha_pos, gscale, d_scores, d_grad_cls,
-                                                                                d_reg_out, CR, ws.pc)));
+              (k_loss_cls_tma<<<nparts, (kTmaComputeWarps + 1) * 32, smem, st>>>(tm_cls, tm_grad, d_cls_t, B, (int)plane, CK, gamma,
+                                                                                alpha_pos, gscale, d_scores,
+                                                                                d_grad_cls != nullptr ? 1 : 0, d_reg_out, CR,
+                                                                                ws.pc)));
   } else {
     const dim3 gc((W + kLossCells - 1) / kLossCells, H, B);
     nparts = (int)((size_t)gc.x * gc.y * gc.z);

@@ -494,6 +494,8 @@ static EncodeTiledFn encode_fn() {
 
 }  // namespace tch
 
+void* tensor_map_encode_fn() { return (void*)tch::encode_fn(); }    // shared with loss.cu
+
 extern int g_opt_pfn_tc_debug;
 extern int g_opt_pfn_tc_timing;
 long long* tc_prof_ptr();   // pfn_tc.cu

@@ -208,9 +208,8 @@ class PPFeatureScatter(nn.Module):
         self.canvas_width = int(_cfg.canvas_width if canvas_width is None else canvas_width)
 
     def forward(self, x, inds, return_features=False, out=None):
-        if _wants_grad(x, self):
-            if return_features or out is not None:
-                raise _lib.PPError("PPFeatureScatter: return_features / out are inference-only arguments")
+        # ``out`` / ``return_features`` are the streaming pipeline's arguments: that call is never differentiated
+        if _wants_grad(x, self) and out is None and not return_features:
             _runtime.require_cuda(inds, "inds")
             return _PFNFunction.apply(x, self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, self,
                                       inds.contiguous())

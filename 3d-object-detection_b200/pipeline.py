@@ -151,7 +151,8 @@ class InputPath:
 
     # -- K2 -----------------------------------------------------------------------------------
     def encode(self, x, inds, out=None, return_features=False):
-        return self.net(x, inds, return_features=return_features, out=out)
+        with torch.no_grad():                       # the streaming path is not differentiated (train through pp_b200.model)
+            return self.net(x, inds, return_features=return_features, out=out)
 
     # -- K1 + K2 fused, x never materialised (pp_input_path) ------------------------------------
     def fused_supported(self, n_sweeps):

@@ -261,6 +261,54 @@ def algorithmic_bytes(B, P, N, C, H, W, A, K, total_points, has_mean):
     }
 
 
+def training_rows(x, inds, targets, dev, peak, steps):
+    """PFN + scatter backward (pp_pfn_backward) and the loss front-end (pp_loss) on the step's own x / inds /
+    targets, network outputs random: per-kernel CUDA-event times and, for the streaming loss kernels, GB/s."""
+    import torch
+    from pp_b200 import _lib, loss as pl, model as pm
+    L = _lib.load()
+    B = x.shape[0]
+    cls_t, reg_t = targets
+    net = pm.PPFeatureScatter(9, 64).to(dev).train()
+    lossm = pl.PPLoss(0, 1, 250, 2, dev)
+    g_canvas = torch.randn((B, 64, net.canvas_height, net.canvas_width), device=dev)
+    cls = torch.randn((B, 54, 300, 300), device=dev) * 1.5 - 3.0
+    reg = torch.randn((B, 48, 300, 300), device=dev)
+
+    def one():
+        net.zero_grad(set_to_none=True)
+        net(x, inds).backward(g_canvas)
+        c = cls.clone().requires_grad_(True)
+        r = reg.clone().requires_grad_(True)
+        lossm(c, r * 1.0, cls_t, reg_t)[4].backward()
+
+    one()
+    torch.cuda.synchronize()
+    L.pp_profile_enable(1)
+    for _ in range(steps):
+        one()
+    rep = _lib.profile_report()
+    L.pp_profile_enable(0)
+    n_cls, n_reg = cls.numel() * 4, reg.numel() * 4
+    alg = {"k_loss_cls_tma": 4 * n_cls + 2 * B * 90000 * 4, "k_loss_reg": reg_t.numel() * 4}
+    rows = {}
+    for name, (n, ms) in rep.items():
+        if not (name.startswith("k_loss") or name.startswith("k_pfn_bwd")):
+            continue
+        k = {"us_per_launch": ms * 1e3 / n}
+        if name in alg:
+            k["alg_bytes_per_launch"] = alg[name]
+            k["GBps"] = alg[name] / (ms / n * 1e-3) / 1e9
+            k["frac_of_peak"] = k["GBps"] / peak
+        rows[name] = k
+    slots = float(x.shape[0] * x.shape[2] * x.shape[3])
+    if "k_pfn_bwd" in rows:
+        rows["k_pfn_bwd"]["note"] = ("FP32-issue bound, not HBM: 30 FMA per (slot, channel) for z and the BatchNorm moment "
+                                     "matrices; %.1f G(slot*channel)/s" % (slots * 64 / rows["k_pfn_bwd"]["us_per_launch"] / 1e3))
+    return {"what": "pp_pfn_backward through PPFeatureScatter.backward (training-mode BatchNorm) and pp_loss through "
+                    "PPLoss forward + backward, batch of %d sweeps" % B, "kernels": rows}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -428,6 +476,7 @@ def run_ours(args):
 
     # the other formulation of the same step, for reference (same inputs, same outputs)
     other = None
+    training = None
     if fused and not args.no_dense_reference:
         path2 = pipeline.InputPath(cfg, device=dev, data_mean=mean, pfn_params=synth.make_pfn_params(0),
                                    training=True, fused=False, anchors=anchors)
@@ -455,6 +504,9 @@ def run_ours(args):
         other = {"what": "signature-preserving sequence pp_pillarize -> x [B,9,P,N] -> pp_pfn_scatter (x materialised)",
                  "value": units2 / (ms2_max / 1e3), "unit": UNIT, "ms_per_step": ms2_max / args.steps,
                  "roofline": roof2, "kernels": k2}
+        # the two training-side rows next to the path, timed on this step's own outputs
+        if rank == 0 and world == 1 and not args.no_training_rows:
+            training = training_rows(out2["pillars"][0], out2["pillars"][1], out["targets"], dev, peak, args.steps)
         del out2, path2
 
     cpu_baseline = None
@@ -486,7 +538,8 @@ def run_ours(args):
                                "overlaps the encode stage of step k; encode stages ordered), <= 2 steps in flight, "
                                "timed region ends after the last step has completed",
                        "parallelism": "dp%d (one process per GPU, sweeps sharded, no collective)" % world},
-            "roofline": roofline, "kernels": kernels, "dense_path": other, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "kernels": kernels, "dense_path": other, "training_rows": training,
+            "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e_max / args.steps, "host_wall_ms_per_step": ms_e_host / args.steps,
                     "pipeline": "step_host_async: copy stream + 2 staging buffers + 2 kernel lanes, at most two steps "
@@ -508,6 +561,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-training-rows", action="store_true", help="skip the PFN backward / loss front-end timings")
     ap.add_argument("--no-dense-reference", action="store_true", help="skip the extra dense_path measurement")
     ap.add_argument("--inflight", type=int, default=2, help="steps in flight in the streaming loops (>= 2)")
     ap.add_argument("--dense-path", action="store_true",
