@@ -227,11 +227,14 @@ class InputPath:
 
     # -- host-facing step -----------------------------------------------------------------------
     @staticmethod
-    def _blob_layout(T, ncol, Gt):
-        """Byte offsets of the sections of one packed batch (each 256-byte aligned)."""
+    def _blob_layout(T, ncol, Gt, F=0):
+        """Byte offsets of the sections of one packed batch (each 256-byte aligned).  F > 0 appends the
+        per-file transforms and file offsets of a batch that is aggregated on the device."""
         al = lambda v: (v + 255) // 256 * 256
         sizes = [("points", max(T, 1) * ncol * 4), ("corners", max(Gt, 1) * 8 * 8), ("centers", max(Gt, 1) * 3 * 8),
                  ("wlh", max(Gt, 1) * 3 * 8), ("yaw", max(Gt, 1) * 8), ("cls", max(Gt, 1) * 4)]
+        if F > 0:
+            sizes += [("xforms", F * 12 * 8), ("file_offsets", (F + 1) * 8)]
         off, o = {}, 0
         for name, n in sizes:
             off[name] = (o, n)
@@ -241,30 +244,85 @@ class InputPath:
     @staticmethod
     def _blob_views(blob, off, T, ncol, Gt):
         v = lambda name, dt: blob[off[name][0]:off[name][0] + off[name][1]].view(dt)
-        return {"points": v("points", torch.float32).view(max(T, 1), ncol),
-                "corners": v("corners", torch.float64).view(max(Gt, 1), 8),
-                "centers": v("centers", torch.float64).view(max(Gt, 1), 3),
-                "wlh": v("wlh", torch.float64).view(max(Gt, 1), 3),
-                "yaw": v("yaw", torch.float64), "cls": v("cls", torch.int32)}
+        views = {"points": v("points", torch.float32).view(max(T, 1), ncol),
+                 "corners": v("corners", torch.float64).view(max(Gt, 1), 8),
+                 "centers": v("centers", torch.float64).view(max(Gt, 1), 3),
+                 "wlh": v("wlh", torch.float64).view(max(Gt, 1), 3),
+                 "yaw": v("yaw", torch.float64), "cls": v("cls", torch.int32)}
+        if "xforms" in off:
+            views["xforms"] = v("xforms", torch.float64).view(-1, 12)
+            views["file_offsets"] = v("file_offsets", torch.int64)
+        return views
 
-    def pack_host_batch(self, sweeps, gts):
+    # -- sweep aggregation in front of K1 (pp_aggregate_sweeps; data/dataset.py:54-88) -------------------
+    def aggregate(self, d_points, file_offsets, transforms, min_dist=0.001, want_kept=False):
+        """In place on device rows ``d_points [T, S>=3]`` float32: every file's points go through its 4x4
+        (or 3x4) float64 ``transmat`` (dataset.py:78) and the SDK's ``remove_close(min_dist)``; dropped points
+        get an out-of-range sentinel that the pillarize stage filters.  ``file_offsets`` (F+1 row offsets) and
+        ``transforms`` may be host sequences or device tensors.  Returns the per-file kept counts if asked."""
+        L = _lib.load()
+        _runtime.require_cuda(d_points, "d_points")
+        if d_points.dtype != torch.float32 or d_points.dim() != 2 or not d_points.is_contiguous():
+            raise _lib.PPError("aggregate: d_points must be a contiguous float32 [T, S] tensor")
+        dev = d_points.device
+        fo = torch.as_tensor(file_offsets, dtype=torch.int64).to(dev).contiguous()
+        if isinstance(transforms, torch.Tensor) and transforms.is_cuda:
+            xf = transforms.to(torch.float64).reshape(fo.numel() - 1, -1, 4)[:, :3, :].contiguous()
+        else:
+            xf = torch.from_numpy(np.ascontiguousarray(
+                np.asarray(transforms, dtype=np.float64).reshape(fo.numel() - 1, -1, 4)[:, :3, :])).to(dev)
+        F = fo.numel() - 1
+        kept = torch.empty(F, dtype=torch.int32, device=dev) if want_kept else None
+        with torch.cuda.device(dev):
+            rc = L.pp_aggregate_sweeps(d_points.data_ptr(), d_points.shape[0], d_points.shape[1], fo.data_ptr(), F,
+                                       xf.data_ptr(), float(min_dist), kept.data_ptr() if kept is not None else None,
+                                       _runtime.stream_ptr(dev))
+        _lib.check(rc, "pp_aggregate_sweeps")
+        return kept
+
+    def pack_host_batch(self, sweeps, gts, transforms=None, min_dist=0.001):
         """Pack a list of float32 [n_i, >=4] sweeps and a list of GT dicts (centers/wlh/yaw/cls in
         canvas space, as the reference's box pickles hold them) into ONE pinned host buffer
         (points | GT corners | centres | wlh | yaw | class ids), so that a step needs a single
-        host-to-device copy and no device-side repacking."""
-        offs = [0]
-        for s in sweeps:
-            offs.append(offs[-1] + int(s.shape[0]))
-        ncol = int(sweeps[0].shape[1])
+        host-to-device copy and no device-side repacking.
+
+        With ``transforms``: ``sweeps[i]`` is the LIST of raw lidar files ([n,5] float32, in the order
+        dataset.py:58-85 visits them) that sample i aggregates and ``transforms[i]`` the matching list of
+        4x4 float64 ``transmat``; the transform and ``remove_close(min_dist)`` then run on the device right
+        after the upload (``aggregate``), nothing is transformed or compacted on the host."""
+        files, xf, foffs = sweeps, None, None
+        if transforms is not None:
+            files, xf, foffs, offs = [], [], [0], [0]
+            for group, mats in zip(sweeps, transforms):
+                group = group if isinstance(group, (list, tuple)) else [group]
+                mats = mats if isinstance(mats, (list, tuple)) else [mats]
+                if len(group) != len(mats):
+                    raise _lib.PPError("pack_host_batch: one transform per lidar file")
+                for f, m in zip(group, mats):
+                    files.append(f)
+                    xf.append(np.asarray(m, dtype=np.float64).reshape(-1, 4)[:3, :])
+                    foffs.append(foffs[-1] + int(f.shape[0]))
+                offs.append(foffs[-1])
+        else:
+            offs = [0]
+            for s in sweeps:
+                offs.append(offs[-1] + int(s.shape[0]))
+        ncol = int(files[0].shape[1])
         goffs = [0]
         for g in gts:
             goffs.append(goffs[-1] + int(len(g["yaw"])))
         T, Gt = offs[-1], goffs[-1]
-        layout, nbytes = self._blob_layout(T, ncol, Gt)
+        F = len(xf) if xf is not None else 0
+        layout, nbytes = self._blob_layout(T, ncol, Gt, F)
         blob = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
         hv = self._blob_views(blob, layout, T, ncol, Gt)
-        for s, lo, hi in zip(sweeps, offs[:-1], offs[1:]):
-            hv["points"][lo:hi] = torch.as_tensor(s, dtype=torch.float32)
+        lo = 0
+        for f in files:
+            hv["points"][lo:lo + f.shape[0]] = torch.as_tensor(f, dtype=torch.float32)
+            lo += int(f.shape[0])
+        if F:
+            hv["xforms"][:] = torch.from_numpy(np.stack(xf).reshape(F, 12))
+            hv["file_offsets"][:] = torch.tensor(foffs, dtype=torch.int64)
         for g, lo, hi in zip(gts, goffs[:-1], goffs[1:]):
             if hi == lo:
                 continue
@@ -275,7 +333,7 @@ class InputPath:
             hv["yaw"][lo:hi] = torch.from_numpy(np.asarray(g["yaw"], dtype=np.float64))
             hv["cls"][lo:hi] = torch.from_numpy(np.asarray(g["cls"], dtype=np.int32))
         return {"blob": blob, "layout": layout, "ncol": ncol, "offsets": offs, "gt_offsets": goffs,
-                "points": hv["points"], "host": hv}
+                "points": hv["points"], "host": hv, "n_files": F, "min_dist": float(min_dist)}
 
     def upload(self, batch, slot=None):
         """One host-to-device copy of a packed batch; returns (d_points, gt_dev) views of the device
@@ -292,7 +350,14 @@ class InputPath:
         dblob[:n].copy_(batch["blob"], non_blocking=True)
         dv = self._blob_views(dblob, batch["layout"], T, batch["ncol"], Gt)
         gt_dev = {k: dv[k] for k in ("corners", "centers", "wlh", "yaw", "cls")}
-        return dv["points"][:max(T, 1)], gt_dev
+        d_pts = dv["points"][:max(T, 1)]
+        if batch.get("n_files"):                     # aggregate on the stream the copy was issued on
+            with torch.cuda.device(dev):
+                rc = _lib.load().pp_aggregate_sweeps(d_pts.data_ptr(), T, batch["ncol"], dv["file_offsets"].data_ptr(),
+                                                     batch["n_files"], dv["xforms"].data_ptr(), batch["min_dist"], None,
+                                                     _runtime.stream_ptr(dev))
+            _lib.check(rc, "pp_aggregate_sweeps")
+        return d_pts, gt_dev
 
     def _run(self, d_pts, offsets, gt_dev, gt_offsets, o, side=None, ordered=False):
         main = torch.cuda.current_stream(self.device)

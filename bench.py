@@ -261,7 +261,7 @@ def algorithmic_bytes(B, P, N, C, H, W, A, K, total_points, has_mean):
     }
 
 
-def training_rows(x, inds, targets, dev, peak, steps):
+def training_rows(x, inds, targets, dev, peak, steps, path=None, d_pts=None, offsets=None):
     """PFN + scatter backward (pp_pfn_backward) and the loss front-end (pp_loss) on the step's own x / inds /
     targets, network outputs random: per-kernel CUDA-event times and, for the streaming loss kernels, GB/s."""
     import torch
@@ -275,12 +275,24 @@ def training_rows(x, inds, targets, dev, peak, steps):
     cls = torch.randn((B, 54, 300, 300), device=dev) * 1.5 - 3.0
     reg = torch.randn((B, 48, 300, 300), device=dev)
 
+    pts_copy = d_pts.clone() if d_pts is not None else None
+    rigid = None
+    if pts_copy is not None:
+        import numpy as np
+        rigid = np.stack([[[np.cos(0.01 * k), -np.sin(0.01 * k), 0, 0.4 * k], [np.sin(0.01 * k), np.cos(0.01 * k), 0, 0.0],
+                           [0, 0, 1, 0.0]] for k in range(len(offsets) - 1)])
+        rigid = torch.from_numpy(rigid.reshape(-1, 12)).to(dev)
+        offs_dev = torch.tensor(offsets, dtype=torch.int64, device=dev)
+
     def one():
         net.zero_grad(set_to_none=True)
         net(x, inds).backward(g_canvas)
         c = cls.clone().requires_grad_(True)
         r = reg.clone().requires_grad_(True)
         lossm(c, r * 1.0, cls_t, reg_t)[4].backward()
+        if pts_copy is not None:
+            pts_copy.copy_(d_pts)
+            path.aggregate(pts_copy, offs_dev, rigid)
 
     one()
     torch.cuda.synchronize()
@@ -291,9 +303,11 @@ def training_rows(x, inds, targets, dev, peak, steps):
     L.pp_profile_enable(0)
     n_cls, n_reg = cls.numel() * 4, reg.numel() * 4
     alg = {"k_loss_cls_tma": 4 * n_cls + 2 * B * 90000 * 4, "k_loss_reg": reg_t.numel() * 4}
+    if d_pts is not None:
+        alg["k_aggregate"] = d_pts.shape[0] * (3 * 4 * 2 + 8)          # x,y,z read + written; sector granularity not counted
     rows = {}
     for name, (n, ms) in rep.items():
-        if not (name.startswith("k_loss") or name.startswith("k_pfn_bwd")):
+        if not (name.startswith("k_loss") or name.startswith("k_pfn_bwd") or name == "k_aggregate"):
             continue
         k = {"us_per_launch": ms * 1e3 / n}
         if name in alg:
@@ -306,7 +320,8 @@ def training_rows(x, inds, targets, dev, peak, steps):
         rows["k_pfn_bwd"]["note"] = ("FP32-issue bound, not HBM: 30 FMA per (slot, channel) for z and the BatchNorm moment "
                                      "matrices; %.1f G(slot*channel)/s" % (slots * 64 / rows["k_pfn_bwd"]["us_per_launch"] / 1e3))
     return {"what": "pp_pfn_backward through PPFeatureScatter.backward (training-mode BatchNorm) and pp_loss through "
-                    "PPLoss forward + backward, batch of %d sweeps" % B, "kernels": rows}
+                    "PPLoss forward + backward, batch of %d sweeps; pp_aggregate_sweeps (rigid transform + remove_close, in "
+                    "place) on the batch's raw points" % B, "kernels": rows}
 
 
 def run_ours(args):
@@ -506,7 +521,8 @@ def run_ours(args):
                  "roofline": roof2, "kernels": k2}
         # the two training-side rows next to the path, timed on this step's own outputs
         if rank == 0 and world == 1 and not args.no_training_rows:
-            training = training_rows(out2["pillars"][0], out2["pillars"][1], out["targets"], dev, peak, args.steps)
+            training = training_rows(out2["pillars"][0], out2["pillars"][1], out["targets"], dev, peak, args.steps,
+                                     path=path2, d_pts=d_pts, offsets=batch["offsets"])
         del out2, path2
 
     cpu_baseline = None

@@ -6,6 +6,7 @@
  *
  *   pp_pillarize          replaces  data/pillars.cpp:236-398  create_pillars  (pybind11 export :433)
  *                         + the tensor glue of                data/dataset.py:99-106
+ *   pp_aggregate_sweeps   replaces  data/dataset.py:54-88     sweep aggregation (SDK transform + remove_close)
  *   pp_pfn_forward        replaces  model/model.py:31-40      PPFeatureNet.forward
  *   pp_scatter            replaces  model/model.py:53-62      PPScatter.forward
  *   pp_pfn_scatter        the two above fused (canvas written straight from the pillar maxima)
@@ -104,6 +105,20 @@ int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_poin
                   float* d_canvas, float* d_x, int64_t* d_indices, int32_t* d_num_pillars,
                   int32_t* d_status, void* d_workspace, size_t workspace_bytes, int32_t stages,
                   pp_stream_t stream);
+
+/* Multi-sweep aggregation in front of pp_pillarize (data/dataset.py:54-88 with the Lyft SDK's
+ * LidarPointCloud.transform and remove_close), IN PLACE on raw lidar rows:
+ *   d_points [n_points, point_stride >= 3] float32 (Lyft .bin rows x,y,z,intensity,ring); file f owns rows
+ *   d_file_offsets[f] .. d_file_offsets[f+1] (int64, n_files + 1 entries, device);
+ *   d_transforms [n_files, 3, 4] float64 row-major = the first three rows of dataset.py:78's transmat.
+ * x,y,z <- float32(M . [x,y,z,1]) (float64 product, one rounding); a point with |x| < min_dist and
+ * |y| < min_dist afterwards (float32 compare, remove_close) gets the finite out-of-range sentinel 3.0e38 in
+ * x,y,z, which pp_pillarize's range filter drops: the surviving points keep their order, so pillars are those
+ * of the compacted cloud and sample offsets stay the file boundaries.  d_kept [n_files] int32 (may be NULL)
+ * receives the number of points each file keeps. */
+int pp_aggregate_sweeps(float* d_points, int64_t n_points, int32_t point_stride, const int64_t* d_file_offsets,
+                        int32_t n_files, const double* d_transforms, float min_dist, int32_t* d_kept,
+                        pp_stream_t stream);
 
 /* Backward of PPFeatureNet: the gradients torch autograd computes through
  * model/model.py:36-39 (conv1 -> relu -> bn1 -> max over N) for the four parameter tensors, from the same
