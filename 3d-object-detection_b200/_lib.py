@@ -64,12 +64,17 @@ _SIGNATURES = {
     "pp_loss_scale_grads": (_c.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _vp]),
     "pp_loss": (_c.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _f32,
                            _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pp_loss_list": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32,
+                                _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pp_make_ious": (_c.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "pp_anchor_index_bytes": (_sz, [_vp, _i64, _i32]),
     "pp_anchor_index_build": (_c.c_int, [_vp, _vp, _i64, _vp, _sz, _vp]),
     "pp_assign_targets_workspace_bytes": (_sz, [_i32, _i64, _i64, _vp]),
     "pp_assign_targets": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64p,
                                      _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pp_assign_targets_list": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64p,
+                                          _i32, _i32, _f64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                          _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -91,11 +91,38 @@ class AnchorSet:
         return cls(a["corners"], a["centers"], a["wlh"], a["yaw"], device=device)
 
 
+class Positives(object):
+    """The targets as a positives list + implicit zeros (pp_assign_targets_list): ``anchor [cap]`` int32 =
+    sweep * A + anchor in ascending order, ``cls [cap,9]`` / ``reg [cap,9]`` float32 rows, ``offsets [B+1]`` int32
+    (device; ``offsets[B]`` is the length), plus the shape ``(B, A)`` they stand for.  ``pp_b200.loss.PPLoss``
+    takes it in place of the two dense tensors."""
+
+    def __init__(self, anchor, cls, reg, offsets, n_sweeps, n_anchors):
+        self.anchor, self.cls, self.reg, self.offsets = anchor, cls, reg, offsets
+        self.n_sweeps, self.n_anchors = int(n_sweeps), int(n_anchors)
+
+    def dense(self):
+        """(cls [B,A,9], reg [B,A,9]) float32: what pp_assign_targets would have written (synchronises)."""
+        n = int(self.offsets[-1].item())
+        B, A = self.n_sweeps, self.n_anchors
+        cls = torch.zeros((B * A, 9), dtype=torch.float32, device=self.anchor.device)
+        reg = torch.zeros((B * A, 9), dtype=torch.float32, device=self.anchor.device)
+        idx = self.anchor[:n].long()
+        cls[idx] = self.cls[:n]
+        reg[idx] = self.reg[:n]
+        return cls.view(B, A, 9), reg.view(B, A, 9)
+
+
 def assign_targets(anchors, g_corners, g_centers, g_wlh, g_yaw, g_cls, gt_offsets, num_classes=None,
-                   pos_thresh=None, out=None):
+                   pos_thresh=None, out=None, as_list=False, capacity=None):
     """Device-native batch target assignment (pp_assign_targets).  GT tensors are CUDA float64
     (g_cls int32), all sweeps concatenated; ``gt_offsets`` is a host list of len n_sweeps+1.
-    Returns (cls [B,A,K] f32, reg [B,A,9] f32, top_anchor [Gt] i32, counts [B,4] i32)."""
+    Returns (cls [B,A,K] f32, reg [B,A,9] f32, top_anchor [Gt] i32, counts [B,4] i32).
+    ``as_list=True`` (pp_assign_targets_list): returns (Positives, None, top_anchor, counts) and writes no
+    dense tensor; ``capacity`` bounds the list (default 4096 per sweep)."""
+    if as_list:
+        return _assign_targets_list(anchors, g_corners, g_centers, g_wlh, g_yaw, g_cls, gt_offsets, num_classes,
+                                    pos_thresh, capacity)
     L = _lib.load()
     dev = anchors.device
     B = len(gt_offsets) - 1
@@ -123,6 +150,35 @@ def assign_targets(anchors, g_corners, g_centers, g_wlh, g_yaw, g_cls, gt_offset
             ws.data_ptr(), ws.numel(), _runtime.stream_ptr(dev))
     _lib.check(rc, "pp_assign_targets")
     return cls, reg, top[:Gt], counts
+
+
+def _assign_targets_list(anchors, g_corners, g_centers, g_wlh, g_yaw, g_cls, gt_offsets, num_classes, pos_thresh,
+                         capacity):
+    L = _lib.load()
+    dev = anchors.device
+    B = len(gt_offsets) - 1
+    K = int(_cfg.num_classes if num_classes is None else num_classes)
+    thr = float(_cfg.iou_pos_thresh if pos_thresh is None else pos_thresh)
+    Gt = int(gt_offsets[-1])
+    A = anchors.A
+    cap = int(capacity if capacity is not None else 4096 * B)
+    pos = Positives(torch.empty(cap, dtype=torch.int32, device=dev), torch.empty((cap, 9), dtype=torch.float32, device=dev),
+                    torch.empty((cap, 9), dtype=torch.float32, device=dev),
+                    torch.empty(B + 1, dtype=torch.int32, device=dev), B, A)
+    top = torch.empty(max(Gt, 1), dtype=torch.int32, device=dev)
+    counts = torch.empty((B, 4), dtype=torch.int32, device=dev)
+    ws = _runtime.workspace(L.pp_assign_targets_workspace_bytes(B, A, Gt, None), dev, "targets")
+    status = _runtime.status_word(dev)
+    ptr = lambda t: t.data_ptr() if (t is not None and t.numel() > 0) else None
+    with torch.cuda.device(dev):
+        rc = L.pp_assign_targets_list(
+            anchors.corners.data_ptr(), anchors.centers.data_ptr(), anchors.wlh.data_ptr(),
+            anchors.yaw.data_ptr(), anchors.index.data_ptr(), A, ptr(g_corners), ptr(g_centers),
+            ptr(g_wlh), ptr(g_yaw), ptr(g_cls), _lib.i64_array(gt_offsets), B, K, thr,
+            pos.anchor.data_ptr(), pos.cls.data_ptr(), pos.reg.data_ptr(), pos.offsets.data_ptr(), cap, None, None,
+            top.data_ptr(), counts.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), _runtime.stream_ptr(dev))
+    _lib.check(rc, "pp_assign_targets_list")
+    return pos, None, top[:Gt], counts
 
 
 _anchor_cache = {}

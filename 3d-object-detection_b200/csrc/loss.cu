@@ -148,13 +148,37 @@ __device__ __forceinline__ float focal_term(float x, float t, float gamma, bool 
   return wgt * bce;
 }
 
+constexpr int kTmaRangeSlots = 128;  // list ranges kept in shared memory for the first 64 tiles of a block
+constexpr int kMaxListSmem = 8192;   // positives whose anchor ids are kept in shared memory (else searched in global)
+
+struct PosListIn {                   // sorted by global anchor id b*A + a (pp_assign_targets_list)
+  const int* anchor;
+  const float* cls;                  // [n, K]
+  const int* offsets;                // [B+1], offsets[B] = n
+  int Ad;
+};
+
+__device__ __forceinline__ int lower_bound_i(const int* __restrict__ v, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (v[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// SPARSE: the targets are implicit zeros plus the positives list; no target tile is loaded.  Tiles that hold
+// positives evaluate those elements first (true t), mark them in a bitmap, and the main loop skips them.
+template <bool SPARSE>
 __global__ void __launch_bounds__((kTmaComputeWarps + 1) * 32, 1)
 k_loss_cls_tma(const __grid_constant__ CUtensorMap tm_cls, const __grid_constant__ CUtensorMap tm_grad,
-               const float* __restrict__ cls_t, int B, int plane, int CK, float gamma, float alpha, float grad_scale,
-               float* __restrict__ scores, int want_grad, float* __restrict__ reg, int CR, double* __restrict__ partials) {
+               const float* __restrict__ cls_t, PosListIn pl, int B, int plane, int CK, float gamma, float alpha,
+               float grad_scale, float* __restrict__ scores, int want_grad, float* __restrict__ reg, int CR,
+               double* __restrict__ partials) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ uint64_t full[kTmaStages], done[kTmaStages];
   __shared__ double s_red[kTmaComputeWarps];
+  __shared__ unsigned s_bits[SPARSE ? kLossMaxCh * kTmaCells / 32 : 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int stage_floats = 2 * CK * kTmaCells;                  // X [CK][128] then T [128*CK]
   float* s_f = reinterpret_cast<float*>(s_raw);
@@ -179,9 +203,10 @@ k_loss_cls_tma(const __grid_constant__ CUtensorMap tm_cls, const __grid_constant
       const int st = it % kTmaStages;
       float* X = s_f + (size_t)st * stage_floats;
       float* T = X + CK * kTmaCells;
-      tcx::mbar_expect_tx(&full[st], (uint32_t)(CK * kTmaCells + nc * CK) * 4u);     // the box always lands whole (zero fill)
+      // the box always lands whole (zero fill past the plane)
+      tcx::mbar_expect_tx(&full[st], (uint32_t)(CK * kTmaCells + (SPARSE ? 0 : nc * CK)) * 4u);
       tma_load_2d(X, &tm_cls, c0, b * CK, &full[st]);
-      tcx::bulk_g2s(T, cls_t + ((size_t)b * plane + c0) * CK, (uint32_t)nc * CK * 4u, &full[st]);
+      if (!SPARSE) tcx::bulk_g2s(T, cls_t + ((size_t)b * plane + c0) * CK, (uint32_t)nc * CK * 4u, &full[st]);
     };
     const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     for (int it = 0; it < min(my_tiles, kTmaStages); ++it) load(it);
@@ -207,6 +232,42 @@ k_loss_cls_tma(const __grid_constant__ CUtensorMap tm_cls, const __grid_constant
 
   // ---------------- compute warps
   const bool g2 = gamma == 2.f;
+  constexpr int kStep = kTmaComputeWarps * 32;
+  const int K = SPARSE ? CK / pl.Ad : 0;
+  int n_list = 0;
+  const int* ids = nullptr;
+  unsigned short* s_mask = nullptr;                              // per listed row: bit k = (t_k == 1), bit 15 = other values
+  __shared__ int s_range[SPARSE ? kTmaRangeSlots + 1 : 1];      // list range start of this block's tiles
+  if (SPARSE) {
+    n_list = pl.offsets[B];
+    int* s_ids = reinterpret_cast<int*>(s_raw + (size_t)kTmaStages * 2 * CK * kTmaCells * sizeof(float));
+    if (n_list <= kMaxListSmem) {
+      s_mask = reinterpret_cast<unsigned short*>(s_ids + kMaxListSmem);
+      for (int i = tid; i < n_list; i += kStep) {
+        s_ids[i] = pl.anchor[i];
+        unsigned m = 0;
+        for (int k = 0; k < K; ++k) {
+          const float t = __ldg(pl.cls + (size_t)i * K + k);
+          if (t == 1.f && k < 15) m |= 1u << k; else if (t != 0.f) m |= 0x8000u;
+        }
+        s_mask[i] = (unsigned short)m;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kStep));
+      ids = s_ids;
+    } else {
+      ids = pl.anchor;
+    }
+    // list ranges of this block's tiles, once: tile j of the block covers ids in [s_range[2j], s_range[2j+1])
+    for (int j = tid; j < kTmaRangeSlots; j += kStep) {
+      const int tile = blockIdx.x + (j >> 1) * gridDim.x;
+      if (tile < ntiles) {
+        const int b = tile / tiles_per_plane, c0 = (tile - b * tiles_per_plane) * kTmaCells;
+        const int a0 = (b * plane + c0) * pl.Ad;
+        s_range[j] = lower_bound_i(ids, n_list, (j & 1) ? a0 + min(kTmaCells, plane - c0) * pl.Ad : a0);
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kStep));
+  }
   double acc = 0.0;
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -215,29 +276,66 @@ k_loss_cls_tma(const __grid_constant__ CUtensorMap tm_cls, const __grid_constant
     const int st = it % kTmaStages;
     float* X = s_f + (size_t)st * stage_floats;
     float* T = X + CK * kTmaCells;
+    int lo = 0, hi = 0;
+    if (SPARSE) {                                                // positives of this tile: ids in [a0, a1)
+      if (2 * it + 1 < kTmaRangeSlots) {
+        lo = s_range[2 * it];
+        hi = s_range[2 * it + 1];
+      } else {
+        const int a0 = (b * plane + c0) * pl.Ad, a1 = a0 + nc * pl.Ad;
+        if (lane == 0) { lo = lower_bound_i(ids, n_list, a0); hi = lower_bound_i(ids, n_list, a1); }
+        lo = __shfl_sync(0xffffffffu, lo, 0);
+        hi = __shfl_sync(0xffffffffu, hi, 0);
+      }
+    }
     tcx::mbar_wait(&full[st], (it / kTmaStages) & 1);
     float part = 0.f, part2 = 0.f;
-    constexpr int kStep = kTmaComputeWarps * 32;
+    const bool marked = SPARSE && hi > lo;                       // uniform over the block
+    if (marked) {
+      const int a0 = (b * plane + c0) * pl.Ad;
+      for (int i = tid; i < CK * kTmaCells / 32; i += kStep) s_bits[i] = 0u;
+      asm volatile("bar.sync 1, %0;" ::"n"(kStep));
+      for (int j = tid; j < (hi - lo) * K; j += kStep) {
+        const int e = lo + j / K, k = j - (j / K) * K;
+        float t;
+        if (s_mask != nullptr && !(s_mask[e] & 0x8000u)) t = (s_mask[e] >> k) & 1u ? 1.f : 0.f;
+        else t = __ldg(pl.cls + (size_t)e * K + k);
+        if (t != 0.f) {
+          const int local = ids[e] - a0, pc = local / pl.Ad, ch = (local - pc * pl.Ad) * K + k;
+          const int idx = ch * kTmaCells + pc;
+          float pa, ga;
+          part += focal_term(X[idx], t, gamma, g2, alpha, grad_scale, pa, ga);
+          T[pc * CK + ch] = pa;
+          X[idx] = ga;
+          atomicOr(&s_bits[idx >> 5], 1u << (idx & 31));
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kStep));
+    }
     const int cell = tid & (kTmaCells - 1);                      // fixed per thread: kStep is a multiple of the tile width
     if (cell < nc) {
       const int total = CK * kTmaCells;
       int idx = tid;
       for (; idx + kStep < total; idx += 2 * kStep) {             // two independent elements per trip
         const int ta = cell * CK + (idx >> 7), tb = ta + kStep / kTmaCells;
+        const bool skip_a = marked && ((s_bits[idx >> 5] >> (idx & 31)) & 1u);
+        const bool skip_b = marked && ((s_bits[(idx + kStep) >> 5] >> ((idx + kStep) & 31)) & 1u);
         float pa, ga, pb, gb;
-        part += focal_term(X[idx], T[ta], gamma, g2, alpha, grad_scale, pa, ga);
-        part2 += focal_term(X[idx + kStep], T[tb], gamma, g2, alpha, grad_scale, pb, gb);
-        T[ta] = pa; X[idx] = ga;
-        T[tb] = pb; X[idx + kStep] = gb;
+        const float va = focal_term(X[idx], SPARSE ? 0.f : T[ta], gamma, g2, alpha, grad_scale, pa, ga);
+        const float vb = focal_term(X[idx + kStep], SPARSE ? 0.f : T[tb], gamma, g2, alpha, grad_scale, pb, gb);
+        if (!skip_a) { part += va; T[ta] = pa; X[idx] = ga; }
+        if (!skip_b) { part2 += vb; T[tb] = pb; X[idx + kStep] = gb; }
       }
       if (idx < total) {
         const int ta = cell * CK + (idx >> 7);
+        const bool skip_a = marked && ((s_bits[idx >> 5] >> (idx & 31)) & 1u);
         float pa, ga;
-        part += focal_term(X[idx], T[ta], gamma, g2, alpha, grad_scale, pa, ga);
-        T[ta] = pa; X[idx] = ga;
+        const float va = focal_term(X[idx], SPARSE ? 0.f : T[ta], gamma, g2, alpha, grad_scale, pa, ga);
+        if (!skip_a) { part += va; T[ta] = pa; X[idx] = ga; }
       }
     }
     acc += (double)(part + part2);
+    if (marked) asm volatile("bar.sync 1, %0;" ::"n"(kStep));     // the bitmap is free for the next marked tile
     tcx::fence_proxy_async();                                    // generic-proxy writes -> visible to the bulk stores
     __syncwarp();
     if (lane == 0) tcx::mbar_arrive(&done[st]);
@@ -352,6 +450,32 @@ __global__ void __launch_bounds__(256, 3) k_loss_reg(const float* __restrict__ r
   }
 }
 
+// the same pass from a positives list (pp_assign_targets_list): one thread per listed row
+__global__ void __launch_bounds__(256) k_loss_reg_list(const float* __restrict__ reg, const int* __restrict__ pos_anchor,
+                                                       const float* __restrict__ pos_reg, const int* __restrict__ pos_offsets,
+                                                       int B, int H, int W, int Ad, int R, float* __restrict__ grad,
+                                                       unsigned* __restrict__ n_pos, unsigned* __restrict__ list,
+                                                       double* __restrict__ partials) {
+  __shared__ double s_red[8];
+  const size_t plane = (size_t)H * W, A = plane * Ad;
+  const int n = pos_offsets[B];
+  double sr = 0.0, so = 0.0;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < n; e += gridDim.x * 256) {
+    const float* tr = pos_reg + (size_t)e * 9;
+    if (__ldg(tr) != 1.f) continue;                                // (:54) pos_anchors = where(reg_targets[...,0] == 1)
+    const size_t i = (size_t)pos_anchor[e];
+    const unsigned slot = atomicAdd(n_pos, 1u);
+    if (list != nullptr) list[slot] = (unsigned)i;
+    loss_reg_row(reg, tr, i, A, plane, Ad, R, grad, sr, so);
+  }
+  const double a0 = block_sum(sr, s_red);
+  const double a1 = block_sum(so, s_red);
+  if (threadIdx.x == 0) {
+    partials[(size_t)blockIdx.x * 2] = a0;
+    partials[(size_t)blockIdx.x * 2 + 1] = a1;
+  }
+}
+
 // Every block re-derives the three sums (a few thousand doubles, fixed order), block 0 writes the losses, and
 // all blocks scale the listed gradient rows by b_reg / (7 n_pos) and b_ort / n_pos.
 __global__ void __launch_bounds__(256) k_loss_finalize(const double* __restrict__ pc, int nc, const double* __restrict__ pr,
@@ -437,19 +561,30 @@ size_t pp_loss_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t anchors_
   return a.used + pp::kAlign;
 }
 
-int pp_loss(const float* d_cls_out, float* d_reg_out, const float* d_cls_t, const float* d_reg_t, int32_t B,
-            int32_t H, int32_t W, int32_t anchors_per_cell, int32_t num_classes, int32_t reg_dims, float gamma,
-            float alpha_pos, float b_cls, float b_reg, float b_ort, float* d_scores, float* d_grad_cls,
-            float* d_grad_reg, float* d_losses, void* d_workspace, size_t workspace_bytes, pp_stream_t stream) {
-  using namespace pp;
+}  // extern "C"
+
+namespace pp {
+struct PosListArgs {
+  const int* anchor;
+  const float* cls;
+  const float* reg;
+  const int* offsets;
+};
+
+static int loss_impl(const float* d_cls_out, float* d_reg_out, const float* d_cls_t, const float* d_reg_t,
+                     const PosListArgs* pl, int32_t B, int32_t H, int32_t W, int32_t anchors_per_cell, int32_t num_classes,
+                     int32_t reg_dims, float gamma, float alpha_pos, float b_cls, float b_reg, float b_ort, float* d_scores,
+                     float* d_grad_cls, float* d_grad_reg, float* d_losses, void* d_workspace, size_t workspace_bytes,
+                     pp_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (!d_cls_out || !d_reg_out || !d_cls_t || !d_reg_t || !d_losses || B < 1 || H < 1 || W < 1 ||
-      anchors_per_cell < 1 || num_classes < 1 || reg_dims < 7)
+  if (!d_cls_out || !d_reg_out || !d_losses || B < 1 || H < 1 || W < 1 || anchors_per_cell < 1 || num_classes < 1 ||
+      reg_dims < 7)
     return PP_ERR_INVALID_ARG;
+  if (pl ? (!pl->anchor || !pl->cls || !pl->reg || !pl->offsets) : (!d_cls_t || !d_reg_t)) return PP_ERR_INVALID_ARG;
   const int CK = anchors_per_cell * num_classes, CR = anchors_per_cell * reg_dims;
   const size_t plane = (size_t)H * W;
   const size_t n_anchors = plane * anchors_per_cell * B;
-  if (CK > kLossMaxCh || CR <= 6 || B > 65535 || H > 65535 || n_anchors >= (1ull << 32) ||
+  if (CK > kLossMaxCh || CR <= 6 || B > 65535 || H > 65535 || n_anchors >= (1ull << 31) ||
       plane * B >= (1ull << 31))
     return PP_ERR_UNSUPPORTED;
   Arena arena(d_workspace, workspace_bytes);
@@ -460,9 +595,11 @@ int pp_loss(const float* d_cls_out, float* d_reg_out, const float* d_cls_t, cons
   const float gscale = (float)((double)b_cls / n_cls);
   PP_CUDA(cudaMemsetAsync(ws.n_pos, 0, sizeof(unsigned), st));
   auto aligned16 = [](const void* q) { return q == nullptr || ((uintptr_t)q % 16) == 0; };
-  const size_t smem = (size_t)kTmaStages * 2 * CK * kTmaCells * sizeof(float);
-  const bool tma = g_opt_loss_tma && tensor_map_encode_fn() != nullptr && plane % 4 == 0 && CK % 2 == 0 && aligned16(d_cls_out) && aligned16(d_cls_t) &&
-                   aligned16(d_scores) && aligned16(d_grad_cls) && smem <= 200 * 1024;
+  const size_t smem = (size_t)kTmaStages * 2 * CK * kTmaCells * sizeof(float) + (pl ? kMaxListSmem * (sizeof(int) + sizeof(unsigned short)) : 0);
+  const bool tma = (g_opt_loss_tma || pl) && tensor_map_encode_fn() != nullptr && plane % 4 == 0 && CK % 2 == 0 &&
+                   aligned16(d_cls_out) && aligned16(d_cls_t) && aligned16(d_scores) && aligned16(d_grad_cls) &&
+                   smem <= 216 * 1024;
+  if (pl && !tma) return PP_ERR_UNSUPPORTED;       // the list form exists for the TMA kernel only: use the dense targets
   int nparts;
   if (tma) {
     const int tiles = B * (int)((plane + kTmaCells - 1) / kTmaCells);
@@ -483,12 +620,22 @@ int pp_loss(const float* d_cls_out, float* d_reg_out, const float* d_cls_t, cons
     };
     if (!encode(&tm_cls, d_cls_out) || !encode(&tm_grad, d_grad_cls != nullptr ? d_grad_cls : d_cls_out))
       return PP_ERR_UNSUPPORTED;
-    PP_CUDA(cudaFuncSetAttribute(k_loss_cls_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PP_KERNEL("k_loss_cls_tma", st,
-              (k_loss_cls_tma<<<nparts, (kTmaComputeWarps + 1) * 32, smem, st>>>(tm_cls, tm_grad, d_cls_t, B, (int)plane, CK, gamma,
-                                                                                alpha_pos, gscale, d_scores,
-                                                                                d_grad_cls != nullptr ? 1 : 0, d_reg_out, CR,
-                                                                                ws.pc)));
+    const int threads = (kTmaComputeWarps + 1) * 32;
+    if (pl) {
+      PosListIn pin{pl->anchor, pl->cls, pl->offsets, anchors_per_cell};
+      PP_CUDA(cudaFuncSetAttribute(k_loss_cls_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PP_KERNEL("k_loss_cls_list", st,
+                (k_loss_cls_tma<true><<<nparts, threads, smem, st>>>(tm_cls, tm_grad, nullptr, pin, B, (int)plane, CK, gamma,
+                                                                     alpha_pos, gscale, d_scores, d_grad_cls != nullptr ? 1 : 0,
+                                                                     d_reg_out, CR, ws.pc)));
+    } else {
+      PosListIn pin{nullptr, nullptr, nullptr, anchors_per_cell};
+      PP_CUDA(cudaFuncSetAttribute(k_loss_cls_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PP_KERNEL("k_loss_cls_tma", st,
+                (k_loss_cls_tma<false><<<nparts, threads, smem, st>>>(tm_cls, tm_grad, d_cls_t, pin, B, (int)plane, CK, gamma,
+                                                                      alpha_pos, gscale, d_scores, d_grad_cls != nullptr ? 1 : 0,
+                                                                      d_reg_out, CR, ws.pc)));
+    }
   } else {
     const dim3 gc((W + kLossCells - 1) / kLossCells, H, B);
     nparts = (int)((size_t)gc.x * gc.y * gc.z);
@@ -496,16 +643,47 @@ int pp_loss(const float* d_cls_out, float* d_reg_out, const float* d_cls_t, cons
               (k_loss_cls<<<gc, 256, 0, st>>>(d_cls_out, d_cls_t, H, W, CK, gamma, alpha_pos, gscale, d_scores, d_grad_cls, ws.pc)));
     PP_KERNEL("k_loss_tanh", st, (k_loss_tanh<<<(int)((B * plane + 255) / 256), 256, 0, st>>>(d_reg_out, B, plane, CR)));
   }
-  const int nb = loss_reg_blocks();
+  int nb = loss_reg_blocks();
   if (d_grad_reg != nullptr) PP_CUDA(cudaMemsetAsync(d_grad_reg, 0, (size_t)B * CR * plane * sizeof(float), st));
-  PP_KERNEL("k_loss_reg", st,
-            (k_loss_reg<<<nb, 256, 0, st>>>(d_reg_out, d_reg_t, B, H, W, anchors_per_cell, reg_dims, d_grad_reg, ws.n_pos,
-                                            d_grad_reg != nullptr ? ws.list : nullptr, ws.pr)));
+  if (pl) {
+    nb = 32;
+    PP_KERNEL("k_loss_reg_list", st,
+              (k_loss_reg_list<<<nb, 256, 0, st>>>(d_reg_out, pl->anchor, pl->reg, pl->offsets, B, H, W, anchors_per_cell,
+                                                   reg_dims, d_grad_reg, ws.n_pos, d_grad_reg != nullptr ? ws.list : nullptr,
+                                                   ws.pr)));
+  } else {
+    PP_KERNEL("k_loss_reg", st,
+              (k_loss_reg<<<nb, 256, 0, st>>>(d_reg_out, d_reg_t, B, H, W, anchors_per_cell, reg_dims, d_grad_reg, ws.n_pos,
+                                              d_grad_reg != nullptr ? ws.list : nullptr, ws.pr)));
+  }
   PP_KERNEL("k_loss_finalize", st,
             (k_loss_finalize<<<kLossFinBlocks, 256, 0, st>>>(ws.pc, nparts, ws.pr, nb, ws.n_pos, ws.list, n_cls, b_cls, b_reg,
                                                              b_ort, B, H, W, anchors_per_cell, reg_dims, d_grad_reg,
                                                              d_losses)));
   return PP_OK;
+}
+}  // namespace pp
+
+extern "C" {
+
+int pp_loss(const float* d_cls_out, float* d_reg_out, const float* d_cls_t, const float* d_reg_t, int32_t B,
+            int32_t H, int32_t W, int32_t anchors_per_cell, int32_t num_classes, int32_t reg_dims, float gamma,
+            float alpha_pos, float b_cls, float b_reg, float b_ort, float* d_scores, float* d_grad_cls,
+            float* d_grad_reg, float* d_losses, void* d_workspace, size_t workspace_bytes, pp_stream_t stream) {
+  return pp::loss_impl(d_cls_out, d_reg_out, d_cls_t, d_reg_t, nullptr, B, H, W, anchors_per_cell, num_classes, reg_dims,
+                       gamma, alpha_pos, b_cls, b_reg, b_ort, d_scores, d_grad_cls, d_grad_reg, d_losses, d_workspace,
+                       workspace_bytes, stream);
+}
+
+int pp_loss_list(const float* d_cls_out, float* d_reg_out, const int32_t* d_pos_anchor, const float* d_pos_cls,
+                 const float* d_pos_reg, const int32_t* d_pos_offsets, int32_t B, int32_t H, int32_t W,
+                 int32_t anchors_per_cell, int32_t num_classes, int32_t reg_dims, float gamma, float alpha_pos,
+                 float b_cls, float b_reg, float b_ort, float* d_scores, float* d_grad_cls, float* d_grad_reg,
+                 float* d_losses, void* d_workspace, size_t workspace_bytes, pp_stream_t stream) {
+  pp::PosListArgs pl{d_pos_anchor, d_pos_cls, d_pos_reg, d_pos_offsets};
+  return pp::loss_impl(d_cls_out, d_reg_out, nullptr, nullptr, &pl, B, H, W, anchors_per_cell, num_classes, reg_dims,
+                       gamma, alpha_pos, b_cls, b_reg, b_ort, d_scores, d_grad_cls, d_grad_reg, d_losses, d_workspace,
+                       workspace_bytes, stream);
 }
 
 int pp_loss_scale_grads(float* d_grad_cls, size_t n_cls, float* d_grad_reg, size_t n_reg, const float* d_scale,

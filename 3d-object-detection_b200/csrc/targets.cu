@@ -504,12 +504,98 @@ __global__ void __launch_bounds__(128) k_encode_patch(EncodeArgs ea, GtParams gp
   }
 }
 
+// Positives list ("emit positives list + implicit zeros"): the flagged anchors of all sweeps in
+// ascending (sweep, anchor) order with their two 9-float rows, instead of the two dense [B,A,9] tensors.
+// Slots come from a prefix sum over the popcounts of the positive / forced mask words (k_pos_count: one sum per
+// block of 256 words; k_pos_emit: block base + in-block scan), so the order is deterministic; the 32 anchors of
+// a flagged word are dealt to the lanes of a warp as in k_encode_patch.
+__global__ void __launch_bounds__(256) k_pos_count(const unsigned* __restrict__ posmask,
+                                                   const unsigned* __restrict__ forcedmask, size_t nwords,
+                                                   int* __restrict__ blocksum) {
+  __shared__ int s_red[8];
+  const size_t wi = (size_t)blockIdx.x * 256 + threadIdx.x;
+  int c = wi < nwords ? __popc(posmask[wi] | forcedmask[wi]) : 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane_id() == 0) s_red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    blocksum[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pos_emit(EncodeArgs ea, GtParams gp, long long A, int B,
+                                                  const int* __restrict__ blocksum, int* __restrict__ pos_anchor,
+                                                  float* __restrict__ pos_cls, float* __restrict__ pos_reg,
+                                                  int* __restrict__ pos_offsets, int cap, int* __restrict__ status) {
+  __shared__ int s_red[8];
+  __shared__ int s_base;
+  const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
+  int part = 0;
+  for (int j = threadIdx.x; j < (int)blockIdx.x; j += 256) part += blocksum[j];
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) s_red[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    s_base = t;
+  }
+  __syncthreads();
+  const size_t words_per_sweep = (size_t)((A + 31) / 32);
+  const size_t nwords = words_per_sweep * B;
+  const size_t wi = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const unsigned w = wi < nwords ? (ea.posmask[wi] | ea.forcedmask[wi]) : 0u;
+  const int c = __popc(w);
+  int incl = c;                                                  // inclusive scan inside the warp
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  __syncthreads();                                               // s_red is reused
+  if (lane == 31) s_red[warp] = incl;
+  __syncthreads();
+  int wbase = s_base + incl - c;
+  for (int q = 0; q < warp; ++q) wbase += s_red[q];
+  if (wi < nwords) {
+    if (wi % words_per_sweep == 0) pos_offsets[wi / words_per_sweep] = wbase;
+    if (wi == nwords - 1) pos_offsets[B] = wbase + c;
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, w != 0u);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const unsigned ws = __shfl_sync(0xffffffffu, w, src);
+    const int wb = __shfl_sync(0xffffffffu, wbase, src);
+    const size_t wsrc = wi - lane + src;
+    if ((ws >> lane) & 1u) {
+      const int b = (int)(wsrc / words_per_sweep);
+      const long long a = (long long)(wsrc - (size_t)b * words_per_sweep) * 32 + lane;
+      const int slot = wb + __popc(ws & ((1u << lane) - 1u));
+      if (a < A) {
+        if (slot < cap) {
+          const unsigned fl = anchor_flags(ea, b, A, a);
+          float crow[9], rrow[9];
+          encode_row(ea, gp, b, A, a, fl, crow, rrow);
+          pos_anchor[slot] = (int)((long long)b * A + a);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) { pos_cls[(size_t)slot * 9 + k] = crow[k]; pos_reg[(size_t)slot * 9 + k] = rrow[k]; }
+        } else {
+          atomicOr(status, PP_STATUS_CAND_OVERFLOW);
+        }
+      }
+    }
+  }
+}
+
 struct TargetWs {
   double* cand_iou;          // [Gt, kCandCap] pass-0 -> pass-1 IoU cache
   unsigned long long* best;  // [B, A]   zero-init
   unsigned* posmask;         // [B, ceil(A/32)] zero-init
   unsigned* forcedmask;      // [B, ceil(A/32)] zero-init
   int* arg;                  // [B, A]   0x7f-init
+  int* blocksum;             // [ceil(B*ceil(A/32)/256)] positives per block of mask words (list output)
   size_t zero_bytes;
 };
 
@@ -523,7 +609,8 @@ static void targets_layout(AR& a, TargetWs* ws, int B, long long A, long long Gt
   auto p3 = a.template take<unsigned>((size_t)B * ((A + 31) / 32));
   size_t z1 = a.used;
   auto p2 = a.template take<int>((size_t)B * A);
-  if (ws) { ws->best = p0; ws->posmask = p1; ws->forcedmask = p3; ws->arg = p2; ws->zero_bytes = z1 - z0; }
+  auto p4 = a.template take<int>(((size_t)B * ((A + 31) / 32) + 255) / 256 + 1);
+  if (ws) { ws->best = p0; ws->posmask = p1; ws->forcedmask = p3; ws->arg = p2; ws->blocksum = p4; ws->zero_bytes = z1 - z0; }
 }
 
 struct SizeArena3 {
@@ -657,19 +744,33 @@ size_t pp_assign_targets_workspace_bytes(int32_t n_sweeps, int64_t A, int64_t to
   return a.used + pp::kAlign;
 }
 
-int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, const double* d_a_wlh,
-                      const double* d_a_yaw, const void* d_anchor_index, int64_t A,
-                      const double* d_g_corners, const double* d_g_centers, const double* d_g_wlh,
-                      const double* d_g_yaw, const int32_t* d_g_cls, const int64_t* h_gt_offsets,
-                      int32_t n_sweeps, int32_t num_classes, double pos_thresh, float* d_cls,
-                      float* d_reg, int32_t* d_top_anchor, int32_t* d_counts, int32_t* d_status,
-                      void* d_workspace, size_t workspace_bytes, pp_stream_t stream) {
-  using namespace pp;
+}  // extern "C"
+
+namespace pp {
+struct PosListOut {
+  int* anchor;
+  float* cls;
+  float* reg;
+  int* offsets;
+  int cap;
+};
+
+static int assign_impl(const double* d_a_corners, const double* d_a_centers, const double* d_a_wlh,
+                       const double* d_a_yaw, const void* d_anchor_index, int64_t A,
+                       const double* d_g_corners, const double* d_g_centers, const double* d_g_wlh,
+                       const double* d_g_yaw, const int32_t* d_g_cls, const int64_t* h_gt_offsets,
+                       int32_t n_sweeps, int32_t num_classes, double pos_thresh, float* d_cls,
+                       float* d_reg, const PosListOut* pl, int32_t* d_top_anchor, int32_t* d_counts, int32_t* d_status,
+                       void* d_workspace, size_t workspace_bytes, pp_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  const bool dense = d_cls != nullptr || d_reg != nullptr;
   if (!d_a_corners || !d_a_centers || !d_a_wlh || !d_a_yaw || !d_anchor_index || A < 1 ||
       A > 0x7fffffffll || !h_gt_offsets || n_sweeps < 1 || n_sweeps > PP_MAX_SWEEPS ||
-      num_classes < 1 || !d_cls || !d_reg || !d_counts || !d_status ||
+      num_classes < 1 || (dense && (!d_cls || !d_reg)) || (!dense && !pl) || !d_counts || !d_status ||
       (long long)A * (num_classes > 9 ? num_classes : 9) > 0x7fffffffll)
+    return PP_ERR_INVALID_ARG;
+  if (pl && (!pl->anchor || !pl->cls || !pl->reg || !pl->offsets || pl->cap < 1 || num_classes != 9 ||
+             (long long)A * n_sweeps > 0x7fffffffll))
     return PP_ERR_INVALID_ARG;
   GtParams gp;
   gp.n_sweeps = n_sweeps;
@@ -701,6 +802,15 @@ int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, cons
   }
   EncodeArgs ea{d_a_centers, d_a_wlh, d_a_yaw, d_g_centers, d_g_wlh, d_g_yaw, d_g_cls, ws.arg,
                 ws.posmask, ws.forcedmask, d_top_anchor};
+  if (pl) {
+    const size_t nwords = (size_t)((A + 31) / 32) * n_sweeps;
+    const int nblk = (int)((nwords + 255) / 256);
+    PP_KERNEL("k_pos_count", st, (k_pos_count<<<nblk, 256, 0, st>>>(ws.posmask, ws.forcedmask, nwords, ws.blocksum)));
+    PP_KERNEL("k_pos_emit", st,
+              (k_pos_emit<<<nblk, 256, 0, st>>>(ea, gp, A, n_sweeps, ws.blocksum, pl->anchor, pl->cls, pl->reg, pl->offsets,
+                                                pl->cap, d_status)));
+    if (!dense) return PP_OK;
+  }
   const bool both = num_classes == 9 && ((long long)A * 9 % 4 == 0) && ((uintptr_t)d_cls % 16 == 0) &&
                     ((uintptr_t)d_reg % 16 == 0);
   if (both) {
@@ -735,6 +845,36 @@ int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, cons
     PP_KERNEL("k_encode", st, (k_encode<true, 9><<<grid, 256, 0, st>>>(ea, gp, A, 9, vec_ok, d_reg)));
   }
   return PP_OK;
+}
+}  // namespace pp
+
+extern "C" {
+
+int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, const double* d_a_wlh,
+                      const double* d_a_yaw, const void* d_anchor_index, int64_t A,
+                      const double* d_g_corners, const double* d_g_centers, const double* d_g_wlh,
+                      const double* d_g_yaw, const int32_t* d_g_cls, const int64_t* h_gt_offsets,
+                      int32_t n_sweeps, int32_t num_classes, double pos_thresh, float* d_cls,
+                      float* d_reg, int32_t* d_top_anchor, int32_t* d_counts, int32_t* d_status,
+                      void* d_workspace, size_t workspace_bytes, pp_stream_t stream) {
+  if (!d_cls || !d_reg) return PP_ERR_INVALID_ARG;
+  return pp::assign_impl(d_a_corners, d_a_centers, d_a_wlh, d_a_yaw, d_anchor_index, A, d_g_corners, d_g_centers, d_g_wlh,
+                         d_g_yaw, d_g_cls, h_gt_offsets, n_sweeps, num_classes, pos_thresh, d_cls, d_reg, nullptr,
+                         d_top_anchor, d_counts, d_status, d_workspace, workspace_bytes, stream);
+}
+
+int pp_assign_targets_list(const double* d_a_corners, const double* d_a_centers, const double* d_a_wlh,
+                           const double* d_a_yaw, const void* d_anchor_index, int64_t A,
+                           const double* d_g_corners, const double* d_g_centers, const double* d_g_wlh,
+                           const double* d_g_yaw, const int32_t* d_g_cls, const int64_t* h_gt_offsets,
+                           int32_t n_sweeps, int32_t num_classes, double pos_thresh, int32_t* d_pos_anchor,
+                           float* d_pos_cls, float* d_pos_reg, int32_t* d_pos_offsets, int32_t capacity,
+                           float* d_cls, float* d_reg, int32_t* d_top_anchor, int32_t* d_counts, int32_t* d_status,
+                           void* d_workspace, size_t workspace_bytes, pp_stream_t stream) {
+  pp::PosListOut pl{d_pos_anchor, d_pos_cls, d_pos_reg, d_pos_offsets, capacity};
+  return pp::assign_impl(d_a_corners, d_a_centers, d_a_wlh, d_a_yaw, d_anchor_index, A, d_g_corners, d_g_centers, d_g_wlh,
+                         d_g_yaw, d_g_cls, h_gt_offsets, n_sweeps, num_classes, pos_thresh, d_cls, d_reg, &pl,
+                         d_top_anchor, d_counts, d_status, d_workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, _runtime
+from .box_utils import Positives
 from .config import PPConfig
 
 _cfg = PPConfig()
@@ -19,7 +20,8 @@ class _PPLossFn(torch.autograd.Function):
         L = _lib.load()
         for t, n in ((cls_tensor, "cls_tensor"), (reg_tensor, "reg_tensor"), (cls_targets, "cls_targets"),
                      (reg_targets, "reg_targets")):
-            _runtime.require_cuda(t, n)
+            if not isinstance(t, Positives) and not (t is None and isinstance(cls_targets, Positives)):
+                _runtime.require_cuda(t, n)
         if cls_tensor.dtype != torch.float32 or reg_tensor.dtype != torch.float32:
             raise _lib.PPError("PPLoss: network outputs must be float32")
         if not reg_tensor.is_contiguous():
@@ -31,8 +33,13 @@ class _PPLossFn(torch.autograd.Function):
         Ad = CK // K
         R = reg_tensor.shape[1] // Ad
         A = H * W * Ad
-        ct = cls_targets.to(torch.float32).contiguous().view(B, A, K)
-        rt = reg_targets.to(torch.float32).contiguous().view(B, A, 9)
+        pos = cls_targets if isinstance(cls_targets, Positives) else None
+        if pos is not None:
+            if (pos.n_sweeps, pos.n_anchors) != (B, A):
+                raise _lib.PPError("PPLoss: the positives list was built for %d sweeps x %d anchors" % (pos.n_sweeps, pos.n_anchors))
+        else:
+            ct = cls_targets.to(torch.float32).contiguous().view(B, A, K)
+            rt = reg_targets.to(torch.float32).contiguous().view(B, A, 9)
         dev = cls_c.device
         scores = torch.empty((B, A * K), dtype=torch.float32, device=dev)
         g_cls = torch.empty_like(cls_c)
@@ -40,11 +47,15 @@ class _PPLossFn(torch.autograd.Function):
         losses = torch.empty(4, dtype=torch.float32, device=dev)
         ws = _runtime.workspace(L.pp_loss_workspace_bytes(B, H, W, Ad), dev, "loss")
         with torch.cuda.device(dev):
-            rc = L.pp_loss(cls_c.data_ptr(), reg_tensor.data_ptr(), ct.data_ptr(), rt.data_ptr(), B, H, W, Ad, K, R,
-                           float(gamma), float(alpha_pos), float(b_cls), float(b_reg), float(b_ort),
-                           scores.data_ptr(), g_cls.data_ptr(), g_reg.data_ptr(), losses.data_ptr(),
-                           ws.data_ptr(), ws.numel(), _runtime.stream_ptr(dev))
-        _lib.check(rc, "pp_loss")
+            tail = (B, H, W, Ad, K, R, float(gamma), float(alpha_pos), float(b_cls), float(b_reg), float(b_ort),
+                    scores.data_ptr(), g_cls.data_ptr(), g_reg.data_ptr(), losses.data_ptr(), ws.data_ptr(), ws.numel(),
+                    _runtime.stream_ptr(dev))
+            if pos is not None:
+                rc = L.pp_loss_list(cls_c.data_ptr(), reg_tensor.data_ptr(), pos.anchor.data_ptr(), pos.cls.data_ptr(),
+                                    pos.reg.data_ptr(), pos.offsets.data_ptr(), *tail)
+            else:
+                rc = L.pp_loss(cls_c.data_ptr(), reg_tensor.data_ptr(), ct.data_ptr(), rt.data_ptr(), *tail)
+        _lib.check(rc, "pp_loss_list" if pos is not None else "pp_loss")
         ctx.mark_dirty(reg_tensor)
         ctx.applied = None
         ctx.save_for_backward(g_cls, g_reg)
@@ -77,7 +88,9 @@ class PPLoss(nn.Module):
         self.num_classes = int(_cfg.num_classes if num_classes is None else num_classes)
         self.alpha_pos = float(alpha_pos)            # torch.Tensor([25]) in model/loss.py:41
 
-    def forward(self, cls_tensor, reg_tensor, cls_targets, reg_targets):
+    def forward(self, cls_tensor, reg_tensor, cls_targets, reg_targets=None):
+        """``cls_targets`` may be a ``box_utils.Positives`` list (then ``reg_targets`` is not used): the targets are
+        taken as zero everywhere except at the listed anchors (pp_loss_list)."""
         total, p, c_loss, r_loss, o_loss, _ = _PPLossFn.apply(
             cls_tensor, reg_tensor, cls_targets, reg_targets, self.gamma, self.alpha_pos, self.b_cls, self.b_reg,
             self.b_ort, self.num_classes)

@@ -77,6 +77,7 @@ class InputPath:
         # latency-bound binning kernels
         self._side = torch.cuda.Stream(device=self.device)
         self.overlap_targets = True
+        self.targets_as_list = False   # K3 emits the positives list instead of the dense [B,A,9] tensors
         # fused=True: the step goes through pp_input_path (x never materialised); False: the
         # signature-preserving pp_pillarize -> x -> pp_pfn_scatter sequence
         self.fused = fused
@@ -219,11 +220,12 @@ class InputPath:
     # -- K3 -----------------------------------------------------------------------------------
     def targets(self, gt_dev, gt_offsets, out=None):
         """gt_dev: dict of CUDA tensors corners [Gt,4,2], centers [Gt,3] (image space), wlh [Gt,3],
-        yaw [Gt] (float64), cls [Gt] (int32)."""
+        yaw [Gt] (float64), cls [Gt] (int32).  With ``self.targets_as_list`` the first return value is a
+        ``box_utils.Positives`` list (for ``loss.PPLoss``) and the second is None: no dense tensor is written."""
         a = self.ensure_anchors()
         return assign_targets(a, gt_dev["corners"], gt_dev["centers"], gt_dev["wlh"], gt_dev["yaw"],
                               gt_dev["cls"], gt_offsets, self.cfg.num_classes,
-                              self.cfg.iou_pos_thresh, out=out)
+                              self.cfg.iou_pos_thresh, out=out, as_list=self.targets_as_list)
 
     # -- host-facing step -----------------------------------------------------------------------
     @staticmethod
@@ -369,7 +371,8 @@ class InputPath:
                 cls, reg, top, counts = self.targets(gt_dev, gt_offsets, out=o.get("targets"))
             canvas, npil = self._k12(d_pts, offsets, o, main, ordered)
             main.wait_stream(side)
-            for t in (cls, reg, top, counts):
+            held = (cls.anchor, cls.cls, cls.reg, cls.offsets, top, counts) if reg is None else (cls, reg, top, counts)
+            for t in held:
                 t.record_stream(main)
         else:
             canvas, npil = self._k12(d_pts, offsets, o, main, ordered)

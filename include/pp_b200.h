@@ -158,6 +158,16 @@ int pp_loss(const float* d_cls_out, float* d_reg_out, const float* d_cls_t, cons
             float alpha_pos, float b_cls, float b_reg, float b_ort, float* d_scores, float* d_grad_cls,
             float* d_grad_reg, float* d_losses, void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
 
+/* pp_loss fed by the positives list of pp_assign_targets_list instead of the dense target tensors: the 78 MB
+ * classification-target read and the 78 MB regression-target scan disappear (targets are zero except at the
+ * listed anchors).  Same outputs as pp_loss on the densified list.  Needs H*W % 4 == 0 and 16-byte aligned
+ * tensors (the TMA kernel); otherwise PP_ERR_UNSUPPORTED -- densify and call pp_loss. */
+int pp_loss_list(const float* d_cls_out, float* d_reg_out, const int32_t* d_pos_anchor, const float* d_pos_cls,
+                 const float* d_pos_reg, const int32_t* d_pos_offsets, int32_t B, int32_t H, int32_t W,
+                 int32_t anchors_per_cell, int32_t num_classes, int32_t reg_dims, float gamma, float alpha_pos,
+                 float b_cls, float b_reg, float b_ort, float* d_scores, float* d_grad_cls, float* d_grad_reg,
+                 float* d_losses, void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
+
 /* Chain rule for a non-unit upstream gradient of the total loss: both gradient tensors are multiplied in place
  * by *d_scale / *d_applied (d_applied NULL = 1).  The kernel returns at once when the factor is exactly 1, the
  * usual total_loss.backward() case, so no pass over the 147 MB of gradients is spent on it. */
@@ -301,6 +311,21 @@ int pp_assign_targets(const double* d_a_corners, const double* d_a_centers, cons
                       int32_t n_sweeps, int32_t num_classes, double pos_thresh, float* d_cls,
                       float* d_reg, int32_t* d_top_anchor, int32_t* d_counts, int32_t* d_status,
                       void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
+
+/* The same assignment with the targets as a POSITIVES LIST + implicit zeros instead of, or next
+ * to, the two dense [B,A,9] tensors (which are > 99.9 % zeros): every anchor whose cls or reg row is non-zero, in
+ * ascending (sweep, anchor) order -- d_pos_anchor[i] = sweep * A + anchor (int32), d_pos_cls [capacity, 9] and
+ * d_pos_reg [capacity, 9] its two rows exactly as pp_assign_targets writes them, d_pos_offsets [n_sweeps + 1]
+ * the list range of each sweep (d_pos_offsets[n_sweeps] = length).  More than `capacity` positives sets
+ * PP_STATUS_CAND_OVERFLOW and drops the excess.  d_cls / d_reg may both be NULL (list only).  num_classes == 9. */
+int pp_assign_targets_list(const double* d_a_corners, const double* d_a_centers, const double* d_a_wlh,
+                           const double* d_a_yaw, const void* d_anchor_index, int64_t A,
+                           const double* d_g_corners, const double* d_g_centers, const double* d_g_wlh,
+                           const double* d_g_yaw, const int32_t* d_g_cls, const int64_t* h_gt_offsets,
+                           int32_t n_sweeps, int32_t num_classes, double pos_thresh, int32_t* d_pos_anchor,
+                           float* d_pos_cls, float* d_pos_reg, int32_t* d_pos_offsets, int32_t capacity,
+                           float* d_cls, float* d_reg, int32_t* d_top_anchor, int32_t* d_counts, int32_t* d_status,
+                           void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -75,20 +75,38 @@ def main():
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e3
 
+    # the same targets as a positives list (what pp_assign_targets_list emits)
+    from pp_b200.box_utils import Positives
+    nzi = torch.nonzero((cls_t.view(B * A, 9) != 0).any(1) | (reg_t.view(B * A, 9) != 0).any(1)).flatten()
+    offs = torch.tensor([int((nzi < b * A).sum()) for b in range(B + 1)], dtype=torch.int32, device="cuda")
+    pos = Positives(nzi.int().contiguous(), cls_t.view(B * A, 9)[nzi].contiguous(), reg_t.view(B * A, 9)[nzi].contiguous(),
+                    offs, B, A)
+
+    def ours_list():
+        c = cls0.clone().requires_grad_(True); r = reg0.clone().requires_grad_(True)
+        r2 = r * 1.0
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        tot = loss(c, r2, pos)[4]
+        tot.backward(inputs=[c, r2])
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3
+
     for _ in range(3):
-        ours(); theirs()
+        ours(); theirs(); ours_list()
     t_ours = float(np.median([ours() for _ in range(a.iters)]))
     t_eager = float(np.median([theirs() for _ in range(a.iters)]))
+    t_list = float(np.median([ours_list() for _ in range(a.iters)]))
     L = _lib.load()
     L.pp_profile_enable(1)
     for _ in range(a.iters):
-        ours()
+        ours(); ours_list()
     prof = {k: round(ms * 1e3 / n, 2) for k, (n, ms) in _lib.profile_report().items() if k.startswith("k_loss")}
     L.pp_profile_enable(0)
     nc, nr = B * 54 * H * W * 4, B * 48 * H * W * 4
-    alg = {"k_loss_cls": 4 * nc, "k_loss_reg": 2 * nr + B * A * 9 * 4, "k_loss_tanh": 2 * B * 6 * H * W * 4,
-           "k_loss_count": B * A * 4}
-    print(json.dumps({"batch": B, "pp_loss_fwd_bwd_us": round(t_ours, 1), "torch_eager_fwd_bwd_us": round(t_eager, 1),
+    alg = {"k_loss_cls_tma": 4 * nc, "k_loss_cls_list": 3 * nc, "k_loss_reg": B * A * 9 * 4}
+    print(json.dumps({"batch": B, "pp_loss_fwd_bwd_us": round(t_ours, 1), "pp_loss_list_fwd_bwd_us": round(t_list, 1), "torch_eager_fwd_bwd_us": round(t_eager, 1),
                       "kernels_us": prof, "alg_bytes": alg,
                       "GBps": {k: round(alg[k] / prof[k] / 1e3, 1) for k in alg if k in prof}}))
 
