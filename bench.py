@@ -261,7 +261,7 @@ def algorithmic_bytes(B, P, N, C, H, W, A, K, total_points, has_mean):
     }
 
 
-def training_rows(x, inds, targets, dev, peak, steps, path=None, d_pts=None, offsets=None):
+def training_rows(x, inds, targets, dev, peak, steps, path=None, d_pts=None, offsets=None, gt=None):
     """PFN + scatter backward (pp_pfn_backward) and the loss front-end (pp_loss) on the step's own x / inds /
     targets, network outputs random: per-kernel CUDA-event times and, for the streaming loss kernels, GB/s."""
     import torch
@@ -293,6 +293,13 @@ def training_rows(x, inds, targets, dev, peak, steps, path=None, d_pts=None, off
         if pts_copy is not None:
             pts_copy.copy_(d_pts)
             path.aggregate(pts_copy, offs_dev, rigid)
+        if gt is not None:                           # the same targets as a positives list, and the loss fed by it
+            path.targets_as_list = True
+            pos = path.targets(gt[0], gt[1])[0]
+            path.targets_as_list = False
+            c = cls.clone().requires_grad_(True)
+            r = reg.clone().requires_grad_(True)
+            lossm(c, r * 1.0, pos)[4].backward()
 
     one()
     torch.cuda.synchronize()
@@ -302,14 +309,16 @@ def training_rows(x, inds, targets, dev, peak, steps, path=None, d_pts=None, off
     rep = _lib.profile_report()
     L.pp_profile_enable(0)
     n_cls, n_reg = cls.numel() * 4, reg.numel() * 4
-    alg = {"k_loss_cls_tma": 4 * n_cls + 2 * B * 90000 * 4, "k_loss_reg": reg_t.numel() * 4}
+    alg = {"k_loss_cls_tma": 4 * n_cls + 2 * B * 90000 * 4, "k_loss_cls_list": 3 * n_cls + 2 * B * 90000 * 4,
+           "k_loss_reg": reg_t.numel() * 4}
     if d_pts is not None:
         alg["k_aggregate"] = d_pts.shape[0] * (3 * 4 * 2 + 8)          # x,y,z read + written; sector granularity not counted
     rows = {}
     for name, (n, ms) in rep.items():
-        if not (name.startswith("k_loss") or name.startswith("k_pfn_bwd") or name == "k_aggregate"):
+        if not (name.startswith("k_loss") or name.startswith("k_pfn_bwd") or name.startswith("k_pos_") or
+                name == "k_aggregate"):
             continue
-        k = {"us_per_launch": ms * 1e3 / n}
+        k = {"us_per_launch": ms * 1e3 / n, "launches_per_step": n / steps}
         if name in alg:
             k["alg_bytes_per_launch"] = alg[name]
             k["GBps"] = alg[name] / (ms / n * 1e-3) / 1e9
@@ -320,7 +329,8 @@ def training_rows(x, inds, targets, dev, peak, steps, path=None, d_pts=None, off
         rows["k_pfn_bwd"]["note"] = ("FP32-issue bound, not HBM: 30 FMA per (slot, channel) for z and the BatchNorm moment "
                                      "matrices; %.1f G(slot*channel)/s" % (slots * 64 / rows["k_pfn_bwd"]["us_per_launch"] / 1e3))
     return {"what": "pp_pfn_backward through PPFeatureScatter.backward (training-mode BatchNorm) and pp_loss through "
-                    "PPLoss forward + backward, batch of %d sweeps; pp_aggregate_sweeps (rigid transform + remove_close, in "
+                    "PPLoss forward + backward from the dense targets and from the positives list of pp_assign_targets_list "
+                    "(k_pos_*, k_loss_*_list), batch of %d sweeps; pp_aggregate_sweeps (rigid transform + remove_close, in "
                     "place) on the batch's raw points" % B, "kernels": rows}
 
 
@@ -522,7 +532,8 @@ def run_ours(args):
         # the two training-side rows next to the path, timed on this step's own outputs
         if rank == 0 and world == 1 and not args.no_training_rows:
             training = training_rows(out2["pillars"][0], out2["pillars"][1], out["targets"], dev, peak, args.steps,
-                                     path=path2, d_pts=d_pts, offsets=batch["offsets"])
+                                     path=path2, d_pts=d_pts, offsets=batch["offsets"],
+                                     gt=(gt_dev, batch["gt_offsets"]))
         del out2, path2
 
     cpu_baseline = None
