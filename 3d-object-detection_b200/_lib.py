@@ -55,6 +55,9 @@ _SIGNATURES = {
     "pp_input_path": (_c.c_int, [_vp, _i32, _i64, _i64, _i64p, _i32, _gridp, _i32, _i32, _vp, _i32,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _i32, _i32,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
+    "pp_input_path_backward_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "pp_input_path_backward": (_c.c_int, [_i64p, _i32, _gridp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _i32,
+                                          _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "pp_aggregate_sweeps": (_c.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _f32, _vp, _vp]),
     "pp_pfn_backward_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "pp_pfn_backward": (_c.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp,

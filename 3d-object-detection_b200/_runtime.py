@@ -29,6 +29,15 @@ def workspace(nbytes, device, tag="default"):
     return buf
 
 
+def take_workspace(device, tag):
+    """Remove and return the scratch buffer of (device, current stream, tag): the caller now owns it (state that
+    must survive until a backward pass); the next ``workspace`` call allocates a fresh one."""
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(dev).cuda_stream, tag)
+    return _workspaces.pop(key, None)
+
+
 def status_word(device):
     """int32[1] device status word (bits PP_STATUS_*), one per device, zeroed at creation."""
     dev = torch.device(device)

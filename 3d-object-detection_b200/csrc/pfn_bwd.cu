@@ -17,7 +17,7 @@
 // channel.  Per-pillar fp32 sums go through a shared staging tile into fp64 accumulators that are spread
 // over the block's threads ((row, channel) pairs), so the inner loop keeps 125 registers and two blocks fit
 // an SM; one fp64 partial tile per block is combined in a fixed order by k_pfn_bwd_finalize (deterministic).
-#include "common.cuh"
+#include "internal.cuh"
 
 namespace pp {
 
@@ -44,7 +44,7 @@ struct BwdGrad {             // where G[b,c,p] lives: the [B,C,P] gradient, or t
 constexpr int kBwdRows = 34;               // staged per pillar and channel: the 33 sums (+1 pad row)
 constexpr int kBwdOwn = (kBwdAcc * kBwdC + 255) / 256;     // (k, c) pairs owned by each thread of the block
 
-template <bool TRAIN>
+template <bool TRAIN, bool ARGMAX = true>
 __device__ __forceinline__ void bwd_slot(const float (&wr)[kBwdD], float bc, float sgn, const float (&xs)[kBwdD], int n,
                                          float (&s1)[10], float (&s2)[10], float& q2, float& best, int& nbest) {
   float z = bc;
@@ -62,11 +62,16 @@ __device__ __forceinline__ void bwd_slot(const float (&wr)[kBwdD], float bc, flo
     s2[9] += r;
     q2 = fmaf(r, r, q2);
   }
-  const float key = sgn * r;
-  if (key > best) { best = key; nbest = n; }                       // strict: the first index wins a tie
+  if (ARGMAX) {
+    const float key = sgn * r;
+    if (key > best) { best = key; nbest = n; }                     // strict: the first index wins a tie
+  }
 }
 
-template <bool TRAIN>
+// PADPASS (sparse formulation, pass A): x is data_mean viewed as [1,9,P,N]; a padding slot holds 0 - mean, so the
+// weights are negated (fmaf(w, -m, z) == fmaf(-w, m, z) exactly) and the moment rows d < 9 change sign in the
+// finalize; no gradient is routed (the arg-max bookkeeping is compiled out).
+template <bool TRAIN, bool PADPASS = false>
 __global__ void __launch_bounds__(256, 2) k_pfn_bwd(const float* __restrict__ x, int B, int P, int N, int Np,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                    const float* __restrict__ bn_w, BwdGrad gr, int vec16,
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd(const float* __restrict__ x,
 
   float wr[kBwdD];
 #pragma unroll
-  for (int d = 0; d < kBwdD; ++d) wr[d] = __ldg(w + c * kBwdD + d);
+  for (int d = 0; d < kBwdD; ++d) wr[d] = PADPASS ? -__ldg(w + c * kBwdD + d) : __ldg(w + c * kBwdD + d);
   const float bc = __ldg(bias + c);
   const float gam = __ldg(bn_w + c);
   const float sgn = gam > 0.f ? 1.f : (gam < 0.f ? -1.f : 0.f);
@@ -149,19 +154,21 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd(const float* __restrict__ x,
           float xs[kBwdD];
 #pragma unroll
           for (int d = 0; d < kBwdD; ++d) xs[d] = j == 0 ? xv[d].x : (j == 1 ? xv[d].y : (j == 2 ? xv[d].z : xv[d].w));
-          bwd_slot<TRAIN>(wr, bc, sgn, xs, n0 + j, s1, s2, q2, best, nbest);
+          bwd_slot<TRAIN, !PADPASS>(wr, bc, sgn, xs, n0 + j, s1, s2, q2, best, nbest);
         }
       }
       for (int n = N4; n < N; ++n) {
         float xs[kBwdD];
 #pragma unroll
         for (int d = 0; d < kBwdD; ++d) xs[d] = t[d * Np + n];
-        bwd_slot<TRAIN>(wr, bc, sgn, xs, n, s1, s2, q2, best, nbest);
+        bwd_slot<TRAIN, !PADPASS>(wr, bc, sgn, xs, n, s1, s2, q2, best, nbest);
       }
       // the arg-max element takes the incoming gradient
       const long long b = task / P, p = task - b * P;
       float G;
-      if (gr.inds != nullptr) {
+      if (PADPASS) {
+        G = 0.f;
+      } else if (gr.inds != nullptr) {
         const long long* row = gr.inds + task * 3;
         const long long fl = row[0], xi = row[1], yi = row[2];
         const bool ok = fl != 0 && xi >= 0 && xi < gr.W && yi >= 0 && yi < gr.H;
@@ -209,9 +216,181 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd(const float* __restrict__ x,
   }
 }
 
+// Sparse formulation, pass B: the live pillars of every sweep straight from K1's compact state (the dense x is
+// never built).  Slot n of live pillar (b,p) holds feat[n] - mean[p,n] for n < cnt and 0 - mean[p,n] beyond.
+// Moments: the padding pass counted every slot with its padding value, so a real slot adds (real - padding);
+// arg-max: over the real slots and the padding slots n >= cnt, exactly the slots of the dense tensor.
+constexpr int kLiveRec = 12;               // floats per staged point record (9 features, 16-byte multiple)
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int Np, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, const float* __restrict__ bn_w,
+                                                        BwdGrad gr, double* __restrict__ partials) {
+  extern __shared__ __align__(16) float s_tile[];            // mean [kBwdPil][9][Np] | feat [kBwdPil][N][12] | staging
+  __shared__ int s_first[PP_MAX_SWEEPS + 1];                 // live pillars before sweep b
+  __shared__ int s_cnt[kBwdPil], s_b[kBwdPil], s_p[kBwdPil];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pl = warp >> 1, c = (warp & 1) * 32 + lane;
+  const int B = cp.sw.n_sweeps, P = cp.P, N = cp.N;
+  float* s_mean = s_tile;
+  float* s_feat = s_tile + (size_t)kBwdPil * kBwdD * Np;
+  float* s_sum = s_feat + (size_t)kBwdPil * N * kLiveRec;
+  if (tid == 0) {
+    int a = 0;
+    for (int b = 0; b < B; ++b) { s_first[b] = a; a += min(max(cp.num_pillars[b], 0), P); }
+    s_first[B] = a;
+  }
+  __syncthreads();
+  const int n_live = s_first[B];
+  const int ngroups = (n_live + kBwdPil - 1) / kBwdPil;
+
+  float wr[kBwdD];
+#pragma unroll
+  for (int d = 0; d < kBwdD; ++d) wr[d] = __ldg(w + c * kBwdD + d);
+  const float bc = __ldg(bias + c);
+  const float gam = __ldg(bn_w + c);
+  const float sgn = gam > 0.f ? 1.f : (gam < 0.f ? -1.f : 0.f);
+  double acc[kBwdOwn];
+#pragma unroll
+  for (int k = 0; k < kBwdOwn; ++k) acc[k] = 0.0;
+
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    if (tid < kBwdPil) {
+      const int L = grp * kBwdPil + tid;
+      int b = -1, p = 0, cnt = 0;
+      if (L < n_live) {
+        b = 0;
+        while (s_first[b + 1] <= L) ++b;
+        p = L - s_first[b];
+        cnt = min(cp.pil_cnt[(size_t)b * P + p], N);
+      }
+      s_b[tid] = b; s_p[tid] = p; s_cnt[tid] = cnt;
+    }
+    __syncthreads();                                           // also: the previous group's staging rows are consumed
+    for (int i = tid; i < kBwdPil * kBwdD * (Np >> 2); i += 256) {
+      const int row = i / (Np >> 2), ck = i - row * (Np >> 2);
+      const int q = row / kBwdD, d = row - q * kBwdD;
+      if (s_b[q] >= 0 && ck * 4 < N)
+        cp_async16(s_mean + ((size_t)q * kBwdD + d) * Np + ck * 4, cp.data_mean + ((size_t)d * P + s_p[q]) * N + ck * 4);
+    }
+    for (int q = 0; q < kBwdPil; ++q) {
+      if (s_b[q] < 0) continue;
+      const float* src = cp.feat_c + ((size_t)cp.sw.off[s_b[q]] + cp.pil_off[(size_t)s_b[q] * P + s_p[q]]) * kBwdD;
+      for (int i = tid; i < s_cnt[q] * kBwdD; i += 256) {
+        const int n = i / kBwdD, d = i - n * kBwdD;
+        cp_async4(s_feat + ((size_t)q * N + n) * kLiveRec + d, src + i);
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    float* srow = s_sum + (size_t)pl * kBwdRows * kBwdC + c;
+    const int b = s_b[pl];
+    if (b >= 0) {
+      const int p = s_p[pl], cnt = s_cnt[pl];
+      const float* tm = s_mean + (size_t)pl * kBwdD * Np;
+      const float* tf = s_feat + (size_t)pl * N * kLiveRec;
+      float s1[10], s2[10], q2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 10; ++d) { s1[d] = 0.f; s2[d] = 0.f; }
+      float best = -INFINITY;
+      int nbest = 0;
+      for (int n = 0; n < N; ++n) {
+        float m[kBwdD];
+#pragma unroll
+        for (int d = 0; d < kBwdD; ++d) m[d] = tm[d * Np + n];
+        float zp = bc;                                          // the padding value of the slot: 0 - mean
+#pragma unroll
+        for (int d = 0; d < kBwdD; ++d) zp = fmaf(-wr[d], m[d], zp);
+        const float rp = fmaxf(zp, 0.f);
+        float key = sgn * rp;
+        if (n < cnt) {                                          // warp-uniform: the slot holds a point
+          float xs[kBwdD];
+          const float4 f0 = *reinterpret_cast<const float4*>(tf + n * kLiveRec);
+          const float4 f1 = *reinterpret_cast<const float4*>(tf + n * kLiveRec + 4);
+          const float f8 = tf[n * kLiveRec + 8];
+          xs[0] = f0.x - m[0]; xs[1] = f0.y - m[1]; xs[2] = f0.z - m[2]; xs[3] = f0.w - m[3];
+          xs[4] = f1.x - m[4]; xs[5] = f1.y - m[5]; xs[6] = f1.z - m[6]; xs[7] = f1.w - m[7];
+          xs[8] = f8 - m[8];
+          float z = bc;
+#pragma unroll
+          for (int d = 0; d < kBwdD; ++d) z = fmaf(wr[d], xs[d], z);
+          const float r = fmaxf(z, 0.f);
+          if (TRAIN) {
+            const float on = z > 0.f ? 1.f : 0.f, onp = zp > 0.f ? 1.f : 0.f;
+#pragma unroll
+            for (int d = 0; d < kBwdD; ++d) {
+              s1[d] = fmaf(on, xs[d], fmaf(onp, m[d], s1[d]));   // + on x_real - onp (0 - mean)
+              s2[d] = fmaf(r, xs[d], fmaf(rp, m[d], s2[d]));
+            }
+            s1[9] += on - onp;
+            s2[9] += r - rp;
+            q2 += r * r - rp * rp;
+          }
+          key = sgn * r;
+        }
+        if (key > best) { best = key; nbest = n; }               // strict: the first index wins a tie
+      }
+      const long long task = (long long)b * P + p;
+      float G = 0.f;
+      {
+        const long long* row = gr.inds + task * 3;
+        const long long fl = row[0], xi = row[1], yi = row[2];
+        const bool ok = fl != 0 && xi >= 0 && xi < gr.W && yi >= 0 && yi < gr.H;
+        if (ok) G = __ldg(gr.g + ((size_t)(b * kBwdC + c) * gr.H + (size_t)yi) * gr.W + (size_t)xi);
+      }
+      float xb[kBwdD];
+#pragma unroll
+      for (int d = 0; d < kBwdD; ++d) {
+        const float md = tm[d * Np + nbest];
+        xb[d] = nbest < cnt ? tf[nbest * kLiveRec + d] - md : 0.f - md;
+      }
+      float zs = bc;
+#pragma unroll
+      for (int d = 0; d < kBwdD; ++d) zs = fmaf(wr[d], xb[d], zs);
+      const float Gon = zs > 0.f ? G : 0.f;
+#pragma unroll
+      for (int d = 0; d < 10; ++d) {
+        srow[d * kBwdC] = s1[d];
+        srow[(10 + d) * kBwdC] = s2[d];
+      }
+      srow[20 * kBwdC] = q2;
+#pragma unroll
+      for (int d = 0; d < kBwdD; ++d) srow[(21 + d) * kBwdC] = Gon * xb[d];
+      srow[30 * kBwdC] = Gon;
+      srow[31 * kBwdC] = G;
+      srow[32 * kBwdC] = G * fmaxf(zs, 0.f);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kBwdAcc; ++k) srow[k * kBwdC] = 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kBwdOwn; ++k) {
+      const int idx = tid + k * 256;
+      if (idx < kBwdAcc * kBwdC) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < kBwdPil; ++q) v += (double)s_sum[(size_t)q * kBwdRows * kBwdC + idx];
+        acc[k] += v;
+      }
+    }
+  }
+  double* dst = partials + (size_t)blockIdx.x * kBwdAcc * kBwdC;
+#pragma unroll
+  for (int k = 0; k < kBwdOwn; ++k) {
+    const int idx = tid + k * 256;
+    if (idx < kBwdAcc * kBwdC) dst[idx] = acc[k];
+  }
+}
+
 // One block per sum row k: sums[k][c] over the per-block partial tiles in a fixed order; the last block to
 // finish (a ticket counter) evaluates the closed forms above.
-__global__ void __launch_bounds__(1024) k_pfn_bwd_finalize(const double* __restrict__ partials, int nblocks, double M,
+// Sparse formulation: sums = multA * flip(partialsA) + partialsB, where set A is the padding pass over
+// data_mean (rows d < 9 of S1 / S2 change sign: the slot value is 0 - mean) and B the live-pillar pass.
+__global__ void __launch_bounds__(1024) k_pfn_bwd_finalize(const double* __restrict__ partials, int nblocks,
+                                                           const double* __restrict__ partialsA, int nblocksA, double multA,
+                                                           double M,
                                                            const float* __restrict__ bn_w,
                                                            const float* __restrict__ running_mean,
                                                            const float* __restrict__ running_var, int training, float eps,
@@ -230,7 +409,11 @@ __global__ void __launch_bounds__(1024) k_pfn_bwd_finalize(const double* __restr
       s1 += partials[((size_t)(blk + 16) * kBwdAcc + k) * kBwdC + c];
     }
     if (blk < nblocks) s0 += partials[((size_t)blk * kBwdAcc + k) * kBwdC + c];
-    part[seg][c] = s0 + s1;
+    double sa = 0.0;
+    if (partialsA != nullptr && k <= 20)
+      for (int blk2 = seg; blk2 < nblocksA; blk2 += 16) sa += partialsA[((size_t)blk2 * kBwdAcc + k) * kBwdC + c];
+    const bool flip = k < 9 || (k >= 10 && k < 19);
+    part[seg][c] = s0 + s1 + (flip ? -multA : multA) * sa;
   }
   __syncthreads();
   if (seg == 0) {
@@ -288,6 +471,57 @@ __global__ void __launch_bounds__(256) k_scatter_bwd(const float* __restrict__ g
 
 static int bwd_blocks() { return sm_count() * 2; }
 
+size_t pfn_sparse_backward_workspace_bytes() {
+  return 2 * align_up((size_t)bwd_blocks() * kBwdAcc * kBwdC * sizeof(double)) +
+         align_up((size_t)kBwdAcc * kBwdC * sizeof(double)) + 3 * kAlign;
+}
+
+// Gradients of conv1 / bn1 from K1's compact state and the canvas gradient (pp_input_path_backward).
+int pfn_sparse_backward(const CompactPillars& cp, const int64_t* d_inds, int C, const float* conv_w, const float* conv_b,
+                        const float* bn_w, const float* running_mean, const float* running_var, int training, float eps,
+                        int H, int W, const float* d_grad_canvas, float* g_w, float* g_b, float* g_gamma, float* g_beta,
+                        void* d_ws, size_t ws_bytes, cudaStream_t st) {
+  const int B = cp.sw.n_sweeps, P = cp.P, N = cp.N;
+  if (C != kBwdC || cp.data_mean == nullptr || N % 4 != 0 || ((uintptr_t)cp.data_mean % 16) != 0) return PP_ERR_UNSUPPORTED;
+  if (!conv_w || !conv_b || !bn_w || !d_grad_canvas || !d_inds) return PP_ERR_INVALID_ARG;
+  if (!training && (!running_mean || !running_var)) return PP_ERR_INVALID_ARG;
+  Arena arena(d_ws, ws_bytes);
+  const int nb = bwd_blocks();
+  double* partialsA = arena.take<double>((size_t)nb * kBwdAcc * kBwdC);
+  double* partialsB = arena.take<double>((size_t)nb * kBwdAcc * kBwdC);
+  double* sums_g = arena.take<double>((size_t)kBwdAcc * kBwdC);
+  unsigned* ticket = arena.take<unsigned>(1);
+  if (!arena.ok) return PP_ERR_WORKSPACE;
+  PP_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+  const int Np = N;
+  BwdGrad gr{d_grad_canvas, (const long long*)d_inds, H, W};
+  if (training) {                                                // pass A: every padding value, once
+    const size_t smem = ((size_t)2 * kBwdPil * kBwdD * Np + (size_t)kBwdPil * kBwdRows * kBwdC) * sizeof(float);
+    if (smem > 110 * 1024) return PP_ERR_UNSUPPORTED;
+    BwdGrad none{nullptr, nullptr, 0, 0};
+    PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PP_KERNEL("k_pfn_bwd_pad", st,
+              (k_pfn_bwd<true, true><<<nb, 256, smem, st>>>(cp.data_mean, 1, P, N, Np, conv_w, conv_b, bn_w, none, 1, partialsA)));
+  }
+  const size_t smem_b = ((size_t)kBwdPil * kBwdD * Np + (size_t)kBwdPil * N * kLiveRec + (size_t)kBwdPil * kBwdRows * kBwdC) *
+                        sizeof(float);
+  if (smem_b > 110 * 1024) return PP_ERR_UNSUPPORTED;
+  if (training) {
+    PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd_live<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    PP_KERNEL("k_pfn_bwd_live", st,
+              (k_pfn_bwd_live<true><<<nb, 256, smem_b, st>>>(cp, Np, conv_w, conv_b, bn_w, gr, partialsB)));
+  } else {
+    PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd_live<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    PP_KERNEL("k_pfn_bwd_live", st,
+              (k_pfn_bwd_live<false><<<nb, 256, smem_b, st>>>(cp, Np, conv_w, conv_b, bn_w, gr, partialsB)));
+  }
+  PP_KERNEL("k_pfn_bwd_finalize", st,
+            (k_pfn_bwd_finalize<<<kBwdAcc, 1024, 0, st>>>(partialsB, nb, training ? partialsA : nullptr, nb, (double)B,
+                                                          (double)B * P * N, bn_w, running_mean, running_var,
+                                                          training ? 1 : 0, eps, sums_g, ticket, g_w, g_b, g_gamma, g_beta)));
+  return PP_OK;
+}
+
 }  // namespace pp
 
 extern "C" {
@@ -332,7 +566,7 @@ int pp_pfn_backward(const float* d_x, int32_t B, int32_t D, int32_t P, int32_t N
               (k_pfn_bwd<false><<<nb, 256, smem, st>>>(d_x, B, P, N, Np, d_conv_w, d_conv_b, d_bn_w, gr, vec16, partials)));
   }
   PP_KERNEL("k_pfn_bwd_finalize", st,
-            (k_pfn_bwd_finalize<<<kBwdAcc, 1024, 0, st>>>(partials, nb, (double)B * P * N, d_bn_w, d_running_mean,
+            (k_pfn_bwd_finalize<<<kBwdAcc, 1024, 0, st>>>(partials, nb, nullptr, 0, 0.0, (double)B * P * N, d_bn_w, d_running_mean,
                                                           d_running_var, training ? 1 : 0, eps, sums_g, ticket, d_grad_conv_w, d_grad_conv_b, d_grad_bn_w,
                                                     d_grad_bn_b)));
   return PP_OK;

@@ -891,6 +891,45 @@ int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_poin
   return PP_ERR_INVALID_ARG;
 }
 
+size_t pp_input_path_backward_workspace_bytes(int32_t n_sweeps, int32_t max_pillars, int32_t C) {
+  if (n_sweeps < 1 || n_sweeps > PP_MAX_SWEEPS || max_pillars < 1 || C != 64) return 0;
+  return pp::pfn_sparse_backward_workspace_bytes();
+}
+
+int pp_input_path_backward(const int64_t* h_sweep_offsets, int32_t n_sweeps, const pp_grid* grid,
+                           int32_t max_points_per_pillar, int32_t max_pillars, const float* d_data_mean, int32_t C,
+                           const float* d_conv_w, const float* d_conv_b, const float* d_bn_w,
+                           const float* d_running_mean, const float* d_running_var, int32_t training, float eps,
+                           int32_t canvas_h, int32_t canvas_w, const float* d_grad_canvas, const int64_t* d_indices,
+                           const int32_t* d_num_pillars, float* d_grad_conv_w, float* d_grad_conv_b,
+                           float* d_grad_bn_w, float* d_grad_bn_b, const void* d_forward_workspace,
+                           size_t forward_workspace_bytes, void* d_workspace, size_t workspace_bytes,
+                           pp_stream_t stream) {
+  using namespace pp;
+  cudaStream_t st = (cudaStream_t)stream;
+  GridDev g;
+  SweepParams sw;
+  if (!make_grid(grid, g)) return PP_ERR_INVALID_ARG;
+  int rc = make_sweeps(h_sweep_offsets, n_sweeps, sw);
+  if (rc != PP_OK) return rc;
+  const int N = max_points_per_pillar, P = max_pillars;
+  if (N < 1 || P < 1 || !d_indices || !d_num_pillars || !d_forward_workspace || canvas_h < 1 || canvas_w < 1)
+    return PP_ERR_INVALID_ARG;
+  if (!pfn_sparse_supported(n_sweeps, P, N, C, d_data_mean)) return PP_ERR_UNSUPPORTED;
+  // the forward's K1 state, found by laying the same workspace out again (pp_input_path, stage 1)
+  Arena arena(const_cast<void*>(d_forward_workspace), forward_workspace_bytes);
+  PillarWs ws{};
+  layout(arena, &ws, n_sweeps, sw.off[n_sweeps], sw.tile_start[n_sweeps], g.ncell, P);
+  if (!arena.ok) return PP_ERR_WORKSPACE;
+  CompactPillars cp;
+  cp.sw = sw; cp.P = P; cp.N = N;
+  cp.feat_c = ws.feat_c; cp.pil_cnt = ws.pil_cnt; cp.pil_off = ws.pil_off;
+  cp.num_pillars = d_num_pillars; cp.data_mean = d_data_mean;
+  return pfn_sparse_backward(cp, d_indices, C, d_conv_w, d_conv_b, d_bn_w, d_running_mean, d_running_var, training, eps,
+                             canvas_h, canvas_w, d_grad_canvas, d_grad_conv_w, d_grad_conv_b, d_grad_bn_w, d_grad_bn_b,
+                             d_workspace, workspace_bytes, st);
+}
+
 int pp_pillarize_compact(const void* d_points, int32_t point_dtype, int64_t stride_point,
                          int64_t stride_col, int64_t n_points, const pp_grid* grid,
                          int32_t max_points_per_pillar, int32_t max_pillars, double* d_rows,

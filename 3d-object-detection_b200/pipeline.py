@@ -51,6 +51,50 @@ class StepHandle:
         return self._pin[:B].clone(), self._pin[B:5 * B].view(B, 4).clone()
 
 
+class _InputPathFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, conv_w, conv_b, bn_w, bn_b, path, points, offsets):
+        net = path.net
+        ctx.training = bool(net.training)
+        ctx.eps = float(net.bn1.eps)
+        ctx.stats = None if ctx.training else (net.bn1.running_mean.clone(), net.bn1.running_var.clone())
+        canvas, inds, npil = path.pillarize_encode(points, offsets)
+        ctx.ws = _runtime.take_workspace(path.device, "input_path")      # K1's compact state lives in it
+        ctx.path, ctx.offsets = path, offsets
+        ctx.save_for_backward(conv_w, conv_b, bn_w, inds, npil)
+        ctx.mark_non_differentiable(inds, npil)
+        return canvas, inds, npil
+
+    @staticmethod
+    def backward(ctx, g_canvas, _gi, _gn):
+        L = _lib.load()
+        conv_w, conv_b, bn_w, inds, npil = ctx.saved_tensors
+        path, offsets = ctx.path, ctx.offsets
+        c = path.cfg
+        B = len(offsets) - 1
+        P, N, C = c.max_pillars, c.max_points_per_pillar, c.feature_net_out
+        dev = g_canvas.device
+        g_canvas = g_canvas.contiguous()
+        if g_canvas.dtype != torch.float32:
+            raise _lib.PPError("input path backward: the canvas gradient must be float32")
+        g_w = torch.empty((C, 9), dtype=torch.float32, device=dev)
+        g_b, g_gamma, g_beta = (torch.empty(C, dtype=torch.float32, device=dev) for _ in range(3))
+        ws2 = _runtime.workspace(L.pp_input_path_backward_workspace_bytes(B, P, C), dev, "input_path_bwd")
+        rm, rv = ctx.stats if ctx.stats is not None else (None, None)
+        w2 = conv_w.detach().reshape(C, 9).contiguous()
+        with torch.cuda.device(dev):
+            rc = L.pp_input_path_backward(
+                _lib.i64_array(offsets), B, c.grid(), N, P, path.data_mean.data_ptr() if path.data_mean is not None else None,
+                C, w2.data_ptr(), conv_b.data_ptr(), bn_w.data_ptr(), rm.data_ptr() if rm is not None else None,
+                rv.data_ptr() if rv is not None else None, 1 if ctx.training else 0, ctx.eps, c.canvas_height,
+                c.canvas_width, g_canvas.data_ptr(), inds.data_ptr(), npil.data_ptr(), g_w.data_ptr(), g_b.data_ptr(),
+                g_gamma.data_ptr(), g_beta.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), ws2.data_ptr(), ws2.numel(),
+                _runtime.stream_ptr(dev))
+        _lib.check(rc, "pp_input_path_backward")
+        ctx.ws = None
+        return g_w.view(C, 9, 1, 1), g_b, g_gamma, g_beta, None, None, None
+
+
 class InputPath:
     def __init__(self, cfg=None, device=None, data_mean=None, pfn_params=None, anchors=None,
                  training=True, fused=False):
@@ -216,6 +260,15 @@ class InputPath:
                 status.data_ptr(), ws.data_ptr(), ws.numel(), int(stages), _runtime.stream_ptr(dev))
         _lib.check(rc, "pp_input_path")
         return (canvas, inds, npil, x) if want_x else (canvas, inds, npil)
+
+    def pillarize_encode_train(self, points, offsets):
+        """``pillarize_encode`` as a differentiable step: returns (canvas, inds, n_pillars) where ``canvas`` carries
+        the autograd graph to ``self.net``'s conv1 / bn1 parameters (pp_input_path_backward: the gradients of the
+        reference's PPFeatureNet + PPScatter from the compact per-point state; the dense x is never built in either
+        direction).  The forward's workspace is kept alive by the graph until backward has run."""
+        net = self.net
+        return _InputPathFunction.apply(net.conv1.weight, net.conv1.bias, net.bn1.weight, net.bn1.bias, self, points,
+                                        list(offsets))
 
     # -- K3 -----------------------------------------------------------------------------------
     def targets(self, gt_dev, gt_offsets, out=None):

@@ -106,6 +106,27 @@ int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_poin
                   int32_t* d_status, void* d_workspace, size_t workspace_bytes, int32_t stages,
                   pp_stream_t stream);
 
+/* Backward of pp_input_path with respect to conv1 / bn1 (the fused path made trainable): the same gradients
+ * pp_pfn_backward produces from the dense x, computed from the forward's compact per-point state -- x is never
+ * materialised.  Training-mode BatchNorm makes the weight gradient dense over all B*P*N slots; the padding slots
+ * hold 0 - data_mean[d,p,n] in every sweep, so their moment sums are taken once over [P,N] (k_pfn_bwd_pad) and
+ * multiplied by n_sweeps, and only the live pillars are visited per sweep (k_pfn_bwd_live: real-minus-padding
+ * corrections and the arg-max routing of the canvas gradient).
+ *   d_forward_workspace: the workspace pp_input_path ran in (all stages), NOT reused since; h_sweep_offsets,
+ *   grid, N, P, d_data_mean as in that call; d_indices / d_num_pillars its outputs; d_grad_canvas [B,C,H,W].
+ *   training == 0: running statistics normalise (no padding pass needed).
+ * Outputs (any may be NULL): d_grad_conv_w [C,9], d_grad_conv_b, d_grad_bn_w, d_grad_bn_b [C]. */
+size_t pp_input_path_backward_workspace_bytes(int32_t n_sweeps, int32_t max_pillars, int32_t C);
+int pp_input_path_backward(const int64_t* h_sweep_offsets, int32_t n_sweeps, const pp_grid* grid,
+                           int32_t max_points_per_pillar, int32_t max_pillars, const float* d_data_mean, int32_t C,
+                           const float* d_conv_w, const float* d_conv_b, const float* d_bn_w,
+                           const float* d_running_mean, const float* d_running_var, int32_t training, float eps,
+                           int32_t canvas_h, int32_t canvas_w, const float* d_grad_canvas, const int64_t* d_indices,
+                           const int32_t* d_num_pillars, float* d_grad_conv_w, float* d_grad_conv_b,
+                           float* d_grad_bn_w, float* d_grad_bn_b, const void* d_forward_workspace,
+                           size_t forward_workspace_bytes, void* d_workspace, size_t workspace_bytes,
+                           pp_stream_t stream);
+
 /* Multi-sweep aggregation in front of pp_pillarize (data/dataset.py:54-88 with the Lyft SDK's
  * LidarPointCloud.transform and remove_close), IN PLACE on raw lidar rows:
  *   d_points [n_points, point_stride >= 3] float32 (Lyft .bin rows x,y,z,intensity,ring); file f owns rows
