@@ -50,7 +50,7 @@ int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, c
 bool pfn_sparse_supported(int B, int P, int N, int C, const void* data_mean);
 
 // backward of the same path (pfn_bwd.cu): conv1 / bn1 gradients from the compact state and the canvas gradient
-size_t pfn_sparse_backward_workspace_bytes();
+size_t pfn_sparse_backward_workspace_bytes(int B, int P);
 int pfn_sparse_backward(const CompactPillars& cp, const int64_t* d_inds, int C, const float* conv_w, const float* conv_b,
                         const float* bn_w, const float* running_mean, const float* running_var, int training, float eps,
                         int H, int W, const float* d_grad_canvas, float* g_w, float* g_b, float* g_gamma, float* g_beta,

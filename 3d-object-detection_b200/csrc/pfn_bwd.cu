@@ -44,7 +44,8 @@ struct BwdGrad {             // where G[b,c,p] lives: the [B,C,P] gradient, or t
 constexpr int kBwdRows = 34;               // staged per pillar and channel: the 33 sums (+1 pad row)
 constexpr int kBwdOwn = (kBwdAcc * kBwdC + 255) / 256;     // (k, c) pairs owned by each thread of the block
 
-template <bool TRAIN, bool ARGMAX = true>
+// DESC: the slots are visited in descending order, so ">=" keeps the first index among equal keys
+template <bool TRAIN, bool DESC = false>
 __device__ __forceinline__ void bwd_slot(const float (&wr)[kBwdD], float bc, float sgn, const float (&xs)[kBwdD], int n,
                                          float (&s1)[10], float (&s2)[10], float& q2, float& best, int& nbest) {
   float z = bc;
@@ -62,16 +63,11 @@ __device__ __forceinline__ void bwd_slot(const float (&wr)[kBwdD], float bc, flo
     s2[9] += r;
     q2 = fmaf(r, r, q2);
   }
-  if (ARGMAX) {
-    const float key = sgn * r;
-    if (key > best) { best = key; nbest = n; }                     // strict: the first index wins a tie
-  }
+  const float key = sgn * r;
+  if (DESC ? key >= best : key > best) { best = key; nbest = n; }  // the first index wins a tie
 }
 
-// PADPASS (sparse formulation, pass A): x is data_mean viewed as [1,9,P,N]; a padding slot holds 0 - mean, so the
-// weights are negated (fmaf(w, -m, z) == fmaf(-w, m, z) exactly) and the moment rows d < 9 change sign in the
-// finalize; no gradient is routed (the arg-max bookkeeping is compiled out).
-template <bool TRAIN, bool PADPASS = false>
+template <bool TRAIN>
 __global__ void __launch_bounds__(256, 2) k_pfn_bwd(const float* __restrict__ x, int B, int P, int N, int Np,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                    const float* __restrict__ bn_w, BwdGrad gr, int vec16,
@@ -86,7 +82,7 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd(const float* __restrict__ x,
 
   float wr[kBwdD];
 #pragma unroll
-  for (int d = 0; d < kBwdD; ++d) wr[d] = PADPASS ? -__ldg(w + c * kBwdD + d) : __ldg(w + c * kBwdD + d);
+  for (int d = 0; d < kBwdD; ++d) wr[d] = __ldg(w + c * kBwdD + d);
   const float bc = __ldg(bias + c);
   const float gam = __ldg(bn_w + c);
   const float sgn = gam > 0.f ? 1.f : (gam < 0.f ? -1.f : 0.f);
@@ -154,21 +150,19 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd(const float* __restrict__ x,
           float xs[kBwdD];
 #pragma unroll
           for (int d = 0; d < kBwdD; ++d) xs[d] = j == 0 ? xv[d].x : (j == 1 ? xv[d].y : (j == 2 ? xv[d].z : xv[d].w));
-          bwd_slot<TRAIN, !PADPASS>(wr, bc, sgn, xs, n0 + j, s1, s2, q2, best, nbest);
+          bwd_slot<TRAIN>(wr, bc, sgn, xs, n0 + j, s1, s2, q2, best, nbest);
         }
       }
       for (int n = N4; n < N; ++n) {
         float xs[kBwdD];
 #pragma unroll
         for (int d = 0; d < kBwdD; ++d) xs[d] = t[d * Np + n];
-        bwd_slot<TRAIN, !PADPASS>(wr, bc, sgn, xs, n, s1, s2, q2, best, nbest);
+        bwd_slot<TRAIN>(wr, bc, sgn, xs, n, s1, s2, q2, best, nbest);
       }
       // the arg-max element takes the incoming gradient
       const long long b = task / P, p = task - b * P;
       float G;
-      if (PADPASS) {
-        G = 0.f;
-      } else if (gr.inds != nullptr) {
+      if (gr.inds != nullptr) {
         const long long* row = gr.inds + task * 3;
         const long long fl = row[0], xi = row[1], yi = row[2];
         const bool ok = fl != 0 && xi >= 0 && xi < gr.W && yi >= 0 && yi < gr.H;
@@ -216,16 +210,144 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd(const float* __restrict__ x,
   }
 }
 
-// Sparse formulation, pass B: the live pillars of every sweep straight from K1's compact state (the dense x is
-// never built).  Slot n of live pillar (b,p) holds feat[n] - mean[p,n] for n < cnt and 0 - mean[p,n] beyond.
-// Moments: the padding pass counted every slot with its padding value, so a real slot adds (real - padding);
-// arg-max: over the real slots and the padding slots n >= cnt, exactly the slots of the dense tensor.
+// ---- sparse formulation (pp_input_path_backward): the dense x is never built -------------------------------
+// Slot n of live pillar (b,p) holds feat[n] - mean[p,n] for n < cnt[b,p] and the padding value 0 - mean[p,n]
+// beyond; every slot of a pillar that is not live in sweep b holds the padding value.
+//   pass A (k_pfn_bwd_pad, once over [P,N]): moment sums of the padding values (x B in the finalize; weights
+//     negated: fmaf(w, -m, z) == fmaf(-w, m, z) exactly, rows d < 9 change sign in the finalize), and, scanning
+//     the slots in descending order, the arg-max over the padding suffix n >= cnt[b,p] of every sweep in which
+//     the pillar is live: ext[b,p,c] = (key, index), snapshot when the scan passes n == cnt[b,p].
+//   pass B (k_pfn_bwd_live, live pillars only): the real slots (real - padding corrections of the moments,
+//     best real slot), the winner against the padding suffix, and the routing of the canvas gradient.
 constexpr int kLiveRec = 12;               // floats per staged point record (9 features, 16-byte multiple)
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(256, 2) k_pfn_bwd_pad(CompactPillars cp, int Np, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, const float* __restrict__ bn_w,
+                                                       float2* __restrict__ ext, double* __restrict__ partials) {
+  extern __shared__ __align__(16) float s_tile[];            // [2][kBwdPil][9][Np] | staging [kBwdPil][kBwdRows][64]
+  __shared__ int s_cnt[kBwdPil][PP_MAX_SWEEPS];              // min(count, N) of the pillar in sweep b, -1 = not live there
+  __shared__ unsigned s_snap[kBwdPil][8];                    // bit n: some sweep has count == n
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pl = warp >> 1, c = (warp & 1) * 32 + lane;
+  const int B = cp.sw.n_sweeps, P = cp.P, N = cp.N;
+  const int ngroups = (P + kBwdPil - 1) / kBwdPil;
+  const size_t stage_floats = (size_t)kBwdPil * kBwdD * Np;
+  float* s_sum = s_tile + 2 * stage_floats;
+  float wr[kBwdD];
+#pragma unroll
+  for (int d = 0; d < kBwdD; ++d) wr[d] = -__ldg(w + c * kBwdD + d);
+  const float bc = __ldg(bias + c);
+  const float gam = __ldg(bn_w + c);
+  const float sgn = gam > 0.f ? 1.f : (gam < 0.f ? -1.f : 0.f);
+  double acc[kBwdOwn];
+#pragma unroll
+  for (int k = 0; k < kBwdOwn; ++k) acc[k] = 0.0;
+
+  auto issue = [&](int grp, int stage) {
+    float* dst0 = s_tile + (size_t)stage * stage_floats;
+    const int chunks = N >> 2;
+    for (int i = tid; i < kBwdPil * kBwdD * chunks; i += 256) {
+      const int row = i / chunks, ck = i - row * chunks;
+      const int q = row / kBwdD, d = row - q * kBwdD;
+      const int p = grp * kBwdPil + q;
+      if (p < P) cp_async16(dst0 + ((size_t)q * kBwdD + d) * Np + ck * 4, cp.data_mean + ((size_t)d * P + p) * N + ck * 4);
+    }
+    cp_async_commit();
+  };
+
+  int stage = 0;
+  int grp = blockIdx.x;
+  if (grp < ngroups) issue(grp, 0);
+  for (; grp < ngroups; grp += gridDim.x) {
+    const int nxt = grp + gridDim.x;
+    if (nxt < ngroups) {
+      issue(nxt, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    if (tid < kBwdPil * 8) s_snap[tid >> 3][tid & 7] = 0u;
+    __syncthreads();                                             // tile landed; previous staging rows consumed
+    for (int i = tid; i < kBwdPil * B; i += 256) {
+      const int q = i / B, b = i - q * B, p = grp * kBwdPil + q;
+      int cnt = -1;
+      if (p < P && p < cp.num_pillars[b]) {
+        cnt = min(cp.pil_cnt[(size_t)b * P + p], N);
+        if (cnt < N) atomicOr(&s_snap[q][cnt >> 5], 1u << (cnt & 31));
+      }
+      s_cnt[q][b] = cnt;
+    }
+    __syncthreads();
+    const int p = grp * kBwdPil + pl;
+    float* srow = s_sum + (size_t)pl * kBwdRows * kBwdC + c;
+    if (p < P) {
+      const float* t = s_tile + (size_t)stage * stage_floats + (size_t)pl * kBwdD * Np;
+      float s1[10], s2[10], q2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 10; ++d) { s1[d] = 0.f; s2[d] = 0.f; }
+      float best = -INFINITY;
+      int nbest = 0;
+      for (int b = 0; b < B; ++b)                                // full pillars: no padding slot competes
+        if (s_cnt[pl][b] >= N) ext[((size_t)b * P + p) * kBwdC + c] = make_float2(-INFINITY, 0.f);
+      for (int n0 = N - 4; n0 >= 0; n0 -= 4) {
+        float4 xv[kBwdD];
+#pragma unroll
+        for (int d = 0; d < kBwdD; ++d) xv[d] = *reinterpret_cast<const float4*>(t + d * Np + n0);
+        const unsigned snap = (s_snap[pl][n0 >> 5] >> (n0 & 31)) & 0xfu;      // n0 % 4 == 0: the four bits share a word
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {
+          float xs[kBwdD];
+#pragma unroll
+          for (int d = 0; d < kBwdD; ++d) xs[d] = j == 0 ? xv[d].x : (j == 1 ? xv[d].y : (j == 2 ? xv[d].z : xv[d].w));
+          bwd_slot<TRAIN, true>(wr, bc, sgn, xs, n0 + j, s1, s2, q2, best, nbest);
+          if ((snap >> j) & 1u) {                                // warp-uniform, a handful of times per pillar
+            for (int b = 0; b < B; ++b)
+              if (s_cnt[pl][b] == n0 + j)
+                ext[((size_t)b * P + p) * kBwdC + c] = make_float2(best, __int_as_float(nbest));
+          }
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < 10; ++d) {
+        srow[d * kBwdC] = s1[d];
+        srow[(10 + d) * kBwdC] = s2[d];
+      }
+      srow[20 * kBwdC] = q2;
+#pragma unroll
+      for (int k = 21; k < kBwdAcc; ++k) srow[k * kBwdC] = 0.f;
+    } else {
+#pragma unroll
+      for (int k = 0; k < kBwdAcc; ++k) srow[k * kBwdC] = 0.f;
+    }
+    __syncthreads();
+    if (TRAIN) {
+#pragma unroll
+      for (int k = 0; k < kBwdOwn; ++k) {
+        const int idx = tid + k * 256;
+        if (idx < kBwdAcc * kBwdC) {
+          double v = 0.0;
+#pragma unroll
+          for (int q = 0; q < kBwdPil; ++q) v += (double)s_sum[(size_t)q * kBwdRows * kBwdC + idx];
+          acc[k] += v;
+        }
+      }
+    }
+    stage ^= 1;
+  }
+  double* dst = partials + (size_t)blockIdx.x * kBwdAcc * kBwdC;
+#pragma unroll
+  for (int k = 0; k < kBwdOwn; ++k) {
+    const int idx = tid + k * 256;
+    if (idx < kBwdAcc * kBwdC) dst[idx] = acc[k];
+  }
+}
 
 template <bool TRAIN>
 __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int Np, const float* __restrict__ w,
                                                         const float* __restrict__ bias, const float* __restrict__ bn_w,
-                                                        BwdGrad gr, double* __restrict__ partials) {
+                                                        BwdGrad gr, const float2* __restrict__ ext,
+                                                        double* __restrict__ partials) {
   extern __shared__ __align__(16) float s_tile[];            // mean [kBwdPil][9][Np] | feat [kBwdPil][N][12] | staging
   __shared__ int s_first[PP_MAX_SWEEPS + 1];                 // live pillars before sweep b
   __shared__ int s_cnt[kBwdPil], s_b[kBwdPil], s_p[kBwdPil];
@@ -288,6 +410,8 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
     const int b = s_b[pl];
     if (b >= 0) {
       const int p = s_p[pl], cnt = s_cnt[pl];
+      const long long task = (long long)b * P + p;
+      const float2 cand = __ldg(ext + (size_t)task * kBwdC + c);   // best padding slot at n >= cnt (pass A)
       const float* tm = s_mean + (size_t)pl * kBwdD * Np;
       const float* tf = s_feat + (size_t)pl * N * kLiveRec;
       float s1[10], s2[10], q2 = 0.f;
@@ -295,43 +419,40 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
       for (int d = 0; d < 10; ++d) { s1[d] = 0.f; s2[d] = 0.f; }
       float best = -INFINITY;
       int nbest = 0;
-      for (int n = 0; n < N; ++n) {
-        float m[kBwdD];
+      for (int n = 0; n < cnt; ++n) {                             // the slots that hold a point
+        float m[kBwdD], xs[kBwdD];
 #pragma unroll
         for (int d = 0; d < kBwdD; ++d) m[d] = tm[d * Np + n];
-        float zp = bc;                                          // the padding value of the slot: 0 - mean
+        const float4 f0 = *reinterpret_cast<const float4*>(tf + n * kLiveRec);
+        const float4 f1 = *reinterpret_cast<const float4*>(tf + n * kLiveRec + 4);
+        const float f8 = tf[n * kLiveRec + 8];
+        xs[0] = f0.x - m[0]; xs[1] = f0.y - m[1]; xs[2] = f0.z - m[2]; xs[3] = f0.w - m[3];
+        xs[4] = f1.x - m[4]; xs[5] = f1.y - m[5]; xs[6] = f1.z - m[6]; xs[7] = f1.w - m[7];
+        xs[8] = f8 - m[8];
+        float z = bc;
 #pragma unroll
-        for (int d = 0; d < kBwdD; ++d) zp = fmaf(-wr[d], m[d], zp);
-        const float rp = fmaxf(zp, 0.f);
-        float key = sgn * rp;
-        if (n < cnt) {                                          // warp-uniform: the slot holds a point
-          float xs[kBwdD];
-          const float4 f0 = *reinterpret_cast<const float4*>(tf + n * kLiveRec);
-          const float4 f1 = *reinterpret_cast<const float4*>(tf + n * kLiveRec + 4);
-          const float f8 = tf[n * kLiveRec + 8];
-          xs[0] = f0.x - m[0]; xs[1] = f0.y - m[1]; xs[2] = f0.z - m[2]; xs[3] = f0.w - m[3];
-          xs[4] = f1.x - m[4]; xs[5] = f1.y - m[5]; xs[6] = f1.z - m[6]; xs[7] = f1.w - m[7];
-          xs[8] = f8 - m[8];
-          float z = bc;
+        for (int d = 0; d < kBwdD; ++d) z = fmaf(wr[d], xs[d], z);
+        const float r = fmaxf(z, 0.f);
+        if (TRAIN) {
+          float zp = bc;                                          // the padding value this slot replaced: 0 - mean
 #pragma unroll
-          for (int d = 0; d < kBwdD; ++d) z = fmaf(wr[d], xs[d], z);
-          const float r = fmaxf(z, 0.f);
-          if (TRAIN) {
-            const float on = z > 0.f ? 1.f : 0.f, onp = zp > 0.f ? 1.f : 0.f;
+          for (int d = 0; d < kBwdD; ++d) zp = fmaf(-wr[d], m[d], zp);
+          const float rp = fmaxf(zp, 0.f);
+          const float on = z > 0.f ? 1.f : 0.f, onp = zp > 0.f ? 1.f : 0.f;
 #pragma unroll
-            for (int d = 0; d < kBwdD; ++d) {
-              s1[d] = fmaf(on, xs[d], fmaf(onp, m[d], s1[d]));   // + on x_real - onp (0 - mean)
-              s2[d] = fmaf(r, xs[d], fmaf(rp, m[d], s2[d]));
-            }
-            s1[9] += on - onp;
-            s2[9] += r - rp;
-            q2 += r * r - rp * rp;
+          for (int d = 0; d < kBwdD; ++d) {
+            s1[d] = fmaf(on, xs[d], fmaf(onp, m[d], s1[d]));     // + on x_real - onp (0 - mean)
+            s2[d] = fmaf(r, xs[d], fmaf(rp, m[d], s2[d]));
           }
-          key = sgn * r;
+          s1[9] += on - onp;
+          s2[9] += r - rp;
+          q2 += r * r - rp * rp;
         }
+        const float key = sgn * r;
         if (key > best) { best = key; nbest = n; }               // strict: the first index wins a tie
       }
-      const long long task = (long long)b * P + p;
+      const bool pad_wins = cand.x > best;                       // padding slots come after the real ones: ties stay real
+      if (pad_wins) nbest = __float_as_int(cand.y);
       float G = 0.f;
       {
         const long long* row = gr.inds + task * 3;
@@ -343,7 +464,7 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
 #pragma unroll
       for (int d = 0; d < kBwdD; ++d) {
         const float md = tm[d * Np + nbest];
-        xb[d] = nbest < cnt ? tf[nbest * kLiveRec + d] - md : 0.f - md;
+        xb[d] = pad_wins ? 0.f - md : tf[nbest * kLiveRec + d] - md;
       }
       float zs = bc;
 #pragma unroll
@@ -384,8 +505,6 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
   }
 }
 
-// One block per sum row k: sums[k][c] over the per-block partial tiles in a fixed order; the last block to
-// finish (a ticket counter) evaluates the closed forms above.
 // Sparse formulation: sums = multA * flip(partialsA) + partialsB, where set A is the padding pass over
 // data_mean (rows d < 9 of S1 / S2 change sign: the slot value is 0 - mean) and B the live-pillar pass.
 __global__ void __launch_bounds__(1024) k_pfn_bwd_finalize(const double* __restrict__ partials, int nblocks,
@@ -471,9 +590,9 @@ __global__ void __launch_bounds__(256) k_scatter_bwd(const float* __restrict__ g
 
 static int bwd_blocks() { return sm_count() * 2; }
 
-size_t pfn_sparse_backward_workspace_bytes() {
+size_t pfn_sparse_backward_workspace_bytes(int B, int P) {
   return 2 * align_up((size_t)bwd_blocks() * kBwdAcc * kBwdC * sizeof(double)) +
-         align_up((size_t)kBwdAcc * kBwdC * sizeof(double)) + 3 * kAlign;
+         align_up((size_t)kBwdAcc * kBwdC * sizeof(double)) + align_up((size_t)B * P * kBwdC * sizeof(float2)) + 4 * kAlign;
 }
 
 // Gradients of conv1 / bn1 from K1's compact state and the canvas gradient (pp_input_path_backward).
@@ -490,30 +609,30 @@ int pfn_sparse_backward(const CompactPillars& cp, const int64_t* d_inds, int C, 
   double* partialsA = arena.take<double>((size_t)nb * kBwdAcc * kBwdC);
   double* partialsB = arena.take<double>((size_t)nb * kBwdAcc * kBwdC);
   double* sums_g = arena.take<double>((size_t)kBwdAcc * kBwdC);
+  float2* ext = arena.take<float2>((size_t)B * P * kBwdC);
   unsigned* ticket = arena.take<unsigned>(1);
   if (!arena.ok) return PP_ERR_WORKSPACE;
   PP_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   const int Np = N;
   BwdGrad gr{d_grad_canvas, (const long long*)d_inds, H, W};
-  if (training) {                                                // pass A: every padding value, once
-    const size_t smem = ((size_t)2 * kBwdPil * kBwdD * Np + (size_t)kBwdPil * kBwdRows * kBwdC) * sizeof(float);
-    if (smem > 110 * 1024) return PP_ERR_UNSUPPORTED;
-    BwdGrad none{nullptr, nullptr, 0, 0};
-    PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PP_KERNEL("k_pfn_bwd_pad", st,
-              (k_pfn_bwd<true, true><<<nb, 256, smem, st>>>(cp.data_mean, 1, P, N, Np, conv_w, conv_b, bn_w, none, 1, partialsA)));
-  }
+  const size_t smem_a = ((size_t)2 * kBwdPil * kBwdD * Np + (size_t)kBwdPil * kBwdRows * kBwdC) * sizeof(float);
   const size_t smem_b = ((size_t)kBwdPil * kBwdD * Np + (size_t)kBwdPil * N * kLiveRec + (size_t)kBwdPil * kBwdRows * kBwdC) *
                         sizeof(float);
-  if (smem_b > 110 * 1024) return PP_ERR_UNSUPPORTED;
+  if (smem_a > 110 * 1024 || smem_b > 110 * 1024) return PP_ERR_UNSUPPORTED;
   if (training) {
+    PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd_pad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    PP_KERNEL("k_pfn_bwd_pad", st,
+              (k_pfn_bwd_pad<true><<<nb, 256, smem_a, st>>>(cp, Np, conv_w, conv_b, bn_w, ext, partialsA)));
     PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd_live<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     PP_KERNEL("k_pfn_bwd_live", st,
-              (k_pfn_bwd_live<true><<<nb, 256, smem_b, st>>>(cp, Np, conv_w, conv_b, bn_w, gr, partialsB)));
+              (k_pfn_bwd_live<true><<<nb, 256, smem_b, st>>>(cp, Np, conv_w, conv_b, bn_w, gr, ext, partialsB)));
   } else {
+    PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd_pad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    PP_KERNEL("k_pfn_bwd_pad", st,
+              (k_pfn_bwd_pad<false><<<nb, 256, smem_a, st>>>(cp, Np, conv_w, conv_b, bn_w, ext, partialsA)));
     PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd_live<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     PP_KERNEL("k_pfn_bwd_live", st,
-              (k_pfn_bwd_live<false><<<nb, 256, smem_b, st>>>(cp, Np, conv_w, conv_b, bn_w, gr, partialsB)));
+              (k_pfn_bwd_live<false><<<nb, 256, smem_b, st>>>(cp, Np, conv_w, conv_b, bn_w, gr, ext, partialsB)));
   }
   PP_KERNEL("k_pfn_bwd_finalize", st,
             (k_pfn_bwd_finalize<<<kBwdAcc, 1024, 0, st>>>(partialsB, nb, training ? partialsA : nullptr, nb, (double)B,

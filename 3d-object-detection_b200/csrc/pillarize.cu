@@ -893,7 +893,7 @@ int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_poin
 
 size_t pp_input_path_backward_workspace_bytes(int32_t n_sweeps, int32_t max_pillars, int32_t C) {
   if (n_sweeps < 1 || n_sweeps > PP_MAX_SWEEPS || max_pillars < 1 || C != 64) return 0;
-  return pp::pfn_sparse_backward_workspace_bytes();
+  return pp::pfn_sparse_backward_workspace_bytes(n_sweeps, max_pillars);
 }
 
 int pp_input_path_backward(const int64_t* h_sweep_offsets, int32_t n_sweeps, const pp_grid* grid,

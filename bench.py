@@ -261,7 +261,7 @@ def algorithmic_bytes(B, P, N, C, H, W, A, K, total_points, has_mean):
     }
 
 
-def training_rows(x, inds, targets, dev, peak, steps, path=None, d_pts=None, offsets=None, gt=None):
+def training_rows(x, inds, targets, dev, peak, steps, path=None, d_pts=None, offsets=None, gt=None, fused_path=None):
     """PFN + scatter backward (pp_pfn_backward) and the loss front-end (pp_loss) on the step's own x / inds /
     targets, network outputs random: per-kernel CUDA-event times and, for the streaming loss kernels, GB/s."""
     import torch
@@ -293,6 +293,9 @@ def training_rows(x, inds, targets, dev, peak, steps, path=None, d_pts=None, off
         if pts_copy is not None:
             pts_copy.copy_(d_pts)
             path.aggregate(pts_copy, offs_dev, rigid)
+        if fused_path is not None:                   # the x-free path made trainable: forward + sparse backward
+            fused_path.net.zero_grad(set_to_none=True)
+            fused_path.pillarize_encode_train(d_pts, offsets)[0].backward(g_canvas)
         if gt is not None:                           # the same targets as a positives list, and the loss fed by it
             path.targets_as_list = True
             pos = path.targets(gt[0], gt[1])[0]
@@ -328,7 +331,11 @@ def training_rows(x, inds, targets, dev, peak, steps, path=None, d_pts=None, off
     if "k_pfn_bwd" in rows:
         rows["k_pfn_bwd"]["note"] = ("FP32-issue bound, not HBM: 30 FMA per (slot, channel) for z and the BatchNorm moment "
                                      "matrices; %.1f G(slot*channel)/s" % (slots * 64 / rows["k_pfn_bwd"]["us_per_launch"] / 1e3))
-    return {"what": "pp_pfn_backward through PPFeatureScatter.backward (training-mode BatchNorm) and pp_loss through "
+    if "k_pfn_bwd_pad" in rows:
+        rows["k_pfn_bwd_pad"]["note"] = ("pp_input_path_backward, pass A: padding-slot moments + per-sweep suffix arg-max once over "
+                                         "[P,N]; k_pfn_bwd_live: the live pillars from the compact state (x never built)")
+    return {"what": "pp_input_path_backward through InputPath.pillarize_encode_train (k_pfn_bwd_pad/_live: sparse formulation); "
+                    "pp_pfn_backward through PPFeatureScatter.backward (training-mode BatchNorm) and pp_loss through "
                     "PPLoss forward + backward from the dense targets and from the positives list of pp_assign_targets_list "
                     "(k_pos_*, k_loss_*_list), batch of %d sweeps; pp_aggregate_sweeps (rigid transform + remove_close, in "
                     "place) on the batch's raw points" % B, "kernels": rows}
@@ -533,7 +540,7 @@ def run_ours(args):
         if rank == 0 and world == 1 and not args.no_training_rows:
             training = training_rows(out2["pillars"][0], out2["pillars"][1], out["targets"], dev, peak, args.steps,
                                      path=path2, d_pts=d_pts, offsets=batch["offsets"],
-                                     gt=(gt_dev, batch["gt_offsets"]))
+                                     gt=(gt_dev, batch["gt_offsets"]), fused_path=path)
         del out2, path2
 
     cpu_baseline = None
