@@ -109,3 +109,40 @@ def test_packed_host_batch_layout_is_aligned_and_disjoint():
     assert off["points"][1] == 271631 * 5 * 4 and off["corners"][1] == 400 * 8 * 8 and off["cls"][1] == 400 * 4
     off0, total0 = InputPath._blob_layout(0, 5, 0)             # empty batch still has one row per section
     assert off0["points"][1] == 5 * 4 and total0 > 0
+
+
+def test_training_side_entries_validate_arguments_without_gpu():
+    """pp_loss / pp_loss_list / pp_pfn_backward / pp_scatter_backward / pp_aggregate_sweeps /
+    pp_input_path_backward / pp_assign_targets_list: workspace queries and NULL / shape rejection before any CUDA
+    call (return code 1 = PP_ERR_INVALID_ARG)."""
+    L = _lib.load()
+    grid = pp_b200.PPConfig().grid()
+    assert L.pp_loss_workspace_bytes(4, 300, 300, 6) > 4 * 300 * 300 * 6 * 4          # holds the positives list
+    assert L.pp_loss_workspace_bytes(0, 300, 300, 6) == 0
+    assert L.pp_pfn_backward_workspace_bytes(4, 24000, 64) > 0
+    assert L.pp_pfn_backward_workspace_bytes(4, 24000, 32) == 0                        # C == 64 only
+    assert L.pp_input_path_backward_workspace_bytes(4, 24000, 64) > 4 * 24000 * 64 * 8  # per-sweep suffix arg-max rows
+    assert L.pp_input_path_backward_workspace_bytes(65, 24000, 64) == 0
+    tail = (2, 300, 300, 6, 9, 8, 2.0, 25.0, 250.0, 1.0, 0.0, None, None, None, None, None, 0, None)
+    assert L.pp_loss(None, None, None, None, *tail) == 1
+    assert L.pp_loss_list(None, None, None, None, None, None, *tail) == 1
+    assert L.pp_loss_scale_grads(None, 8, None, 0, None, None, None) == 1
+    assert L.pp_pfn_backward(None, 1, 9, 8, 16, 64, None, None, None, None, None, 1, 1e-5, None, None, 0, 0,
+                             None, None, None, None, None, 0, None) == 1
+    assert L.pp_scatter_backward(None, None, 1, 64, 8, 600, 600, None, None) == 1
+    assert L.pp_aggregate_sweeps(None, 10, 5, None, 1, None, 0.001, None, None) == 1
+    assert L.pp_input_path_backward(_lib.i64_array([0, 0]), 1, grid, 200, 24000, None, 64, None, None, None, None, None,
+                                    1, 1e-5, 600, 600, None, None, None, None, None, None, None, None, 0, None, 0,
+                                    None) == 1
+    assert L.pp_assign_targets_list(None, None, None, None, None, 540000, None, None, None, None, None,
+                                    _lib.i64_array([0, 0]), 1, 9, 0.6, None, None, None, None, 16, None, None, None,
+                                    None, None, None, 0, None) == 1
+
+
+def test_packed_batch_with_transforms_layout():
+    from pp_b200.pipeline import InputPath
+    off, total = InputPath._blob_layout(1000, 5, 10, F=3)
+    assert list(off)[-2:] == ["xforms", "file_offsets"]
+    assert off["xforms"] == (off["xforms"][0], 3 * 12 * 8) and off["file_offsets"][1] == 4 * 8
+    assert off["xforms"][0] % 256 == 0 and off["file_offsets"][0] % 256 == 0 and total % 256 == 0
+    assert list(InputPath._blob_layout(1000, 5, 10)[0]) == list(off)[:-2]             # F = 0: unchanged layout
