@@ -64,3 +64,33 @@ def test_fused_backward_equals_dense_backward_and_float64_autograd(training, B):
     (out * g_canvas.double()).sum().backward()
     for k, t in zip(KEYS, prm64):
         _close(got[k], t.grad)
+
+
+def test_fused_backward_edge_cases():
+    """More than eight sweeps, one of them empty; N = 16 so many pillars overflow the point cap (no padding slot
+    competes there); P = 500 so the pillar cap binds.  Against the dense module backward on the materialised x."""
+    import pp_b200
+    from pp_b200 import model as pm, pipeline, synth
+    cfg = pp_b200.PPConfig(max_pillars=500, max_points_per_pillar=16)
+    P, N = cfg.max_pillars, cfg.max_points_per_pillar
+    mean = synth.make_data_mean(P, N, seed=6, dense=True)
+    prm = synth.make_pfn_params(2, flip_gamma=True)
+    path = pipeline.InputPath(cfg, device=torch.device("cuda"), data_mean=mean, pfn_params=prm, training=True, fused=True)
+    sweeps = [synth.make_sweep(60 + b)[:6000] for b in range(9)]
+    sweeps[4] = sweeps[4][:0]                                                     # an empty sweep
+    sweeps[7] = sweeps[7][:40]                                                    # a nearly empty one
+    pts = torch.tensor(np.concatenate(sweeps), device="cuda")
+    offs = [0] + list(np.cumsum([len(s) for s in sweeps]))
+    sd0 = {k: v.clone() for k, v in path.net.state_dict().items()}
+    canvas, inds, npil = path.pillarize_encode_train(pts, offs)
+    assert npil.tolist()[4] == 0 and npil.max().item() == P
+    g_canvas = torch.randn(canvas.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    canvas.backward(g_canvas)
+    got = {k: dict(path.net.named_parameters())[k].grad.clone() for k in KEYS}
+    dense = pipeline.InputPath(cfg, device=torch.device("cuda"), data_mean=mean, pfn_params=prm, training=True, fused=False)
+    x, inds2, _ = dense.pillarize(pts, offs)
+    net = pm.PPFeatureScatter(9, 64, cfg.canvas_height, cfg.canvas_width).cuda().train()
+    net.load_state_dict(sd0)
+    net(x, inds2).backward(g_canvas)
+    for k in KEYS:
+        _close(got[k], dict(net.named_parameters())[k].grad)
