@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd(const float* __restrict__ x,
 //   pass B (k_pfn_bwd_live, live pillars only): the real slots (real - padding corrections of the moments,
 //     best real slot), the winner against the padding suffix, and the routing of the canvas gradient.
 constexpr int kLiveRec = 12;               // floats per staged point record (9 features, 16-byte multiple)
+constexpr int kLiveStage = 32;            // points per pillar staged in shared memory; longer pillars read the rest from L2
 
 template <bool TRAIN>
 __global__ void __launch_bounds__(256, 2) k_pfn_bwd_pad(CompactPillars cp, int Np, const float* __restrict__ w,
@@ -256,9 +257,17 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_pad(CompactPillars cp, int N
     cp_async_commit();
   };
 
+  // thread i < 4*B owns (pillar q = i / B, sweep b = i % B) of a group: its count is fetched one group ahead
+  auto fetch_cnt = [&](int g) -> int {
+    if (tid >= kBwdPil * B) return -1;
+    const int q = tid / B, b = tid - q * B, p = g * kBwdPil + q;
+    if (g >= ngroups || p >= P || p >= cp.num_pillars[b]) return -1;
+    return min(cp.pil_cnt[(size_t)b * P + p], N);
+  };
   int stage = 0;
   int grp = blockIdx.x;
   if (grp < ngroups) issue(grp, 0);
+  int cnt_now = fetch_cnt(grp);
   for (; grp < ngroups; grp += gridDim.x) {
     const int nxt = grp + gridDim.x;
     if (nxt < ngroups) {
@@ -267,17 +276,15 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_pad(CompactPillars cp, int N
     } else {
       cp_async_wait<0>();
     }
+    const int cnt_next = fetch_cnt(nxt);                        // in flight during this group's arithmetic
     if (tid < kBwdPil * 8) s_snap[tid >> 3][tid & 7] = 0u;
     __syncthreads();                                             // tile landed; previous staging rows consumed
-    for (int i = tid; i < kBwdPil * B; i += 256) {
-      const int q = i / B, b = i - q * B, p = grp * kBwdPil + q;
-      int cnt = -1;
-      if (p < P && p < cp.num_pillars[b]) {
-        cnt = min(cp.pil_cnt[(size_t)b * P + p], N);
-        if (cnt < N) atomicOr(&s_snap[q][cnt >> 5], 1u << (cnt & 31));
-      }
-      s_cnt[q][b] = cnt;
+    if (tid < kBwdPil * B) {
+      const int q = tid / B, b = tid - q * B;
+      if (cnt_now >= 0 && cnt_now < N) atomicOr(&s_snap[q][cnt_now >> 5], 1u << (cnt_now & 31));
+      s_cnt[q][b] = cnt_now;
     }
+    cnt_now = cnt_next;
     __syncthreads();
     const int p = grp * kBwdPil + pl;
     float* srow = s_sum + (size_t)pl * kBwdRows * kBwdC + c;
@@ -295,16 +302,26 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_pad(CompactPillars cp, int N
 #pragma unroll
         for (int d = 0; d < kBwdD; ++d) xv[d] = *reinterpret_cast<const float4*>(t + d * Np + n0);
         const unsigned snap = (s_snap[pl][n0 >> 5] >> (n0 & 31)) & 0xfu;      // n0 % 4 == 0: the four bits share a word
+        if (snap == 0u) {                                        // the common group: no sweep's count falls in it
 #pragma unroll
-        for (int j = 3; j >= 0; --j) {
-          float xs[kBwdD];
+          for (int j = 3; j >= 0; --j) {
+            float xs[kBwdD];
 #pragma unroll
-          for (int d = 0; d < kBwdD; ++d) xs[d] = j == 0 ? xv[d].x : (j == 1 ? xv[d].y : (j == 2 ? xv[d].z : xv[d].w));
-          bwd_slot<TRAIN, true>(wr, bc, sgn, xs, n0 + j, s1, s2, q2, best, nbest);
-          if ((snap >> j) & 1u) {                                // warp-uniform, a handful of times per pillar
-            for (int b = 0; b < B; ++b)
-              if (s_cnt[pl][b] == n0 + j)
-                ext[((size_t)b * P + p) * kBwdC + c] = make_float2(best, __int_as_float(nbest));
+            for (int d = 0; d < kBwdD; ++d) xs[d] = j == 0 ? xv[d].x : (j == 1 ? xv[d].y : (j == 2 ? xv[d].z : xv[d].w));
+            bwd_slot<TRAIN, true>(wr, bc, sgn, xs, n0 + j, s1, s2, q2, best, nbest);
+          }
+        } else {
+#pragma unroll
+          for (int j = 3; j >= 0; --j) {
+            float xs[kBwdD];
+#pragma unroll
+            for (int d = 0; d < kBwdD; ++d) xs[d] = j == 0 ? xv[d].x : (j == 1 ? xv[d].y : (j == 2 ? xv[d].z : xv[d].w));
+            bwd_slot<TRAIN, true>(wr, bc, sgn, xs, n0 + j, s1, s2, q2, best, nbest);
+            if ((snap >> j) & 1u) {                              // warp-uniform, a handful of times per pillar
+              for (int b = 0; b < B; ++b)
+                if (s_cnt[pl][b] == n0 + j)
+                  ext[((size_t)b * P + p) * kBwdC + c] = make_float2(best, __int_as_float(nbest));
+            }
           }
         }
       }
@@ -348,15 +365,15 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
                                                         const float* __restrict__ bias, const float* __restrict__ bn_w,
                                                         BwdGrad gr, const float2* __restrict__ ext,
                                                         double* __restrict__ partials) {
-  extern __shared__ __align__(16) float s_tile[];            // mean [kBwdPil][9][Np] | feat [kBwdPil][N][12] | staging
+  extern __shared__ __align__(16) float s_tile[];            // 2 x { mean [kBwdPil][9][Np] | feat [kBwdPil][32][12] } | staging
   __shared__ int s_first[PP_MAX_SWEEPS + 1];                 // live pillars before sweep b
-  __shared__ int s_cnt[kBwdPil], s_b[kBwdPil], s_p[kBwdPil];
+  __shared__ int s_cnt2[3][kBwdPil], s_b2[3][kBwdPil], s_p2[3][kBwdPil];   // three slots: written one group ahead,
+                                                                          // read without a barrier after the arithmetic
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pl = warp >> 1, c = (warp & 1) * 32 + lane;
   const int B = cp.sw.n_sweeps, P = cp.P, N = cp.N;
-  float* s_mean = s_tile;
-  float* s_feat = s_tile + (size_t)kBwdPil * kBwdD * Np;
-  float* s_sum = s_feat + (size_t)kBwdPil * N * kLiveRec;
+  const size_t stage_floats = (size_t)kBwdPil * kBwdD * Np + (size_t)kBwdPil * kLiveStage * kLiveRec;
+  float* s_sum = s_tile + 2 * stage_floats;
   if (tid == 0) {
     int a = 0;
     for (int b = 0; b < B; ++b) { s_first[b] = a; a += min(max(cp.num_pillars[b], 0), P); }
@@ -372,63 +389,102 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
   const float bc = __ldg(bias + c);
   const float gam = __ldg(bn_w + c);
   const float sgn = gam > 0.f ? 1.f : (gam < 0.f ? -1.f : 0.f);
-  double acc[kBwdOwn];
+  // per-warp fp32 sums over this warp's ~60 pillars (a few hundred terms each); fp64 from the block level up
+  float s1[10], s2[10], q2 = 0.f, tt[10], sG = 0.f, sGr = 0.f;
 #pragma unroll
-  for (int k = 0; k < kBwdOwn; ++k) acc[k] = 0.0;
+  for (int d = 0; d < 10; ++d) { s1[d] = 0.f; s2[d] = 0.f; tt[d] = 0.f; }
 
-  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+  // (sweep, pillar, count) of the four pillars of a group: threads 0..3
+  auto meta = [&](int g, int ms) {
     if (tid < kBwdPil) {
-      const int L = grp * kBwdPil + tid;
+      const int L = g * kBwdPil + tid;
       int b = -1, p = 0, cnt = 0;
-      if (L < n_live) {
+      if (g < ngroups && L < n_live) {
         b = 0;
         while (s_first[b + 1] <= L) ++b;
         p = L - s_first[b];
         cnt = min(cp.pil_cnt[(size_t)b * P + p], N);
       }
-      s_b[tid] = b; s_p[tid] = p; s_cnt[tid] = cnt;
+      s_b2[ms][tid] = b; s_p2[ms][tid] = p; s_cnt2[ms][tid] = cnt;
     }
-    __syncthreads();                                           // also: the previous group's staging rows are consumed
-    for (int i = tid; i < kBwdPil * kBwdD * (Np >> 2); i += 256) {
-      const int row = i / (Np >> 2), ck = i - row * (Np >> 2);
-      const int q = row / kBwdD, d = row - q * kBwdD;
-      if (s_b[q] >= 0 && ck * 4 < N)
-        cp_async16(s_mean + ((size_t)q * kBwdD + d) * Np + ck * 4, cp.data_mean + ((size_t)d * P + s_p[q]) * N + ck * 4);
+  };
+  auto issue = [&](int st, int ms) {
+    float* s_mean = s_tile + (size_t)st * stage_floats;
+    float* s_feat = s_mean + (size_t)kBwdPil * kBwdD * Np;
+    for (int row = tid >> 3; row < kBwdPil * kBwdD; row += 32) {     // 8 threads per row of N floats
+      const int q = row / kBwdD, d = row - q * kBwdD;                 // constant divisor
+      if (s_b2[ms][q] < 0) continue;
+      const float* src = cp.data_mean + ((size_t)d * P + s_p2[ms][q]) * N;
+      float* dst = s_mean + ((size_t)q * kBwdD + d) * Np;
+      for (int ck = tid & 7; ck * 4 < N; ck += 8) cp_async16(dst + ck * 4, src + ck * 4);
     }
     for (int q = 0; q < kBwdPil; ++q) {
-      if (s_b[q] < 0) continue;
-      const float* src = cp.feat_c + ((size_t)cp.sw.off[s_b[q]] + cp.pil_off[(size_t)s_b[q] * P + s_p[q]]) * kBwdD;
-      for (int i = tid; i < s_cnt[q] * kBwdD; i += 256) {
+      if (s_b2[ms][q] < 0) continue;
+      const float* src = cp.feat_c + ((size_t)cp.sw.off[s_b2[ms][q]] + cp.pil_off[(size_t)s_b2[ms][q] * P + s_p2[ms][q]]) * kBwdD;
+      for (int i = tid; i < min(s_cnt2[ms][q], kLiveStage) * kBwdD; i += 256) {
         const int n = i / kBwdD, d = i - n * kBwdD;
-        cp_async4(s_feat + ((size_t)q * N + n) * kLiveRec + d, src + i);
+        cp_async4(s_feat + ((size_t)q * kLiveStage + n) * kLiveRec + d, src + i);
       }
     }
     cp_async_commit();
+  };
+
+  int stage = 0, ms = 0;
+  meta(blockIdx.x, 0);
+  __syncthreads();
+  if ((int)blockIdx.x < ngroups) issue(0, 0);
+  // the scatter row (flag, x, y) of this warp's pillar is fetched one group ahead, the canvas gradient at the
+  // top of the group: both round trips overlap the arithmetic instead of trailing it
+  long long cfl = 0, cxi = 0, cyi = 0;
+  if (s_b2[0][pl] >= 0) {
+    const long long* row = gr.inds + ((long long)s_b2[0][pl] * P + s_p2[0][pl]) * 3;
+    cfl = row[0]; cxi = row[1]; cyi = row[2];
+  }
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int ms_next = ms == 2 ? 0 : ms + 1;
+    meta(grp + gridDim.x, ms_next);                            // the next group's pillars (threads 0..3)
     cp_async_wait<0>();
-    __syncthreads();
-    float* srow = s_sum + (size_t)pl * kBwdRows * kBwdC + c;
+    __syncthreads();                                           // this group's tile landed, next metadata visible, the
+                                                               // other tile stage is no longer read
+    if (grp + (int)gridDim.x < ngroups) issue(stage ^ 1, ms_next);   // in flight during this group's arithmetic
+    const float* s_mean = s_tile + (size_t)stage * stage_floats;
+    const float* s_feat = s_mean + (size_t)kBwdPil * kBwdD * Np;
+    const int* s_b = s_b2[ms];
+    const int* s_p = s_p2[ms];
+    const int* s_cnt = s_cnt2[ms];
     const int b = s_b[pl];
+    float G = 0.f;
+    if (b >= 0 && cfl != 0 && cxi >= 0 && cxi < gr.W && cyi >= 0 && cyi < gr.H)
+      G = __ldg(gr.g + ((size_t)(b * kBwdC + c) * gr.H + (size_t)cyi) * gr.W + (size_t)cxi);
+    long long nfl = 0, nxi = 0, nyi = 0;
+    if (s_b2[ms_next][pl] >= 0) {
+      const long long* row = gr.inds + ((long long)s_b2[ms_next][pl] * P + s_p2[ms_next][pl]) * 3;
+      nfl = __ldg(row); nxi = __ldg(row + 1); nyi = __ldg(row + 2);
+    }
     if (b >= 0) {
       const int p = s_p[pl], cnt = s_cnt[pl];
       const long long task = (long long)b * P + p;
       const float2 cand = __ldg(ext + (size_t)task * kBwdC + c);   // best padding slot at n >= cnt (pass A)
       const float* tm = s_mean + (size_t)pl * kBwdD * Np;
-      const float* tf = s_feat + (size_t)pl * N * kLiveRec;
-      float s1[10], s2[10], q2 = 0.f;
-#pragma unroll
-      for (int d = 0; d < 10; ++d) { s1[d] = 0.f; s2[d] = 0.f; }
+      const float* tf = s_feat + (size_t)pl * kLiveStage * kLiveRec;
+      const float* gf = cp.feat_c + ((size_t)cp.sw.off[b] + cp.pil_off[(size_t)b * P + p]) * kBwdD;   // the pillar's rows in HBM
       float best = -INFINITY;
       int nbest = 0;
       for (int n = 0; n < cnt; ++n) {                             // the slots that hold a point
         float m[kBwdD], xs[kBwdD];
 #pragma unroll
         for (int d = 0; d < kBwdD; ++d) m[d] = tm[d * Np + n];
-        const float4 f0 = *reinterpret_cast<const float4*>(tf + n * kLiveRec);
-        const float4 f1 = *reinterpret_cast<const float4*>(tf + n * kLiveRec + 4);
-        const float f8 = tf[n * kLiveRec + 8];
-        xs[0] = f0.x - m[0]; xs[1] = f0.y - m[1]; xs[2] = f0.z - m[2]; xs[3] = f0.w - m[3];
-        xs[4] = f1.x - m[4]; xs[5] = f1.y - m[5]; xs[6] = f1.z - m[6]; xs[7] = f1.w - m[7];
-        xs[8] = f8 - m[8];
+        if (n < kLiveStage) {
+          const float4 f0 = *reinterpret_cast<const float4*>(tf + n * kLiveRec);
+          const float4 f1 = *reinterpret_cast<const float4*>(tf + n * kLiveRec + 4);
+          const float f8 = tf[n * kLiveRec + 8];
+          xs[0] = f0.x - m[0]; xs[1] = f0.y - m[1]; xs[2] = f0.z - m[2]; xs[3] = f0.w - m[3];
+          xs[4] = f1.x - m[4]; xs[5] = f1.y - m[5]; xs[6] = f1.z - m[6]; xs[7] = f1.w - m[7];
+          xs[8] = f8 - m[8];
+        } else {
+#pragma unroll
+          for (int d = 0; d < kBwdD; ++d) xs[d] = __ldg(gf + (size_t)n * kBwdD + d) - m[d];
+        }
         float z = bc;
 #pragma unroll
         for (int d = 0; d < kBwdD; ++d) z = fmaf(wr[d], xs[d], z);
@@ -453,48 +509,50 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
       }
       const bool pad_wins = cand.x > best;                       // padding slots come after the real ones: ties stay real
       if (pad_wins) nbest = __float_as_int(cand.y);
-      float G = 0.f;
-      {
-        const long long* row = gr.inds + task * 3;
-        const long long fl = row[0], xi = row[1], yi = row[2];
-        const bool ok = fl != 0 && xi >= 0 && xi < gr.W && yi >= 0 && yi < gr.H;
-        if (ok) G = __ldg(gr.g + ((size_t)(b * kBwdC + c) * gr.H + (size_t)yi) * gr.W + (size_t)xi);
-      }
       float xb[kBwdD];
 #pragma unroll
       for (int d = 0; d < kBwdD; ++d) {
         const float md = tm[d * Np + nbest];
-        xb[d] = pad_wins ? 0.f - md : tf[nbest * kLiveRec + d] - md;
+        xb[d] = pad_wins ? 0.f - md : (nbest < kLiveStage ? tf[nbest * kLiveRec + d] : __ldg(gf + (size_t)nbest * kBwdD + d)) - md;
       }
       float zs = bc;
 #pragma unroll
       for (int d = 0; d < kBwdD; ++d) zs = fmaf(wr[d], xb[d], zs);
       const float Gon = zs > 0.f ? G : 0.f;
 #pragma unroll
-      for (int d = 0; d < 10; ++d) {
-        srow[d * kBwdC] = s1[d];
-        srow[(10 + d) * kBwdC] = s2[d];
-      }
-      srow[20 * kBwdC] = q2;
-#pragma unroll
-      for (int d = 0; d < kBwdD; ++d) srow[(21 + d) * kBwdC] = Gon * xb[d];
-      srow[30 * kBwdC] = Gon;
-      srow[31 * kBwdC] = G;
-      srow[32 * kBwdC] = G * fmaxf(zs, 0.f);
-    } else {
-#pragma unroll
-      for (int k = 0; k < kBwdAcc; ++k) srow[k * kBwdC] = 0.f;
+      for (int d = 0; d < kBwdD; ++d) tt[d] = fmaf(Gon, xb[d], tt[d]);
+      tt[9] += Gon;
+      sG += G;
+      sGr = fmaf(G, fmaxf(zs, 0.f), sGr);
     }
-    __syncthreads();
+    stage ^= 1;
+    ms = ms_next;
+    cfl = nfl; cxi = nxi; cyi = nyi;
+  }
+  // one reduction per block: the eight warps' rows through the staging tile, pairs (pillar slot, half) as above
+  cp_async_wait<0>();
+  __syncthreads();
+  {
+    float* srow = s_sum + (size_t)pl * kBwdRows * kBwdC + c;
 #pragma unroll
-    for (int k = 0; k < kBwdOwn; ++k) {
-      const int idx = tid + k * 256;
-      if (idx < kBwdAcc * kBwdC) {
-        double v = 0.0;
+    for (int d = 0; d < 10; ++d) {
+      srow[d * kBwdC] = s1[d];
+      srow[(10 + d) * kBwdC] = s2[d];
+      srow[(21 + d) * kBwdC] = tt[d];
+    }
+    srow[20 * kBwdC] = q2;
+    srow[31 * kBwdC] = sG;
+    srow[32 * kBwdC] = sGr;
+  }
+  __syncthreads();
+  double acc[kBwdOwn];
 #pragma unroll
-        for (int q = 0; q < kBwdPil; ++q) v += (double)s_sum[(size_t)q * kBwdRows * kBwdC + idx];
-        acc[k] += v;
-      }
+  for (int k = 0; k < kBwdOwn; ++k) {
+    acc[k] = 0.0;
+    const int idx = tid + k * 256;
+    if (idx < kBwdAcc * kBwdC) {
+#pragma unroll
+      for (int q = 0; q < kBwdPil; ++q) acc[k] += (double)s_sum[(size_t)q * kBwdRows * kBwdC + idx];
     }
   }
   double* dst = partials + (size_t)blockIdx.x * kBwdAcc * kBwdC;
@@ -589,9 +647,11 @@ __global__ void __launch_bounds__(256) k_scatter_bwd(const float* __restrict__ g
 }
 
 static int bwd_blocks() { return sm_count() * 2; }
+static int bwd_live_blocks() { return sm_count() * 2; }
 
 size_t pfn_sparse_backward_workspace_bytes(int B, int P) {
-  return 2 * align_up((size_t)bwd_blocks() * kBwdAcc * kBwdC * sizeof(double)) +
+  return align_up((size_t)bwd_blocks() * kBwdAcc * kBwdC * sizeof(double)) +
+         align_up((size_t)bwd_live_blocks() * kBwdAcc * kBwdC * sizeof(double)) +
          align_up((size_t)kBwdAcc * kBwdC * sizeof(double)) + align_up((size_t)B * P * kBwdC * sizeof(float2)) + 4 * kAlign;
 }
 
@@ -607,7 +667,8 @@ int pfn_sparse_backward(const CompactPillars& cp, const int64_t* d_inds, int C, 
   Arena arena(d_ws, ws_bytes);
   const int nb = bwd_blocks();
   double* partialsA = arena.take<double>((size_t)nb * kBwdAcc * kBwdC);
-  double* partialsB = arena.take<double>((size_t)nb * kBwdAcc * kBwdC);
+  const int nbl = bwd_live_blocks();
+  double* partialsB = arena.take<double>((size_t)nbl * kBwdAcc * kBwdC);
   double* sums_g = arena.take<double>((size_t)kBwdAcc * kBwdC);
   float2* ext = arena.take<float2>((size_t)B * P * kBwdC);
   unsigned* ticket = arena.take<unsigned>(1);
@@ -616,8 +677,8 @@ int pfn_sparse_backward(const CompactPillars& cp, const int64_t* d_inds, int C, 
   const int Np = N;
   BwdGrad gr{d_grad_canvas, (const long long*)d_inds, H, W};
   const size_t smem_a = ((size_t)2 * kBwdPil * kBwdD * Np + (size_t)kBwdPil * kBwdRows * kBwdC) * sizeof(float);
-  const size_t smem_b = ((size_t)kBwdPil * kBwdD * Np + (size_t)kBwdPil * N * kLiveRec + (size_t)kBwdPil * kBwdRows * kBwdC) *
-                        sizeof(float);
+  const size_t smem_b = (2 * ((size_t)kBwdPil * kBwdD * Np + (size_t)kBwdPil * kLiveStage * kLiveRec) +
+                         (size_t)kBwdPil * kBwdRows * kBwdC) * sizeof(float);
   if (smem_a > 110 * 1024 || smem_b > 110 * 1024) return PP_ERR_UNSUPPORTED;
   if (training) {
     PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd_pad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
@@ -625,17 +686,17 @@ int pfn_sparse_backward(const CompactPillars& cp, const int64_t* d_inds, int C, 
               (k_pfn_bwd_pad<true><<<nb, 256, smem_a, st>>>(cp, Np, conv_w, conv_b, bn_w, ext, partialsA)));
     PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd_live<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     PP_KERNEL("k_pfn_bwd_live", st,
-              (k_pfn_bwd_live<true><<<nb, 256, smem_b, st>>>(cp, Np, conv_w, conv_b, bn_w, gr, ext, partialsB)));
+              (k_pfn_bwd_live<true><<<nbl, 256, smem_b, st>>>(cp, Np, conv_w, conv_b, bn_w, gr, ext, partialsB)));
   } else {
     PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd_pad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
     PP_KERNEL("k_pfn_bwd_pad", st,
               (k_pfn_bwd_pad<false><<<nb, 256, smem_a, st>>>(cp, Np, conv_w, conv_b, bn_w, ext, partialsA)));
     PP_CUDA(cudaFuncSetAttribute(k_pfn_bwd_live<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     PP_KERNEL("k_pfn_bwd_live", st,
-              (k_pfn_bwd_live<false><<<nb, 256, smem_b, st>>>(cp, Np, conv_w, conv_b, bn_w, gr, ext, partialsB)));
+              (k_pfn_bwd_live<false><<<nbl, 256, smem_b, st>>>(cp, Np, conv_w, conv_b, bn_w, gr, ext, partialsB)));
   }
   PP_KERNEL("k_pfn_bwd_finalize", st,
-            (k_pfn_bwd_finalize<<<kBwdAcc, 1024, 0, st>>>(partialsB, nb, training ? partialsA : nullptr, nb, (double)B,
+            (k_pfn_bwd_finalize<<<kBwdAcc, 1024, 0, st>>>(partialsB, nbl, training ? partialsA : nullptr, nb, (double)B,
                                                           (double)B * P * N, bn_w, running_mean, running_var,
                                                           training ? 1 : 0, eps, sums_g, ticket, g_w, g_b, g_gamma, g_beta)));
   return PP_OK;
