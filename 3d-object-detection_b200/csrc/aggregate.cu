@@ -60,10 +60,10 @@ int pp_aggregate_sweeps(float* d_points, int64_t n_points, int32_t point_stride,
                         pp_stream_t stream) {
   using namespace pp;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!d_points || !d_file_offsets || !d_transforms || n_points < 0 || point_stride < 3 || n_files < 1)
+  if (!d_file_offsets || !d_transforms || n_points < 0 || point_stride < 3 || n_files < 1 || (!d_points && n_points > 0))
     return PP_ERR_INVALID_ARG;
-  if (n_points == 0) return PP_OK;
   if (d_kept != nullptr) PP_CUDA(cudaMemsetAsync(d_kept, 0, (size_t)n_files * sizeof(int32_t), st));
+  if (n_points == 0) return PP_OK;
   const long long want = (n_points + 255) / 256;
   const int blocks = (int)(want < (long long)sm_count() * 8 ? want : (long long)sm_count() * 8);
   PP_KERNEL("k_aggregate", st,

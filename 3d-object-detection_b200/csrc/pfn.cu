@@ -588,6 +588,7 @@ int launch_stats_tc16(const float* d_x, int B, int P, int N, const float* w, con
                       const float* bn_w, int training, float* ext, double* partials, int nblocks,
                       int* range_flag, const tch::PadArgs* pad, cudaStream_t st);
 extern int g_opt_pfn_tensor_cores;
+extern int g_opt_pad_reserve_sms;
 extern int g_opt_pfn_tc_debug;
 
 static int launch_stats(const float* d_x, int B, int P, int N, int C, const float* w, const float* bias,
@@ -869,7 +870,8 @@ int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, c
   int nblocks = 0;
   if (cp.data_mean != nullptr) {
     const long long pairs = P / 2;
-    nblocks = (int)(pairs < sm_count() ? pairs : sm_count());
+    const int sms = sm_count() - g_opt_pad_reserve_sms > 8 ? sm_count() - g_opt_pad_reserve_sms : 8;
+    nblocks = (int)(pairs < sms ? pairs : sms);
     const int nchunks = (B + kSparseMaxSweeps - 1) / kSparseMaxSweeps;
     PP_KERNEL("k_pack_counts", st,
               k_pack_counts<<<dim3((P + 255) / 256, nchunks), 256, 0, st>>>(B, P, N, cp.num_pillars, cp.pil_cnt, ws.packed));

@@ -327,7 +327,7 @@ class InputPath:
             xf = torch.from_numpy(np.ascontiguousarray(
                 np.asarray(transforms, dtype=np.float64).reshape(fo.numel() - 1, -1, 4)[:, :3, :])).to(dev)
         F = fo.numel() - 1
-        kept = torch.empty(F, dtype=torch.int32, device=dev) if want_kept else None
+        kept = torch.zeros(F, dtype=torch.int32, device=dev) if want_kept else None
         with torch.cuda.device(dev):
             rc = L.pp_aggregate_sweeps(d_points.data_ptr(), d_points.shape[0], d_points.shape[1], fo.data_ptr(), F,
                                        xf.data_ptr(), float(min_dist), kept.data_ptr() if kept is not None else None,

@@ -357,6 +357,8 @@ def run_ours(args):
     import pp_b200
     from pp_b200 import _lib, pipeline, synth
     L = _lib.load()
+    if getattr(args, "reserve_sms", None) is not None:
+        L.pp_set_option(b"pad_reserve_sms", int(args.reserve_sms))
     cfg = pp_b200.PPConfig()
     P, N, C, H, W = cfg.max_pillars, cfg.max_points_per_pillar, cfg.feature_net_out, cfg.canvas_height, cfg.canvas_width
     mean = synth.make_data_mean(P, N, seed=0, dense=True)
@@ -595,6 +597,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reserve-sms", type=int, default=None, help="SMs the padding pass leaves free (experiment)")
     ap.add_argument("--no-training-rows", action="store_true", help="skip the PFN backward / loss front-end timings")
     ap.add_argument("--no-dense-reference", action="store_true", help="skip the extra dense_path measurement")
     ap.add_argument("--inflight", type=int, default=2, help="steps in flight in the streaming loops (>= 2)")

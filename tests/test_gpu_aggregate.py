@@ -98,3 +98,21 @@ def test_ten_file_stress_cloud_through_the_fused_step():
     cb, clsb, regb, nb, kb = pb.step_host(pb.pack_host_batch([host_cloud.astype(np.float32)], gts))
     assert int(na[0]) == 30000 and torch.equal(na, nb)
     assert torch.equal(ca, cb) and torch.equal(clsa, clsb) and torch.equal(rega, regb)
+
+
+def test_empty_file_in_the_middle_four_column_rows_and_no_points():
+    from oracle import aggregate as og
+    from pp_b200 import pipeline
+    path = pipeline.InputPath(device=torch.device("cuda"))
+    raws, mats = _files(3, seed=5, n_pts=3000)
+    raws[1] = raws[1][:0]                                                       # a file without points
+    want, keeps = og.aggregate(raws, mats)
+    rows4 = np.ascontiguousarray(np.concatenate(raws)[:, :4])                  # S = 4: the float4 layout K1 prefers
+    d = torch.tensor(rows4, device="cuda")
+    kept = path.aggregate(d, [0, 3000, 3000, 6000], np.stack(mats), want_kept=True)
+    got = d.cpu().numpy()
+    keep = got[:, 0] != SENTINEL
+    assert np.array_equal(keep, np.concatenate(keeps)) and kept.cpu().tolist() == [int(k.sum()) for k in keeps]
+    assert np.array_equal(got[keep].astype(np.float64), want)
+    empty = torch.empty((0, 5), dtype=torch.float32, device="cuda")
+    assert path.aggregate(empty, [0, 0], np.eye(4)[None], want_kept=True).cpu().tolist() == [0]
