@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
                                                         double* __restrict__ partials) {
   extern __shared__ __align__(16) float s_tile[];            // 2 x { mean [kBwdPil][9][Np] | feat [kBwdPil][32][12] } | staging
   __shared__ int s_first[PP_MAX_SWEEPS + 1];                 // live pillars before sweep b
-  __shared__ int s_cnt2[3][kBwdPil], s_b2[3][kBwdPil], s_p2[3][kBwdPil];   // three slots: written one group ahead,
+  __shared__ int s_cnt2[3][kBwdPil], s_b2[3][kBwdPil], s_p2[3][kBwdPil];   // three slots: written one pillar ahead,
                                                                           // read without a barrier after the arithmetic
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pl = warp >> 1, c = (warp & 1) * 32 + lane;
@@ -381,7 +381,11 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
   }
   __syncthreads();
   const int n_live = s_first[B];
-  const int ngroups = (n_live + kBwdPil - 1) / kBwdPil;
+  // The four warp pairs of a block run independently (pair-level named barriers): pair `pl` of block k takes the
+  // live pillars pg, pg + npairs, ...  A pair that draws a 200-point pillar no longer stalls the other three.
+  const int pg = blockIdx.x * kBwdPil + pl, npairs = gridDim.x * kBwdPil;
+  const int t64 = tid & 63;
+  auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + pl) : "memory"); };
 
   float wr[kBwdD];
 #pragma unroll
@@ -394,45 +398,41 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
 #pragma unroll
   for (int d = 0; d < 10; ++d) { s1[d] = 0.f; s2[d] = 0.f; tt[d] = 0.f; }
 
-  // (sweep, pillar, count) of the four pillars of a group: threads 0..3
-  auto meta = [&](int g, int ms) {
-    if (tid < kBwdPil) {
-      const int L = g * kBwdPil + tid;
+  // (sweep, pillar, count) of live pillar L: the pair's first thread
+  auto meta = [&](int L, int ms) {
+    if (t64 == 0) {
       int b = -1, p = 0, cnt = 0;
-      if (g < ngroups && L < n_live) {
+      if (L < n_live) {
         b = 0;
         while (s_first[b + 1] <= L) ++b;
         p = L - s_first[b];
         cnt = min(cp.pil_cnt[(size_t)b * P + p], N);
       }
-      s_b2[ms][tid] = b; s_p2[ms][tid] = p; s_cnt2[ms][tid] = cnt;
+      s_b2[ms][pl] = b; s_p2[ms][pl] = p; s_cnt2[ms][pl] = cnt;
     }
   };
-  auto issue = [&](int st, int ms) {
-    float* s_mean = s_tile + (size_t)st * stage_floats;
-    float* s_feat = s_mean + (size_t)kBwdPil * kBwdD * Np;
-    for (int row = tid >> 3; row < kBwdPil * kBwdD; row += 32) {     // 8 threads per row of N floats
-      const int q = row / kBwdD, d = row - q * kBwdD;                 // constant divisor
-      if (s_b2[ms][q] < 0) continue;
-      const float* src = cp.data_mean + ((size_t)d * P + s_p2[ms][q]) * N;
-      float* dst = s_mean + ((size_t)q * kBwdD + d) * Np;
-      for (int ck = tid & 7; ck * 4 < N; ck += 8) cp_async16(dst + ck * 4, src + ck * 4);
-    }
-    for (int q = 0; q < kBwdPil; ++q) {
-      if (s_b2[ms][q] < 0) continue;
-      const float* src = cp.feat_c + ((size_t)cp.sw.off[s_b2[ms][q]] + cp.pil_off[(size_t)s_b2[ms][q] * P + s_p2[ms][q]]) * kBwdD;
-      for (int i = tid; i < min(s_cnt2[ms][q], kLiveStage) * kBwdD; i += 256) {
+  auto issue = [&](int st, int ms) {                           // the pair's 64 threads stage the pair's pillar
+    float* s_mean = s_tile + (size_t)st * stage_floats + (size_t)pl * kBwdD * Np;
+    float* s_feat = s_tile + (size_t)st * stage_floats + (size_t)kBwdPil * kBwdD * Np + (size_t)pl * kLiveStage * kLiveRec;
+    if (s_b2[ms][pl] >= 0) {
+      const int p = s_p2[ms][pl];
+      for (int d = t64 >> 3; d < kBwdD; d += 8) {              // 8 threads per row of N floats
+        const float* src = cp.data_mean + ((size_t)d * P + p) * N;
+        for (int ck = t64 & 7; ck * 4 < N; ck += 8) cp_async16(s_mean + (size_t)d * Np + ck * 4, src + ck * 4);
+      }
+      const float* src = cp.feat_c + ((size_t)cp.sw.off[s_b2[ms][pl]] + cp.pil_off[(size_t)s_b2[ms][pl] * P + p]) * kBwdD;
+      for (int i = t64; i < min(s_cnt2[ms][pl], kLiveStage) * kBwdD; i += 64) {
         const int n = i / kBwdD, d = i - n * kBwdD;
-        cp_async4(s_feat + ((size_t)q * kLiveStage + n) * kLiveRec + d, src + i);
+        cp_async4(s_feat + (size_t)n * kLiveRec + d, src + i);
       }
     }
     cp_async_commit();
   };
 
   int stage = 0, ms = 0;
-  meta(blockIdx.x, 0);
-  __syncthreads();
-  if ((int)blockIdx.x < ngroups) issue(0, 0);
+  meta(pg, 0);
+  pair_sync();
+  if (pg < n_live) issue(0, 0);
   // the scatter row (flag, x, y) of this warp's pillar is fetched one group ahead, the canvas gradient at the
   // top of the group: both round trips overlap the arithmetic instead of trailing it
   long long cfl = 0, cxi = 0, cyi = 0;
@@ -440,13 +440,13 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
     const long long* row = gr.inds + ((long long)s_b2[0][pl] * P + s_p2[0][pl]) * 3;
     cfl = row[0]; cxi = row[1]; cyi = row[2];
   }
-  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+  for (int L = pg; L < n_live; L += npairs) {
     const int ms_next = ms == 2 ? 0 : ms + 1;
-    meta(grp + gridDim.x, ms_next);                            // the next group's pillars (threads 0..3)
+    meta(L + npairs, ms_next);                                 // the pair's next pillar
     cp_async_wait<0>();
-    __syncthreads();                                           // this group's tile landed, next metadata visible, the
+    pair_sync();                                               // this pillar's tile landed, next metadata visible, the
                                                                // other tile stage is no longer read
-    if (grp + (int)gridDim.x < ngroups) issue(stage ^ 1, ms_next);   // in flight during this group's arithmetic
+    if (L + npairs < n_live) issue(stage ^ 1, ms_next);        // in flight during this pillar's arithmetic
     const float* s_mean = s_tile + (size_t)stage * stage_floats;
     const float* s_feat = s_mean + (size_t)kBwdPil * kBwdD * Np;
     const int* s_b = s_b2[ms];
