@@ -448,6 +448,20 @@ def run_ours(args):
     ms_max, units = reduce_over_ranks(ms, float(BATCH * args.steps), dev)
     value = units / (ms_max / 1e3)
 
+    # the same device loop with K3 emitting the positives list instead of the dense [B,A,9] tensors
+    list_mode = None
+    if fused and not args.no_dense_reference:
+        path.targets_as_list = True
+        for _ in range(3):
+            step_dev()
+        drain_dev()
+        ms_l = timed(timed_loop, 1)
+        path.targets_as_list = False
+        ms_l_max, units_l = reduce_over_ranks(ms_l, float(BATCH * args.steps), dev)
+        list_mode = {"what": "same streaming loop, targets as a positives list (pp_assign_targets_list): K3 writes a few KB "
+                             "instead of 155 MB per step; consumer pp_loss_list", "value": units_l / (ms_l_max / 1e3),
+                     "unit": UNIT, "ms_per_step": ms_l_max / args.steps}
+
     # end-to-end through the host-facing call: pinned host buffers in, counters out, every step
     for _ in range(3):
         step_e2e()
@@ -574,7 +588,7 @@ def run_ours(args):
                                "overlaps the encode stage of step k; encode stages ordered), <= 2 steps in flight, "
                                "timed region ends after the last step has completed",
                        "parallelism": "dp%d (one process per GPU, sweeps sharded, no collective)" % world},
-            "roofline": roofline, "kernels": kernels, "dense_path": other, "training_rows": training,
+            "roofline": roofline, "kernels": kernels, "dense_path": other, "list_targets": list_mode, "training_rows": training,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e_max / args.steps, "host_wall_ms_per_step": ms_e_host / args.steps,
