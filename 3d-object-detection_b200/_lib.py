@@ -116,8 +116,17 @@ def check(rc, what):
         raise PPError("%s failed: %s (code %d, cudaError %d)" % (what, msg, rc, L.pp_last_cuda_error()))
 
 
+_i64_cache = {}
+
+
 def i64_array(values):
-    arr = (ctypes.c_int64 * len(values))(*[int(v) for v in values])
+    """ctypes int64 array of a short host sequence (sweep / GT offsets); the same offsets recur step after step."""
+    key = tuple(int(v) for v in values)
+    arr = _i64_cache.get(key)
+    if arr is None:
+        if len(_i64_cache) > 256:
+            _i64_cache.clear()
+        arr = _i64_cache[key] = (ctypes.c_int64 * len(key))(*key)
     return arr
 
 

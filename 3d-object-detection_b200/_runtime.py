@@ -13,15 +13,44 @@ def require_cuda(t, name):
         raise _lib.PPError("%s must be a CUDA tensor: this path has no CPU implementation" % name)
 
 
+def _index(device):
+    if isinstance(device, torch.device):
+        idx = device.index
+    elif device is None:
+        idx = None
+    else:
+        idx = torch.device(device).index
+    return torch.cuda.current_device() if idx is None else idx
+
+
 def stream_ptr(device=None):
-    return torch.cuda.current_stream(device).cuda_stream
+    """cudaStream_t of torch's current stream on ``device`` (raw C call: this sits on every kernel launch)."""
+    return torch._C._cuda_getCurrentRawStream(_index(device))
+
+
+class _NoGuard(object):
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(device):
+    """``torch.cuda.device(device)`` only when it is not the current device already (the context manager costs
+    several microseconds per launch otherwise)."""
+    idx = _index(device)
+    return _NO_GUARD if torch.cuda.current_device() == idx else torch.cuda.device(idx)
 
 
 def workspace(nbytes, device, tag="default"):
     """Grow-only scratch buffer per (device, stream, tag); 256-byte aligned by the caching allocator."""
-    dev = torch.device(device)
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(dev).cuda_stream, tag)
+    dev = device if isinstance(device, torch.device) else torch.device(device)
+    idx = _index(dev)
+    key = (idx, torch._C._cuda_getCurrentRawStream(idx), tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
@@ -32,16 +61,14 @@ def workspace(nbytes, device, tag="default"):
 def take_workspace(device, tag):
     """Remove and return the scratch buffer of (device, current stream, tag): the caller now owns it (state that
     must survive until a backward pass); the next ``workspace`` call allocates a fresh one."""
-    dev = torch.device(device)
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(dev).cuda_stream, tag)
-    return _workspaces.pop(key, None)
+    idx = _index(device)
+    return _workspaces.pop((idx, torch._C._cuda_getCurrentRawStream(idx), tag), None)
 
 
 def status_word(device):
     """int32[1] device status word (bits PP_STATUS_*), one per device, zeroed at creation."""
-    dev = torch.device(device)
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    dev = device if isinstance(device, torch.device) else torch.device(device)
+    key = _index(dev)
     s = _status.get(key)
     if s is None:
         s = torch.zeros(1, dtype=torch.int32, device=dev)

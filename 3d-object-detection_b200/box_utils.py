@@ -141,7 +141,7 @@ def assign_targets(anchors, g_corners, g_centers, g_wlh, g_yaw, g_cls, gt_offset
     ws = _runtime.workspace(nbytes, dev, "targets")
     status = _runtime.status_word(dev)
     ptr = lambda t: t.data_ptr() if (t is not None and t.numel() > 0) else None
-    with torch.cuda.device(dev):
+    with _runtime.on_device(dev):
         rc = L.pp_assign_targets(
             anchors.corners.data_ptr(), anchors.centers.data_ptr(), anchors.wlh.data_ptr(),
             anchors.yaw.data_ptr(), anchors.index.data_ptr(), A, ptr(g_corners), ptr(g_centers),
@@ -170,7 +170,7 @@ def _assign_targets_list(anchors, g_corners, g_centers, g_wlh, g_yaw, g_cls, gt_
     ws = _runtime.workspace(L.pp_assign_targets_workspace_bytes(B, A, Gt, None), dev, "targets")
     status = _runtime.status_word(dev)
     ptr = lambda t: t.data_ptr() if (t is not None and t.numel() > 0) else None
-    with torch.cuda.device(dev):
+    with _runtime.on_device(dev):
         rc = L.pp_assign_targets_list(
             anchors.corners.data_ptr(), anchors.centers.data_ptr(), anchors.wlh.data_ptr(),
             anchors.yaw.data_ptr(), anchors.index.data_ptr(), A, ptr(g_corners), ptr(g_centers),

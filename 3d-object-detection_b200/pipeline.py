@@ -82,9 +82,9 @@ class _InputPathFunction(torch.autograd.Function):
         ws2 = _runtime.workspace(L.pp_input_path_backward_workspace_bytes(B, P, C), dev, "input_path_bwd")
         rm, rv = ctx.stats if ctx.stats is not None else (None, None)
         w2 = conv_w.detach().reshape(C, 9).contiguous()
-        with torch.cuda.device(dev):
+        with _runtime.on_device(dev):
             rc = L.pp_input_path_backward(
-                _lib.i64_array(offsets), B, c.grid(), N, P, path.data_mean.data_ptr() if path.data_mean is not None else None,
+                _lib.i64_array(offsets), B, path._grid_struct(), N, P, path.data_mean.data_ptr() if path.data_mean is not None else None,
                 C, w2.data_ptr(), conv_b.data_ptr(), bn_w.data_ptr(), rm.data_ptr() if rm is not None else None,
                 rv.data_ptr() if rv is not None else None, 1 if ctx.training else 0, ctx.eps, c.canvas_height,
                 c.canvas_width, g_canvas.data_ptr(), inds.data_ptr(), npil.data_ptr(), g_w.data_ptr(), g_b.data_ptr(),
@@ -181,11 +181,11 @@ class InputPath:
             npil = torch.empty(B, dtype=torch.int32, device=dev)
         else:
             x, inds, npil = out
-        grid = c.grid()
+        grid = self._grid_struct()
         nbytes = L.pp_pillarize_workspace_bytes(B, T, grid, P)
         ws = _runtime.workspace(nbytes, dev, "pillarize")
         status = _runtime.status_word(dev)
-        with torch.cuda.device(dev):
+        with _runtime.on_device(dev):
             rc = L.pp_pillarize(points.data_ptr() if T > 0 else None, dt, points.stride(0),
                                 points.stride(1), _lib.i64_array(offsets), B, grid, N, P,
                                 self.data_mean.data_ptr() if self.data_mean is not None else None,
@@ -200,6 +200,12 @@ class InputPath:
             return self.net(x, inds, return_features=return_features, out=out)
 
     # -- K1 + K2 fused, x never materialised (pp_input_path) ------------------------------------
+    def _grid_struct(self):
+        g = self.__dict__.get("_grid_cache")
+        if g is None:
+            g = self.__dict__["_grid_cache"] = self.cfg.grid()
+        return g
+
     def fused_supported(self, n_sweeps):
         c = self.cfg
         return (1 <= n_sweeps <= _lib.PP_MAX_SWEEPS and c.feature_net_out == 64 and c.max_points_per_pillar <= 255
@@ -240,20 +246,22 @@ class InputPath:
         if not want_x:
             x = None
         net = self.net
-        grid = c.grid()
+        grid = self._grid_struct()
         nbytes = L.pp_input_path_workspace_bytes(B, T, grid, P, C, H, W)
         ws = _runtime.workspace(nbytes, dev, "input_path")
         status = _runtime.status_word(dev)
         momentum, eps = _bn_args(net.bn1)
-        w = net.conv1.weight.detach().reshape(C, 9).contiguous()
+        w = net.conv1.weight
+        if not w.is_contiguous():
+            w = w.detach().contiguous()
         nbt = net.bn1.num_batches_tracked
-        with torch.cuda.device(dev):
+        with _runtime.on_device(dev):
             rc = L.pp_input_path(
                 points.data_ptr() if T > 0 else None, dt, points.stride(0), points.stride(1),
                 _lib.i64_array(offsets), B, grid, N, P,
                 self.data_mean.data_ptr() if self.data_mean is not None else None, C,
-                w.data_ptr(), net.conv1.bias.detach().data_ptr(), net.bn1.weight.detach().data_ptr(),
-                net.bn1.bias.detach().data_ptr(), net.bn1.running_mean.data_ptr(),
+                w.data_ptr(), net.conv1.bias.data_ptr(), net.bn1.weight.data_ptr(),
+                net.bn1.bias.data_ptr(), net.bn1.running_mean.data_ptr(),
                 net.bn1.running_var.data_ptr(), nbt.data_ptr() if nbt is not None else None,
                 1 if net.training else 0, momentum, eps, H, W, canvas.data_ptr(),
                 x.data_ptr() if x is not None else None, inds.data_ptr(), npil.data_ptr(),
@@ -328,7 +336,7 @@ class InputPath:
                 np.asarray(transforms, dtype=np.float64).reshape(fo.numel() - 1, -1, 4)[:, :3, :])).to(dev)
         F = fo.numel() - 1
         kept = torch.zeros(F, dtype=torch.int32, device=dev) if want_kept else None
-        with torch.cuda.device(dev):
+        with _runtime.on_device(dev):
             rc = L.pp_aggregate_sweeps(d_points.data_ptr(), d_points.shape[0], d_points.shape[1], fo.data_ptr(), F,
                                        xf.data_ptr(), float(min_dist), kept.data_ptr() if kept is not None else None,
                                        _runtime.stream_ptr(dev))
@@ -407,7 +415,7 @@ class InputPath:
         gt_dev = {k: dv[k] for k in ("corners", "centers", "wlh", "yaw", "cls")}
         d_pts = dv["points"][:max(T, 1)]
         if batch.get("n_files"):                     # aggregate on the stream the copy was issued on
-            with torch.cuda.device(dev):
+            with _runtime.on_device(dev):
                 rc = _lib.load().pp_aggregate_sweeps(d_pts.data_ptr(), T, batch["ncol"], dv["file_offsets"].data_ptr(),
                                                      batch["n_files"], dv["xforms"].data_ptr(), batch["min_dist"], None,
                                                      _runtime.stream_ptr(dev))
