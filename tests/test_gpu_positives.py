@@ -88,3 +88,41 @@ def test_loss_from_the_list_equals_loss_from_dense_targets_and_oracle(B, n_gt):
         ref = np.array([want["cls_loss"], want["reg_loss"], want["ort_loss"], want["total"]])
         assert np.abs(got - ref).max() <= 5e-6 * np.abs(ref).max()
         assert np.abs(b[2].cpu().numpy() - want["grad_cls"]).max() <= 1e-5 * np.abs(want["grad_cls"]).max()
+
+
+def test_loss_list_with_more_positives_than_fit_in_shared_memory():
+    """More than 8192 listed anchors: the ids are searched in global memory and the class rows read from there;
+    also rows with a class value that is neither 0 nor 1 (general floats)."""
+    from pp_b200.box_utils import Positives
+    from pp_b200.loss import PPLoss
+    rng = np.random.default_rng(12)
+    B, H, W = 2, 300, 300
+    A = H * W * 6
+    n_per = 5000
+    cls_t = torch.zeros((B, A, 9), device="cuda"); reg_t = torch.zeros((B, A, 9), device="cuda")
+    for b in range(B):
+        idx = torch.tensor(np.sort(rng.choice(A, n_per, replace=False)), device="cuda")
+        cls_t[b, idx, torch.tensor(rng.integers(0, 9, n_per), device="cuda")] = 1
+        reg_t[b, idx, 0] = 1
+        reg_t[b, idx, 1:8] = torch.tensor(rng.normal(0, 1, (n_per, 7)), dtype=torch.float32, device="cuda")
+        reg_t[b, idx, 8] = torch.tensor(rng.integers(0, 2, n_per), dtype=torch.float32, device="cuda")
+    cls_t[0, 17, 3] = 0.25                                                        # a soft label
+    reg_t[0, 17, 0] = 1
+    nz = torch.nonzero((cls_t.view(B * A, 9) != 0).any(1) | (reg_t.view(B * A, 9) != 0).any(1)).flatten()
+    assert nz.numel() > 8192
+    offs = torch.tensor([int((nz < b * A).sum()) for b in range(B + 1)], dtype=torch.int32, device="cuda")
+    pos = Positives(nz.int().contiguous(), cls_t.view(B * A, 9)[nz].contiguous(), reg_t.view(B * A, 9)[nz].contiguous(), offs, B, A)
+    torch.manual_seed(3)
+    cls = torch.randn((B, 54, H, W), device="cuda") * 1.5 - 3.0
+    reg = torch.randn((B, 48, H, W), device="cuda")
+    lossm = PPLoss(0.4, 1.0, 250.0, 2, torch.device("cuda"))
+
+    def run(*targets):
+        c = cls.clone().requires_grad_(True); r = reg.clone().requires_grad_(True)
+        p, cl, rl, ol_, tot = lossm(c, r * 1.0, *targets)
+        tot.backward()
+        return p.detach(), torch.stack([cl, rl, ol_, tot]).detach(), c.grad, r.grad
+
+    a, b = run(cls_t, reg_t), run(pos)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert torch.allclose(a[1], b[1], rtol=2e-6, atol=0)
