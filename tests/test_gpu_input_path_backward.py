@@ -22,7 +22,7 @@ def _close(got, want, tol=1e-5):
 def test_fused_backward_equals_dense_backward_and_float64_autograd(training, B):
     import pp_b200
     from pp_b200 import model as pm, pipeline, synth
-    cfg = pp_b200.PPConfig(max_pillars=3000, max_points_per_pillar=48)
+    cfg = pp_b200.PPConfig(max_pillars=3002 if B == 3 else 3000, max_points_per_pillar=48)   # 3002: a half-empty last group
     P, N = cfg.max_pillars, cfg.max_points_per_pillar
     mean = synth.make_data_mean(P, N, seed=3, dense=True)
     prm = synth.make_pfn_params(5, flip_gamma=True)

@@ -124,3 +124,21 @@ def test_scatter_backward_bit_exact_and_input_gradient_refused():
     net = pm.PPFeatureNet(9, 64).cuda()
     with pytest.raises(_lib.PPError):
         net(torch.randn((1, 9, 8, 16), device="cuda", requires_grad=True))
+
+
+def test_pillar_count_not_a_multiple_of_the_group_size():
+    """B*P = 50: the last four-pillar group of the kernel is half empty."""
+    from pp_b200 import model as pm
+    torch.manual_seed(8)
+    x = torch.randn((1, 9, 50, 24), device="cuda")
+    net = pm.PPFeatureNet(9, 64).cuda().train()
+    g_out = torch.randn((1, 64, 50), device="cuda")
+    net(x).backward(g_out)
+    got = _grads(net)
+    prm = [p.detach().double().requires_grad_(True) for p in (net.conv1.weight, net.conv1.bias, net.bn1.weight, net.bn1.bias)]
+    y = F.batch_norm(F.relu(F.conv2d(x.double(), prm[0], prm[1])), None, None, prm[2], prm[3], True, 0.1, net.bn1.eps)
+    y.max(dim=3)[0].backward(g_out.double())
+    want = {"grad_weight": prm[0].grad.cpu().numpy().reshape(64, 9), "grad_bias": prm[1].grad.cpu().numpy(),
+            "grad_bn_weight": prm[2].grad.cpu().numpy(), "grad_bn_bias": prm[3].grad.cpu().numpy()}
+    for k in KEYS:
+        _close(got[k], want[k])
