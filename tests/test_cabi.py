@@ -146,3 +146,16 @@ def test_packed_batch_with_transforms_layout():
     assert off["xforms"] == (off["xforms"][0], 3 * 12 * 8) and off["file_offsets"][1] == 4 * 8
     assert off["xforms"][0] % 256 == 0 and off["file_offsets"][0] % 256 == 0 and total % 256 == 0
     assert list(InputPath._blob_layout(1000, 5, 10)[0]) == list(off)[:-2]             # F = 0: unchanged layout
+
+
+def test_header_is_plain_c():
+    """include/pp_b200.h is the FFI boundary: it must compile as C99 and as C++ with no torch / CUDA headers."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "pp_b200.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    subprocess.run(["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", hdr], check=True)
+    subprocess.run(["g++", "-fsyntax-only", "-x", "c++", "-Wall", "-Werror", hdr], check=True)
+    includes = [l.strip() for l in open(hdr) if l.strip().startswith("#include")]
+    assert includes and all(i in ("#include <stddef.h>", "#include <stdint.h>") for i in includes), includes
