@@ -24,11 +24,20 @@ def make_anchor_arrays(cfg=None):
     ys, xs, ds = ys.reshape(-1), xs.reshape(-1), ds.reshape(-1)
     dims = np.stack([np.asarray(d, dtype=np.float64) for d in cfg.anchor_dims])
     wlh = dims[ds]
-    yaw = np.deg2rad(np.asarray(cfg.anchor_yaws_deg, dtype=np.float64))[ds]
+    yaw = np.array([_sdk_yaw(float(d)) for d in cfg.anchor_yaws_deg], dtype=np.float64)[ds]
     centers = np.stack([(xs + 0.5) / cfg.fm_scale, (ys + 0.5) / cfg.fm_scale,
                         np.asarray(cfg.anchor_zs, dtype=np.float64)[ds]], axis=1)
     corners = box_corners(centers, wlh, yaw)
     return {"corners": corners, "centers": centers, "wlh": wlh, "yaw": yaw}
+
+
+def _sdk_yaw(deg):
+    """The yaw the reference reads back from an anchor built as ``Quaternion(axis=[0,0,1], degrees=deg)``
+    (utils/box_utils.py:80,147): pyquaternion's ``yaw_pitch_roll[0] = atan2(2 w z, 1 - 2 z^2)`` of
+    ``(w, z) = (cos(a/2), sin(a/2))``, ``a = deg/180*pi``.  For 90 degrees that is pi/2 - 2.2e-16, not pi/2."""
+    a = deg / 180.0 * np.pi
+    w, z = np.cos(a / 2.0), np.sin(a / 2.0)
+    return float(np.arctan2(2 * (w * z), 1 - 2 * (z ** 2)))
 
 
 def box_corners(centers, wlh, yaw):

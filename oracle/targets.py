@@ -1,10 +1,17 @@
 """numpy restatement of /root/reference/utils/box_utils.py target assignment.
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
-Lyft ``Box`` / pyquaternion are not installed; ``Box`` below is a duck-typed stand-in exposing
-exactly the attributes the reference touches: ``center``, ``wlh``, ``name``,
-``orientation.yaw_pitch_roll[0]`` and ``bottom_corners()`` (corner order [2,3,7,6] of the
-nuScenes-style corner table -- quoted from memory of lyft_dataset_sdk, UNPINNED).
+PINNED: ``create_target`` / ``make_target`` / ``boxes_to_image_space`` / the anchor lattice reproduce, bit for
+bit, the outputs of the reference's own utils/box_utils.py run unmodified in the build container
+(oracle/refpy.py + oracle/sdk_shim; fixture tests/golden/targets_small.npz made by
+tests/golden/make_golden_targets.py; tests/test_oracle_targets_pinned.py, which also re-runs the reference live
+where /root/reference exists).  Still from memory of the absent packages (see oracle/sdk_shim/README.md): the
+arithmetic inside lyft_dataset_sdk ``Box.corners()`` and pyquaternion.
+
+``Box`` below is a duck-typed stand-in exposing exactly the attributes the reference touches: ``center``,
+``wlh``, ``name``, ``orientation.yaw_pitch_roll[0]`` and ``bottom_corners()`` (corner order [2,3,7,6] of the
+nuScenes-style corner table).  It rotates with cos/sin of the yaw; the SDK goes through a quaternion rotation
+matrix and ``np.dot`` (BLAS, FMA-dependent last bits), so corners agree to 1 ulp, not bit for bit.
 """
 import numpy as np
 
@@ -39,6 +46,15 @@ class Box:
         c, s = np.cos(self.yaw), np.sin(self.yaw)
         out = np.vstack((c * xs - s * ys, s * xs + c * ys, zs))
         return out + self.center.reshape(3, 1)
+
+
+def _sdk_yaw(deg):
+    """yaw_pitch_roll[0] of pyquaternion's Quaternion(axis=[0,0,1], degrees=deg) (utils/box_utils.py:80,147):
+    atan2(2 w z, 1 - 2 z^2) with (w, z) = (cos(a/2), sin(a/2)), a = deg/180*pi.  90 degrees -> pi/2 - 2.2e-16.
+    Pinned against the reference run through oracle/sdk_shim (tests/test_oracle_targets_pinned.py)."""
+    a = float(deg) / 180.0 * np.pi
+    w, z = np.cos(a / 2.0), np.sin(a / 2.0)
+    return float(np.arctan2(2 * (w * z), 1 - 2 * (z ** 2)))
 
 
 def boxes_to_image_space(boxes):
@@ -97,7 +113,7 @@ def make_anchor_boxes(fm_height=None, fm_width=None):
                 z_center = cfg.ANCHOR_ZS[d]
                 width, length, height = cfg.ANCHOR_DIMS[d]
                 yaw = cfg.ANCHOR_YAWS[d]
-                box = Box([x_center, y_center, z_center], [width, length, height], np.deg2rad(yaw))
+                box = Box([x_center, y_center, z_center], [width, length, height], _sdk_yaw(yaw))
                 boxes_list.append(box)
                 bc = box.bottom_corners().transpose([1, 0])
                 corners_list.append(bc[:, :2])
@@ -175,7 +191,7 @@ def anchor_arrays(fm_height=None, fm_width=None):
     ys, xs, ds = np.meshgrid(np.arange(fm_height), np.arange(fm_width), np.arange(nd), indexing="ij")
     ys, xs, ds = ys.reshape(-1), xs.reshape(-1), ds.reshape(-1)
     wlh = np.stack(cfg.ANCHOR_DIMS)[ds]
-    yaw = np.deg2rad(np.asarray(cfg.ANCHOR_YAWS, dtype=np.float64))[ds]
+    yaw = np.array([_sdk_yaw(d) for d in cfg.ANCHOR_YAWS], dtype=np.float64)[ds]
     centers = np.stack([(xs + 0.5) / cfg.FM_SCALE, (ys + 0.5) / cfg.FM_SCALE,
                         np.asarray(cfg.ANCHOR_ZS, dtype=np.float64)[ds]], axis=1)
     w, l = wlh[:, 0:1], wlh[:, 1:2]

@@ -55,3 +55,26 @@ def run_create_pillars(fn, pts, P, N, grid=GRID):
 def boxes_from_gt(gt, Box, names):
     return [Box(gt["centers"][i], gt["wlh"][i], gt["yaw"][i], names[int(gt["cls"][i])])
             for i in range(len(gt["yaw"]))]
+
+
+def targets_fixture():
+    """tests/golden/targets_small.npz (made by the reference's own utils/box_utils.py, see
+    tests/golden/make_golden_targets.py) as a dict, plus dense (cls, reg, ious) builders."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    z = np.load(os.path.join(here, "golden", "targets_small.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def fixture_case(fx, tag):
+    """Dense reference outputs of one fixture case: dict with the GT arrays and cls [A,9], reg [A,9], ious [A,G]."""
+    A = fx["a_centers"].shape[0]
+    G = fx[tag + "/g_cls"].shape[0]
+    cls = np.zeros((A, fx[tag + "/cls_rows"].shape[1])); reg = np.zeros((A, fx[tag + "/reg_rows"].shape[1]))
+    cls[fx[tag + "/rows"]] = fx[tag + "/cls_rows"]
+    reg[fx[tag + "/rows"]] = fx[tag + "/reg_rows"]
+    ious = np.zeros((A, G))
+    ious[fx[tag + "/iou_a"], fx[tag + "/iou_g"]] = fx[tag + "/iou_v"]
+    out = {k.split("/", 1)[1]: v for k, v in fx.items() if k.startswith(tag + "/")}
+    out.update(cls=cls, reg=reg, ious=ious)
+    return out

@@ -151,3 +151,54 @@ def test_full_anchor_grid_config3():
     print("A=%d G=100 positives=%d forced=%d reg rows bit-identical=%d/%d near-threshold=%d" % (
         n, npos, int((ious.argmax(0) != 0).sum()), same, n, int((np.abs(ious.max(1) - 0.6) < 1e-6).sum())))
     assert npos > 20
+
+
+# ---- against the REFERENCE's own utils/box_utils.py (tests/golden/targets_small.npz, made by
+# ---- tests/golden/make_golden_targets.py: the reference module imported unmodified, run in the build container)
+def _fixture_inputs(fx, tag):
+    from helpers import fixture_case
+    c = fixture_case(fx, tag)
+    f = lambda a, dt=np.float64: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).cuda()
+    return c, (f(c["g_corners_img"]), f(c["g_centers_img"]), f(c["g_wlh"]), f(c["g_yaw"]), f(c["g_cls"], np.int32))
+
+
+@pytest.mark.parametrize("tag", ["rand_G12", "rand_G30", "rand_G60", "anchor0", "shared_top", "overwrite",
+                                 "iou_eq_thresh", "no_overlap"])
+def test_assign_targets_equals_reference_fixture(tag):
+    """pp_assign_targets and pp_assign_targets_list on the fixture's inputs: cls labels, reg columns 0 and 8
+    bit for bit, reg columns 1..7 to 1e-5 relative + 1e-7 against what the reference's create_target returned."""
+    from helpers import targets_fixture
+    from pp_b200 import box_utils
+    fx = targets_fixture()
+    anchors = box_utils.AnchorSet(fx["a_corners"], fx["a_centers"], fx["a_wlh"], fx["a_yaw"])
+    c, gt = _fixture_inputs(fx, tag)
+    G = len(c["g_cls"])
+    cls, reg, top, counts = box_utils.assign_targets(anchors, *gt, [0, G])
+    torch.cuda.synchronize()
+    same, n = _compare(cls[0].cpu().numpy(), reg[0].cpu().numpy(), c["cls"], c["reg"])
+    # per-GT best anchors = the reference's np.argmax over the transposed matrix (first index on ties)
+    np.testing.assert_array_equal(top.cpu().numpy(), c["ious"].argmax(0).astype(np.int32))
+    pos, _, top2, _ = box_utils.assign_targets(anchors, *gt, [0, G], as_list=True)
+    dc, dr = pos.dense()
+    assert torch.equal(dc, cls) and torch.equal(dr, reg) and torch.equal(top2, top)
+    if tag == "iou_eq_thresh":
+        eq = np.nonzero(c["ious"][:, 0] == 0.6)[0]
+        assert len(eq) >= 4 and not cls[0].cpu().numpy()[eq[1:]].any()      # == 0.6 is not positive
+    print("%s: reg rows bit-identical %d/%d, flagged rows %d" % (tag, same, n, int((c["reg"][:, 0] != 0).sum())))
+
+
+def test_create_target_dropin_equals_reference_fixture():
+    """The numpy-signature drop-in (box_utils.create_target) called the way data/dataset.py:113-116 calls the
+    reference: arrays + box lists."""
+    from helpers import fixture_case, targets_fixture
+    from oracle import targets as T
+    from pp_b200 import box_utils
+    fx = targets_fixture()
+    names = [str(s) for s in fx["class_names"]]
+    boxes = T.LazyAnchorBoxes(fx["a_centers"], fx["a_wlh"], fx["a_yaw"])
+    boxes = [boxes[a] for a in range(len(boxes))]
+    for tag in ("rand_G30", "overwrite"):
+        c = fixture_case(fx, tag)
+        g = [T.Box(c["g_centers"][i], c["g_wlh"][i], c["g_yaw"][i], names[int(c["g_cls"][i])]) for i in range(len(c["g_yaw"]))]
+        cls, reg = box_utils.create_target(fx["a_corners"], c["g_corners_img"], fx["a_centers"], c["g_centers_img"], boxes, g)
+        _compare(cls.astype(np.float32), reg.astype(np.float32), c["cls"], c["reg"])
