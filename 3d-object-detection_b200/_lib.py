@@ -51,8 +51,10 @@ _SIGNATURES = {
     "pp_pfn_scatter": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _i32, _f32, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _sz,
                                   _vp]),
-    "pp_input_path_workspace_bytes": (_sz, [_i32, _i64, _gridp, _i32, _i32, _i32, _i32]),
-    "pp_input_path": (_c.c_int, [_vp, _i32, _i64, _i64, _i64p, _i32, _gridp, _i32, _i32, _vp, _i32,
+    "pp_input_path_workspace_bytes": (_sz, [_i32, _i64, _gridp, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "pp_mean_prepared_bytes": (_sz, [_i32, _i32]),
+    "pp_mean_prepare": (_c.c_int, [_vp, _i32, _i32, _vp, _sz, _vp]),
+    "pp_input_path": (_c.c_int, [_vp, _i32, _i64, _i64, _i64p, _i32, _gridp, _i32, _i32, _vp, _vp, _i32,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _i32, _i32,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     "pp_input_path_backward_workspace_bytes": (_sz, [_i32, _i32, _i32]),

@@ -22,9 +22,10 @@ struct CompactPillars {
   const int* pil_off;        // [B*P] first entry of the pillar's segment (relative to the sweep)
   const int* num_pillars;    // [B]
   const float* data_mean;    // [9*P*N] or nullptr
+  const void* mean_prepared; // pp_mean_prepare's output for data_mean, or nullptr (prepared per call in the workspace)
 };
 
-constexpr int kSparseMaxSweeps = 8;   // sweeps per padding pass (per-sweep suffix maxima live in registers); larger batches take several passes
+constexpr int kSparseMaxSweeps = 8;   // sweeps per padding pass of the BACKWARD (pfn_bwd.cu); the forward's padding pass is batch-independent
 
 struct PfnParams {
   const float *conv_w, *conv_b, *bn_w, *bn_b;
@@ -43,7 +44,9 @@ struct PadArgs {
 };
 }  // namespace tch
 
-size_t pfn_sparse_workspace_bytes(int B, int P, int C, int H, int W);
+size_t pfn_sparse_workspace_bytes(int B, int P, int N, int C, int H, int W, bool own_prep);
+size_t mean_prepared_bytes(int P, int N);
+int mean_prepare(const float* d_mean, int P, int N, void* d_prep, size_t bytes, cudaStream_t st);
 // canvas [B,C,H,W] from K1's compact state; d_inds is K1's [B,P,3] indices output
 int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, const PfnParams& prm, int H, int W,
                        float* d_canvas, int32_t* d_status, void* d_ws, size_t ws_bytes, cudaStream_t st);

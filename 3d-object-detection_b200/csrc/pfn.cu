@@ -276,6 +276,13 @@ struct SparseFinalize {
   double pad_count;
   const int* range_flag;   // non-null: raise PP_STATUS_RANGE in *status when set
   int* status;
+  // padding pass of pfn_pad.cu: its partials are sum |y| and sum y|y|; with the input moments mom[10][10]
+  // (x_0..x_8, 1) they give sum relu(y) = (sum y + sum |y|) / 2 and sum relu(y)^2 = (sum y^2 + sum y|y|) / 2
+  const double* mom;       // non-null: add mom_mult * (linear / quadratic form of the moments)
+  const float* mom_w;      // conv weight [C,9]
+  const float* mom_b;      // conv bias [C]
+  double mom_mult;
+  const int* range_flag2;  // second range flag (the prepared operand's)
 };
 
 constexpr int kFinSegs = 16;
@@ -291,6 +298,7 @@ __global__ void __launch_bounds__(64 * kFinSegs) k_bn_finalize(int C, int nparts
   __shared__ double s_part[2][kFinSegs][64];
   const int c = threadIdx.x & 63, seg = threadIdx.x >> 6;
   if (threadIdx.x == 0 && sf.range_flag != nullptr && *sf.range_flag != 0) atomicOr(sf.status, PP_STATUS_RANGE);
+  if (threadIdx.x == 0 && sf.range_flag2 != nullptr && *sf.range_flag2 != 0) atomicOr(sf.status, PP_STATUS_RANGE);
   if (training && c < C) {
     const int per = (nparts + kFinSegs - 1) / kFinSegs;
     const int k0 = seg * per, k1 = min(nparts, k0 + per);
@@ -340,6 +348,20 @@ __global__ void __launch_bounds__(64 * kFinSegs) k_bn_finalize(int C, int nparts
       const double rb = (double)fmaxf(sf.conv_b[c], 0.f);
       S += sf.pad_count * rb;
       Q += sf.pad_count * rb * rb;
+    }
+    if (sf.mom != nullptr && seg == 0) {
+      double wt[10];
+      for (int d = 0; d < 9; ++d) wt[d] = (double)sf.mom_w[c * 9 + d];
+      wt[9] = (double)sf.mom_b[c];
+      double lin = 0.0, quad = 0.0;
+      for (int d = 0; d < 10; ++d) {
+        lin += wt[d] * sf.mom[d * 10 + 9];
+        double row = 0.0;
+        for (int e2 = 0; e2 < 10; ++e2) row += wt[e2] * sf.mom[d * 10 + e2];
+        quad += wt[d] * row;
+      }
+      S += sf.mom_mult * lin;
+      Q += sf.mom_mult * quad;
     }
     s_part[0][seg][c] = S;
     s_part[1][seg][c] = Q;
@@ -437,7 +459,7 @@ __global__ void __launch_bounds__(256) k_build_map(const long long* __restrict__
 //   FROM_EXT: source is ext[b*P+p][2][C] + affine (fused path); else feat[b][c][p] (PPScatter).
 constexpr int kChanPerUnit = 16;
 constexpr int kStage = 20;      // occupied cells staged per unit
-// FROM_EXT: 0 = feature tensor, 2 / 3 = ext rows with that many fields per (pillar, channel)
+// FROM_EXT: 0 = feature tensor, 2 = ext rows with two fields per (pillar, channel), 3 = sparse path (one field)
 template <int FROM_EXT>
 __global__ void __launch_bounds__(256) k_canvas(const float* __restrict__ src,
                                                 const Affine* __restrict__ affine,
@@ -470,8 +492,8 @@ __global__ void __launch_bounds__(256) k_canvas(const float* __restrict__ src,
         const float* e = src + ((size_t)b * P + slot) * 2 * C;
         return apply_affine(s_aff[c], e[c], e[C + c]);
       }
-      if (FROM_EXT == 3) {       // sparse path: field 0 of a 3-field row is already the pillar's extreme
-        const float* e = src + ((size_t)b * P + slot) * 3 * C;
+      if (FROM_EXT == 3) {       // sparse path: one field per (pillar, channel), already the pillar's extreme
+        const float* e = src + ((size_t)b * P + slot) * C;
         return apply_affine(s_aff[c], e[c], e[c]);
       }
       return src[((size_t)b * C + c) * P + slot];
@@ -635,7 +657,7 @@ static int pfn_common(const float* d_x, int B, int D, int P, int N, int C, const
   if (rc != PP_OK) return rc;
   PP_KERNEL("k_bn_finalize", st,
             k_bn_finalize<<<1, 64 * kFinSegs, 0, st>>>(C, nblocks, (double)B * P * N, training, momentum, eps,
-                                            SparseFinalize{1.0, nullptr, 0, nullptr, 0.0, nullptr, nullptr}, ws.partials, bn_w, bn_b,
+                                            SparseFinalize{1.0, nullptr, 0, nullptr, 0.0, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, nullptr}, ws.partials, bn_w, bn_b,
                                             rm, rv, (long long*)nbt, ws.affine));
   return PP_OK;
 }
@@ -692,125 +714,202 @@ static int build_map(const int64_t* d_inds, int B, int P, int H, int W, int* map
 // instead of once per sweep and keeps one suffix maximum per sweep; k_pfn_real below handles the
 // ~1.3 % of slots that hold a point.  Results equal the dense path's up to summation order.
 
-// packed[chunk][p]: byte b = min(count of pillar p in sweep 8*chunk + b, N), 0xff = not a live pillar there
-__global__ void __launch_bounds__(256) k_pack_counts(int B, int P, int N, const int* __restrict__ num_pillars,
-                                                     const int* __restrict__ pil_cnt,
-                                                     unsigned long long* __restrict__ packed) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b0 = blockIdx.y * kSparseMaxSweeps;
-  if (p >= P) return;
-  unsigned long long v = 0ull;
-  for (int b = 0; b < kSparseMaxSweeps; ++b) {
-    unsigned long long cb = 0xffull;
-    if (b0 + b < B && p < num_pillars[b0 + b]) cb = (unsigned long long)min(pil_cnt[(size_t)(b0 + b) * P + p], N);
-    v |= cb << (8 * b);
-  }
-  packed[(size_t)blockIdx.y * P + p] = v;
-}
-
-// One warp per live pillar, CPL channels per lane; conv weights in registers.  The points of the
-// pillar are fetched 32 at a time with lanes = points (features and per-slot means, 18 loads per
-// lane, all in flight together), staged in a per-warp shared-memory tile as {x_real[9], x_pad[9]}
-// records and read back as warp-uniform LDS.128 broadcasts, so the per-point loop has neither
-// global latency nor shuffles in it.  ext_s[b*P+p][0][c] = extreme of y over the pillar's points.
+// k_pfn_real: the live pillars (~1.3 % of the slots hold a point).  One warp per live pillar, CPL channels per
+// lane, conv weights in registers (pre-multiplied by sign(gamma): f = s*y, so only a maximum is tracked).  For a
+// pillar with cnt points the warp evaluates
+//   slots n <  cnt : y_real and y_pad  -> extreme of y_real, statistics corrections g(y_real) - g(y_pad)
+//   slots cnt <= n < E : y_pad only    -> extreme over the padding slots below the next ladder boundary E
+// (E = 4, 16, 48 or N, see pfn_pad.cu) and takes the extreme over n >= E from the padding table.  Slots are
+// fetched 32 at a time with lanes = slots (features and per-slot means, 18 loads per lane), staged in a per-warp
+// shared-memory tile as {x_real[9], x_pad[9]} records and read back as warp-uniform LDS.128 broadcasts.  The
+// loads of the NEXT pillar (metadata two pillars ahead, slot data and table row one pillar ahead) are in flight
+// while the current one is evaluated: the round-1 kernel paid three dependent memory round trips per pillar
+// (86 us for 66 k pillars at 34 % occupancy).
+// ext_s[b*P+p][c] = extreme pre-activation of the whole pillar (sign-selected).
 constexpr int kRealWarps = 8;
-constexpr int kRealRec = 20;       // floats per staged point: 9 real + 9 padding + 2 pad (16-byte multiples)
+constexpr int kRealRec = 20;       // floats per staged slot: 9 real + 9 padding + 2 pad (16-byte multiples)
 template <int CPL>
-__global__ void __launch_bounds__(kRealWarps * 32, 3) k_pfn_real(CompactPillars cp, int C,
+__global__ void __launch_bounds__(kRealWarps * 32, 2) k_pfn_real(CompactPillars cp, int C,
                                                   const float* __restrict__ conv_w,
                                                   const float* __restrict__ conv_b,
                                                   const float* __restrict__ bn_w,
+                                                  const float* __restrict__ padtab,
                                                   float* __restrict__ ext_s,
                                                   double* __restrict__ partials2) {
   const int warp = threadIdx.x >> 5;
   const unsigned lane = lane_id();
   __shared__ double s_red[kRealWarps][2][64];
   __shared__ __align__(16) float s_pts[kRealWarps][32][kRealRec];
-  float w[CPL][kD], bias[CPL], sgn[CPL];
+  __shared__ int s_pref[PP_MAX_SWEEPS + 1];
+  const int P = cp.P, N = cp.N, B = cp.sw.n_sweeps;
+  if (threadIdx.x == 0) {
+    int a = 0;
+    for (int b = 0; b < B; ++b) { s_pref[b] = a; a += min(cp.num_pillars[b], P); }
+    s_pref[B] = a;
+  }
+  float w[CPL][kD], bias[CPL], sgn[CPL];       // sign-folded: f = s*y = sum_d w*x + bias
 #pragma unroll
   for (int j = 0; j < CPL; ++j) {
     const int c = CPL * lane + j;
-    bias[j] = conv_b[c];
     sgn[j] = bn_w[c] < 0.f ? -1.f : 1.f;
+    bias[j] = sgn[j] * conv_b[c];
 #pragma unroll
-    for (int d = 0; d < kD; ++d) w[j][d] = conv_w[c * kD + d];
+    for (int d = 0; d < kD; ++d) w[j][d] = sgn[j] * conv_w[c * kD + d];
   }
+  __syncthreads();
   double accS[CPL], accQ[CPL];
 #pragma unroll
   for (int j = 0; j < CPL; ++j) { accS[j] = 0.0; accQ[j] = 0.0; }
-  const int P = cp.P, N = cp.N;
   const unsigned PN = (unsigned)P * (unsigned)N;          // host guarantees P*N < 2^31
   const bool has_mean = cp.data_mean != nullptr;
-  const long long rows = (long long)cp.sw.n_sweeps * P;
-  const long long nw = (long long)gridDim.x * kRealWarps;
+  const int total = s_pref[B];
+  const int nw = (int)gridDim.x * kRealWarps;
   float* tile = &s_pts[warp][0][0];
-  for (long long r = (long long)blockIdx.x * kRealWarps + warp; r < rows; r += nw) {
-    const int b = (int)(r / P), p = (int)(r - (long long)b * P);
-    if (p >= cp.num_pillars[b]) continue;
-    const int cnt = min(cp.pil_cnt[r], N);
-    const float* f = cp.feat_c + (size_t)(cp.sw.off[b] + cp.pil_off[r]) * kD;
-    const float* m = has_mean ? cp.data_mean + (size_t)p * N : nullptr;
-    float mx[CPL], mn[CPL], ds[CPL], dq[CPL];
+
+  struct Meta { int r, p, cnt, off; long long base; };
+  int bcur = 0;
+  auto locate = [&](int i, Meta& m) {                     // i < total, non-decreasing across calls
+    while (i >= s_pref[bcur + 1]) ++bcur;
+    m.p = i - s_pref[bcur];
+    m.r = bcur * P + m.p;
+    m.base = cp.sw.off[bcur];
+    m.cnt = __ldg(cp.pil_cnt + m.r);
+    m.off = __ldg(cp.pil_off + m.r);
+  };
+  auto limit = [&](int cnt, int& row) -> int {            // first slot covered by the padding table, and its row
+    if (!has_mean) { row = -1; return cnt; }
+    if (cnt <= 4) { row = 0; return min(4, N); }
+    if (cnt <= 16) { row = 1; return min(16, N); }
+    if (cnt <= 48) { row = 2; return min(48, N); }
+    row = -1;
+    return N;
+  };
+  float fv[kD], mv[kD];
+  float2 tab = make_float2(0.f, 0.f);
+  auto load_batch = [&](const Meta& m, int cnt, int E, int n0) {
+    const int n = n0 + (int)lane;
+    if (n < E) {
+      const float* f = cp.feat_c + (size_t)(m.base + m.off) * kD;
+      const float* mp = cp.data_mean + (size_t)m.p * N;
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) { mx[j] = -INFINITY; mn[j] = INFINITY; ds[j] = 0.f; dq[j] = 0.f; }
-    for (int n0 = 0; n0 < cnt; n0 += 32) {
-      const int n = n0 + (int)lane;
-      if (n < cnt) {
-        float fv[kD], mv[kD];
+      for (int d = 0; d < kD; ++d) {
+        fv[d] = n < cnt ? __ldg(f + (unsigned)n * kD + d) : 0.f;
+        mv[d] = has_mean ? __ldg(mp + (unsigned)d * PN + (unsigned)n) : 0.f;
+      }
+    }
+  };
+  auto stage = [&](int cnt, int E, int n0) {
+    const int n = n0 + (int)lane;
+    if (n < E) {
+      float* rec = tile + lane * kRealRec;
 #pragma unroll
-        for (int d = 0; d < kD; ++d) {
-          fv[d] = __ldg(f + (unsigned)n * kD + d);
-          mv[d] = has_mean ? __ldg(m + (unsigned)d * PN + (unsigned)n) : 0.f;
-        }
-        float* rec = tile + lane * kRealRec;
+      for (int d = 0; d < kD; ++d) {
+        rec[d] = __fsub_rn(fv[d], mv[d]);                  // data/dataset.py:105
+        rec[kD + d] = __fsub_rn(0.f, mv[d]);               // what the slot holds when it is padding
+      }
+    }
+  };
+  float mx[CPL], ds[CPL], dq[CPL];
+  auto compute = [&](int cnt, int E, int n0) {
+    const int k_real = min(32, cnt - n0), k_all = min(32, E - n0);
+    int k = 0;
+    for (; k < k_real; ++k) {
+      const float4* rec = reinterpret_cast<const float4*>(tile + k * kRealRec);
+      const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4];
+      const float a[kD] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
+      const float q[kD] = {r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w, r4.x, r4.y};
 #pragma unroll
-        for (int d = 0; d < kD; ++d) {
-          rec[d] = __fsub_rn(fv[d], mv[d]);                // data/dataset.py:105
-          rec[kD + d] = __fsub_rn(0.f, mv[d]);             // what the slot holds when it is padding
-        }
+      for (int j = 0; j < CPL; ++j) {
+        float f = bias[j], fp = bias[j];
+#pragma unroll
+        for (int d = 0; d < kD; ++d) { f = fmaf(w[j][d], a[d], f); fp = fmaf(w[j][d], q[d], fp); }
+        mx[j] = fmaxf(mx[j], f);
+        const float t = fmaf(sgn[j], f, fabsf(f)), tp = fmaf(sgn[j], fp, fabsf(fp));   // 2 relu(y), y = s f
+        ds[j] += t - tp;                                   // the padding pass counted this slot as padding
+        dq[j] += fmaf(t, t, -tp * tp);
+      }
+    }
+    for (; k < k_all; ++k) {                               // padding slots below the table's first slot
+      const float4* rec = reinterpret_cast<const float4*>(tile + k * kRealRec);
+      const float4 r2 = rec[2], r3 = rec[3], r4 = rec[4];
+      const float q[kD] = {r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w, r4.x, r4.y};
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        float fp = bias[j];
+#pragma unroll
+        for (int d = 0; d < kD; ++d) fp = fmaf(w[j][d], q[d], fp);
+        mx[j] = fmaxf(mx[j], fp);
+      }
+    }
+  };
+
+  int i = (int)blockIdx.x * kRealWarps + warp;
+  Meta mA{}, mB{};
+  bool vA = i < total, vB = false;
+  int cntA = 0, EA = 0, rowA = -1;
+  if (vA) {
+    locate(i, mA);
+    vB = i + nw < total;
+    if (vB) locate(i + nw, mB);
+    cntA = min(mA.cnt, N);
+    EA = limit(cntA, rowA);
+    load_batch(mA, cntA, EA, 0);
+    if (rowA >= 0) tab = __ldg(reinterpret_cast<const float2*>(padtab + (size_t)mA.p * 192 + rowA * 64) + lane);
+  }
+  while (vA) {
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { mx[j] = -INFINITY; ds[j] = 0.f; dq[j] = 0.f; }
+    const float2 tabA = tab;
+    stage(cntA, EA, 0);
+    __syncwarp();
+    // metadata two pillars ahead, slot data one pillar ahead
+    Meta mC{};
+    const bool vC = vB && i + 2 * nw < total;
+    if (vC) locate(i + 2 * nw, mC);
+    int cntB = 0, EB = 0, rowB = -1;
+    if (vB) { cntB = min(mB.cnt, N); EB = limit(cntB, rowB); }
+    if (EA <= 32) {
+      if (vB) {
+        load_batch(mB, cntB, EB, 0);
+        if (rowB >= 0) tab = __ldg(reinterpret_cast<const float2*>(padtab + (size_t)mB.p * 192 + rowB * 64) + lane);
+      }
+      compute(cntA, EA, 0);
+      __syncwarp();
+    } else {
+      compute(cntA, EA, 0);
+      for (int n0 = 32; n0 < EA; n0 += 32) {
+        __syncwarp();
+        load_batch(mA, cntA, EA, n0);
+        stage(cntA, EA, n0);
+        __syncwarp();
+        compute(cntA, EA, n0);
       }
       __syncwarp();
-      const int steps = min(32, cnt - n0);
-      for (int k = 0; k < steps; ++k) {
-        const float4* rec = reinterpret_cast<const float4*>(tile + k * kRealRec);
-        const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4];
-        const float a[kD] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
-        const float q[kD] = {r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w, r4.x, r4.y};
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          float y = bias[j], yp = bias[j];
-#pragma unroll
-          for (int d = 0; d < kD; ++d) { y = fmaf(w[j][d], a[d], y); yp = fmaf(w[j][d], q[d], yp); }
-          mx[j] = fmaxf(mx[j], y);
-          mn[j] = fminf(mn[j], y);
-          const float ry = fmaxf(y, 0.f), rp = fmaxf(yp, 0.f);
-          ds[j] += ry - rp;                                // the padding pass counted this slot as padding
-          dq[j] += fmaf(ry, ry, -rp * rp);
-        }
+      if (vB) {
+        load_batch(mB, cntB, EB, 0);
+        if (rowB >= 0) tab = __ldg(reinterpret_cast<const float2*>(padtab + (size_t)mB.p * 192 + rowB * 64) + lane);
       }
-      __syncwarp();                                        // the tile is refilled by the next chunk / pillar
     }
-    // field 0 <- extreme over the whole pillar: its points (here) and its padding slots (fields 1, 2,
-    // written by the padding pass, which ran before this kernel; y == bias without a data_mean)
-    float* e = ext_s + (size_t)r * 3 * C + CPL * lane;
+    // extreme over the whole pillar: its points and padding slots below E (above), the table row for n >= E
+    float* e = ext_s + (size_t)mA.r * C + CPL * lane;
+    const float tb[2] = {tabA.x, tabA.y};
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
-      float p1, p2;
-      if (has_mean) {
-        p1 = e[C + j];
-        p2 = e[2 * C + j];
-      } else {
-        p1 = p2 = cnt < N ? bias[j] : (sgn[j] > 0.f ? -INFINITY : INFINITY);
-      }
-      e[j] = sgn[j] > 0.f ? fmaxf(mx[j], fmaxf(p1, p2)) : fminf(mn[j], fminf(p1, p2));
+      float m = mx[j];
+      if (has_mean) { if (rowA >= 0) m = fmaxf(m, sgn[j] * tb[j]); }
+      else if (cntA < N) m = fmaxf(m, bias[j]);
+      e[j] = sgn[j] * m;
       accS[j] += (double)ds[j];
       accQ[j] += (double)dq[j];
     }
+    mA = mB; vA = vB; cntA = cntB; EA = EB; rowA = rowB;
+    mB = mC; vB = vC;
+    i += nw;
   }
 #pragma unroll
   for (int j = 0; j < CPL; ++j) {
-    s_red[warp][0][CPL * lane + j] = accS[j];
-    s_red[warp][1][CPL * lane + j] = accQ[j];
+    s_red[warp][0][CPL * lane + j] = accS[j] * 0.5;           // t = 2 relu(y)
+    s_red[warp][1][CPL * lane + j] = accQ[j] * 0.25;
   }
   __syncthreads();
   if (threadIdx.x < 2 * C) {
@@ -822,76 +921,101 @@ __global__ void __launch_bounds__(kRealWarps * 32, 3) k_pfn_real(CompactPillars 
 }
 
 struct SparseWs {
-  float* ext_s;        // [B*P, 3, C]
+  float* ext_s;        // [B*P, C]
+  float* padtab;       // [P, 3, C]   padding table (pfn_pad.cu)
   double* partials;    // [nblocks, 2, C]   padding pass
   double* partials2;   // [nblocks2, 2, C]  k_pfn_real
   Affine* affine;
   int* map;
   int* flags;
-  unsigned long long* packed;   // [P] per-sweep counts of pillar p, one byte each
+  void* prep;          // operand prepared on the fly when the caller did not pass one
 };
 
-static int real_blocks() { return sm_count() * 3; }
+static int real_blocks() { return sm_count() * 2; }
+
+bool pfn_pad_supported(int N, int C, int P);
+size_t mean_prepared_bytes(int P, int N);
+const double* mean_prepared_moments(const void* prep, int P, int N);
+const int* mean_prepared_flag(const void* prep, int P, int N);
+int mean_prepare(const float* d_mean, int P, int N, void* d_prep, size_t bytes, cudaStream_t st);
+int launch_pad_tc(const void* d_prep, int P, int N, const float* w, const float* bias, const float* bn_w, int training,
+                  float* padtab, double* partials, int nblocks, int* range_flag, cudaStream_t st);
 
 template <class A>
-static void sparse_layout(A& a, SparseWs* ws, int B, int P, int C, int H, int W) {
-  auto p0 = a.template take<float>((size_t)B * P * 3 * C);
+static void sparse_layout(A& a, SparseWs* ws, int B, int P, int N, int C, int H, int W, bool own_prep) {
+  auto p0 = a.template take<float>((size_t)B * P * C);
   auto p1 = a.template take<double>((size_t)sm_count() * 2 * C);
   auto p2 = a.template take<double>((size_t)real_blocks() * 2 * C);
   auto p3 = a.template take<Affine>(64);
   auto p4 = a.template take<int>((size_t)B * H * W + 1);
   auto p5 = a.template take<int>(64);
-  auto p6 = a.template take<unsigned long long>((size_t)P * ((B + kSparseMaxSweeps - 1) / kSparseMaxSweeps));
-  if (ws) { ws->ext_s = p0; ws->partials = p1; ws->partials2 = p2; ws->affine = p3; ws->map = p4; ws->flags = p5; ws->packed = p6; }
+  auto p6 = a.template take<float>((size_t)P * 3 * C);
+  auto p7 = a.template take<char>(own_prep ? mean_prepared_bytes(P, N) : 0);
+  if (ws) { ws->ext_s = p0; ws->partials = p1; ws->partials2 = p2; ws->affine = p3; ws->map = p4; ws->flags = p5; ws->padtab = p6; ws->prep = p7; }
 }
 
-size_t pfn_sparse_workspace_bytes(int B, int P, int C, int H, int W) {
+size_t pfn_sparse_workspace_bytes(int B, int P, int N, int C, int H, int W, bool own_prep) {
   SizeArena2 a;
-  sparse_layout(a, (SparseWs*)nullptr, B, P, C, H, W);
+  sparse_layout(a, (SparseWs*)nullptr, B, P, N, C, H, W, own_prep);
   return a.used + kAlign;
 }
 
 bool pfn_sparse_supported(int B, int P, int N, int C, const void* data_mean) {
   if (!g_opt_pfn_tensor_cores) return false;
   if (B < 1 || B > PP_MAX_SWEEPS || C != 64 || N > 255) return false;
-  return data_mean == nullptr || pfn_tc16_supported(kD, N, C, P, data_mean);
+  return data_mean == nullptr || pfn_pad_supported(N, C, P);
 }
 
 int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, const PfnParams& prm, int H, int W,
                        float* d_canvas, int32_t* d_status, void* d_ws, size_t ws_bytes, cudaStream_t st) {
   const int B = cp.sw.n_sweeps, P = cp.P, N = cp.N;
   if (!pfn_sparse_supported(B, P, N, C, cp.data_mean)) return PP_ERR_UNSUPPORTED;
+  const bool own_prep = cp.data_mean != nullptr && cp.mean_prepared == nullptr;
   Arena arena(d_ws, ws_bytes);
   SparseWs ws{};
-  sparse_layout(arena, &ws, B, P, C, H, W);
+  sparse_layout(arena, &ws, B, P, N, C, H, W, own_prep);
   if (!arena.ok) return PP_ERR_WORKSPACE;
   int rc = build_map(d_inds, B, P, H, W, ws.map, d_status, st);
   if (rc != PP_OK) return rc;
   int nblocks = 0;
+  const void* prep = cp.mean_prepared;
   if (cp.data_mean != nullptr) {
+    if (own_prep) {
+      // a caller without a prepared operand pays a streaming pass over data_mean per call (pp_mean_prepare once
+      // per data_mean avoids it)
+      rc = mean_prepare(cp.data_mean, P, N, ws.prep, mean_prepared_bytes(P, N), st);
+      if (rc != PP_OK) return rc;
+      prep = ws.prep;
+    }
     const long long pairs = P / 2;
     const int sms = sm_count() - g_opt_pad_reserve_sms > 8 ? sm_count() - g_opt_pad_reserve_sms : 8;
     nblocks = (int)(pairs < sms ? pairs : sms);
-    const int nchunks = (B + kSparseMaxSweeps - 1) / kSparseMaxSweeps;
-    PP_KERNEL("k_pack_counts", st,
-              k_pack_counts<<<dim3((P + 255) / 256, nchunks), 256, 0, st>>>(B, P, N, cp.num_pillars, cp.pil_cnt, ws.packed));
-    // one padding pass per 8 sweeps (their suffix maxima); the statistics come from the first pass only
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int b0 = ch * kSparseMaxSweeps;
-      tch::PadArgs pad{min(kSparseMaxSweeps, B - b0), b0, ws.packed + (size_t)ch * P};
-      rc = launch_stats_tc16(cp.data_mean, 1, P, N, prm.conv_w, prm.conv_b, prm.bn_w, (prm.training && ch == 0) ? 1 : 0,
-                             ws.ext_s, ws.partials, nblocks, ws.flags + ch, &pad, st);
-      if (rc != PP_OK) return rc;
-    }
+    // the padding pass does not depend on the sweeps: once per call, whatever the batch size
+    rc = launch_pad_tc(prep, P, N, prm.conv_w, prm.conv_b, prm.bn_w, prm.training ? 1 : 0, ws.padtab, ws.partials, nblocks,
+                       ws.flags, st);
+    if (rc != PP_OK) return rc;
   }
   const int nb2 = real_blocks();
   PP_KERNEL("k_pfn_real", st,
-            k_pfn_real<2><<<nb2, kRealWarps * 32, 0, st>>>(cp, C, prm.conv_w, prm.conv_b, prm.bn_w, ws.ext_s, ws.partials2));
-  // the padding pass has no TF32 fallback: a mean or weight outside the fp16 range is reported through
-  // the status word (by the finalize kernel, which runs anyway)
-  SparseFinalize sf{(double)B, prm.training ? ws.partials2 : nullptr, nb2,
-                    cp.data_mean == nullptr ? prm.conv_b : nullptr, (double)B * P * N,
-                    cp.data_mean != nullptr ? ws.flags : nullptr, d_status};
+            k_pfn_real<2><<<nb2, kRealWarps * 32, 0, st>>>(cp, C, prm.conv_w, prm.conv_b, prm.bn_w, ws.padtab, ws.ext_s,
+                                                           ws.partials2));
+  // a mean or weight outside the fp16 range is reported through the status word (by the finalize kernel, which
+  // runs anyway)
+  SparseFinalize sf{};
+  sf.mult = 0.5 * (double)B;
+  sf.partials2 = prm.training ? ws.partials2 : nullptr;
+  sf.nparts2 = nb2;
+  sf.conv_b = cp.data_mean == nullptr ? prm.conv_b : nullptr;
+  sf.pad_count = (double)B * P * N;
+  sf.range_flag = cp.data_mean != nullptr ? ws.flags : nullptr;
+  sf.status = d_status;
+  if (cp.data_mean != nullptr) {
+    sf.mom = mean_prepared_moments(prep, P, N);
+    sf.mom_w = prm.conv_w;
+    sf.mom_b = prm.conv_b;
+    sf.mom_mult = 0.5 * (double)B;
+    sf.range_flag2 = mean_prepared_flag(prep, P, N);
+  }
   PP_KERNEL("k_bn_finalize", st,
             k_bn_finalize<<<1, 64 * kFinSegs, 0, st>>>(C, nblocks, (double)B * P * N, prm.training, prm.momentum, prm.eps, sf,
                                             ws.partials, prm.bn_w, prm.bn_b, prm.running_mean, prm.running_var,

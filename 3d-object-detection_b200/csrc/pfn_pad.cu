@@ -1,0 +1,476 @@
+// pfn_pad.cu -- the padding pass of the fused input path (pp_input_path) on tcgen05 tensor cores, sm_100a.
+//
+// A padding slot (p, n) of the network input holds x = 0 - data_mean[:, p, n] in every sweep
+// (data/dataset.py:99-105), so y_pad[c, p, n] = W x + b is evaluated ONCE per (p, n), whatever the batch
+// size and whatever the pillars' point counts.  This pass produces
+//   * padtab[p][3][64]: the sign-selected extreme of y_pad over the slot suffixes n >= 4, n >= 16, n >= 48
+//     (a pillar with cnt points needs the extreme over n >= cnt; k_pfn_real evaluates the few slots between
+//     cnt and the next ladder boundary itself and takes the rest from this table), and
+//   * per-channel sums of |y_pad| and y_pad |y_pad| over all (p, n).  With the first and second moments of
+//     the input (a constant of the dataset, pp_mean_prepare) they give the BatchNorm statistics of the
+//     padding slots: sum relu(y) = (sum y + sum |y|) / 2, sum relu(y)^2 = (sum y^2 + sum y |y|) / 2, where
+//     sum y and sum y^2 are linear / quadratic forms of the moments (k_bn_finalize).  That is one FADD and one
+//     FFMA per accumulator value instead of three FMA-pipe operations for relu, sum and sum of squares: the
+//     epilogue is bound by the FMA pipe (scripts/ubench/epi4.cu: 4.2 -> 3.15 cycles per warp-value).
+//
+// Operand (pp_mean_prepare, once per data_mean): x = -mean split into fp16 pieces x = xh + xl, stored in the
+// exact shared-memory image of the UMMA B operand (K-major, no swizzle): per pillar three planes of
+// [N slots][8 halves = 16 B]
+//     plane 0: xh_0 .. xh_7      plane 1: xh_8, xl_0 .. xl_6      plane 2: xl_7, xl_8, 1, 1, 0, 0, 0, 0
+// so ONE contiguous cp.async.bulk per pillar pair fills a stage and no thread touches the data before the
+// tensor core does (the round-1 kernel spent ~235 issue cycles per pair and sub-partition converting fp32 rows).
+// 48 bytes per slot instead of 36 for the raw fp32 means.
+//
+// Contraction (fp32 accumulation in TMEM, M = 64 channels, N = the pillar's slots), W' = 256 W = Wh + Wl:
+//     A1 (K = 32): k 0..8 Wh_d | k 9..17 Wh_d | k 18 bh | k 19 bl | 0 ...   x  planes 0,1 | plane 2, zero plane
+//     A2 (K = 16): k 0..8 Wl_d | 0 ...                                       x  planes 0,1
+// = 256 (W x + b) up to the dropped Wl*xl term (~2^-22 |w||x|); rows pre-multiplied by sign(gamma) so that only
+// a maximum is tracked.  The fourth k-chunk of A1's second k-step is a shared all-zero plane reached through the
+// descriptor's leading-dimension byte offset.
+//
+// Roles (576 threads, one persistent CTA per SM, work unit = pair of adjacent pillars at TMEM lane offset 16):
+//   warps 0-15  epilogue, ALL on the same pair: lane quarter q = warp % 4, column range j = warp / 4; two TMEM
+//               accumulator buffers alternate, so the MMAs of pair k+1 run under the epilogue of pair k.
+//               The four column ranges of a row meet in shared memory; the j = 3 warp writes the table rows.
+//   warp 16     producer (one bulk copy per pair into an 8-stage ring)
+//   warp 17     TMEM allocation + MMA issuer (6 tcgen05.mma per pair)
+#include "tc_common.cuh"
+#include "internal.cuh"
+
+namespace pp {
+namespace padk {
+
+using namespace tcx;
+
+constexpr int kThreads = 18 * 32;
+constexpr int kProducerWarp = 16, kMmaWarp = 17;
+constexpr int kMaxStages = 8;
+constexpr int kAccCols = 256;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kABytes = 3 * 2048;          // A1 (two k-steps) + A2 (one k-step), 64 rows x 16 k fp16 each
+
+struct Smem {
+  int a_off, stage_off, stage_bytes, stages, zero_off, part_off, stat_off, bar_off, total;
+};
+
+__host__ __device__ inline Smem smem_plan(int N) {
+  Smem s;
+  s.a_off = 0;
+  s.stage_off = kABytes;                               // 6144: 128-byte aligned
+  s.stage_bytes = 2 * 3 * N * 16;                      // pair of pillars x 3 planes x N x 16 B
+  const int fixed = kABytes + N * 16 + 2 * 4 * 128 * 4 + 4 * 2 * 64 * 8 + 512 + 128;
+  int st = (kSmemBudget - fixed) / s.stage_bytes;
+  s.stages = st > kMaxStages ? kMaxStages : st;
+  s.zero_off = s.stage_off + s.stages * s.stage_bytes;
+  s.part_off = s.zero_off + N * 16;
+  s.stat_off = s.part_off + 2 * 4 * 128 * 4;
+  s.bar_off = s.stat_off + 4 * 2 * 64 * 8;
+  s.total = s.bar_off + 512 + 128;                     // +128: manual base alignment
+  return s;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ unsigned short h_bits(float v) {
+  unsigned short r;
+  asm("cvt.rn.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float h_value(unsigned short h) {
+  float r;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(r) : "h"(h));
+  return r;
+}
+
+#define PP_TMEM_LD16(taddr, v)                                                                      \
+  asm volatile(                                                                                     \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                     \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                             \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),        \
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),   \
+        "=r"(v[14]), "=r"(v[15])                                                                    \
+      : "r"(taddr))
+
+// max over v[FROM, CNT) into (m0, m1); |v| and v|v| of all CNT values into four fp32 chains each
+template <int CNT, int FROM, bool TRAIN>
+__device__ __forceinline__ void consume(const uint32_t* v, float& m0, float& m1, float* S, float* Q) {
+#pragma unroll
+  for (int i = FROM; i < CNT; i += 2) {
+    const float a = __uint_as_float(v[i]), b = __uint_as_float(v[i + 1]);
+    if (((i >> 1) & 1) == 0) m0 = fmaxf(m0, fmaxf(a, b)); else m1 = fmaxf(m1, fmaxf(a, b));
+  }
+  if (TRAIN) {
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) {
+      const float y = __uint_as_float(v[i]);
+      S[i & 3] += fabsf(y);
+      Q[i & 3] = fmaf(y, fabsf(y), Q[i & 3]);
+    }
+  }
+}
+
+// columns [a, b) of this thread's TMEM row, widest loads first; b - a is a multiple of 8
+template <bool TRAIN>
+__device__ __forceinline__ void consume_range(uint32_t taddr, int a, int b, float& m0, float& m1, float* S, float* Q) {
+  uint32_t v[32];
+  int col = a;
+  for (; col + 32 <= b; col += 32) {
+    PP_TMEM_LD32(taddr + col, v);
+    tmem_ld_wait();
+    consume<32, 0, TRAIN>(v, m0, m1, S, Q);
+  }
+  if (b - col >= 16) {
+    PP_TMEM_LD16(taddr + col, v);
+    tmem_ld_wait();
+    consume<16, 0, TRAIN>(v, m0, m1, S, Q);
+    col += 16;
+  }
+  if (b - col >= 8) {
+    PP_TMEM_LD8(taddr + col, v);
+    tmem_ld_wait();
+    consume<8, 0, TRAIN>(v, m0, m1, S, Q);
+  }
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kThreads, 1)
+k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
+             const float* __restrict__ conv_w, const float* __restrict__ conv_b, const float* __restrict__ bn_w,
+             float* __restrict__ padtab, double* __restrict__ partials, int* __restrict__ range_flag) {
+  extern __shared__ unsigned char smem_unaligned[];
+  unsigned char* smem = smem_unaligned + ((128u - (smem_u32(smem_unaligned) & 127u)) & 127u);
+  const Smem sp = smem_plan(N);
+  const int warp = threadIdx.x >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  const int R = sp.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
+  uint64_t* full = bars;                            // [kMaxStages] stage filled by the bulk copy
+  uint64_t* empty = bars + kMaxStages;              // [kMaxStages] stage read by the MMAs
+  uint64_t* acc_full = bars + 2 * kMaxStages;       // [2]
+  uint64_t* acc_empty = acc_full + 2;               // [2]
+  uint64_t* pbar = acc_empty + 2;                   // [2 buffers][4 quarters] partial maxima of ranges 0..2 published
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pbar + 8);
+  float* s_part = reinterpret_cast<float*>(smem + sp.part_off);      // [2][4][128]
+  double* s_stat = reinterpret_cast<double*>(smem + sp.stat_off);    // [4 ranges][sum |y|, sum y|y|][64]
+
+  const int pairs = P >> 1;                          // host guarantees P even
+  const int my_pairs = (int)blockIdx.x < pairs ? (pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  // ---- one-time setup -------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
+    for (int i = 0; i < 8; ++i) mbar_init(&pbar[i], 3);
+    fence_barrier_init();
+  }
+  // A tiles: 64 x 16 fp16 per k-step, K-major, no swizzle: core matrix = 8 rows x 16 B (8 k), k-chunk stride
+  // 128 B, row-group stride 256 B.  Tile 0, 1 = A1 (k 0..15, 16..31), tile 2 = A2.
+  {
+    bool bad = false;
+    for (int idx = threadIdx.x; idx < 3 * 64 * 16; idx += kThreads) {
+      const int t = idx >> 10, m = (idx >> 4) & 63, kk = idx & 15;
+      const int K = t == 1 ? 16 + kk : kk;
+      const float sgn = bn_w[m] < 0.f ? -1.f : 1.f;
+      float v = 0.f;
+      if (t < 2) {
+        if (K < 18) {
+          const float w = 256.f * conv_w[m * 9 + (K < 9 ? K : K - 9)];
+          bad |= !(fabsf(w) < 32768.f);
+          v = h_value(h_bits(w));
+        } else if (K < 20) {
+          const float bb = 256.f * conv_b[m];
+          bad |= !(fabsf(bb) < 32768.f);
+          const float bh = h_value(h_bits(bb));
+          v = K == 18 ? bh : (bb - bh);
+        }
+      } else if (K < 9) {
+        const float w = 256.f * conv_w[m * 9 + K];
+        v = w - h_value(h_bits(w));
+      }
+      *reinterpret_cast<unsigned short*>(smem + sp.a_off + t * 2048 + (m >> 3) * 256 + (kk >> 3) * 128 + (m & 7) * 16 + (kk & 7) * 2) =
+          h_bits(sgn * v);
+    }
+    if (bad) atomicOr(range_flag, 1);
+    for (int idx = threadIdx.x; idx < N * 4; idx += kThreads) reinterpret_cast<uint32_t*>(smem + sp.zero_off)[idx] = 0u;
+  }
+  fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  if (warp == kMmaWarp) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == kProducerWarp) {
+    // ===== producer: one contiguous bulk copy per pair =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;                                  // parity to wait on empty[] (first pass falls through)
+      const uint32_t bytes = (uint32_t)sp.stage_bytes;
+      for (int it = 0; it < my_pairs; ++it) {
+        const size_t pair = (size_t)blockIdx.x + (size_t)it * gridDim.x;
+        mbar_wait(&empty[s], ph);
+        mbar_expect_tx(&full[s], bytes);
+        bulk_g2s(smem + sp.stage_off + s * sp.stage_bytes, hl + pair * bytes, bytes, &full[s]);
+        if (++s == R) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): fp32 accumulate, A = B = f16,
+      // both K-major, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+      const uint32_t a_addr = smem_u32(smem + sp.a_off);
+      const uint32_t zero_addr = smem_u32(smem + sp.zero_off);
+      const uint32_t plane = (uint32_t)N * 16u;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_pairs; ++it) {
+        const int e = it & 1;
+        mbar_wait(&full[s], ph);
+        mbar_wait(&acc_empty[e], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t b_addr = smem_u32(smem + sp.stage_off + s * sp.stage_bytes) + (uint32_t)h * 3u * plane;
+          const uint32_t d_tmem = tmem_base + ((uint32_t)(h * 16) << 16) + (uint32_t)(e * kAccCols);
+          umma_f16(d_tmem, smem_desc(a_addr, 128, 256), smem_desc(b_addr, plane, 128), idesc, 0u);
+          umma_f16(d_tmem, smem_desc(a_addr + 2048, 128, 256),
+                   smem_desc(b_addr + 2u * plane, zero_addr - (b_addr + 2u * plane), 128), idesc, 1u);
+          umma_f16(d_tmem, smem_desc(a_addr + 4096, 128, 256), smem_desc(b_addr, plane, 128), idesc, 1u);
+        }
+        umma_commit(&empty[s]);       // stage free once these MMAs have read it
+        umma_commit(&acc_full[e]);    // accumulators ready for the epilogue
+        if (++s == R) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue: one (pillar-of-pair, channel) row per thread over this warp's column range =====
+    const int q = warp & 3;                // TMEM lane quarter (must equal warp % 4)
+    const int j = warp >> 2;               // column range
+    const int h = (int)(lane >> 4);
+    const int c = 16 * q + (int)(lane & 15u);
+    const int rowid = 32 * q + (int)lane;
+    const float sgn = bn_w[c] < 0.f ? -1.f : 1.f;
+    // ranges: [0, e1) | three near-equal parts of [e1, N); e1 = min(N, 48) carries the ladder boundaries 4 and 16
+    const int e1 = N < 48 ? N : 48;
+    const int g = (N - e1) >> 3;
+    const int c1 = e1 + 8 * (g / 3), c2 = c1 + 8 * (g / 3);
+    const int n0 = j == 0 ? 0 : (j == 1 ? e1 : (j == 2 ? c1 : c2));
+    const int n1 = j == 0 ? e1 : (j == 1 ? c1 : (j == 2 ? c2 : N));
+    double accS = 0.0, accQ = 0.0;
+    for (int it = 0; it < my_pairs; ++it) {
+      const int e = it & 1;
+      const uint32_t n = (uint32_t)(it >> 1);
+      mbar_wait(&acc_full[e], n & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(e * kAccCols);
+      float S[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
+      float m0 = -INFINITY, m1 = -INFINITY, lo = -INFINITY;
+      if (j == 0) {
+        // slots 0..3 never enter a table row (a live pillar holds at least one point and k_pfn_real evaluates
+        // the slots below the first boundary itself); slots 4..15 only enter the first row
+        uint32_t v[16];
+        PP_TMEM_LD16(taddr, v);
+        tmem_ld_wait();
+        float a0 = -INFINITY, a1 = -INFINITY;
+        consume<16, 4, TRAIN>(v, a0, a1, S, Q);
+        lo = fmaxf(a0, a1);
+        consume_range<TRAIN>(taddr, 16, n1, m0, m1, S, Q);
+      } else {
+        consume_range<TRAIN>(taddr, n0, n1, m0, m1, S, Q);
+      }
+      const float m = fmaxf(m0, m1);
+      tc_fence_before();
+      float* part = s_part + e * 512;
+      if (j < 3) {
+        if (j == 0) { part[rowid] = fmaxf(lo, m); part[128 + rowid] = m; }
+        else part[(j + 1) * 128 + rowid] = m;
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&pbar[e * 4 + q]); mbar_arrive(&acc_empty[e]); }
+      } else {
+        mbar_wait(&pbar[e * 4 + q], n & 1u);
+        const float t = fmaxf(m, fmaxf(part[2 * 128 + rowid], part[3 * 128 + rowid]));
+        const float r4 = fmaxf(part[rowid], t), r16 = fmaxf(part[128 + rowid], t);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[e]);
+        // TMEM holds 256*s*y; rows of y's sign-selected extreme (max when gamma >= 0, min otherwise); an empty
+        // suffix stays -inf (+inf after the sign): neutral for the consumer
+        const size_t pillar = 2 * ((size_t)blockIdx.x + (size_t)it * gridDim.x) + h;
+        float* o = padtab + pillar * 192 + c;
+        o[0] = sgn * r4 * (1.f / 256.f);
+        o[64] = sgn * r16 * (1.f / 256.f);
+        o[128] = sgn * t * (1.f / 256.f);
+      }
+      if (TRAIN) {
+        accS += (double)((S[0] + S[1]) + (S[2] + S[3]));
+        accQ += (double)((Q[0] + Q[1]) + (Q[2] + Q[3]));
+      }
+    }
+    if (TRAIN) {
+      accS += __shfl_xor_sync(0xffffffffu, accS, 16);
+      accQ += __shfl_xor_sync(0xffffffffu, accQ, 16);
+      if (lane < 16) {
+        s_stat[(j * 2 + 0) * 64 + c] = accS * (1.0 / 256.0);                          // sum |y|
+        s_stat[(j * 2 + 1) * 64 + c] = accQ * ((double)sgn / (256.0 * 256.0));        // sum y |y|  (y = s v / 256)
+      }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+  if (TRAIN && threadIdx.x < 128) {
+    // fixed-order combination of the four column ranges -> deterministic per-CTA partials
+    const int qq = threadIdx.x >> 6, cc = threadIdx.x & 63;
+    double v = 0.0;
+    for (int k = 0; k < 4; ++k) v += s_stat[(k * 2 + qq) * 64 + cc];
+    partials[((size_t)blockIdx.x * 2 + qq) * 64 + cc] = v;
+  }
+}
+
+// ---- pp_mean_prepare: data_mean [9,P,N] fp32 -> operand image + moments (once per data_mean) ------------
+constexpr int kPrepBlocks = 592;
+constexpr int kMom = 55;            // upper triangle of the 10 x 10 moment matrix of (x_0..x_8, 1)
+
+__global__ void __launch_bounds__(256) k_mean_prepare(const float* __restrict__ mean, int P, int N,
+                                                      unsigned char* __restrict__ hl, double* __restrict__ scratch,
+                                                      int* __restrict__ flag) {
+  __shared__ double s_red[8][kMom];
+  const long long PN = (long long)P * N;
+  double acc[kMom];
+#pragma unroll
+  for (int i = 0; i < kMom; ++i) acc[i] = 0.0;
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < PN; i += (long long)gridDim.x * 256) {
+    const int p = (int)(i / N), n = (int)(i - (long long)p * N);
+    unsigned short xh[9], xl[9];
+    double xv[10];
+#pragma unroll
+    for (int d = 0; d < 9; ++d) {
+      const float x = __fsub_rn(0.f, mean[(long long)d * PN + i]);       // what a padding slot holds
+      bad |= !(fabsf(x) < 32768.f);
+      xh[d] = h_bits(x);
+      const float fh = h_value(xh[d]);
+      xl[d] = h_bits(x - fh);                                             // x - fh is exact in fp32
+      xv[d] = (double)fh + (double)h_value(xl[d]);                        // the value the tensor core sees
+    }
+    xv[9] = 1.0;
+    int k = 0;
+#pragma unroll
+    for (int d = 0; d < 10; ++d)
+#pragma unroll
+      for (int e = d; e < 10; ++e) acc[k++] += xv[d] * xv[e];
+    uint4 w0, w1, w2;
+    w0.x = xh[0] | ((unsigned)xh[1] << 16); w0.y = xh[2] | ((unsigned)xh[3] << 16);
+    w0.z = xh[4] | ((unsigned)xh[5] << 16); w0.w = xh[6] | ((unsigned)xh[7] << 16);
+    w1.x = xh[8] | ((unsigned)xl[0] << 16); w1.y = xl[1] | ((unsigned)xl[2] << 16);
+    w1.z = xl[3] | ((unsigned)xl[4] << 16); w1.w = xl[5] | ((unsigned)xl[6] << 16);
+    w2.x = xl[7] | ((unsigned)xl[8] << 16); w2.y = 0x3c003c00u; w2.z = 0u; w2.w = 0u;
+    uint4* o = reinterpret_cast<uint4*>(hl + ((size_t)p * 3 * N + n) * 16);
+    o[0] = w0;
+    o[N] = w1;
+    o[2 * N] = w2;
+  }
+  if (bad) atomicOr(flag, 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < kMom; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kMom) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += s_red[w][threadIdx.x];
+    scratch[(size_t)blockIdx.x * kMom + threadIdx.x] = v;
+  }
+}
+
+__global__ void k_mean_moments(const double* __restrict__ scratch, int nblk, double* __restrict__ mom) {
+  __shared__ double s[kMom];
+  if (threadIdx.x < kMom) {
+    double v = 0.0;
+    for (int b = 0; b < nblk; ++b) v += scratch[(size_t)b * kMom + threadIdx.x];     // fixed order: deterministic
+    s[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 100) {
+    int d = threadIdx.x / 10, e = threadIdx.x % 10;
+    if (d > e) { const int t = d; d = e; e = t; }
+    const int k = d * 10 - d * (d - 1) / 2 + (e - d);
+    mom[threadIdx.x] = s[k];
+  }
+}
+
+struct PrepLayout { size_t hl, mom, flag, scratch, total; };
+static PrepLayout prep_layout(int P, int N) {
+  PrepLayout l;
+  l.hl = 0;
+  l.mom = align_up((size_t)P * N * 48);
+  l.flag = l.mom + align_up(100 * sizeof(double));
+  l.scratch = l.flag + kAlign;
+  l.total = l.scratch + align_up((size_t)kPrepBlocks * kMom * sizeof(double));
+  return l;
+}
+
+}  // namespace padk
+
+bool pfn_pad_supported(int N, int C, int P) {
+  return C == 64 && N >= 16 && N <= 256 && (N % 8) == 0 && (P % 2) == 0 && padk::smem_plan(N).stages >= 2;
+}
+
+size_t mean_prepared_bytes(int P, int N) { return padk::prep_layout(P, N).total; }
+const double* mean_prepared_moments(const void* prep, int P, int N) {
+  return reinterpret_cast<const double*>((const char*)prep + padk::prep_layout(P, N).mom);
+}
+const int* mean_prepared_flag(const void* prep, int P, int N) {
+  return reinterpret_cast<const int*>((const char*)prep + padk::prep_layout(P, N).flag);
+}
+
+int mean_prepare(const float* d_mean, int P, int N, void* d_prep, size_t bytes, cudaStream_t st) {
+  using namespace padk;
+  if (d_mean == nullptr || d_prep == nullptr || P < 1 || N < 1 || ((uintptr_t)d_prep % kAlign) != 0) return PP_ERR_INVALID_ARG;
+  const PrepLayout l = prep_layout(P, N);
+  if (bytes < l.total) return PP_ERR_WORKSPACE;
+  char* base = (char*)d_prep;
+  PP_CUDA(cudaMemsetAsync(base + l.flag, 0, sizeof(int), st));
+  PP_KERNEL("k_mean_prepare", st,
+            k_mean_prepare<<<kPrepBlocks, 256, 0, st>>>(d_mean, P, N, (unsigned char*)base + l.hl, (double*)(base + l.scratch),
+                                                        (int*)(base + l.flag)));
+  PP_KERNEL("k_mean_moments", st, k_mean_moments<<<1, 128, 0, st>>>((const double*)(base + l.scratch), kPrepBlocks,
+                                                                   (double*)(base + l.mom)));
+  return PP_OK;
+}
+
+// padding pass over the prepared operand: padtab [P][3][64], partials [nblocks][2][64] (training only)
+int launch_pad_tc(const void* d_prep, int P, int N, const float* w, const float* bias, const float* bn_w, int training,
+                  float* padtab, double* partials, int nblocks, int* range_flag, cudaStream_t st) {
+  using namespace padk;
+  const Smem sp = smem_plan(N);
+  if (sp.stages < 2) return PP_ERR_UNSUPPORTED;
+  const unsigned char* hl = (const unsigned char*)d_prep + prep_layout(P, N).hl;
+  PP_CUDA(cudaMemsetAsync(range_flag, 0, sizeof(int), st));
+  if (training) {
+    PP_CUDA(cudaFuncSetAttribute(k_pfn_pad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+    PP_KERNEL("k_pfn_pad_tc", st,
+              (k_pfn_pad_tc<true><<<nblocks, kThreads, sp.total, st>>>(hl, P, N, w, bias, bn_w, padtab, partials, range_flag)));
+  } else {
+    PP_CUDA(cudaFuncSetAttribute(k_pfn_pad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+    PP_KERNEL("k_pfn_pad_tc", st,
+              (k_pfn_pad_tc<false><<<nblocks, kThreads, sp.total, st>>>(hl, P, N, w, bias, bn_w, padtab, partials, range_flag)));
+  }
+  return PP_OK;
+}
+
+}  // namespace pp

@@ -740,8 +740,8 @@ static int pillarize_impl(const T* pts, long long sp, long long sc, const int64_
 // pp_input_path: K1 stages + (optional) dense emit + sparse PFN + canvas
 template <typename T>
 static int input_path_impl(const T* pts, long long sp, long long sc, const int64_t* h_off, int B,
-                           const pp_grid* grid, int N, int P, const float* d_mean, int C, const PfnParams& prm,
-                           int H, int W, float* d_canvas, float* d_x, int64_t* d_indices,
+                           const pp_grid* grid, int N, int P, const float* d_mean, const void* d_mean_prep, int C,
+                           const PfnParams& prm, int H, int W, float* d_canvas, float* d_x, int64_t* d_indices,
                            int32_t* d_num_pillars, int32_t* d_status, void* d_ws, size_t ws_bytes,
                            int stages, cudaStream_t st) {
   GridDev g;
@@ -780,7 +780,7 @@ static int input_path_impl(const T* pts, long long sp, long long sc, const int64
   CompactPillars cp;
   cp.sw = sw; cp.P = P; cp.N = N;
   cp.feat_c = ws.feat_c; cp.pil_cnt = ws.pil_cnt; cp.pil_off = ws.pil_off;
-  cp.num_pillars = d_num_pillars; cp.data_mean = d_mean;
+  cp.num_pillars = d_num_pillars; cp.data_mean = d_mean; cp.mean_prepared = d_mean != nullptr ? d_mean_prep : nullptr;
   return pfn_sparse_scatter(cp, d_indices, C, prm, H, W, d_canvas, d_status, (char*)d_ws + k1_bytes,
                             ws_bytes - k1_bytes, st);
 }
@@ -858,15 +858,28 @@ int pp_pillarize(const void* d_points, int32_t point_dtype, int64_t stride_point
 }
 
 size_t pp_input_path_workspace_bytes(int32_t n_sweeps, int64_t total_points, const pp_grid* grid,
-                                     int32_t max_pillars, int32_t C, int32_t canvas_h, int32_t canvas_w) {
+                                     int32_t max_points_per_pillar, int32_t max_pillars, int32_t C, int32_t canvas_h,
+                                     int32_t canvas_w, int32_t prepare_in_workspace) {
   const size_t k1 = pp_pillarize_workspace_bytes(n_sweeps, total_points, grid, max_pillars);
-  if (k1 == 0 || C < 1 || canvas_h < 1 || canvas_w < 1) return 0;
-  return k1 + pp::pfn_sparse_workspace_bytes(n_sweeps, max_pillars, C, canvas_h, canvas_w);
+  if (k1 == 0 || C < 1 || canvas_h < 1 || canvas_w < 1 || max_points_per_pillar < 1) return 0;
+  return k1 + pp::pfn_sparse_workspace_bytes(n_sweeps, max_pillars, max_points_per_pillar, C, canvas_h, canvas_w,
+                                             prepare_in_workspace != 0);
+}
+
+size_t pp_mean_prepared_bytes(int32_t max_pillars, int32_t max_points_per_pillar) {
+  if (max_pillars < 1 || max_points_per_pillar < 1) return 0;
+  return pp::mean_prepared_bytes(max_pillars, max_points_per_pillar);
+}
+
+int pp_mean_prepare(const float* d_data_mean, int32_t max_pillars, int32_t max_points_per_pillar, void* d_prepared,
+                    size_t prepared_bytes, pp_stream_t stream) {
+  return pp::mean_prepare(d_data_mean, max_pillars, max_points_per_pillar, d_prepared, prepared_bytes, (cudaStream_t)stream);
 }
 
 int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_point, int64_t stride_col,
                   const int64_t* h_sweep_offsets, int32_t n_sweeps, const pp_grid* grid,
-                  int32_t max_points_per_pillar, int32_t max_pillars, const float* d_data_mean, int32_t C,
+                  int32_t max_points_per_pillar, int32_t max_pillars, const float* d_data_mean,
+                  const void* d_mean_prepared, int32_t C,
                   const float* d_conv_w, const float* d_conv_b, const float* d_bn_w, const float* d_bn_b,
                   float* d_running_mean, float* d_running_var, int64_t* d_num_batches_tracked,
                   int32_t training, float momentum, float eps, int32_t canvas_h, int32_t canvas_w,
@@ -880,12 +893,12 @@ int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_poin
                     d_num_batches_tracked, training, momentum, eps};
   if (point_dtype == PP_F32)
     return pp::input_path_impl<float>((const float*)d_points, stride_point, stride_col, h_sweep_offsets,
-                                      n_sweeps, grid, max_points_per_pillar, max_pillars, d_data_mean, C, prm,
+                                      n_sweeps, grid, max_points_per_pillar, max_pillars, d_data_mean, d_mean_prepared, C, prm,
                                       canvas_h, canvas_w, d_canvas, d_x, d_indices, d_num_pillars, d_status,
                                       d_workspace, workspace_bytes, stages, st);
   if (point_dtype == PP_F64)
     return pp::input_path_impl<double>((const double*)d_points, stride_point, stride_col, h_sweep_offsets,
-                                       n_sweeps, grid, max_points_per_pillar, max_pillars, d_data_mean, C, prm,
+                                       n_sweeps, grid, max_points_per_pillar, max_pillars, d_data_mean, d_mean_prepared, C, prm,
                                        canvas_h, canvas_w, d_canvas, d_x, d_indices, d_num_pillars, d_status,
                                        d_workspace, workspace_bytes, stages, st);
   return PP_ERR_INVALID_ARG;
@@ -924,7 +937,7 @@ int pp_input_path_backward(const int64_t* h_sweep_offsets, int32_t n_sweeps, con
   CompactPillars cp;
   cp.sw = sw; cp.P = P; cp.N = N;
   cp.feat_c = ws.feat_c; cp.pil_cnt = ws.pil_cnt; cp.pil_off = ws.pil_off;
-  cp.num_pillars = d_num_pillars; cp.data_mean = d_data_mean;
+  cp.num_pillars = d_num_pillars; cp.data_mean = d_data_mean; cp.mean_prepared = nullptr;
   return pfn_sparse_backward(cp, d_indices, C, d_conv_w, d_conv_b, d_bn_w, d_running_mean, d_running_var, training, eps,
                              canvas_h, canvas_w, d_grad_canvas, d_grad_conv_w, d_grad_conv_b, d_grad_bn_w, d_grad_bn_b,
                              d_workspace, workspace_bytes, st);

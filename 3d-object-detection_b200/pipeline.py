@@ -110,6 +110,7 @@ class InputPath:
             if dm.numel() != 9 * c.max_pillars * c.max_points_per_pillar:
                 raise _lib.PPError("data_mean must have 9*P*N elements (make_means.py:28)")
             self.data_mean = dm.to(self.device)
+        self.mean_prepared = None      # pp_mean_prepare's output, made on first use of the fused path
         self.net = PPFeatureScatter(c.feature_net_in, c.feature_net_out, c.canvas_height,
                                     c.canvas_width).to(self.device)
         if pfn_params is not None:
@@ -208,8 +209,28 @@ class InputPath:
 
     def fused_supported(self, n_sweeps):
         c = self.cfg
-        return (1 <= n_sweeps <= _lib.PP_MAX_SWEEPS and c.feature_net_out == 64 and c.max_points_per_pillar <= 255
+        return (1 <= n_sweeps <= _lib.PP_MAX_SWEEPS and c.feature_net_out == 64 and 16 <= c.max_points_per_pillar <= 255
                 and c.max_points_per_pillar % 8 == 0 and c.max_pillars % 2 == 0)
+
+    def prepare_mean(self):
+        """pp_mean_prepare once per data_mean: the fp16-split tensor-core operand + input moments of the fused
+        path's padding pass (pillar_means.pkl is a constant of the dataset)."""
+        if self.data_mean is None or self.mean_prepared is not None:
+            return self.mean_prepared
+        L = _lib.load()
+        c = self.cfg
+        n = L.pp_mean_prepared_bytes(c.max_pillars, c.max_points_per_pillar)
+        buf = torch.empty(n + 256, dtype=torch.uint8, device=self.device)
+        buf = buf[(-buf.data_ptr()) % 256:][:n]
+        with _runtime.on_device(self.device):
+            rc = L.pp_mean_prepare(self.data_mean.data_ptr(), c.max_pillars, c.max_points_per_pillar, buf.data_ptr(), n,
+                                   _runtime.stream_ptr(self.device))
+        _lib.check(rc, "pp_mean_prepare")
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._mean_ready = ev
+        self.mean_prepared = buf
+        return buf
 
     def pillarize_encode(self, points, offsets, out=None, want_x=False, stages=3):
         """points/offsets as in ``pillarize``.  Returns (canvas, inds, n_pillars[, x]): the canvas of
@@ -247,7 +268,12 @@ class InputPath:
             x = None
         net = self.net
         grid = self._grid_struct()
-        nbytes = L.pp_input_path_workspace_bytes(B, T, grid, P, C, H, W)
+        prep = self.mean_prepared
+        if prep is None and self.data_mean is not None:
+            prep = self.prepare_mean()
+        if prep is not None:
+            torch.cuda.current_stream(dev).wait_event(self._mean_ready)
+        nbytes = L.pp_input_path_workspace_bytes(B, T, grid, N, P, C, H, W, 0)
         ws = _runtime.workspace(nbytes, dev, "input_path")
         status = _runtime.status_word(dev)
         momentum, eps = _bn_args(net.bn1)
@@ -259,7 +285,8 @@ class InputPath:
             rc = L.pp_input_path(
                 points.data_ptr() if T > 0 else None, dt, points.stride(0), points.stride(1),
                 _lib.i64_array(offsets), B, grid, N, P,
-                self.data_mean.data_ptr() if self.data_mean is not None else None, C,
+                self.data_mean.data_ptr() if self.data_mean is not None else None,
+                prep.data_ptr() if prep is not None else None, C,
                 w.data_ptr(), net.conv1.bias.data_ptr(), net.bn1.weight.data_ptr(),
                 net.bn1.bias.data_ptr(), net.bn1.running_mean.data_ptr(),
                 net.bn1.running_var.data_ptr(), nbt.data_ptr() if nbt is not None else None,

@@ -82,29 +82,46 @@ int pp_last_cuda_error(void);
  * materialised unless d_x is non-NULL.  Same canvas as pp_pillarize + pp_pfn_scatter up to fp32
  * summation order (model/model.py:31-40,53-62; BatchNorm statistics over all B*P*N slots, padding
  * included).  It uses that a padding slot holds 0 - data_mean[d,p,n] in every sweep: the padding
- * slots are evaluated once per (p,n) on the tensor cores (with one suffix maximum per sweep), the
- * ~1.3 % of slots that hold a point are evaluated separately (one padding pass per 8 sweeps).
+ * slots are evaluated once per (p,n) on the tensor cores, whatever the batch size (suffix extremes at the
+ * slot boundaries 4 / 16 / 48 + BatchNorm sums), the ~1.3 % of slots that hold a point -- and the few
+ * padding slots between a pillar's count and the next boundary -- are evaluated separately.
  * Supported: 1 <= n_sweeps <= PP_MAX_SWEEPS, C = 64,
- * max_points_per_pillar <= 255 and a multiple of 8, max_pillars even; otherwise PP_ERR_UNSUPPORTED
+ * max_points_per_pillar in [16, 255] and a multiple of 8, max_pillars even; otherwise PP_ERR_UNSUPPORTED
  * (call pp_pillarize + pp_pfn_scatter).  d_indices [B,P,3] int64 and d_num_pillars [B] int32 are
  * outputs as in pp_pillarize.  A data_mean value or weight outside the fp16 range of the padding
  * pass raises PP_STATUS_RANGE in *d_status.
+ * d_mean_prepared: the output of pp_mean_prepare for d_data_mean (pillar_means.pkl is a constant of the
+ * dataset, make_means.py: prepare it once).  NULL with a non-NULL d_data_mean: the operand is prepared inside
+ * the workspace on every call (ask pp_input_path_workspace_bytes with prepare_in_workspace = 1); correct, but
+ * it costs a streaming pass over data_mean per call.
  * stages: PP_STAGE_PILLARIZE | PP_STAGE_ENCODE (3) runs everything.  A streaming caller may issue the
  * two stages separately (same arguments, same workspace) -- e.g. the pillarize stage of batch k+1 on
  * one stream while the encode stage of batch k runs on another; with training != 0 the encode stages
  * of successive batches must be ordered by the caller (they update the running statistics). */
 enum { PP_STAGE_PILLARIZE = 1, PP_STAGE_ENCODE = 2 };
 size_t pp_input_path_workspace_bytes(int32_t n_sweeps, int64_t total_points, const pp_grid* grid,
-                                     int32_t max_pillars, int32_t C, int32_t canvas_h, int32_t canvas_w);
+                                     int32_t max_points_per_pillar, int32_t max_pillars, int32_t C, int32_t canvas_h,
+                                     int32_t canvas_w, int32_t prepare_in_workspace);
 int pp_input_path(const void* d_points, int32_t point_dtype, int64_t stride_point, int64_t stride_col,
                   const int64_t* h_sweep_offsets, int32_t n_sweeps, const pp_grid* grid,
-                  int32_t max_points_per_pillar, int32_t max_pillars, const float* d_data_mean, int32_t C,
+                  int32_t max_points_per_pillar, int32_t max_pillars, const float* d_data_mean,
+                  const void* d_mean_prepared, int32_t C,
                   const float* d_conv_w, const float* d_conv_b, const float* d_bn_w, const float* d_bn_b,
                   float* d_running_mean, float* d_running_var, int64_t* d_num_batches_tracked,
                   int32_t training, float momentum, float eps, int32_t canvas_h, int32_t canvas_w,
                   float* d_canvas, float* d_x, int64_t* d_indices, int32_t* d_num_pillars,
                   int32_t* d_status, void* d_workspace, size_t workspace_bytes, int32_t stages,
                   pp_stream_t stream);
+
+/* The per-slot normalisation constant of data/dataset.py:99-105 (pillar_means.pkl, make_means.py:28-37) in the
+ * form the padding pass of pp_input_path consumes: x = 0 - data_mean[d,p,n] split into two fp16 pieces and laid
+ * out as the tensor-core operand ([P][3][N][8] halves, 48 bytes per slot), plus the first and second moments of x
+ * over all (p,n) in float64 (they turn the padding slots' BatchNorm sums into sums of |y| and y|y|) and a range
+ * flag (|x| >= 2^15).  d_prepared: pp_mean_prepared_bytes() bytes, 256-byte aligned, owned by the caller; valid
+ * for this data_mean, max_pillars and max_points_per_pillar until overwritten.  Deterministic. */
+size_t pp_mean_prepared_bytes(int32_t max_pillars, int32_t max_points_per_pillar);
+int pp_mean_prepare(const float* d_data_mean, int32_t max_pillars, int32_t max_points_per_pillar, void* d_prepared,
+                    size_t prepared_bytes, pp_stream_t stream);
 
 /* Backward of pp_input_path with respect to conv1 / bn1 (the fused path made trainable): the same gradients
  * pp_pfn_backward produces from the dense x, computed from the forward's compact per-point state -- x is never

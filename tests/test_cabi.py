@@ -84,11 +84,16 @@ def test_input_path_workspace_and_validation_without_gpu():
     L = _lib.load()
     grid = pp_b200.PPConfig().grid()
     k1 = L.pp_pillarize_workspace_bytes(4, 280000, grid, 24000)
-    n = L.pp_input_path_workspace_bytes(4, 280000, grid, 24000, 64, 600, 600)
-    assert n > k1 + 4 * 24000 * 3 * 64 * 4                     # K1 state + ext rows of the sparse PFN
-    assert L.pp_input_path_workspace_bytes(4, 280000, grid, 24000, 0, 600, 600) == 0
-    assert L.pp_input_path_workspace_bytes(0, 280000, grid, 24000, 64, 600, 600) == 0
-    args = [None, 0, 4, 1, _lib.i64_array([0, 0]), 1, grid, 200, 24000, None, 64,
+    n = L.pp_input_path_workspace_bytes(4, 280000, grid, 200, 24000, 64, 600, 600, 0)
+    assert n > k1 + 4 * 24000 * 64 * 4 + 24000 * 3 * 64 * 4    # K1 state + ext rows + padding table of the sparse PFN
+    prep = L.pp_mean_prepared_bytes(24000, 200)
+    assert prep >= 24000 * 200 * 48 + 100 * 8                  # operand image (48 B per slot) + moments
+    assert L.pp_input_path_workspace_bytes(4, 280000, grid, 200, 24000, 64, 600, 600, 1) >= n + prep
+    assert L.pp_input_path_workspace_bytes(4, 280000, grid, 200, 24000, 0, 600, 600, 0) == 0
+    assert L.pp_input_path_workspace_bytes(0, 280000, grid, 200, 24000, 64, 600, 600, 0) == 0
+    assert L.pp_mean_prepared_bytes(0, 200) == 0
+    assert L.pp_mean_prepare(None, 24000, 200, None, 0, None) == 1     # PP_ERR_INVALID_ARG before any CUDA call
+    args = [None, 0, 4, 1, _lib.i64_array([0, 0]), 1, grid, 200, 24000, None, None, 64,
             None, None, None, None, None, None, None, 1, 0.1, 1e-5, 600, 600,
             None, None, None, None, None, None, 0, 3, None]
     assert L.pp_input_path(*args) == 1                           # NULL weights: PP_ERR_INVALID_ARG
