@@ -15,25 +15,27 @@
 //
 // Operand (pp_mean_prepare, once per data_mean): x = -mean split into fp16 pieces x = xh + xl, stored in the
 // exact shared-memory image of the UMMA B operand (K-major, no swizzle): per pillar three planes of
-// [N slots][8 halves = 16 B]
-//     plane 0: xh_0 .. xh_7      plane 1: xh_8, xl_0 .. xl_6      plane 2: xl_7, xl_8, 1, 1, 0, 0, 0, 0
+// [N slots][8 halves = 16 B], in memory order P2, P0, P1:
+//     P0: xh_0 .. xh_7      P1: xh_8, xl_0 .. xl_6      P2: xl_7, xl_8, 1, 1, xh_8, 0, 0, 0
 // so ONE contiguous cp.async.bulk per pillar pair fills a stage and no thread touches the data before the
 // tensor core does (the round-1 kernel spent ~235 issue cycles per pair and sub-partition converting fp32 rows).
 // 48 bytes per slot instead of 36 for the raw fp32 means.
 //
-// Contraction (fp32 accumulation in TMEM, M = 64 channels, N = the pillar's slots), W' = 256 W = Wh + Wl:
-//     A1 (K = 32): k 0..8 Wh_d | k 9..17 Wh_d | k 18 bh | k 19 bl | 0 ...   x  planes 0,1 | plane 2, zero plane
-//     A2 (K = 16): k 0..8 Wl_d | 0 ...                                       x  planes 0,1
+// Contraction (fp32 accumulation in TMEM, M = 64 channels, N = the pillar's slots, K = 32 = two k-steps),
+// W' = 256 W = Wh + Wl:
+//     k-step 0 = planes P0, P1:  k 0..8 Wh_d x xh_d | k 9..15 Wh_0..6 x xl_0..6
+//     k-step 1 = planes P2, P0:  k 16,17 Wh_7, Wh_8 x xl_7, xl_8 | k 18,19 bh, bl x 1, 1 | k 20 Wl_8 x xh_8 |
+//                                k 24..31 Wl_0..7 x xh_0..7      (P0 is read by both k-steps: no duplicate in HBM)
 // = 256 (W x + b) up to the dropped Wl*xl term (~2^-22 |w||x|); rows pre-multiplied by sign(gamma) so that only
-// a maximum is tracked.  The fourth k-chunk of A1's second k-step is a shared all-zero plane reached through the
-// descriptor's leading-dimension byte offset.
+// a maximum is tracked.  Four tcgen05.mma per pillar pair (a first version with a separate Wl operand needed six
+// and was bound by the tensor pipe: M = 64 runs at half rate, ~150 cycles per instruction).
 //
 // Roles (576 threads, one persistent CTA per SM, work unit = pair of adjacent pillars at TMEM lane offset 16):
 //   warps 0-15  epilogue, ALL on the same pair: lane quarter q = warp % 4, column range j = warp / 4; two TMEM
 //               accumulator buffers alternate, so the MMAs of pair k+1 run under the epilogue of pair k.
 //               The four column ranges of a row meet in shared memory; the j = 3 warp writes the table rows.
 //   warp 16     producer (one bulk copy per pair into an 8-stage ring)
-//   warp 17     TMEM allocation + MMA issuer (6 tcgen05.mma per pair)
+//   warp 17     TMEM allocation + MMA issuer (4 tcgen05.mma per pair)
 #include "tc_common.cuh"
 #include "internal.cuh"
 
@@ -47,23 +49,22 @@ constexpr int kProducerWarp = 16, kMmaWarp = 17;
 constexpr int kMaxStages = 8;
 constexpr int kAccCols = 256;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kABytes = 3 * 2048;          // A1 (two k-steps) + A2 (one k-step), 64 rows x 16 k fp16 each
+constexpr int kABytes = 2 * 2048;          // two k-steps of 64 rows x 16 k fp16
 
 struct Smem {
-  int a_off, stage_off, stage_bytes, stages, zero_off, part_off, stat_off, bar_off, total;
+  int a_off, stage_off, stage_bytes, stages, part_off, stat_off, bar_off, total;
 };
 
 __host__ __device__ inline Smem smem_plan(int N) {
   Smem s;
   s.a_off = 0;
-  s.stage_off = kABytes;                               // 6144: 128-byte aligned
+  s.stage_off = kABytes;                               // 4096: 128-byte aligned
   s.stage_bytes = 2 * 3 * N * 16;                      // pair of pillars x 3 planes x N x 16 B
-  const int fixed = kABytes + N * 16 + 2 * 4 * 128 * 4 + 4 * 2 * 64 * 8 + 512 + 128;
+  const int fixed = kABytes + 4 * 4 * 128 * 4 + 4 * 2 * 64 * 8 + 512 + 128;
   int st = (kSmemBudget - fixed) / s.stage_bytes;
   s.stages = st > kMaxStages ? kMaxStages : st;
-  s.zero_off = s.stage_off + s.stages * s.stage_bytes;
-  s.part_off = s.zero_off + N * 16;
-  s.stat_off = s.part_off + 2 * 4 * 128 * 4;
+  s.part_off = s.stage_off + s.stages * s.stage_bytes;
+  s.stat_off = s.part_off + 4 * 4 * 128 * 4;
   s.bar_off = s.stat_off + 4 * 2 * 64 * 8;
   s.total = s.bar_off + 512 + 128;                     // +128: manual base alignment
   return s;
@@ -118,6 +119,7 @@ template <bool TRAIN>
 __device__ __forceinline__ void consume_range(uint32_t taddr, int a, int b, float& m0, float& m1, float* S, float* Q) {
   uint32_t v[32];
   int col = a;
+#pragma unroll
   for (; col + 32 <= b; col += 32) {
     PP_TMEM_LD32(taddr + col, v);
     tmem_ld_wait();
@@ -136,11 +138,13 @@ __device__ __forceinline__ void consume_range(uint32_t taddr, int a, int b, floa
   }
 }
 
-template <bool TRAIN>
+// NT: compile-time copy of N for the reference shape (the column loops unroll completely), 0 = any supported N
+template <bool TRAIN, int NT>
 __global__ void __launch_bounds__(kThreads, 1)
 k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
              const float* __restrict__ conv_w, const float* __restrict__ conv_b, const float* __restrict__ bn_w,
-             float* __restrict__ padtab, double* __restrict__ partials, int* __restrict__ range_flag) {
+             float* __restrict__ padtab, double* __restrict__ partials, int* __restrict__ range_flag,
+             long long* __restrict__ prof, int dbg) {
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((128u - (smem_u32(smem_unaligned) & 127u)) & 127u);
   const Smem sp = smem_plan(N);
@@ -152,9 +156,9 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
   uint64_t* empty = bars + kMaxStages;              // [kMaxStages] stage read by the MMAs
   uint64_t* acc_full = bars + 2 * kMaxStages;       // [2]
   uint64_t* acc_empty = acc_full + 2;               // [2]
-  uint64_t* pbar = acc_empty + 2;                   // [2 buffers][4 quarters] partial maxima of ranges 0..2 published
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pbar + 8);
-  float* s_part = reinterpret_cast<float*>(smem + sp.part_off);      // [2][4][128]
+  uint64_t* pbar = acc_empty + 2;                   // [4 slots][4 quarters] partial maxima of ranges 0..2 published
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pbar + 16);
+  float* s_part = reinterpret_cast<float*>(smem + sp.part_off);      // [4 slots][4][128]
   double* s_stat = reinterpret_cast<double*>(smem + sp.stat_off);    // [4 ranges][sum |y|, sum y|y|][64]
 
   const int pairs = P >> 1;                          // host guarantees P even
@@ -164,38 +168,40 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
   if (threadIdx.x == 0) {
     for (int i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
-    for (int i = 0; i < 8; ++i) mbar_init(&pbar[i], 3);
+    for (int i = 0; i < 16; ++i) mbar_init(&pbar[i], 3);
     fence_barrier_init();
   }
-  // A tiles: 64 x 16 fp16 per k-step, K-major, no swizzle: core matrix = 8 rows x 16 B (8 k), k-chunk stride
-  // 128 B, row-group stride 256 B.  Tile 0, 1 = A1 (k 0..15, 16..31), tile 2 = A2.
+  // A tile: 64 x 32 fp16, K-major, no swizzle: core matrix = 8 rows x 16 B (8 k), k-chunk stride 128 B,
+  // row-group stride 256 B, k-step stride 2048 B
   {
     bool bad = false;
-    for (int idx = threadIdx.x; idx < 3 * 64 * 16; idx += kThreads) {
-      const int t = idx >> 10, m = (idx >> 4) & 63, kk = idx & 15;
-      const int K = t == 1 ? 16 + kk : kk;
+    for (int idx = threadIdx.x; idx < 64 * 32; idx += kThreads) {
+      const int m = idx >> 5, K = idx & 31;
       const float sgn = bn_w[m] < 0.f ? -1.f : 1.f;
+      int d = -1;
+      bool lo = false;
+      if (K < 9) d = K;                           // Wh_d x xh_d
+      else if (K < 16) d = K - 9;                 // Wh_d x xl_d, d = 0..6
+      else if (K < 18) d = K - 9;                 // Wh_7, Wh_8 x xl_7, xl_8
+      else if (K == 20) { d = 8; lo = true; }     // Wl_8 x xh_8
+      else if (K >= 24) { d = K - 24; lo = true; }  // Wl_d x xh_d, d = 0..7
       float v = 0.f;
-      if (t < 2) {
-        if (K < 18) {
-          const float w = 256.f * conv_w[m * 9 + (K < 9 ? K : K - 9)];
-          bad |= !(fabsf(w) < 32768.f);
-          v = h_value(h_bits(w));
-        } else if (K < 20) {
-          const float bb = 256.f * conv_b[m];
-          bad |= !(fabsf(bb) < 32768.f);
-          const float bh = h_value(h_bits(bb));
-          v = K == 18 ? bh : (bb - bh);
-        }
-      } else if (K < 9) {
-        const float w = 256.f * conv_w[m * 9 + K];
-        v = w - h_value(h_bits(w));
+      if (d >= 0) {
+        const float w = 256.f * conv_w[m * 9 + d];
+        bad |= !(fabsf(w) < 32768.f);
+        const float wh = h_value(h_bits(w));
+        v = lo ? (w - wh) : wh;
+      } else if (K == 18 || K == 19) {
+        const float bb = 256.f * conv_b[m];
+        bad |= !(fabsf(bb) < 32768.f);
+        const float bh = h_value(h_bits(bb));
+        v = K == 18 ? bh : (bb - bh);
       }
-      *reinterpret_cast<unsigned short*>(smem + sp.a_off + t * 2048 + (m >> 3) * 256 + (kk >> 3) * 128 + (m & 7) * 16 + (kk & 7) * 2) =
+      const int j = K >> 4, kk = K & 15;
+      *reinterpret_cast<unsigned short*>(smem + sp.a_off + j * 2048 + (m >> 3) * 256 + (kk >> 3) * 128 + (m & 7) * 16 + (kk & 7) * 2) =
           h_bits(sgn * v);
     }
     if (bad) atomicOr(range_flag, 1);
-    for (int idx = threadIdx.x; idx < N * 4; idx += kThreads) reinterpret_cast<uint32_t*>(smem + sp.zero_off)[idx] = 0u;
   }
   fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
   if (warp == kMmaWarp) tmem_alloc(tmem_holder, 512);
@@ -203,50 +209,73 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // development timing (pp_debug.h): per-role wait cycles of CTA 0
+  const bool pon = prof != nullptr && blockIdx.x == 0;
+  long long pacc[4] = {0, 0, 0, 0};
+  const long long prole0 = pon ? clock64() : 0;
 
   if (warp == kProducerWarp) {
-    // ===== producer: one contiguous bulk copy per pair =====
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 1;                                  // parity to wait on empty[] (first pass falls through)
-      const uint32_t bytes = (uint32_t)sp.stage_bytes;
-      for (int it = 0; it < my_pairs; ++it) {
-        const size_t pair = (size_t)blockIdx.x + (size_t)it * gridDim.x;
-        mbar_wait(&empty[s], ph);
+    // ===== producer: one contiguous bulk copy per pair.  The whole warp runs the loop converged and one elected
+    // lane issues (elect.sync): the loop state stays in uniform registers.  A lane-0-only role compiled into
+    // ELECT / BRA.U.ANY retry loops around every uniform-datapath instruction.
+    int s = 0;
+    uint32_t ph = 1;                                  // parity to wait on empty[] (first pass falls through)
+    const uint32_t bytes = (uint32_t)sp.stage_bytes;
+    for (int it = 0; it < my_pairs; ++it) {
+      const size_t pair = (size_t)blockIdx.x + (size_t)it * gridDim.x;
+      mbar_wait_t(&empty[s], ph, pon, pacc[0]);
+      if (elect_one()) {
+        if (dbg & 16) { mbar_arrive(&full[s]); }
+        else
         mbar_expect_tx(&full[s], bytes);
-        bulk_g2s(smem + sp.stage_off + s * sp.stage_bytes, hl + pair * bytes, bytes, &full[s]);
-        if (++s == R) { s = 0; ph ^= 1u; }
+        if (dbg & 16) {
+        } else if (dbg & 8) {
+          const uint32_t part = bytes / 6;
+          for (int k = 0; k < 6; ++k)
+            bulk_g2s(smem + sp.stage_off + s * sp.stage_bytes + k * part, hl + pair * bytes + k * part, part, &full[s]);
+        } else {
+          bulk_g2s(smem + sp.stage_off + s * sp.stage_bytes, hl + pair * bytes, bytes, &full[s]);
+        }
       }
+      __syncwarp();
+      if (++s == R) { s = 0; ph ^= 1u; }
     }
   } else if (warp == kMmaWarp) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      // instruction descriptor (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): fp32 accumulate, A = B = f16,
-      // both K-major, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
-      const uint32_t a_addr = smem_u32(smem + sp.a_off);
-      const uint32_t zero_addr = smem_u32(smem + sp.zero_off);
-      const uint32_t plane = (uint32_t)N * 16u;
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < my_pairs; ++it) {
-        const int e = it & 1;
-        mbar_wait(&full[s], ph);
-        mbar_wait(&acc_empty[e], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t b_addr = smem_u32(smem + sp.stage_off + s * sp.stage_bytes) + (uint32_t)h * 3u * plane;
-          const uint32_t d_tmem = tmem_base + ((uint32_t)(h * 16) << 16) + (uint32_t)(e * kAccCols);
-          umma_f16(d_tmem, smem_desc(a_addr, 128, 256), smem_desc(b_addr, plane, 128), idesc, 0u);
-          umma_f16(d_tmem, smem_desc(a_addr + 2048, 128, 256),
-                   smem_desc(b_addr + 2u * plane, zero_addr - (b_addr + 2u * plane), 128), idesc, 1u);
-          umma_f16(d_tmem, smem_desc(a_addr + 4096, 128, 256), smem_desc(b_addr, plane, 128), idesc, 1u);
+    // ===== MMA issuer (converged warp, one elected lane issues) =====
+    // instruction descriptor (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): fp32 accumulate, A = B = f16,
+    // both K-major, N>>3, M>>4
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+    const uint32_t a_addr = smem_u32(smem + sp.a_off);
+    const uint32_t plane = (uint32_t)N * 16u;
+    const uint64_t a0 = smem_desc(a_addr, 128, 256), a1 = smem_desc(a_addr + 2048, 128, 256);
+    // B descriptors differ only in the start-address field (bits 0..13, units of 16 bytes)
+    const uint64_t b_base = smem_desc(smem_u32(smem + sp.stage_off), plane, 128);
+    const uint32_t plane16 = plane >> 4, stage16 = (uint32_t)sp.stage_bytes >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < my_pairs; ++it) {
+      const int e = it & 1;
+      mbar_wait_spin_t(&full[s], ph, pon, pacc[0]);
+      mbar_wait_spin_t(&acc_empty[e], ((uint32_t)(it >> 1) & 1u) ^ 1u, pon, pacc[1]);
+      tc_fence_after();
+      const long long tq0 = pon ? clock64() : 0;
+      if (elect_one()) {
+        const uint64_t b0 = b_base + (uint64_t)((uint32_t)s * stage16);       // pillar h = 0: P2 | P0 | P1
+        const uint32_t d0 = tmem_base + (uint32_t)(e * kAccCols);
+        const uint64_t b1 = b0 + 3u * plane16;                                // pillar h = 1
+        const uint32_t d1 = d0 + (16u << 16);
+        if (!(dbg & 2)) {
+          umma_f16(d0, a0, b0 + plane16, idesc, 0u);                          // k-step 0: P0, P1
+          umma_f16(d0, a1, b0, idesc, 1u);                                    // k-step 1: P2, P0
+          umma_f16(d1, a0, b1 + plane16, idesc, 0u);
+          umma_f16(d1, a1, b1, idesc, 1u);
         }
         umma_commit(&empty[s]);       // stage free once these MMAs have read it
         umma_commit(&acc_full[e]);    // accumulators ready for the epilogue
-        if (++s == R) { s = 0; ph ^= 1u; }
       }
+      __syncwarp();
+      if (pon) pacc[2] += clock64() - tq0;
+      if (++s == R) { s = 0; ph ^= 1u; }
     }
   } else {
     // ===== epilogue: one (pillar-of-pair, channel) row per thread over this warp's column range =====
@@ -262,18 +291,71 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
     const int c1 = e1 + 8 * (g / 3), c2 = c1 + 8 * (g / 3);
     const int n0 = j == 0 ? 0 : (j == 1 ? e1 : (j == 2 ? c1 : c2));
     const int n1 = j == 0 ? e1 : (j == 1 ? c1 : (j == 2 ? c2 : N));
-    double accS = 0.0, accQ = 0.0;
+    // running sums of the visits as unevaluated fp32 pairs (hi + lo, TwoSum): the fp64 pipe stays out of the
+    // loop (ncu r2d: 13 % of the warps' stall samples sat on the per-visit F2F + DADD chain)
+    float sh = 0.f, sl = 0.f, qh = 0.f, ql = 0.f;
+    auto two_sum = [](float& hi, float& lo, float b) {
+      const float s = __fadd_rn(hi, b);
+      const float bb = __fsub_rn(s, hi);
+      lo = __fadd_rn(lo, __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(b, bb)));
+      hi = s;
+    };
     for (int it = 0; it < my_pairs; ++it) {
       const int e = it & 1;
       const uint32_t n = (uint32_t)(it >> 1);
-      mbar_wait(&acc_full[e], n & 1u);
+      mbar_wait_spin_t(&acc_full[e], n & 1u, pon, pacc[0]);
       tc_fence_after();
+      const long long tq0 = pon ? clock64() : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(e * kAccCols);
       float S[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
       float m0 = -INFINITY, m1 = -INFINITY, lo = -INFINITY;
-      if (j == 0) {
-        // slots 0..3 never enter a table row (a live pillar holds at least one point and k_pfn_real evaluates
-        // the slots below the first boundary itself); slots 4..15 only enter the first row
+      bool released = false;
+      // accumulator buffer back to the MMA issuer: all lanes' tcgen05.ld have completed (wait::ld is warp-wide)
+      auto release = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[e]);
+        released = true;
+      };
+      if (dbg & 4) {
+      } else if (NT == 200) {
+        // The warp's whole column block goes to registers first and the accumulator buffer is released BEFORE the
+        // arithmetic: the MMAs of the pair after next start ~700 cycles earlier.  With the buffer held until the
+        // end of the visit the hand-off chain (release -> MMA issue + execution -> commit -> epilogue wake-up,
+        // ~1200 cycles) was longer than one epilogue visit (~800) and the epilogue waited ~350 cycles per pair.
+        if (j == 0) {
+          // slots 0..3 never enter a table row (a live pillar holds at least one point and k_pfn_real evaluates
+          // the slots below the first boundary itself); slots 4..15 only enter the first row
+          uint32_t va[16], vb[32];
+          PP_TMEM_LD16(taddr, va);
+          PP_TMEM_LD32(taddr + 16, vb);
+          tmem_ld_wait();
+          release();
+          float a0 = -INFINITY, a1 = -INFINITY;
+          consume<16, 4, TRAIN>(va, a0, a1, S, Q);
+          lo = fmaxf(a0, a1);
+          consume<32, 0, TRAIN>(vb, m0, m1, S, Q);
+        } else if (j < 3) {
+          uint32_t va[32], vb[16];
+          const uint32_t t0 = taddr + (j == 1 ? 48u : 96u);
+          PP_TMEM_LD32(t0, va);
+          PP_TMEM_LD16(t0 + 32, vb);
+          tmem_ld_wait();
+          release();
+          consume<32, 0, TRAIN>(va, m0, m1, S, Q);
+          consume<16, 0, TRAIN>(vb, m0, m1, S, Q);
+        } else {
+          uint32_t va[32], vb[16], vc[8];
+          PP_TMEM_LD32(taddr + 144, va);
+          PP_TMEM_LD16(taddr + 176, vb);
+          PP_TMEM_LD8(taddr + 192, vc);
+          tmem_ld_wait();
+          release();
+          consume<32, 0, TRAIN>(va, m0, m1, S, Q);
+          consume<16, 0, TRAIN>(vb, m0, m1, S, Q);
+          consume<8, 0, TRAIN>(vc, m0, m1, S, Q);
+        }
+      } else if (j == 0) {
         uint32_t v[16];
         PP_TMEM_LD16(taddr, v);
         tmem_ld_wait();
@@ -284,20 +366,23 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
       } else {
         consume_range<TRAIN>(taddr, n0, n1, m0, m1, S, Q);
       }
+      if (!released) release();
       const float m = fmaxf(m0, m1);
-      tc_fence_before();
-      float* part = s_part + e * 512;
+      // the four column ranges of a row meet in shared memory; four slots (it & 3): a warp can only be two visits
+      // ahead of the j = 3 warp of its quarter when it writes a slot again (the accumulator hand-off orders them)
+      float* part = s_part + (it & 3) * 512;
+      uint64_t* pb = &pbar[(it & 3) * 4 + q];
       if (j < 3) {
         if (j == 0) { part[rowid] = fmaxf(lo, m); part[128 + rowid] = m; }
         else part[(j + 1) * 128 + rowid] = m;
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&pbar[e * 4 + q]); mbar_arrive(&acc_empty[e]); }
+        if (lane == 0) mbar_arrive(pb);
+        if (pon) pacc[1] += clock64() - tq0;
       } else {
-        mbar_wait(&pbar[e * 4 + q], n & 1u);
+        if (pon) pacc[1] += clock64() - tq0;
+        mbar_wait_spin_t(pb, (uint32_t)(it >> 2) & 1u, pon, pacc[2]);
         const float t = fmaxf(m, fmaxf(part[2 * 128 + rowid], part[3 * 128 + rowid]));
         const float r4 = fmaxf(part[rowid], t), r16 = fmaxf(part[128 + rowid], t);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[e]);
         // TMEM holds 256*s*y; rows of y's sign-selected extreme (max when gamma >= 0, min otherwise); an empty
         // suffix stays -inf (+inf after the sign): neutral for the consumer
         const size_t pillar = 2 * ((size_t)blockIdx.x + (size_t)it * gridDim.x) + h;
@@ -307,11 +392,12 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
         o[128] = sgn * t * (1.f / 256.f);
       }
       if (TRAIN) {
-        accS += (double)((S[0] + S[1]) + (S[2] + S[3]));
-        accQ += (double)((Q[0] + Q[1]) + (Q[2] + Q[3]));
+        two_sum(sh, sl, (S[0] + S[1]) + (S[2] + S[3]));
+        two_sum(qh, ql, (Q[0] + Q[1]) + (Q[2] + Q[3]));
       }
     }
     if (TRAIN) {
+      double accS = (double)sh + (double)sl, accQ = (double)qh + (double)ql;
       accS += __shfl_xor_sync(0xffffffffu, accS, 16);
       accQ += __shfl_xor_sync(0xffffffffu, accQ, 16);
       if (lane < 16) {
@@ -321,6 +407,10 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
     }
   }
 
+  if (pon && lane == 0) {
+    pacc[3] = clock64() - prole0;
+    for (int kq = 0; kq < 4; ++kq) prof[warp * 4 + kq] = pacc[kq];
+  }
   // ---- teardown ---------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
@@ -374,11 +464,11 @@ __global__ void __launch_bounds__(256) k_mean_prepare(const float* __restrict__ 
     w0.z = xh[4] | ((unsigned)xh[5] << 16); w0.w = xh[6] | ((unsigned)xh[7] << 16);
     w1.x = xh[8] | ((unsigned)xl[0] << 16); w1.y = xl[1] | ((unsigned)xl[2] << 16);
     w1.z = xl[3] | ((unsigned)xl[4] << 16); w1.w = xl[5] | ((unsigned)xl[6] << 16);
-    w2.x = xl[7] | ((unsigned)xl[8] << 16); w2.y = 0x3c003c00u; w2.z = 0u; w2.w = 0u;
+    w2.x = xl[7] | ((unsigned)xl[8] << 16); w2.y = 0x3c003c00u; w2.z = xh[8]; w2.w = 0u;
     uint4* o = reinterpret_cast<uint4*>(hl + ((size_t)p * 3 * N + n) * 16);
-    o[0] = w0;
-    o[N] = w1;
-    o[2 * N] = w2;
+    o[0] = w2;              // memory order P2, P0, P1
+    o[N] = w0;
+    o[2 * N] = w1;
   }
   if (bad) atomicOr(flag, 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -454,22 +544,31 @@ int mean_prepare(const float* d_mean, int P, int N, void* d_prep, size_t bytes, 
 }
 
 // padding pass over the prepared operand: padtab [P][3][64], partials [nblocks][2][64] (training only)
+extern int g_opt_pfn_tc_timing;
+extern int g_opt_pfn_tc_debug;
+long long* tc_prof_ptr();   // pfn_tc.cu
+
 int launch_pad_tc(const void* d_prep, int P, int N, const float* w, const float* bias, const float* bn_w, int training,
                   float* padtab, double* partials, int nblocks, int* range_flag, cudaStream_t st) {
   using namespace padk;
+  long long* prof = g_opt_pfn_tc_timing ? tc_prof_ptr() : nullptr;
   const Smem sp = smem_plan(N);
   if (sp.stages < 2) return PP_ERR_UNSUPPORTED;
   const unsigned char* hl = (const unsigned char*)d_prep + prep_layout(P, N).hl;
   PP_CUDA(cudaMemsetAsync(range_flag, 0, sizeof(int), st));
-  if (training) {
-    PP_CUDA(cudaFuncSetAttribute(k_pfn_pad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-    PP_KERNEL("k_pfn_pad_tc", st,
-              (k_pfn_pad_tc<true><<<nblocks, kThreads, sp.total, st>>>(hl, P, N, w, bias, bn_w, padtab, partials, range_flag)));
+#define PP_PAD(TR, NT)                                                                                              \
+  do {                                                                                                              \
+    PP_CUDA(cudaFuncSetAttribute(k_pfn_pad_tc<TR, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));     \
+    PP_KERNEL("k_pfn_pad_tc", st,                                                                                   \
+              (k_pfn_pad_tc<TR, NT><<<nblocks, kThreads, sp.total, st>>>(hl, P, N, w, bias, bn_w, padtab, partials, \
+                                                                         range_flag, prof, g_opt_pfn_tc_debug)));   \
+  } while (0)
+  if (N == 200) {
+    if (training) PP_PAD(true, 200); else PP_PAD(false, 200);
   } else {
-    PP_CUDA(cudaFuncSetAttribute(k_pfn_pad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-    PP_KERNEL("k_pfn_pad_tc", st,
-              (k_pfn_pad_tc<false><<<nblocks, kThreads, sp.total, st>>>(hl, P, N, w, bias, bn_w, padtab, partials, range_flag)));
+    if (training) PP_PAD(true, 0); else PP_PAD(false, 0);
   }
+#undef PP_PAD
   return PP_OK;
 }
 

@@ -47,6 +47,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 255u) == 0u && clock64() - t0 > kSpinLimit) __trap();
   }
 }
+// Latency-critical hand-offs: poll with plain try_wait.  A try_wait with a suspend-time hint parks the thread and
+// it wakes ~0.5 us after the phase completes (measured: k_pfn_pad_tc with neither MMAs nor epilogue arithmetic
+// took 56 us for 81 barrier round trips per CTA), which serialised every TMEM hand-off.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 4095u) == 0u && clock64() - t0 > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_spin_t(uint64_t* bar, uint32_t parity, bool on, long long& acc) {
+  if (!on) { mbar_wait_spin(bar, parity); return; }
+  const long long t = clock64();
+  mbar_wait_spin(bar, parity);
+  acc += clock64() - t;
+}
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool on, long long& acc) {
   if (!on) { mbar_wait(bar, parity); return; }
   const long long t = clock64();
@@ -56,6 +73,12 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// one lane of the (converged) warp, chosen by the hardware
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
