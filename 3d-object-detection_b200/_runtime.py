@@ -76,12 +76,11 @@ def status_word(device):
     return s
 
 
-def check_status(device, what):
-    """Synchronising read of the status word; raises on a set bit and clears it."""
-    s = status_word(device)
-    v = int(s.item())
+_polls = {}
+
+
+def _raise_status(v, what):
     if v:
-        s.zero_()
         msgs = []
         if v & _lib.STATUS_NEG_IOU:
             msgs.append("IOU < 0 (wrong corner winding; the reference exits the process here, "
@@ -96,3 +95,44 @@ def check_status(device, what):
             msgs.append("fused input path: data_mean / conv weight outside the fp16 range of the padding "
                         "pass; use pillarize + encode")
         raise _lib.PPError("%s: %s" % (what, "; ".join(msgs)))
+
+
+def check_status(device, what):
+    """Synchronising read of the status word; raises on a set bit and clears it."""
+    s = status_word(device)
+    v = int(s.item())
+    if v:
+        s.zero_()
+    st = _polls.get(_index(device if isinstance(device, torch.device) else torch.device(device)))
+    if st is not None:                                   # a pending deferred copy would report the same bits again
+        if st["ev"] is not None:
+            st["ev"].synchronize()
+        st["ev"] = None
+        st["pin"].zero_()
+    _raise_status(v, what)
+
+
+def poll_status(device, what):
+    """Deferred, non-blocking form of ``check_status`` for the asynchronous entry points (modules, target
+    assignment, loss): every call copies the status word to pinned memory on the current stream and raises if the
+    copy issued by an EARLIER call has completed with a bit set -- the error surfaces at the next call (or at
+    ``check_status``) instead of forcing a device synchronisation into every forward."""
+    dev = device if isinstance(device, torch.device) else torch.device(device)
+    idx = _index(dev)
+    s = status_word(dev)
+    st = _polls.get(idx)
+    if st is None:
+        st = _polls[idx] = {"pin": torch.zeros(1, dtype=torch.int32).pin_memory(), "ev": None, "what": what}
+    if st["ev"] is not None:
+        if not st["ev"].query():
+            return                                   # the previous copy is still in flight: look next time
+        v, prev = int(st["pin"][0]), st["what"]
+        st["ev"] = None
+        if v:
+            s.zero_()
+            st["pin"].zero_()
+            _raise_status(v, prev + " (reported by a later call)")
+    st["pin"].copy_(s, non_blocking=True)
+    st["ev"] = torch.cuda.Event()
+    st["ev"].record(torch.cuda.current_stream(dev))
+    st["what"] = what

@@ -111,8 +111,11 @@ class Positives(object):
         self.n_sweeps, self.n_anchors = int(n_sweeps), int(n_anchors)
 
     def dense(self):
-        """(cls [B,A,9], reg [B,A,9]) float32: what pp_assign_targets would have written (synchronises)."""
+        """(cls [B,A,9], reg [B,A,9]) float32: what pp_assign_targets would have written (synchronises; raises if
+        the list overflowed its capacity -- offsets are clamped to it, the dropped rows are lost)."""
         n = int(self.offsets[-1].item())
+        if self.anchor.is_cuda:
+            _runtime.check_status(self.anchor.device, "Positives.dense")
         B, A = self.n_sweeps, self.n_anchors
         cls = torch.zeros((B * A, 9), dtype=torch.float32, device=self.anchor.device)
         reg = torch.zeros((B * A, 9), dtype=torch.float32, device=self.anchor.device)
@@ -158,6 +161,7 @@ def assign_targets(anchors, g_corners, g_centers, g_wlh, g_yaw, g_cls, gt_offset
             cls.data_ptr(), reg.data_ptr(), top.data_ptr(), counts.data_ptr(), status.data_ptr(),
             ws.data_ptr(), ws.numel(), _runtime.stream_ptr(dev))
     _lib.check(rc, "pp_assign_targets")
+    _runtime.poll_status(dev, "assign_targets")
     return cls, reg, top[:Gt], counts
 
 
@@ -187,6 +191,7 @@ def _assign_targets_list(anchors, g_corners, g_centers, g_wlh, g_yaw, g_cls, gt_
             pos.anchor.data_ptr(), pos.cls.data_ptr(), pos.reg.data_ptr(), pos.offsets.data_ptr(), cap, None, None,
             top.data_ptr(), counts.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), _runtime.stream_ptr(dev))
     _lib.check(rc, "pp_assign_targets_list")
+    _runtime.poll_status(dev, "assign_targets(as_list=True): positives list capacity %d" % cap)
     return pos, None, top[:Gt], counts
 
 

@@ -297,8 +297,10 @@ __global__ void __launch_bounds__(64 * kFinSegs) k_bn_finalize(int C, int nparts
                                                      Affine* __restrict__ affine) {
   __shared__ double s_part[2][kFinSegs][64];
   const int c = threadIdx.x & 63, seg = threadIdx.x >> 6;
-  if (threadIdx.x == 0 && sf.range_flag != nullptr && *sf.range_flag != 0) atomicOr(sf.status, PP_STATUS_RANGE);
-  if (threadIdx.x == 0 && sf.range_flag2 != nullptr && *sf.range_flag2 != 0) atomicOr(sf.status, PP_STATUS_RANGE);
+  // a data_mean value or weight outside the fp16 range of the padding pass: the statistics of this pass are not
+  // valid -- report it and leave the running statistics untouched (the canvas of this call is invalid)
+  const bool out_of_range = (sf.range_flag != nullptr && *sf.range_flag != 0) || (sf.range_flag2 != nullptr && *sf.range_flag2 != 0);
+  if (threadIdx.x == 0 && out_of_range) atomicOr(sf.status, PP_STATUS_RANGE);
   if (training && c < C) {
     const int per = (nparts + kFinSegs - 1) / kFinSegs;
     const int k0 = seg * per, k1 = min(nparts, k0 + per);
@@ -376,9 +378,11 @@ __global__ void __launch_bounds__(64 * kFinSegs) k_bn_finalize(int C, int nparts
     var = Q / count - mean * mean;
     if (var < 0.0) var = 0.0;
     const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
-    running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
-    running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
-    if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+    if (!out_of_range) {
+      running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
+      running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
+      if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+    }
   } else {
     mean = (double)running_mean[c];
     var = (double)running_var[c];
@@ -714,20 +718,23 @@ static int build_map(const int64_t* d_inds, int B, int P, int H, int W, int* map
 // instead of once per sweep and keeps one suffix maximum per sweep; k_pfn_real below handles the
 // ~1.3 % of slots that hold a point.  Results equal the dense path's up to summation order.
 
-// k_pfn_real: the live pillars (~1.3 % of the slots hold a point).  One warp per live pillar, CPL channels per
-// lane, conv weights in registers (pre-multiplied by sign(gamma): f = s*y, so only a maximum is tracked).  For a
-// pillar with cnt points the warp evaluates
+// k_pfn_real: the live pillars (~1.3 % of the slots hold a point).  CPL channels per lane, conv weights in
+// registers (pre-multiplied by sign(gamma): f = s*y, so only a maximum is tracked).  For a pillar with cnt points
 //   slots n <  cnt : y_real and y_pad  -> extreme of y_real, statistics corrections g(y_real) - g(y_pad)
 //   slots cnt <= n < E : y_pad only    -> extreme over the padding slots below the next ladder boundary E
-// (E = 4, 16, 48 or N, see pfn_pad.cu) and takes the extreme over n >= E from the padding table.  Slots are
-// fetched 32 at a time with lanes = slots (features and per-slot means, 18 loads per lane), staged in a per-warp
-// shared-memory tile as {x_real[9], x_pad[9]} records and read back as warp-uniform LDS.128 broadcasts.  The
-// loads of the NEXT pillar (metadata two pillars ahead, slot data and table row one pillar ahead) are in flight
-// while the current one is evaluated: the round-1 kernel paid three dependent memory round trips per pillar
-// (86 us for 66 k pillars at 34 % occupancy).
+// (E = 4, 16, 48 or N, see pfn_pad.cu) and the extreme over n >= E comes from the padding table.
+// Work unit = group of 8 consecutive live pillars, handed out by an atomic counter (the median pillar holds 2
+// points, p99 22, max 200: static assignment left a 15 % tail).  One batch of loads covers the first four slots
+// of all eight pillars (lane = pillar * 4 + slot: features and per-slot means, 18 loads per lane, plus the eight
+// table rows), staged in a per-warp shared-memory tile as {x_real[9], x_pad[9]} records and read back as
+// warp-uniform LDS.128 broadcasts; pillars with more than four slots to evaluate (30 %) continue 32 slots at a
+// time.  The metadata of the next group is in flight while the current one is evaluated.  The round-1 kernel
+// took one pillar per warp with three dependent memory round trips each and ~670 instructions per pillar
+// (86 us for 66 k pillars).
 // ext_s[b*P+p][c] = extreme pre-activation of the whole pillar (sign-selected).
 constexpr int kRealWarps = 8;
 constexpr int kRealRec = 20;       // floats per staged slot: 9 real + 9 padding + 2 pad (16-byte multiples)
+constexpr int kRealGroup = 8;      // pillars per work unit
 template <int CPL>
 __global__ void __launch_bounds__(kRealWarps * 32, 2) k_pfn_real(CompactPillars cp, int C,
                                                   const float* __restrict__ conv_w,
@@ -735,12 +742,17 @@ __global__ void __launch_bounds__(kRealWarps * 32, 2) k_pfn_real(CompactPillars 
                                                   const float* __restrict__ bn_w,
                                                   const float* __restrict__ padtab,
                                                   float* __restrict__ ext_s,
-                                                  double* __restrict__ partials2) {
+                                                  double* __restrict__ partials2,
+                                                  int* __restrict__ work_counter) {
   const int warp = threadIdx.x >> 5;
   const unsigned lane = lane_id();
-  __shared__ double s_red[kRealWarps][2][64];
-  __shared__ __align__(16) float s_pts[kRealWarps][32][kRealRec];
-  __shared__ int s_pref[PP_MAX_SWEEPS + 1];
+  extern __shared__ __align__(16) unsigned char real_smem[];
+  typedef float Tile[32][kRealRec];
+  typedef float Rows[kRealGroup][64];
+  Tile* s_pts = reinterpret_cast<Tile*>(real_smem);                                   // [warps] batch tile
+  Tile* s_pts2 = s_pts + kRealWarps;                                                  // [warps] long-pillar tile; the fp64 sums at the end
+  Rows* s_tab = reinterpret_cast<Rows*>(s_pts2 + kRealWarps);                         // [warps] the group's eight table rows
+  int* s_pref = reinterpret_cast<int*>(s_tab + kRealWarps);                           // [PP_MAX_SWEEPS + 1]
   const int P = cp.P, N = cp.N, B = cp.sw.n_sweeps;
   if (threadIdx.x == 0) {
     int a = 0;
@@ -763,58 +775,48 @@ __global__ void __launch_bounds__(kRealWarps * 32, 2) k_pfn_real(CompactPillars 
   const unsigned PN = (unsigned)P * (unsigned)N;          // host guarantees P*N < 2^31
   const bool has_mean = cp.data_mean != nullptr;
   const int total = s_pref[B];
-  const int nw = (int)gridDim.x * kRealWarps;
+  const int ngroups = (total + kRealGroup - 1) / kRealGroup;
   float* tile = &s_pts[warp][0][0];
 
-  struct Meta { int r, p, cnt, off; long long base; };
-  int bcur = 0;
-  auto locate = [&](int i, Meta& m) {                     // i < total, non-decreasing across calls
-    while (i >= s_pref[bcur + 1]) ++bcur;
-    m.p = i - s_pref[bcur];
-    m.r = bcur * P + m.p;
-    m.base = cp.sw.off[bcur];
-    m.cnt = __ldg(cp.pil_cnt + m.r);
-    m.off = __ldg(cp.pil_off + m.r);
+  // per-lane metadata of pillar g = lane (lanes 0..7): row, pillar, first point, clamped count, table limit / row
+  struct Meta { int r, p, cnt, E, row; long long first; };
+  auto next_group = [&]() -> int {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(work_counter, 1);
+    return __shfl_sync(0xffffffffu, g, 0);
   };
-  auto limit = [&](int cnt, int& row) -> int {            // first slot covered by the padding table, and its row
-    if (!has_mean) { row = -1; return cnt; }
-    if (cnt <= 4) { row = 0; return min(4, N); }
-    if (cnt <= 16) { row = 1; return min(16, N); }
-    if (cnt <= 48) { row = 2; return min(48, N); }
-    row = -1;
-    return N;
-  };
-  float fv[kD], mv[kD];
-  float2 tab = make_float2(0.f, 0.f);
-  auto load_batch = [&](const Meta& m, int cnt, int E, int n0) {
-    const int n = n0 + (int)lane;
-    if (n < E) {
-      const float* f = cp.feat_c + (size_t)(m.base + m.off) * kD;
-      const float* mp = cp.data_mean + (size_t)m.p * N;
-#pragma unroll
-      for (int d = 0; d < kD; ++d) {
-        fv[d] = n < cnt ? __ldg(f + (unsigned)n * kD + d) : 0.f;
-        mv[d] = has_mean ? __ldg(mp + (unsigned)d * PN + (unsigned)n) : 0.f;
-      }
+  auto load_meta = [&](int gid, Meta& m, int& cnt_raw, int& off_raw) {
+    m.r = -1;
+    cnt_raw = 0; off_raw = 0;
+    // group gid = live pillars gid, gid + ngroups, gid + 2 ngroups, ...: dense pillars sit next to each other in
+    // slot order (first-touch order follows the lidar rings), and a group of eight CONSECUTIVE pillars could hold
+    // eight 200-point pillars (ncu r2g: 28 % of the samples were warps waiting at the end for such a group)
+    const int i = gid + (int)lane * ngroups;
+    if (gid < ngroups && lane < kRealGroup && i < total) {
+      int b = 0;
+      while (i >= s_pref[b + 1]) ++b;
+      m.p = i - s_pref[b];
+      m.r = b * P + m.p;
+      m.first = cp.sw.off[b];
+      cnt_raw = __ldg(cp.pil_cnt + m.r);
+      off_raw = __ldg(cp.pil_off + m.r);
     }
   };
-  auto stage = [&](int cnt, int E, int n0) {
-    const int n = n0 + (int)lane;
-    if (n < E) {
-      float* rec = tile + lane * kRealRec;
-#pragma unroll
-      for (int d = 0; d < kD; ++d) {
-        rec[d] = __fsub_rn(fv[d], mv[d]);                  // data/dataset.py:105
-        rec[kD + d] = __fsub_rn(0.f, mv[d]);               // what the slot holds when it is padding
-      }
-    }
+  auto finish_meta = [&](Meta& m, int cnt_raw, int off_raw) {
+    if (m.r < 0) return;
+    m.cnt = min(cnt_raw, N);
+    m.first += off_raw;
+    if (!has_mean) { m.row = -1; m.E = m.cnt; }
+    else if (m.cnt <= 4) { m.row = 0; m.E = min(4, N); }
+    else if (m.cnt <= 16) { m.row = 1; m.E = min(16, N); }
+    else if (m.cnt <= 48) { m.row = 2; m.E = min(48, N); }
+    else { m.row = -1; m.E = N; }
   };
   float mx[CPL], ds[CPL], dq[CPL];
-  auto compute = [&](int cnt, int E, int n0) {
-    const int k_real = min(32, cnt - n0), k_all = min(32, E - n0);
+  auto eval = [&](const float* rec_base, int k_real, int k_all) {
     int k = 0;
     for (; k < k_real; ++k) {
-      const float4* rec = reinterpret_cast<const float4*>(tile + k * kRealRec);
+      const float4* rec = reinterpret_cast<const float4*>(rec_base + k * kRealRec);
       const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4];
       const float a[kD] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
       const float q[kD] = {r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w, r4.x, r4.y};
@@ -830,7 +832,7 @@ __global__ void __launch_bounds__(kRealWarps * 32, 2) k_pfn_real(CompactPillars 
       }
     }
     for (; k < k_all; ++k) {                               // padding slots below the table's first slot
-      const float4* rec = reinterpret_cast<const float4*>(tile + k * kRealRec);
+      const float4* rec = reinterpret_cast<const float4*>(rec_base + k * kRealRec);
       const float4 r2 = rec[2], r3 = rec[3], r4 = rec[4];
       const float q[kD] = {r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w, r4.x, r4.y};
 #pragma unroll
@@ -842,80 +844,111 @@ __global__ void __launch_bounds__(kRealWarps * 32, 2) k_pfn_real(CompactPillars 
       }
     }
   };
+  // slot n of the pillar (first point `first`, pillar index p) -> record at tile[slot_in_tile]
+  auto fetch_stage = [&](bool on, long long first, int p, int n, int cnt, float* rec) {
+    if (!on) return;
+    const float* f = cp.feat_c + (size_t)first * kD;
+    float fv[kD], mv[kD];
+#pragma unroll
+    for (int d = 0; d < kD; ++d) {
+      fv[d] = n < cnt ? __ldg(f + (unsigned)n * kD + d) : 0.f;
+      mv[d] = has_mean ? __ldg(cp.data_mean + (size_t)p * N + (unsigned)d * PN + (unsigned)n) : 0.f;
+    }
+#pragma unroll
+    for (int d = 0; d < kD; ++d) {
+      rec[d] = __fsub_rn(fv[d], mv[d]);                    // data/dataset.py:105
+      rec[kD + d] = __fsub_rn(0.f, mv[d]);                 // what the slot holds when it is padding
+    }
+  };
 
-  int i = (int)blockIdx.x * kRealWarps + warp;
   Meta mA{}, mB{};
-  bool vA = i < total, vB = false;
-  int cntA = 0, EA = 0, rowA = -1;
-  if (vA) {
-    locate(i, mA);
-    vB = i + nw < total;
-    if (vB) locate(i + nw, mB);
-    cntA = min(mA.cnt, N);
-    EA = limit(cntA, rowA);
-    load_batch(mA, cntA, EA, 0);
-    if (rowA >= 0) tab = __ldg(reinterpret_cast<const float2*>(padtab + (size_t)mA.p * 192 + rowA * 64) + lane);
-  }
-  while (vA) {
+  int cntA = 0, offA = 0, cntB = 0, offB = 0;
+  int gidA = next_group();
+  load_meta(gidA, mA, cntA, offA);
+  int gidB = next_group();
+  load_meta(gidB, mB, cntB, offB);
+  while (gidA < ngroups) {
+    finish_meta(mA, cntA, offA);
+    // one batch: lane = 4 * pillar + slot
+    {
+      const int g = (int)lane >> 2, n = (int)lane & 3;
+      const int r_g = __shfl_sync(0xffffffffu, mA.r, g);
+      const int p_g = __shfl_sync(0xffffffffu, mA.p, g);
+      const int cnt_g = __shfl_sync(0xffffffffu, mA.cnt, g);
+      const int E_g = __shfl_sync(0xffffffffu, mA.E, g);
+      const long long first_g = __shfl_sync(0xffffffffu, mA.first, g);
+      // the eight table rows (one float2 per lane each), all in flight together with the slot loads
+      float2 tb[kRealGroup];
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) { mx[j] = -INFINITY; ds[j] = 0.f; dq[j] = 0.f; }
-    const float2 tabA = tab;
-    stage(cntA, EA, 0);
+      for (int k = 0; k < kRealGroup; ++k) {
+        const int row_k = __shfl_sync(0xffffffffu, mA.row, k);
+        const int p_k = __shfl_sync(0xffffffffu, mA.p, k);
+        tb[k] = make_float2(0.f, 0.f);
+        if (row_k >= 0) tb[k] = __ldg(reinterpret_cast<const float2*>(padtab + (size_t)p_k * 192 + row_k * 64) + lane);
+      }
+      fetch_stage(r_g >= 0 && n < E_g, first_g, p_g, n, cnt_g, tile + lane * kRealRec);
+#pragma unroll
+      for (int k = 0; k < kRealGroup; ++k) reinterpret_cast<float2*>(&s_tab[warp][k][0])[lane] = tb[k];
+    }
     __syncwarp();
-    // metadata two pillars ahead, slot data one pillar ahead
+    // the metadata of the group after next is in flight during this group's evaluation (each warp holds at most
+    // two groups: with ~3.5 groups per warp a deeper pipeline would hand out everything in the prologue)
     Meta mC{};
-    const bool vC = vB && i + 2 * nw < total;
-    if (vC) locate(i + 2 * nw, mC);
-    int cntB = 0, EB = 0, rowB = -1;
-    if (vB) { cntB = min(mB.cnt, N); EB = limit(cntB, rowB); }
-    if (EA <= 32) {
-      if (vB) {
-        load_batch(mB, cntB, EB, 0);
-        if (rowB >= 0) tab = __ldg(reinterpret_cast<const float2*>(padtab + (size_t)mB.p * 192 + rowB * 64) + lane);
-      }
-      compute(cntA, EA, 0);
-      __syncwarp();
-    } else {
-      compute(cntA, EA, 0);
-      for (int n0 = 32; n0 < EA; n0 += 32) {
-        __syncwarp();
-        load_batch(mA, cntA, EA, n0);
-        stage(cntA, EA, n0);
-        __syncwarp();
-        compute(cntA, EA, n0);
-      }
-      __syncwarp();
-      if (vB) {
-        load_batch(mB, cntB, EB, 0);
-        if (rowB >= 0) tab = __ldg(reinterpret_cast<const float2*>(padtab + (size_t)mB.p * 192 + rowB * 64) + lane);
-      }
-    }
-    // extreme over the whole pillar: its points and padding slots below E (above), the table row for n >= E
-    float* e = ext_s + (size_t)mA.r * C + CPL * lane;
-    const float tb[2] = {tabA.x, tabA.y};
+    int cntC = 0, offC = 0;
+    const int gidC = next_group();
+    load_meta(gidC, mC, cntC, offC);
+#pragma unroll 1
+    for (int g = 0; g < kRealGroup; ++g) {
+      const int r_g = __shfl_sync(0xffffffffu, mA.r, g);
+      if (r_g < 0) continue;
+      const int p_g = __shfl_sync(0xffffffffu, mA.p, g);
+      const int cnt_g = __shfl_sync(0xffffffffu, mA.cnt, g);
+      const int E_g = __shfl_sync(0xffffffffu, mA.E, g);
+      const int row_g = __shfl_sync(0xffffffffu, mA.row, g);
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) {
-      float m = mx[j];
-      if (has_mean) { if (rowA >= 0) m = fmaxf(m, sgn[j] * tb[j]); }
-      else if (cntA < N) m = fmaxf(m, bias[j]);
-      e[j] = sgn[j] * m;
-      accS[j] += (double)ds[j];
-      accQ[j] += (double)dq[j];
+      for (int j = 0; j < CPL; ++j) { mx[j] = -INFINITY; ds[j] = 0.f; dq[j] = 0.f; }
+      eval(tile + 4 * g * kRealRec, min(cnt_g, 4), min(E_g, 4));
+      if (E_g > 4) {
+        // the rest of a longer pillar, 32 slots at a time; the batch tile is still needed by the following pillars
+        // of the group, so these records go to a second tile
+        const long long first_g = __shfl_sync(0xffffffffu, mA.first, g);
+        for (int n0 = 4; n0 < E_g; n0 += 32) {
+          __syncwarp();
+          fetch_stage(n0 + (int)lane < E_g, first_g, p_g, n0 + (int)lane, cnt_g, &s_pts2[warp][lane][0]);
+          __syncwarp();
+          eval(&s_pts2[warp][0][0], max(0, min(32, cnt_g - n0)), min(32, E_g - n0));
+        }
+      }
+      // extreme over the whole pillar: its points and padding slots below E (above), the table row for n >= E
+      float* e = ext_s + (size_t)r_g * C + CPL * lane;
+      const float2 tab = reinterpret_cast<const float2*>(&s_tab[warp][g][0])[lane];
+      const float tb2[2] = {tab.x, tab.y};
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        float m = mx[j];
+        if (has_mean) { if (row_g >= 0) m = fmaxf(m, sgn[j] * tb2[j]); }
+        else if (cnt_g < N) m = fmaxf(m, bias[j]);
+        e[j] = sgn[j] * m;
+        accS[j] += (double)ds[j];
+        accQ[j] += (double)dq[j];
+      }
     }
-    mA = mB; vA = vB; cntA = cntB; EA = EB; rowA = rowB;
-    mB = mC; vB = vC;
-    i += nw;
+    __syncwarp();                                          // the tile is refilled by the next group
+    mA = mB; cntA = cntB; offA = offB; gidA = gidB;
+    mB = mC; cntB = cntC; offB = offC; gidB = gidC;
   }
+  static_assert(32 * kRealRec * 4 >= 2 * 64 * 8, "per-warp tile holds the warp's fp64 sums");
+  double* red = reinterpret_cast<double*>(&s_pts2[warp][0][0]);   // [2][64], this warp's own tile
 #pragma unroll
   for (int j = 0; j < CPL; ++j) {
-    s_red[warp][0][CPL * lane + j] = accS[j] * 0.5;           // t = 2 relu(y)
-    s_red[warp][1][CPL * lane + j] = accQ[j] * 0.25;
+    red[CPL * lane + j] = accS[j] * 0.5;                      // t = 2 relu(y)
+    red[64 + CPL * lane + j] = accQ[j] * 0.25;
   }
   __syncthreads();
   if (threadIdx.x < 2 * C) {
     const int q = threadIdx.x / C, c = threadIdx.x % C;
     double v = 0.0;
-    for (int wv = 0; wv < kRealWarps; ++wv) v += s_red[wv][q][c];
+    for (int wv = 0; wv < kRealWarps; ++wv) v += reinterpret_cast<const double*>(&s_pts2[wv][0][0])[q * 64 + c];
     partials2[((size_t)blockIdx.x * 2 + q) * C + c] = v;
   }
 }
@@ -932,6 +965,7 @@ struct SparseWs {
 };
 
 static int real_blocks() { return sm_count() * 2; }
+constexpr size_t kRealSmem = (size_t)kRealWarps * (2 * 32 * kRealRec * 4 + kRealGroup * 64 * 4) + (PP_MAX_SWEEPS + 1) * 4 + 12;
 
 bool pfn_pad_supported(int N, int C, int P);
 size_t mean_prepared_bytes(int P, int N);
@@ -979,6 +1013,7 @@ int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, c
   if (rc != PP_OK) return rc;
   int nblocks = 0;
   const void* prep = cp.mean_prepared;
+  PP_CUDA(cudaMemsetAsync(ws.flags, 0, 2 * sizeof(int), st));     // [0] range flag of the padding pass, [1] k_pfn_real's work counter
   if (cp.data_mean != nullptr) {
     if (own_prep) {
       // a caller without a prepared operand pays a streaming pass over data_mean per call (pp_mean_prepare once
@@ -996,9 +1031,10 @@ int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, c
     if (rc != PP_OK) return rc;
   }
   const int nb2 = real_blocks();
+  PP_CUDA(cudaFuncSetAttribute(k_pfn_real<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRealSmem));
   PP_KERNEL("k_pfn_real", st,
-            k_pfn_real<2><<<nb2, kRealWarps * 32, 0, st>>>(cp, C, prm.conv_w, prm.conv_b, prm.bn_w, ws.padtab, ws.ext_s,
-                                                           ws.partials2));
+            k_pfn_real<2><<<nb2, kRealWarps * 32, kRealSmem, st>>>(cp, C, prm.conv_w, prm.conv_b, prm.bn_w, ws.padtab, ws.ext_s,
+                                                           ws.partials2, ws.flags + 1));
   // a mean or weight outside the fp16 range is reported through the status word (by the finalize kernel, which
   // runs anyway)
   SparseFinalize sf{};

@@ -559,8 +559,10 @@ __global__ void __launch_bounds__(256) k_pos_emit(EncodeArgs ea, GtParams gp, lo
   int wbase = s_base + incl - c;
   for (int q = 0; q < warp; ++q) wbase += s_red[q];
   if (wi < nwords) {
-    if (wi % words_per_sweep == 0) pos_offsets[wi / words_per_sweep] = wbase;
-    if (wi == nwords - 1) pos_offsets[B] = wbase + c;
+    // offsets never exceed the capacity: rows beyond it are dropped (PP_STATUS_CAND_OVERFLOW) and the consumers
+    // (pp_loss_list) index the list arrays up to offsets[B]
+    if (wi % words_per_sweep == 0) pos_offsets[wi / words_per_sweep] = min(wbase, cap);
+    if (wi == nwords - 1) pos_offsets[B] = min(wbase + c, cap);
   }
   unsigned todo = __ballot_sync(0xffffffffu, w != 0u);
   while (todo) {

@@ -193,6 +193,7 @@ class PPScatter(nn.Module):
             rc = L.pp_scatter(x.data_ptr(), inds.data_ptr(), B, C, P, H, W, out.data_ptr(),
                               status.data_ptr(), ws.data_ptr(), ws.numel(), _runtime.stream_ptr(dev))
         _lib.check(rc, "pp_scatter")
+        _runtime.poll_status(dev, "PPScatter (the reference raises IndexError on an index outside the canvas, model/model.py:61)")
         return out
 
 
@@ -243,4 +244,5 @@ class PPFeatureScatter(nn.Module):
                 feat.data_ptr() if feat is not None else None, status.data_ptr(), ws.data_ptr(),
                 ws.numel(), _runtime.stream_ptr(dev))
         _lib.check(rc, "pp_pfn_scatter")
+        _runtime.poll_status(dev, "PPFeatureScatter")
         return (canvas, feat) if return_features else canvas

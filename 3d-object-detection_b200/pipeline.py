@@ -36,18 +36,40 @@ class StepHandle:
         self._pin, self._B, self._done = pinned, n_sweeps, done
 
     def wait(self, stream=None):
-        """Order ``stream`` (default: the current one) after this step; the outputs are then safe to use there."""
-        (stream or torch.cuda.current_stream()).wait_event(self._done)
+        """Order ``stream`` (default: the current one) after this step; the outputs are then safe to use there.
+        The outputs were allocated on a lane stream: they are recorded on ``stream`` so that the caching allocator
+        does not hand their memory to a later step of that lane while kernels queued on ``stream`` still read it."""
+        stream = stream or torch.cuda.current_stream()
+        stream.wait_event(self._done)
+        for t in self._tensors():
+            t.record_stream(stream)
+
+    def _tensors(self):
+        out = []
+        for t in (self.canvas, self.cls, self.reg, self.n_pillars, self.counts):
+            if isinstance(t, torch.Tensor):
+                out.append(t)
+            elif t is not None and hasattr(t, "anchor"):                    # box_utils.Positives
+                out += [t.anchor, t.cls, t.reg, t.offsets]
+        return out
 
     def synchronize(self):
         self._done.synchronize()
 
     def counters(self):
-        """(n_pillars [B], counts [B,4]) as host int32 tensors; waits for this step's D2H copy."""
+        """(n_pillars [B], counts [B,4]) as host int32 tensors; waits for this step's D2H copy.  The device status
+        word travels with them: a set bit (scatter index outside the canvas, NaN point, positives-list overflow,
+        value outside the fp16 range of the padding pass ...) raises here."""
         self._done.synchronize()
         B = self._B
         if self._pin is None:
+            _runtime.check_status(self.n_pillars.device, "input path step")
             return self.n_pillars.cpu(), self.counts.cpu()
+        status = int(self._pin[5 * B])
+        if status:
+            _runtime.status_word(self.n_pillars.device).zero_()
+            self._pin[5 * B] = 0
+            _runtime._raise_status(status, "input path step")
         return self._pin[:B].clone(), self._pin[B:5 * B].view(B, 4).clone()
 
 
@@ -504,12 +526,18 @@ class InputPath:
         self._lane_no += 1
         return lane
 
-    def step_host(self, batch, out=None):
+    def step_host(self, batch, out=None, check=True):
         """One pass of the whole path from a pinned HOST batch (``pack_host_batch``): H2D copy,
         pillarize, PFN + scatter, target assignment.  Outputs stay on the device, where the
-        backbone and the loss consume them; returns (canvas, cls, reg, n_pillars, counts)."""
+        backbone and the loss consume them; returns (canvas, cls, reg, n_pillars, counts).
+        ``check``: read the device status word afterwards (synchronises) and raise on a set bit, as the
+        reference raises on an out-of-canvas scatter index; the streaming ``step_host_async`` reports it
+        through ``StepHandle.counters()`` instead."""
         d_pts, gt_dev = self.upload(batch)
-        return self._run(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out or {})
+        res = self._run(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out or {})
+        if check:
+            _runtime.check_status(self.device, "step_host")
+        return res
 
     def step_host_async(self, batch, out=None):
         """Pipelined form of ``step_host`` for a streaming loop: the H2D copy goes to a copy stream
@@ -537,10 +565,11 @@ class InputPath:
             B = len(batch["offsets"]) - 1
             ring = (self._step_no - 1) % len(self._result_pin)
             pin = self._result_pin[ring]
-            if pin is None or pin.numel() < 5 * B:
-                pin = self._result_pin[ring] = torch.empty(5 * B, dtype=torch.int32).pin_memory()
+            if pin is None or pin.numel() < 5 * B + 1:
+                pin = self._result_pin[ring] = torch.empty(5 * B + 1, dtype=torch.int32).pin_memory()
             pin[:B].copy_(res[3], non_blocking=True)
             pin[B:5 * B].view(B, 4).copy_(res[4], non_blocking=True)
+            pin[5 * B:5 * B + 1].copy_(_runtime.status_word(dev), non_blocking=True)
             done = torch.cuda.Event()
             done.record(main)
         return StepHandle(res, pin, B, done)
@@ -557,6 +586,14 @@ class InputPath:
             done.record(main)
         return StepHandle(res, None, len(offsets) - 1, done)
 
-    def step_device(self, d_pts, offsets, gt_dev, gt_offsets, out=None):
-        """Same pass with inputs already resident in HBM."""
-        return self._run(d_pts, offsets, gt_dev, gt_offsets, out or {})
+    def step_device(self, d_pts, offsets, gt_dev, gt_offsets, out=None, check=False):
+        """Same pass with inputs already resident in HBM.  ``check`` as in ``step_host`` (default off: the caller
+        polls ``check_status`` itself)."""
+        res = self._run(d_pts, offsets, gt_dev, gt_offsets, out or {})
+        if check:
+            _runtime.check_status(self.device, "step_device")
+        return res
+
+    def check_status(self):
+        """Synchronising read of the device status word; raises on a set bit and clears it."""
+        _runtime.check_status(self.device, "input path")

@@ -28,6 +28,11 @@ def close(a, b, rtol=RTOL, atol=ATOL, amp=None):
     if amp is not None:
         tol = tol + 1e-6 * amp
     err = np.abs(a - b) - tol
+    # how many outputs lie outside north_star's PLAIN 1e-5 relative bound (no absolute / conditioning term):
+    # reported, not asserted -- these are the cancelled results the module docstring explains
+    plain = np.abs(a - b) > rtol * np.maximum(np.abs(a), np.abs(b))
+    print("outside plain %.0e relative: %d of %d outputs (max |diff| among them %.3g)" % (
+        rtol, int(plain.sum()), a.size, float(np.abs(a - b)[plain].max()) if plain.any() else 0.0))
     assert err.max() <= 0, "max violation %g (max abs diff %g)" % (err.max(), np.abs(a - b).max())
 
 

@@ -47,11 +47,13 @@ def test_step_host_matches_oracle_composition():
     for b, gt in enumerate(gts):
         g = boxes_from_gt(gt, T.Box, ocfg.CLASS_NAMES)
         gc, gcor = T.boxes_to_image_space(g)
-        c0, r0 = T.create_target(corners, gcor, centers, gc, boxes, g)
+        c0, r0, ious = T.create_target(corners, gcor, centers, gc, boxes, g, return_ious=True)
         assert np.array_equal(cls[b].cpu().numpy(), c0.astype(np.float32))
         r = reg[b].cpu().numpy().astype(np.float64); r0 = r0.astype(np.float32).astype(np.float64)
         assert (np.abs(r - r0) <= 1e-5 * np.maximum(np.abs(r), np.abs(r0)) + 1e-7).all()
-        assert int(counts[b, 0]) == int((c0.sum(1) > 0).sum()) or int(counts[b, 0]) <= int((c0.sum(1) > 0).sum())
+        # counters: anchors positive by threshold (strict >), per-GT forced matches kept (best anchor != 0)
+        assert int(counts[b, 0]) == int((ious.max(1) > 0.6).sum())
+        assert int(counts[b, 1]) == int((ious.argmax(0) != 0).sum())
 
 
 def test_full_size_batch_properties():
@@ -147,7 +149,14 @@ def test_fused_input_path_equals_pillarize_then_encode(dense_mean, training):
     sigma = float(torch.sqrt(pa.net.bn1.running_var.min() + 1e-5)) if not training else 1.0
     amp = float(absdot) * float(np.abs(prm["bn_w"]).max()) / min(sigma, 1.0) * 4.0
     _canvas_close(canvas, want, amp)
-    assert torch.equal(canvas != 0, want != 0) or ((canvas != 0) ^ (want != 0)).sum() < 10
+    # support: identical up to elements whose value is an exact zero in one evaluation and below the absolute
+    # tolerance in the other (BN(relu(.)) of a pillar extreme that cancels); each such element is checked
+    diff = (canvas != 0) ^ (want != 0)
+    n_diff = int(diff.sum())
+    print("canvas support mismatches: %d of %d non-zeros" % (n_diff, int((want != 0).sum())))
+    assert n_diff <= 10
+    if n_diff:
+        assert float(torch.maximum(canvas[diff].abs(), want[diff].abs()).max()) <= 2e-6 + 1e-6 * amp
     if training:
         assert torch.allclose(pa.net.bn1.running_mean, pb.net.bn1.running_mean, rtol=1e-5, atol=1e-6)
         assert torch.allclose(pa.net.bn1.running_var, pb.net.bn1.running_var, rtol=1e-5, atol=1e-6)
@@ -189,6 +198,58 @@ def test_fused_input_path_against_fp64_oracle():
     absdot = torch.einsum('cd,bdpn->bcpn', t(prm["conv_w"]).abs().double(), x.abs().double()).amax()
     _canvas_close(canvas, want, float(absdot) * 4.0)
     assert torch.allclose(path.net.bn1.running_var.cpu(), rv.float(), rtol=1e-5, atol=1e-6)
+
+
+def test_fused_input_path_full_size_against_fp64_oracle():
+    """The reference shape (P = 24000, N = 200, C = 64, 600 x 600 canvas), one sweep, training-mode BatchNorm:
+    pp_input_path against the float64 oracle (oracle.glue + the PPFeatureNet algebra of oracle.pfn, evaluated in
+    pillar chunks so that the [64,P,N] float64 intermediate never exists: per-channel sums of relu(y) and
+    relu(y)^2 and the per-(pillar, channel) maximum AND minimum of y in one pass, BatchNorm + the monotone-map
+    selection afterwards -- the same values as pfn.pfn_forward, checked against it at the small size above)."""
+    from oracle import glue
+    from pp_b200 import pipeline, synth
+    P, N = 24000, 200
+    mean = synth.make_data_mean(P, N, dense=True)
+    prm = synth.make_pfn_params(7, flip_gamma=True)
+    path = pipeline.InputPath(data_mean=mean, pfn_params=prm, training=True)
+    sweep = synth.make_sweep(31)
+    canvas, inds, npil = path.pillarize_encode(torch.from_numpy(sweep).cuda(), [0, len(sweep)])
+    x, ii = glue.pillarize(sweep[:, :4].astype(np.float64), torch.from_numpy(mean), max_pillars=P, max_points=N)
+    assert torch.equal(inds[0].cpu(), ii)
+    W = torch.from_numpy(prm["conv_w"]).double(); bias = torch.from_numpy(prm["conv_b"]).double()
+    S = torch.zeros(64, dtype=torch.float64); Q = torch.zeros(64, dtype=torch.float64)
+    ymax = torch.empty((64, P), dtype=torch.float64); ymin = torch.empty((64, P), dtype=torch.float64)
+    amp_abs = 0.0
+    step = 1500
+    for p0 in range(0, P, step):
+        xc = x[:, p0:p0 + step].double()                                    # [9, p, N]
+        y = torch.einsum('cd,dpn->cpn', W, xc) + bias.view(-1, 1, 1)
+        r = torch.relu(y)
+        S += r.sum(dim=(1, 2)); Q += (r * r).sum(dim=(1, 2))
+        ymax[:, p0:p0 + step] = y.amax(dim=2); ymin[:, p0:p0 + step] = y.amin(dim=2)
+        amp_abs = max(amp_abs, float((torch.einsum('cd,dpn->cpn', W.abs(), xc.abs()).amax() + bias.abs().max())))
+    M = float(P * N)
+    mu = S / M
+    var = Q / M - mu * mu
+    g = torch.from_numpy(prm["bn_w"]).double(); beta = torch.from_numpy(prm["bn_b"]).double()
+    scale = g / torch.sqrt(var + 1e-5)
+    ext = torch.where((scale >= 0).view(-1, 1), ymax, ymin)               # max_n BN(relu(y)) by monotonicity
+    out = (torch.relu(ext) - mu.view(-1, 1)) * scale.view(-1, 1) + beta.view(-1, 1)     # [64, P]
+    want = torch.zeros((64, 600, 600), dtype=torch.float64)
+    live = ii[:, 0] != 0
+    want[:, ii[live, 2], ii[live, 1]] = out[:, live]
+    amp = amp_abs * float((g.abs() / torch.sqrt(var + 1e-5)).max())
+    got = canvas[0].double().cpu()
+    tol = 1e-5 * torch.maximum(got.abs(), want.abs()) + 2e-6 + 1e-6 * amp
+    viol = (got - want).abs() - tol
+    plain = (got - want).abs() > 1e-5 * torch.maximum(got.abs(), want.abs())
+    print("full size: %d non-zero outputs, %d outside plain 1e-5 relative, max |diff| %.3g, amp %.3g" % (
+        int((want != 0).sum()), int(plain.sum()), float((got - want).abs().max()), amp))
+    assert float(viol.max()) <= 0
+    rv = 0.9 * torch.from_numpy(prm["running_var"]).double() + 0.1 * var * (M / (M - 1))
+    rm = 0.9 * torch.from_numpy(prm["running_mean"]).double() + 0.1 * mu
+    assert torch.allclose(path.net.bn1.running_var.double().cpu(), rv, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(path.net.bn1.running_mean.double().cpu(), rm, rtol=1e-5, atol=1e-7)
 
 
 @pytest.mark.parametrize("fused", [True, False])

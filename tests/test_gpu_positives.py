@@ -49,11 +49,28 @@ def test_list_overflow_is_reported():
     batch = path.pack_host_batch([synth.make_sweep(0)[:100]], gts)
     _, g = path.upload(batch)
     a = path.ensure_anchors()
+    full, _, _, _ = box_utils.assign_targets(a, g["corners"], g["centers"], g["wlh"], g["yaw"], g["cls"], batch["gt_offsets"],
+                                             as_list=True)
+    n_full = int(full.offsets[-1].item())
+    assert n_full > 10
     pos, _, _, _ = box_utils.assign_targets(a, g["corners"], g["centers"], g["wlh"], g["yaw"], g["cls"], batch["gt_offsets"],
                                             as_list=True, capacity=10)
-    assert int(pos.offsets[-1].item()) > 10
+    # offsets are clamped to the capacity (the consumers index the list arrays up to offsets[B]); the kept rows are
+    # the first ones in (sweep, anchor) order
+    assert pos.offsets.tolist() == [0, 10]
+    assert torch.equal(pos.anchor[:10], full.anchor[:10]) and torch.equal(pos.cls[:10], full.cls[:10])
+    # the loss over the truncated list stays inside the arrays (run under compute-sanitizer by scripts/sanitize.sh)
+    from pp_b200.loss import PPLoss
+    cls = torch.randn((1, 54, 300, 300), device="cuda") - 3.0
+    reg = torch.randn((1, 48, 300, 300), device="cuda")
+    out = PPLoss(0.4, 1.0, 250.0, 2, torch.device("cuda"))(cls, reg, pos)
+    assert torch.isfinite(out[4])
     with pytest.raises(_lib.PPError):
         _runtime.check_status(torch.device("cuda"), "targets")
+    with pytest.raises(_lib.PPError):                      # Positives.dense() refuses a truncated list
+        pos2, _, _, _ = box_utils.assign_targets(a, g["corners"], g["centers"], g["wlh"], g["yaw"], g["cls"],
+                                                 batch["gt_offsets"], as_list=True, capacity=10)
+        pos2.dense()
 
 
 @pytest.mark.parametrize("B,n_gt", [(2, 60), (1, 0)])
