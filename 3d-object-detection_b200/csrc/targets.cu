@@ -795,10 +795,10 @@ static int assign_impl(const double* d_a_corners, const double* d_a_centers, con
   PP_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)n_sweeps * 4 * sizeof(int), st));
   const unsigned char* idx = (const unsigned char*)d_anchor_index;
   if (Gt > 0) {
-    PP_KERNEL("k_iou_pass", st, k_iou_pass<0><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
+    PP_KERNEL("k_iou_pass0", st, k_iou_pass<0><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
                                            d_g_centers, gp, pos_thresh, ws.best, ws.arg, ws.posmask,
                                            ws.forcedmask, d_top_anchor, d_counts, ws.cand_iou, d_status));
-    PP_KERNEL("k_iou_pass", st, k_iou_pass<1><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
+    PP_KERNEL("k_iou_pass1", st, k_iou_pass<1><<<(int)Gt, 256, 0, st>>>(d_a_corners, d_a_centers, idx, A, d_g_corners,
                                            d_g_centers, gp, pos_thresh, ws.best, ws.arg, ws.posmask,
                                            ws.forcedmask, d_top_anchor, d_counts, ws.cand_iou, d_status));
   }

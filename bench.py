@@ -28,6 +28,12 @@ UNIT = "sweeps/s"
 WORKLOAD = ("batch-%d synthetic Lyft-shaped sweeps (~67k pts x5 f32), config.py grid 600x600, P=24000 N=200 "
             "D=9 C=64: pillarize+decorate+data_mean -> PFN (train-mode BN) + scatter to [64,600,600] -> "
             "IoU/target encode, %d GT boxes vs 540000 anchors" % (BATCH, N_GT))
+# BASELINE.json configs[3] and [4] (--config b64 / stress); the default line stays configs[1]+[2]
+WORKLOAD_B64 = ("batch-64 end-to-end input path (pillarize + PFN + targets), 64 synthetic sweeps per step sharded "
+                "%d per GPU over %d GPU(s), P=24000 N=200 C=64, 100 GT boxes per sweep vs 540000 anchors")
+WORKLOAD_STRESS = ("dense stress: batch of %d samples per GPU, each a 10-sweep aggregated cloud (~660k raw points, "
+                   "pp_aggregate_sweeps on the device), max pillars 30000, N=200, 200 GT boxes per sample vs 540000 anchors")
+MIN_TIMED_S = 0.6      # every timed region lasts at least this long, whatever --steps is
 
 
 # ------------------------------------------------------------------------------------------------
@@ -50,7 +56,7 @@ class ClockSampler(threading.Thread):
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index, period=0.002):
+    def __init__(self, index, period=0.05):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -191,17 +197,22 @@ def cpu_kind_note():
 
 
 def run_cpu_pool(seeds, cores):
-    """Process the given sweeps on `cores` worker processes; returns wall seconds."""
+    """Process the given sweeps on `cores` WARM worker processes; returns wall seconds of the timed map only (pool
+    start-up, imports, the anchor arrays / data_mean of each worker and one sweep per worker happen before)."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
-    t0 = time.perf_counter()
     if cores <= 1:
+        cpu_path_one_sweep(499)
+        t0 = time.perf_counter()
         for s in seeds:
             cpu_path_one_sweep(s)
-    else:
-        with ctx.Pool(min(cores, len(seeds))) as pool:
-            pool.map(cpu_path_one_sweep, seeds, chunksize=1)
-    return time.perf_counter() - t0
+        return time.perf_counter() - t0
+    n = min(cores, len(seeds))
+    with ctx.Pool(n) as pool:
+        pool.map(cpu_path_one_sweep, list(range(400, 400 + n)), chunksize=1)      # warm-up: one sweep per worker
+        t0 = time.perf_counter()
+        pool.map(cpu_path_one_sweep, seeds, chunksize=1)
+        return time.perf_counter() - t0
 
 
 def run_reference(args):
@@ -246,19 +257,64 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def algorithmic_bytes(B, P, N, C, H, W, A, K, total_points, has_mean):
-    """Algorithmic (compulsory) HBM bytes per launch of each streaming kernel."""
+def algorithmic_bytes(B, P, N, C, H, W, A, K, total_points, has_mean, live, real_slots, n_gt):
+    """Algorithmic (compulsory) HBM bytes per launch of each kernel.  ``live`` = live pillars
+    of the batch (sum of n_pillars, read back from the step), ``real_slots`` = slots that hold a point."""
     x_bytes = 9 * P * N * 4
     return {
         "k_emit_dense": B * x_bytes + (x_bytes if has_mean else 0) + total_points * 16 + B * P * 24,
         "k_pfn_stats": B * x_bytes + B * P * 2 * C * 4,
         "k_pfn_stats_tc": B * x_bytes + B * P * 2 * C * 4,
         "k_canvas": B * C * H * W * 4 + B * H * W * 4,
-        # fused path: data_mean read once + the ext rows of the live pillars (2 padding fields per sweep)
-        "k_pfn_pad_tc": (x_bytes if has_mean else 0) + B * 16500 * 2 * C * 4,
+        # padding pass: the per-slot means once (36 B per slot as float32; the prepared fp16-split operand the
+        # kernel actually reads is 48 B per slot -- see roofline.traffic) + the padding table [P,3,C]
+        "k_pfn_pad_tc": (x_bytes if has_mean else 0) + P * 3 * C * 4,
+        # live pillars: features + per-slot means of the slots that hold a point, one table row and one ext row each
+        "k_pfn_real": real_slots * 72 + live * 2 * C * 4,
+        # K3: the candidate anchors of every GT (<= 11 x 11 x 6 pass the centre prefilter): corners + centre
+        "k_iou_pass0": n_gt * 726 * (64 + 24),
         "k_encode_zero": 2 * B * A * 9 * 4,  # zero stream of cls [B,A,9] and reg [B,A,9] (flagged rows patched after)
         "k_encode": B * A * 9 * 4,
     }
+
+
+def source_hash():
+    """sha256 over the CUDA sources + header: ties profiles/ncu_traffic.json to the build it was captured from."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    pkg = os.path.join(ROOT, "3d-object-detection_b200", "csrc")
+    for f in sorted(glob.glob(os.path.join(pkg, "*.cu")) + glob.glob(os.path.join(pkg, "*.cuh")) +
+                    [os.path.join(ROOT, "include", "pp_b200.h")]):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of ``kernel`` from the ncu --set full capture committed with THIS build (profiles/
+    ncu_traffic.json records the source hash it was captured from); None when the capture is of another build."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if d.get("source_hash") != source_hash():
+            return None, "profiles/ncu_traffic.json is from build %s, this is %s" % (d.get("source_hash"), source_hash())
+        return d.get("kernels", {}).get(kernel), "ncu --set full, build %s (%s)" % (d["source_hash"], d.get("capture", ""))
+    except Exception as e:  # noqa: BLE001
+        return None, "no capture: %s" % e
+
+
+def count_slots(sweeps, cfg):
+    """(live pillars, slots holding a point) of a list of [n,>=3] clouds on cfg's grid (host, numpy)."""
+    import numpy as np
+    live = real = 0
+    for s in sweeps:
+        x, y, z = s[:, 0].astype(np.float64), s[:, 1].astype(np.float64), s[:, 2].astype(np.float64)
+        m = (x >= cfg.x_min) & (x < cfg.x_max) & (y >= cfg.y_min) & (y < cfg.y_max) & (z >= cfg.z_min) & (z < cfg.z_max)
+        cell = np.floor((x[m] - cfg.x_min) / cfg.x_step).astype(np.int64) * 100000 + np.floor((y[m] - cfg.y_min) / cfg.y_step).astype(np.int64)
+        _, first, cnt = np.unique(cell, return_index=True, return_counts=True)
+        keep = np.argsort(first)[:cfg.max_pillars]                   # first-touch order, P cap
+        live += len(keep)
+        real += int(np.minimum(cnt[keep], cfg.max_points_per_pillar).sum())
+    return live, real
 
 
 def training_rows(x, inds, targets, dev, peak, steps, path=None, d_pts=None, offsets=None, gt=None, fused_path=None):
@@ -341,7 +397,95 @@ def training_rows(x, inds, targets, dev, peak, steps, path=None, d_pts=None, off
                     "place) on the batch's raw points" % B, "kernels": rows}
 
 
+def build_workload(args, cfg_mod, synth, rank, world):
+    """The synthetic batch this rank processes per step, for --config default | b64 | stress."""
+    import numpy as np
+    if args.config == "b64":
+        if 64 % world:
+            raise SystemExit("--config b64 needs 1, 2, 4 or 8 GPUs")
+        B = 64 // world
+        cfg = cfg_mod.PPConfig()
+        sweeps = [synth.make_sweep(rank * B + i) for i in range(B)]
+        gts = [synth.make_gt(rank * B + i, N_GT) for i in range(B)]
+        return {"cfg": cfg, "B": B, "n_gt": N_GT, "sweeps": sweeps, "gts": gts, "transforms": None, "scaling": "strong",
+                "workload": WORKLOAD_B64 % (B, world), "flat": sweeps}
+    if args.config == "stress":
+        B = BATCH
+        cfg = cfg_mod.PPConfig(max_pillars=30000)
+        groups, mats, flat = [], [], []
+        for i in range(B):
+            files = [synth.make_sweep(100 + 10 * (rank * B + i) + k) for k in range(10)]
+            ms = []
+            for k in range(10):
+                m = np.eye(4)
+                m[0, 3] = 0.3 * k                      # ego shift between the aggregated sweeps (data/dataset.py:78)
+                ms.append(m)
+            groups.append(files); mats.append(ms)
+            flat.append(np.concatenate([f + np.array([0.3 * k, 0, 0, 0, 0], np.float32) for k, f in enumerate(files)]))
+        gts = [synth.make_gt(rank * B + i, 200) for i in range(B)]
+        return {"cfg": cfg, "B": B, "n_gt": 200, "sweeps": groups, "gts": gts, "transforms": mats, "scaling": "weak",
+                "workload": WORKLOAD_STRESS % B, "flat": flat}
+    cfg = cfg_mod.PPConfig()
+    sweeps = [synth.make_sweep(rank * BATCH + i) for i in range(BATCH)]
+    gts = [synth.make_gt(rank * BATCH + i, N_GT) for i in range(BATCH)]
+    return {"cfg": cfg, "B": BATCH, "n_gt": N_GT, "sweeps": sweeps, "gts": gts, "transforms": None, "scaling": "weak",
+            "workload": WORKLOAD, "flat": sweeps}
+
+
+def gpu_comparator(x, inds, prm, dev, path_dense, path_fused, d_pts, offsets, out_fused, reps=5):
+    """The reference's OWN PPFeatureNet + PPScatter (model/model.py:13-62, loaded by oracle/refmodel.py: sources in
+    the build container, byte-compiled copy on the GPU box) run eagerly on this GPU with TF32 off, on the same x /
+    inds, CUDA-event timed -- next to this repo's K2 on the same inputs.  This is the comparator the real system
+    uses: the reference never runs its network on the CPU."""
+    import torch
+    from oracle import refmodel
+    loaded = refmodel.load()
+    if loaded is None:
+        return {"unavailable": "reference modules not present (oracle/_ref/refpy missing: run make -C oracle refpy)"}
+    mod, rcfg, kind = loaded
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        fnet = mod.PPFeatureNet(9, 64).to(dev).train()
+        scat = mod.PPScatter(dev)
+        t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            fnet.conv1.weight.copy_(t(prm["conv_w"]).view(64, 9, 1, 1)); fnet.conv1.bias.copy_(t(prm["conv_b"]))
+            fnet.bn1.weight.copy_(t(prm["bn_w"])); fnet.bn1.bias.copy_(t(prm["bn_b"]))
+
+        def timed(fn, n):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                r = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n, r
+
+        with torch.no_grad():
+            ms_ref, ref_canvas = timed(lambda: scat(fnet(x), inds), reps)
+            ms_dense, ours = timed(lambda: path_dense.encode(x, inds), reps)
+            ms_fused, _ = timed(lambda: path_fused.pillarize_encode(d_pts, offsets, out=out_fused, stages=2), reps)
+        diff = float((ours - ref_canvas).abs().max())
+        scale = float(ref_canvas.abs().max())
+        del ref_canvas
+        return {"what": "reference PPFeatureNet + PPScatter (model/model.py:31-40,53-62; %s), eager PyTorch %s on this GPU, "
+                        "train-mode BatchNorm, cudnn.allow_tf32 = matmul.allow_tf32 = False, same x [%d,9,%d,%d] / inds; "
+                        "ours_dense = pp_pfn_scatter on the same x, ours_fused_encode = the encode stage of pp_input_path "
+                        "(padding pass + live pillars + BatchNorm + canvas; x never read)" % (
+                            kind, torch.__version__, x.shape[0], x.shape[2], x.shape[3]),
+                "reference_ms": ms_ref, "ours_dense_ms": ms_dense, "ours_fused_encode_ms": ms_fused,
+                "speedup_dense": ms_ref / ms_dense, "speedup_fused": ms_ref / ms_fused,
+                "max_abs_diff_vs_reference": diff, "reference_max_abs": scale}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def run_ours(args):
+    import math
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -357,55 +501,52 @@ def run_ours(args):
     import pp_b200
     from pp_b200 import _lib, pipeline, synth
     L = _lib.load()
-    if getattr(args, "reserve_sms", None) is not None:
-        L.pp_set_option(b"pad_reserve_sms", int(args.reserve_sms))
-    cfg = pp_b200.PPConfig()
+    wl = build_workload(args, pp_b200, synth, rank, world)
+    cfg, B = wl["cfg"], wl["B"]
+    default_cfg = args.config == "default"
     P, N, C, H, W = cfg.max_pillars, cfg.max_points_per_pillar, cfg.feature_net_out, cfg.canvas_height, cfg.canvas_width
     mean = synth.make_data_mean(P, N, seed=0, dense=True)
+    prm = synth.make_pfn_params(0)
     fused = not args.dense_path
-    path = pipeline.InputPath(cfg, device=dev, data_mean=mean, pfn_params=synth.make_pfn_params(0), training=True,
-                              fused=fused)
+    path = pipeline.InputPath(cfg, device=dev, data_mean=mean, pfn_params=prm, training=True, fused=fused)
     anchors = path.ensure_anchors()
     A = anchors.A
-    # each rank owns its own batch of BATCH sweeps per step (weak scaling, no data-path collective)
-    sweeps = [synth.make_sweep(rank * BATCH + i) for i in range(BATCH)]
-    gts = [synth.make_gt(rank * BATCH + i, N_GT) for i in range(BATCH)]
-    batch = path.pack_host_batch(sweeps, gts)
+    batch = path.pack_host_batch(wl["sweeps"], wl["gts"], transforms=wl["transforms"])
     T = batch["offsets"][-1]
-    d_pts, gt_dev = path.upload(batch)
-    out = {
-        "pillars": (torch.empty((BATCH, 9, P, N), dtype=torch.float32, device=dev) if not fused else None,
-                    torch.empty((BATCH, P, 3), dtype=torch.int64, device=dev),
-                    torch.empty(BATCH, dtype=torch.int32, device=dev)),
-        "canvas": torch.empty((BATCH, C, H, W), dtype=torch.float32, device=dev),
-        "targets": (torch.empty((BATCH, A, cfg.num_classes), dtype=torch.float32, device=dev),
-                    torch.empty((BATCH, A, 9), dtype=torch.float32, device=dev)),
-    }
+    d_pts, gt_dev = path.upload(batch)          # device-resident inputs of the `value` loop (aggregated, if configured)
+
+    def make_out(with_x):
+        return {"pillars": (torch.empty((B, 9, P, N), dtype=torch.float32, device=dev) if with_x else None,
+                            torch.empty((B, P, 3), dtype=torch.int64, device=dev),
+                            torch.empty(B, dtype=torch.int32, device=dev)),
+                "canvas": torch.empty((B, C, H, W), dtype=torch.float32, device=dev),
+                "targets": (torch.empty((B, A, cfg.num_classes), dtype=torch.float32, device=dev),
+                            torch.empty((B, A, 9), dtype=torch.float32, device=dev))}
+
+    outs = [make_out(not fused), make_out(not fused)]
+    out = outs[0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        fn()
         e1.record()
         barrier()
         return e0.elapsed_time(e1)
 
-    # streaming loop: consecutive steps alternate between the two lanes of the InputPath (and between two
-    # sets of output buffers), at most two steps in flight; every step is a full pass over its batch
-    outs = [out, {k: (tuple(torch.empty_like(t) if t is not None else None for t in v) if isinstance(v, tuple)
-                      else torch.empty_like(v)) for k, v in out.items()}]
+    # streaming loop: consecutive batches alternate between the two lanes of the InputPath (and between two sets
+    # of output buffers), at most `inflight` batches in flight; every batch is a full pass
     inflight = []
     tick = [0]
 
-    def step_dev():
-        h = path.step_device_async(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out=outs[tick[0] & 1])
+    def batch_dev(pth=None, oo=None):
+        h = (pth or path).step_device_async(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out=(oo or outs)[tick[0] & 1])
         tick[0] += 1
         inflight.append(h)
         if len(inflight) > args.inflight - 1:
@@ -417,10 +558,10 @@ def run_ours(args):
 
     pending = []
 
-    def step_e2e():
-        # same loop from pinned HOST buffers: the H2D copy and the pillarize stage of this step overlap the
-        # encode stage of the previous one; every step's counters are read back on the host inside the timed
-        # region
+    def batch_e2e():
+        # from pinned HOST buffers: the H2D copy (and the on-device aggregation, when configured) and the pillarize
+        # stage of this batch overlap the encode stage of the previous one; every batch's counters + status word
+        # are read back on the host inside the timed region
         pending.append(path.step_host_async(batch, out=outs[tick[0] & 1]))
         tick[0] += 1
         if len(pending) > args.inflight - 1:
@@ -430,68 +571,79 @@ def run_ours(args):
         while pending:
             pending.pop(0).counters()
 
+    # warm-up + calibration of the batches per driver step: the timed region lasts >= MIN_TIMED_S whatever --steps is
     for _ in range(max(args.warmup, 3)):
-        step_dev()
+        batch_dev()
     drain_dev()
+    ms_cal = timed(lambda: ([batch_dev() for _ in range(10)], drain_dev())) / 10.0
+    ms_cal, _ = reduce_over_ranks(ms_cal, 0.0, dev)
+    reps = max(1, int(math.ceil(MIN_TIMED_S * 1e3 / (args.steps * ms_cal))))
+    n_batches = args.steps * reps
+
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.start()
     n0 = L.pp_launch_count()
 
-    def timed_loop():
-        for _ in range(args.steps):
-            step_dev()
+    def loop_dev(pth=None, oo=None):
+        for _ in range(n_batches):
+            batch_dev(pth, oo)
         drain_dev()
 
-    ms = timed(timed_loop, 1)
+    ms = timed(loop_dev)
     launches = (L.pp_launch_count() - n0)
     clocks = sampler.stop()
-    ms_max, units = reduce_over_ranks(ms, float(BATCH * args.steps), dev)
+    ms_max, units = reduce_over_ranks(ms, float(B * n_batches), dev)
     value = units / (ms_max / 1e3)
+    n_pil = out["pillars"][2].cpu().numpy()
+    live = int(n_pil.sum())
 
     # the same device loop with K3 emitting the positives list instead of the dense [B,A,9] tensors
     list_mode = None
-    if fused and not args.no_dense_reference:
+    if fused and default_cfg and not args.no_dense_reference:
         path.targets_as_list = True
         for _ in range(3):
-            step_dev()
+            batch_dev()
         drain_dev()
-        ms_l = timed(timed_loop, 1)
+        ms_l = timed(loop_dev)
         path.targets_as_list = False
-        ms_l_max, units_l = reduce_over_ranks(ms_l, float(BATCH * args.steps), dev)
+        ms_l_max, units_l = reduce_over_ranks(ms_l, float(B * n_batches), dev)
         list_mode = {"what": "same streaming loop, targets as a positives list (pp_assign_targets_list): K3 writes a few KB "
-                             "instead of 155 MB per step; consumer pp_loss_list", "value": units_l / (ms_l_max / 1e3),
-                     "unit": UNIT, "ms_per_step": ms_l_max / args.steps}
+                             "instead of 155 MB per batch; consumer pp_loss_list", "value": units_l / (ms_l_max / 1e3),
+                     "unit": UNIT, "ms_per_batch": ms_l_max / n_batches}
 
-    # end-to-end through the host-facing call: pinned host buffers in, counters out, every step
+    # end-to-end through the host-facing call: pinned host buffers in, counters + status out, every batch
     for _ in range(3):
-        step_e2e()
+        batch_e2e()
     drain_e2e()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    drain_e2e()                                # the last step's counters are read before the clock stops
+    for _ in range(n_batches):
+        batch_e2e()
+    drain_e2e()                                # the last batch's counters are read before the clock stops
     e1.record()
     barrier()
     ms_e = max(e0.elapsed_time(e1), 0.0)
     ms_e_host = (time.perf_counter() - t_host0) * 1e3
-    ms_e_max, units_e = reduce_over_ranks(ms_e, float(BATCH * args.steps), dev)
+    ms_e_max, units_e = reduce_over_ranks(ms_e, float(B * n_batches), dev)
     e2e_value = units_e / (ms_e_max / 1e3)
-    h2d = int(batch["blob"].numel())
-    d2h = int(BATCH * 4 + BATCH * 4 * 4)
+    h2d = int(batch["blob"].numel()) * reps
+    d2h = int(B * 4 + B * 4 * 4 + 4) * reps
 
-    alg = algorithmic_bytes(BATCH, P, N, C, H, W, A, cfg.num_classes, T, True)
+    _, real_slots = count_slots(wl["flat"], cfg)
+    alg = algorithmic_bytes(B, P, N, C, H, W, A, cfg.num_classes, T, True, live, real_slots, B * wl["n_gt"])
     peak, peak_src = measured_peak()
+    prof_steps = max(3, min(args.steps, 10))
 
     def kernel_table(pth, o):
         """Per-kernel durations, live, CUDA events on the launching stream (separate instrumented pass,
-        stream overlap off so that each kernel is timed running alone)."""
+        stream overlap off so that each kernel is timed running alone).  The dominant kernel is the one with the
+        largest share of the step's kernel time, whichever it is."""
         pth.overlap_targets = False
         L.pp_profile_enable(1)
         barrier()
-        for _ in range(args.steps):
+        for _ in range(prof_steps):
             pth.step_device(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out=o)
         rep = _lib.profile_report()
         L.pp_profile_enable(0)
@@ -499,7 +651,7 @@ def run_ours(args):
         ks = []
         tot_ms = sum(v[1] for v in rep.values()) or 1.0
         for name, (n, total_ms) in rep.items():
-            k = {"name": name, "launches_per_step": n / args.steps, "ms_per_launch": total_ms / n,
+            k = {"name": name, "launches_per_batch": n / prof_steps, "ms_per_launch": total_ms / n,
                  "share_of_kernel_time": total_ms / tot_ms}
             if name in alg:
                 k["alg_bytes_per_launch"] = alg[name]
@@ -508,94 +660,102 @@ def run_ours(args):
             ks.append(k)
         ks.sort(key=lambda k: -k["share_of_kernel_time"])
         dom = next((k for k in ks if "GBps" in k), None)
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom["name"])
-        except Exception:  # noqa: BLE001
-            pass
         roof = None
         if dom is not None:
+            traffic, traffic_src = ncu_traffic(dom["name"])
             roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": dom["frac_of_peak"], "traffic": traffic, "peak_source": peak_src,
-                    "alg_bytes_per_launch": dom["alg_bytes_per_launch"], "ms_per_launch": dom["ms_per_launch"]}
+                    "frac": dom["frac_of_peak"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "alg_bytes_per_launch": dom["alg_bytes_per_launch"], "ms_per_launch": dom["ms_per_launch"],
+                    "kernel_ms_per_batch": tot_ms / prof_steps}
+        ks.sort(key=lambda k: -k["share_of_kernel_time"])
         return ks, roof
 
     kernels, roofline = kernel_table(path, out)
 
-    # the other formulation of the same step, for reference (same inputs, same outputs)
+    # the other formulation of the same step (same inputs, same outputs), the reference's K2 on this GPU, and the
+    # training-side rows
     other = None
     training = None
-    if fused and not args.no_dense_reference:
-        path2 = pipeline.InputPath(cfg, device=dev, data_mean=mean, pfn_params=synth.make_pfn_params(0),
-                                   training=True, fused=False, anchors=anchors)
-        out2 = dict(out)
-        out2["pillars"] = (torch.empty((BATCH, 9, P, N), dtype=torch.float32, device=dev), out["pillars"][1],
-                           out["pillars"][2])
-        outs2 = [out2, dict(outs[1])]
-        outs2[1]["pillars"] = (torch.empty((BATCH, 9, P, N), dtype=torch.float32, device=dev), outs[1]["pillars"][1],
-                               outs[1]["pillars"][2])
-        infl2 = []
-
-        def loop2():
-            for i in range(args.steps):
-                h = path2.step_device_async(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out=outs2[i & 1])
-                infl2.append(h)
-                if len(infl2) > 1:
-                    infl2.pop(0).synchronize()
-            while infl2:
-                infl2.pop(0).synchronize()
-
-        loop2()
-        ms2 = timed(loop2, 1)
-        ms2_max, units2 = reduce_over_ranks(ms2, float(BATCH * args.steps), dev)
-        k2, roof2 = kernel_table(path2, out2)
+    comparator = None
+    if fused and default_cfg and not args.no_dense_reference:
+        path2 = pipeline.InputPath(cfg, device=dev, data_mean=mean, pfn_params=prm, training=True, fused=False, anchors=anchors)
+        outs2 = []
+        for o in outs:
+            o2 = dict(o)
+            o2["pillars"] = (torch.empty((B, 9, P, N), dtype=torch.float32, device=dev), o["pillars"][1], o["pillars"][2])
+            outs2.append(o2)
+        for _ in range(3):
+            batch_dev(path2, outs2)
+        drain_dev()
+        ms_c2 = timed(lambda: ([batch_dev(path2, outs2) for _ in range(10)], drain_dev())) / 10.0
+        ms_c2, _ = reduce_over_ranks(ms_c2, 0.0, dev)
+        nb2 = max(10, int(math.ceil(MIN_TIMED_S * 1e3 / ms_c2)))
+        ms2 = timed(lambda: ([batch_dev(path2, outs2) for _ in range(nb2)], drain_dev()))
+        ms2_max, units2 = reduce_over_ranks(ms2, float(B * nb2), dev)
+        k2, roof2 = kernel_table(path2, outs2[0])
         other = {"what": "signature-preserving sequence pp_pillarize -> x [B,9,P,N] -> pp_pfn_scatter (x materialised)",
-                 "value": units2 / (ms2_max / 1e3), "unit": UNIT, "ms_per_step": ms2_max / args.steps,
+                 "value": units2 / (ms2_max / 1e3), "unit": UNIT, "ms_per_batch": ms2_max / nb2,
                  "roofline": roof2, "kernels": k2}
-        # the two training-side rows next to the path, timed on this step's own outputs
+        if rank == 0 and not args.no_gpu_comparator:
+            try:
+                comparator = gpu_comparator(outs2[0]["pillars"][0], outs2[0]["pillars"][1], prm, dev, path2, path, d_pts,
+                                            batch["offsets"], outs[0])
+            except Exception as e:  # noqa: BLE001
+                comparator = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        # the training-side rows next to the path, timed on this batch's own outputs
         if rank == 0 and world == 1 and not args.no_training_rows:
-            training = training_rows(out2["pillars"][0], out2["pillars"][1], out["targets"], dev, peak, args.steps,
+            training = training_rows(outs2[0]["pillars"][0], outs2[0]["pillars"][1], out["targets"], dev, peak, prof_steps,
                                      path=path2, d_pts=d_pts, offsets=batch["offsets"],
                                      gt=(gt_dev, batch["gt_offsets"]), fused_path=path)
-        del out2, path2
+        del outs2, path2
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and default_cfg and not args.no_cpu_baseline:
         from oracle import native
         native.build()
         cores = cpu_cores()
         n_s = max(cores, 2) if cores > 1 else 2
         wall = run_cpu_pool(list(range(500, 500 + n_s)), cores)
         cpu_baseline = {"value": n_s / wall, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
-                        "sample": "%d sweeps of the workload on %d worker processes, %.1f s wall; %s" % (
-                            n_s, cores, wall, cpu_kind_note())}
+                        "sample": "%d sweeps of the workload on %d warm worker processes (anchors, data_mean and one "
+                                  "sweep done before the clock starts), %.1f s wall; %s" % (n_s, cores, wall, cpu_kind_note())}
 
     if rank == 0:
+        sweeps_per_step = B * reps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (PFN, features) + f64 (binning, means, IoU)",
+            "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32 (PFN, features) + f64 (binning, means, IoU)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sweeps_per_gpu_per_step": BATCH, "points_per_step_per_gpu": int(T),
-                       "path": ("fused pp_input_path: pillarize stages -> PFN + scatter straight from the compact "
-                                "per-point state, x [B,9,P,N] never materialised (padding slots evaluated once per "
-                                "(p,n)); see dense_path for the signature-preserving sequence") if fused else
-                               "pp_pillarize -> x [B,9,P,N] -> pp_pfn_scatter",
-                       "data_mean": "dense synthetic per-slot mean [9*P*N]", "bn": "training mode",
-                       "l2": "no flush: per-step working set ~1.5 GB (x 691 MB, canvas 369 MB, targets 156 MB, "
-                             "data_mean 173 MB) >> 126 MB L2",
-                       "loop": "streaming: steps alternate between two stream lanes (pillarize stage of step k+1 "
-                               "overlaps the encode stage of step k; encode stages ordered), <= 2 steps in flight, "
-                               "timed region ends after the last step has completed",
-                       "parallelism": "dp%d (one process per GPU, sweeps sharded, no collective)" % world},
-            "roofline": roofline, "kernels": kernels, "dense_path": other, "list_targets": list_mode, "training_rows": training,
-            "cpu_baseline": cpu_baseline,
+            "dense_path_value": other["value"] if other else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e_max / args.steps, "host_wall_ms_per_step": ms_e_host / args.steps,
-                    "pipeline": "step_host_async: copy stream + 2 staging buffers + 2 kernel lanes, at most two steps "
-                                "in flight; each step's counters are read back from pinned memory before the "
-                                "next-but-one step is issued"},
+                    "pipeline": "step_host_async: copy stream + 2 staging buffers + 2 kernel lanes, at most two batches "
+                                "in flight; each batch's counters and status word are read back from pinned memory "
+                                "before the next-but-one batch is issued.  The outputs (canvas %d MB, cls + reg targets "
+                                "%d MB per batch) STAY in HBM, where the reference's backbone and loss consume them "
+                                "(model/model.py:170-177, model/loss.py); D2H = per-sweep counters + status" % (
+                                    B * C * H * W * 4 // 2 ** 20, 2 * B * A * 9 * 4 // 2 ** 20)},
+            "roofline": roofline,
+            "config": {"workload": wl["workload"], "config": args.config, "sweeps_per_gpu_per_step": sweeps_per_step,
+                       "batches_per_step": reps, "sweeps_per_gpu_per_batch": B, "points_per_batch_per_gpu": int(T),
+                       "live_pillars_per_batch": live, "timed_region_s": ms_max / 1e3,
+                       "path": ("fused pp_input_path: pillarize stages -> PFN + scatter straight from the compact "
+                                "per-point state, x [B,9,P,N] never materialised (padding slots evaluated once per "
+                                "(p,n), batch-independent); see dense_path for the signature-preserving sequence") if fused else
+                               "pp_pillarize -> x [B,9,P,N] -> pp_pfn_scatter",
+                       "padding_passes_per_batch": 1 if fused else 0,
+                       "data_mean": "dense synthetic per-slot mean [9*P*N]", "bn": "training mode",
+                       "l2": "no flush: per-batch working set (canvas %d MB, targets %d MB, prepared data_mean %d MB) "
+                             ">> 126 MB L2" % (B * C * H * W * 4 // 2 ** 20, 2 * B * A * 9 * 4 // 2 ** 20, P * N * 48 // 2 ** 20),
+                       "loop": "streaming: batches alternate between two stream lanes (pillarize stage of batch k+1 "
+                               "overlaps the encode stage of batch k; encode stages ordered), <= %d batches in flight; one "
+                               "driver step = %d back-to-back batches so that the timed region is >= %.1f s; it ends "
+                               "after the last batch has completed" % (args.inflight, reps, MIN_TIMED_S),
+                       "parallelism": "dp%d (one process per GPU, sweeps sharded, no collective)" % world},
+            "gpu_comparator": comparator, "list_targets": list_mode, "cpu_baseline": cpu_baseline,
             "gpu_launches": int(launches), "clocks": clocks,
+            "kernels": kernels, "dense_path": other, "training_rows": training,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -610,8 +770,12 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="default", choices=["default", "b64", "stress"],
+                    help="default: BASELINE configs[1]+[2] (batch-4 per GPU, the line the driver records); b64: configs[3] "
+                         "(64 sweeps per step sharded over the GPUs, strong scaling); stress: configs[4] (10-sweep aggregated "
+                         "clouds, P = 30000, 200 GT boxes)")
+    ap.add_argument("--no-gpu-comparator", action="store_true", help="skip timing the reference's PPFeatureNet + PPScatter on the GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--reserve-sms", type=int, default=None, help="SMs the padding pass leaves free (experiment)")
     ap.add_argument("--no-training-rows", action="store_true", help="skip the PFN backward / loss front-end timings")
     ap.add_argument("--no-dense-reference", action="store_true", help="skip the extra dense_path measurement")
     ap.add_argument("--inflight", type=int, default=2, help="steps in flight in the streaming loops (>= 2)")

@@ -18,7 +18,7 @@ def build(reference_root="/root/reference"):
     """Compile the reference module if its sources are present; returns True on success."""
     if not os.path.exists(os.path.join(reference_root, "data", "pillars.cpp")):
         return False
-    subprocess.check_call(["make", "-s", "-C", _HERE, "ref", "REF=" + reference_root])
+    subprocess.check_call(["make", "-s", "-C", _HERE, "ref", "refpy", "REF=" + reference_root])
     return True
 
 
