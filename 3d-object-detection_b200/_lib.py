@@ -37,7 +37,6 @@ _SIGNATURES = {
     "pp_launch_count": (_i64, []),
     "pp_set_option": (_c.c_int, [_c.c_char_p, _c.c_int]),
     "pp_profile_enable": (_c.c_int, [_c.c_int]),
-    "pp_debug_tc_timing": (_c.c_int, [_i64p]),
     "pp_profile_report": (_i64, [_c.c_char_p, _i64]),
     "pp_pillarize_workspace_bytes": (_sz, [_i32, _i64, _gridp, _i32]),
     "pp_pillarize": (_c.c_int, [_vp, _i32, _i64, _i64, _i64p, _i32, _gridp, _i32, _i32, _vp, _vp,
@@ -84,6 +83,12 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
+# include/pp_b200_debug.h: bound only when the library was built with -DPP_DEBUG (build.py --debug)
+_DEBUG_SIGNATURES = {
+    "pp_debug_set": (_c.c_int, [_c.c_char_p, _c.c_int]),
+    "pp_debug_tc_timing": (_c.c_int, [_i64p]),
+}
+
 
 def lib_path():
     return _build.LIB_PATH
@@ -107,6 +112,11 @@ def load():
         fn = getattr(L, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    for name, (res, args) in _DEBUG_SIGNATURES.items():
+        fn = getattr(L, name, None)
+        if fn is not None:
+            fn.restype = res
+            fn.argtypes = args
     _lib = L
     return L
 

@@ -22,7 +22,7 @@ def sources():
 
 def _deps():
     return sources() + sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + [
-        os.path.join(HERE, "..", "include", "pp_b200.h")]
+        os.path.join(HERE, "..", "include", "pp_b200.h"), os.path.join(HERE, "..", "include", "pp_b200_debug.h")]
 
 
 def is_stale():
@@ -32,12 +32,17 @@ def is_stale():
     return any(os.path.getmtime(p) > t for p in _deps())
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into libpp_b200.so.  Returns the library path."""
-    if not force and not is_stale():
+def build(force=False, verbose=False, debug=None):
+    """Compile every CUDA source for sm_100a into libpp_b200.so.  Returns the library path.
+    ``debug`` (default: environment PP_DEBUG=1) adds -DPP_DEBUG: the development entry points of
+    include/pp_b200_debug.h; the product build does not export them."""
+    if debug is None:
+        debug = os.environ.get("PP_DEBUG", "0") == "1"
+    if not force and not is_stale() and not debug:
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    cmd = ([nvcc] + NVCC_FLAGS + (["-DPP_DEBUG"] if debug else []) + (["-Xptxas", "-v"] if verbose else []) +
+           ["-o", LIB_PATH] + sources())
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout)
@@ -48,4 +53,4 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     import sys
-    print(build(force=True, verbose="-v" in sys.argv))
+    print(build(force=True, verbose="-v" in sys.argv, debug=("--debug" in sys.argv) or None))

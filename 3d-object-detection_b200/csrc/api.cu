@@ -53,15 +53,23 @@ int pp_last_cuda_error(void) { return pp::g_last_cuda_error; }
 int pp_set_option(const char* key, int value) {
   if (key == nullptr) return PP_ERR_INVALID_ARG;
   if (strcmp(key, "pfn_tensor_cores") == 0) { pp::g_opt_pfn_tensor_cores = value; return PP_OK; }   // 0 CUDA cores, 1 fp16 split (+TF32 fallback), 2 TF32 split
-  if (strcmp(key, "pad_reserve_sms") == 0) { pp::g_opt_pad_reserve_sms = value < 0 ? 0 : value; return PP_OK; }
   if (strcmp(key, "loss_tma") == 0) { pp::g_opt_loss_tma = value; return PP_OK; }
+  return PP_ERR_INVALID_ARG;
+}
+
+#ifdef PP_DEBUG
+/* Development entry points (include/pp_b200_debug.h): only in a library built with -DPP_DEBUG (build.py --debug). */
+int pp_debug_set(const char* key, int value) {
+  if (key == nullptr) return PP_ERR_INVALID_ARG;
+  if (strcmp(key, "pad_reserve_sms") == 0) { pp::g_opt_pad_reserve_sms = value < 0 ? 0 : value; return PP_OK; }
   if (strcmp(key, "pfn_tc_timing") == 0) { pp::g_opt_pfn_tc_timing = value; return PP_OK; }
   if (strcmp(key, "pfn_tc_debug") == 0) { pp::g_opt_pfn_tc_debug = value; return PP_OK; }
   return PP_ERR_INVALID_ARG;
 }
 
-/* development: per-role wait cycles of CTA 0 of the last k_pfn_stats_tc launch (64 int64) */
+/* per-role wait cycles of CTA 0 of the last tensor-core PFN launch (128 int64) */
 int pp_debug_tc_timing(int64_t* out64) { return out64 ? pp::read_tc_prof((long long*)out64) : PP_ERR_INVALID_ARG; }
+#endif
 
 int64_t pp_launch_count(void) { return (int64_t)pp::g_launches.load(); }
 

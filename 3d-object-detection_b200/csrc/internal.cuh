@@ -25,8 +25,6 @@ struct CompactPillars {
   const void* mean_prepared; // pp_mean_prepare's output for data_mean, or nullptr (prepared per call in the workspace)
 };
 
-constexpr int kSparseMaxSweeps = 8;   // sweeps per padding pass of the BACKWARD (pfn_bwd.cu); the forward's padding pass is batch-independent
-
 struct PfnParams {
   const float *conv_w, *conv_b, *bn_w, *bn_b;
   float *running_mean, *running_var;
@@ -34,15 +32,6 @@ struct PfnParams {
   int training;
   float momentum, eps;
 };
-
-namespace tch {
-// arguments of the padding pass (k_pfn_stats_tc<.., PAD = true>, pfn_tc16.cu)
-struct PadArgs {
-  int nb;                                   // real sweeps of this pass (<= kSparseMaxSweeps)
-  int b0;                                   // first sweep of this pass (ext rows are indexed by b0 + b)
-  const unsigned long long* packed;         // [P]: byte b = min(count of pillar p in sweep b, N), 0xff = not a live pillar there
-};
-}  // namespace tch
 
 size_t pfn_sparse_workspace_bytes(int B, int P, int N, int C, int H, int W, bool own_prep);
 size_t mean_prepared_bytes(int P, int N);

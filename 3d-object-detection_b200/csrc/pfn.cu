@@ -612,7 +612,7 @@ int launch_stats_tc(const float* d_x, int B, int P, int N, const float* w, const
 bool pfn_tc16_supported(int D, int N, int C, int P, const void* x);
 int launch_stats_tc16(const float* d_x, int B, int P, int N, const float* w, const float* bias,
                       const float* bn_w, int training, float* ext, double* partials, int nblocks,
-                      int* range_flag, const tch::PadArgs* pad, cudaStream_t st);
+                      int* range_flag, cudaStream_t st);
 extern int g_opt_pfn_tensor_cores;
 extern int g_opt_pad_reserve_sms;
 extern int g_opt_pfn_tc_debug;
@@ -625,7 +625,7 @@ static int launch_stats(const float* d_x, int B, int P, int N, int C, const floa
     if (g_opt_pfn_tensor_cores == 1 && pfn_tc16_supported(kD, N, C, P, d_x)) {
       // fp16 fast path, then the TF32 kernel as a guarded fallback: it returns at once unless the
       // fast path found a value outside the fp16 range, in which case it recomputes every output
-      const int rc = launch_stats_tc16(d_x, B, P, N, w, bias, bn_w, training, ws.ext, ws.partials, nblocks, ws.flags, nullptr, st);
+      const int rc = launch_stats_tc16(d_x, B, P, N, w, bias, bn_w, training, ws.ext, ws.partials, nblocks, ws.flags, st);
       if (rc != PP_OK) return rc;
       return launch_stats_tc(d_x, B, P, N, w, bias, bn_w, training, ws.ext, ws.partials, nblocks, ws.flags, st);
     }

@@ -123,17 +123,12 @@ __device__ __forceinline__ float h_value(unsigned short h) {
         "=r"(v[14]), "=r"(v[15])                                                                    \
       : "r"(taddr))
 
-// PAD = true is the padding pass of the sparse path (pfn.cu: pfn_sparse_scatter): the input tensor is
-// data_mean viewed as one sweep [9,P,N], the weights are negated (a padding slot holds x = 0 - mean),
-// and instead of one maximum per pillar the epilogue keeps, for each of the `pad.nb` real sweeps, the
-// maximum over the slots n >= cnt[b][p] that are padding in THAT sweep; the statistics are summed
-// unweighted over all (p, n) (the caller multiplies by the number of sweeps).
-template <bool TRAIN, bool PAD, int NBMAX>
+template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_pfn_stats_tc(const __grid_constant__ CUtensorMap tmap, int B, int P, int N,
                const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                const float* __restrict__ bn_w, float* __restrict__ ext, double* __restrict__ partials,
-               int* __restrict__ range_flag, int dbg, long long* __restrict__ prof, PadArgs pad) {
+               int* __restrict__ range_flag, int dbg, long long* __restrict__ prof) {
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((128u - (smem_u32(smem_unaligned) & 127u)) & 127u);
   const Smem sp = smem_plan(N);
@@ -184,7 +179,6 @@ k_pfn_stats_tc(const __grid_constant__ CUtensorMap tmap, int B, int P, int N,
         v = K == 27 ? bh : (bb - bh);
       }
       const int j = K >> 4, kk = K & 15;
-      if (PAD && K < 27) v = -v;             // x = 0 - mean
       *reinterpret_cast<unsigned short*>(smem + sp.a_off + j * 2048 + (m >> 3) * 256 + (kk >> 3) * 128 + (m & 7) * 16 + (kk & 7) * 2) =
           h_bits(sgn * v);
     }
@@ -260,79 +254,37 @@ k_pfn_stats_tc(const __grid_constant__ CUtensorMap tmap, int B, int P, int N,
     const int h = lane >> 4;
     const int c = 16 * q + (int)(lane & 15u);
     const float sgn = bn_w[c] < 0.f ? -1.f : 1.f;
-    double accS = 0.0, accQ = 0.0;
-    // PAD: the first half also carries the per-sweep masked maxima of the chunks that straddle a count
-    // (~1400 cycles per visit, measured), so it gets fewer columns
-    const int split = (PAD && N >= 136) ? 72 : ((N / 8 + 1) / 2) * 8;
+    // running sums of the visits as unevaluated fp32 pairs (TwoSum): keeps the fp64 pipe (F2F + DADD chain, 13 %
+    // of the stall samples of the padding pass in ncu r2d) out of the loop
+    float sh = 0.f, sl = 0.f, qh = 0.f, ql = 0.f;
+    auto two_sum = [](float& hi, float& lo, float b) {
+      const float s2 = __fadd_rn(hi, b);
+      const float bb = __fsub_rn(s2, hi);
+      lo = __fadd_rn(lo, __fadd_rn(__fsub_rn(hi, __fsub_rn(s2, bb)), __fsub_rn(b, bb)));
+      hi = s2;
+    };
+    const int split = ((N / 8 + 1) / 2) * 8;
     const int n0 = j ? split : 0, n1 = j ? N : split;
     const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(e * kAccCols + n0);
     const int ncols = n1 - n0;             // multiple of 8
-    // PAD: the packed per-sweep counts of a pillar are fetched one visit ahead (the epilogue is the
-    // bottleneck, so the accumulator is usually ready and a load issued at the wait would be exposed)
-    unsigned long long pk_next = 0ull;
-    if (PAD && e < my_pairs) pk_next = __ldg(pad.packed + 2 * ((int)blockIdx.x + e * (int)gridDim.x) + h);
     for (int it = e; it < my_pairs; it += 2) {
       const uint32_t n = (uint32_t)(it >> 1);
-      const int r = 2 * ((int)blockIdx.x + it * (int)gridDim.x) + h;      // row: pillar (b,p); PAD: pillar p
-      const unsigned long long pk = pk_next;
-      if (PAD && it + 2 < my_pairs) pk_next = __ldg(pad.packed + 2 * ((int)blockIdx.x + (it + 2) * (int)gridDim.x) + h);
+      const int r = 2 * ((int)blockIdx.x + it * (int)gridDim.x) + h;      // row: pillar (b,p)
       mbar_wait_t(&acc_full[e], n & 1u, pon, pacc[0]);
       tc_fence_after();
       const long long tq0 = pon ? clock64() : 0;
       // four independent accumulator sets break the dependent chains; sums are packed fp32 pairs.
       // 2*relu(s*y) = s*y + |y| is one FFMA (the ALU pipe that FMNMX runs on is half rate).
       float mx[2] = {-INFINITY, -INFINITY};
-      constexpr int NCH = PAD ? 2 : 4;       // accumulator chains (the padding pass is short of registers)
+      constexpr int NCH = 4;                 // accumulator chains
       unsigned long long S[4] = {0ull, 0ull, 0ull, 0ull}, Q[4] = {0ull, 0ull, 0ull, 0ull};
-      // PAD: per real sweep, first padding slot of this pillar (one byte each; 0xff = not live there)
-      // sm[b]: chunks below the largest count; common: chunks that are padding in every sweep (most)
-      float sm[NBMAX], common = -INFINITY;
-      int cmaxcnt = 0;
-      if (PAD) {
-#pragma unroll
-        for (int b = 0; b < NBMAX; ++b) {
-          sm[b] = -INFINITY;
-          if (b < pad.nb) {
-            const int cb = (int)((pk >> (8 * b)) & 0xffull);
-            if (cb != 0xff) cmaxcnt = max(cmaxcnt, cb);
-          }
-        }
-      }
       // three passes over the chunk keep every instruction independent of its neighbours (the t values
       // replace the y values in place).  One 32-column tcgen05.ld per chunk, no register double buffer:
       // the four epilogue warps of a scheduler hide each other's TMEM latency, and ptxas sinks a
       // prefetching tcgen05.ld below the arithmetic anyway (measured: x32 single 4.2 cycles per
       // warp-value per scheduler, x16 double-buffered 5.1; scripts/ubench/epi3.cu)
       auto consume = [&](uint32_t* v, const int cnt, const int col0) {
-        if (PAD) {
-          // maximum of the chunk, folded into the suffix maximum of every sweep whose padding range
-          // covers it; a chunk that straddles a sweep's first padding slot is masked per column
-          float c0 = -INFINITY, c1 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            if (i < cnt) { if (i & 2) c1 = fmaxf(c1, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1]))); else c0 = fmaxf(c0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1]))); }
-          const float cm = fmaxf(c0, c1);
-          if (col0 >= cmaxcnt) {
-            common = fmaxf(common, cm);
-          } else {
-#pragma unroll
-          for (int b = 0; b < NBMAX; ++b) {
-            if (b < pad.nb) {
-              int cb = (int)((pk >> (8 * b)) & 0xffull);
-              if (cb == 0xff) cb = 0;                 // not live: never written, treat as all padding
-              if (cb <= col0) {
-                sm[b] = fmaxf(sm[b], cm);
-              } else if (cb < col0 + cnt) {
-                float t = sm[b];
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < cnt && col0 + i >= cb) t = fmaxf(t, __uint_as_float(v[i]));
-                sm[b] = t;
-              }
-            }
-          }
-          }
-        } else {
+        {
 #pragma unroll
           for (int i = 0; i < 32; i += 2)
             if (i < cnt) mx[(i >> 1) & 1] = fmaxf(mx[(i >> 1) & 1], fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
@@ -351,8 +303,7 @@ k_pfn_stats_tc(const __grid_constant__ CUtensorMap tmap, int B, int P, int N,
       if (!(dbg & 4)) {
         uint32_t v[32];
         int col = 0;
-        // the narrow chunks come first: most pillars hold < 8 points, so the chunk that straddles the
-        // first padding slot (PAD: masked per column) is the 8-column one
+        // the narrow chunks come first
         if (ncols & 8) {
           PP_TMEM_LD8(taddr + col, v);
           tmem_ld_wait();
@@ -377,22 +328,14 @@ k_pfn_stats_tc(const __grid_constant__ CUtensorMap tmap, int B, int P, int N,
       if (pon) pacc[1] += clock64() - tq0;
       // TMEM holds 256*s*y: the partial extreme of this column half goes to ext[r][j][c]; consumers
       // combine the fields (max when gamma >= 0, min otherwise)
-      if (PAD) {
-        // sparse layout ext[b*P+p][3][64]: field 0 = real points (k_pfn_real), fields 1, 2 = padding
-        // slots of the two column halves; an empty range stays -inf (+inf after the sign), neutral
-#pragma unroll
-        for (int b = 0; b < NBMAX; ++b)
-          if (b < pad.nb && ((pk >> (8 * b)) & 0xffull) != 0xffull)
-            ext[(((size_t)(pad.b0 + b) * P + r) * 3 + 1 + j) * 64 + c] = sgn * fmaxf(sm[b], common) * (1.f / 256.f);
-      } else {
-        ext[(size_t)r * 128 + j * 64 + c] = sgn * fmaxf(mx[0], mx[1]) * (1.f / 256.f);
-      }
+      ext[(size_t)r * 128 + j * 64 + c] = sgn * fmaxf(mx[0], mx[1]) * (1.f / 256.f);
       if (TRAIN) {
-        accS += (double)((pair_sum(S[0]) + pair_sum(S[1])) + (pair_sum(S[2]) + pair_sum(S[3])));
-        accQ += (double)((pair_sum(Q[0]) + pair_sum(Q[1])) + (pair_sum(Q[2]) + pair_sum(Q[3])));
+        two_sum(sh, sl, (pair_sum(S[0]) + pair_sum(S[1])) + (pair_sum(S[2]) + pair_sum(S[3])));
+        two_sum(qh, ql, (pair_sum(Q[0]) + pair_sum(Q[1])) + (pair_sum(Q[2]) + pair_sum(Q[3])));
       }
     }
     if (TRAIN) {
+      double accS = (double)sh + (double)sl, accQ = (double)qh + (double)ql;
       accS += __shfl_xor_sync(0xffffffffu, accS, 16);
       accQ += __shfl_xor_sync(0xffffffffu, accQ, 16);
       if (lane < 16) {
@@ -505,11 +448,10 @@ bool pfn_tc16_supported(int D, int N, int C, int P, const void* x) {
          tch::encode_fn() != nullptr;
 }
 
-// pad == nullptr: statistics + per-pillar extremes of x [B,9,P,N] -> ext [B*P][2][64].
-// pad != nullptr: padding pass of the sparse path over d_x = data_mean ([9,P,N], B must be 1).
+// statistics + per-pillar extremes of x [B,9,P,N] -> ext [B*P][2][64]
 int launch_stats_tc16(const float* d_x, int B, int P, int N, const float* w, const float* bias,
                       const float* bn_w, int training, float* ext, double* partials, int nblocks,
-                      int* range_flag, const tch::PadArgs* pad, cudaStream_t st) {
+                      int* range_flag, cudaStream_t st) {
   const tch::Smem sp = tch::smem_plan(N);
   if (sp.raw_stages < 2) return PP_ERR_UNSUPPORTED;
   CUtensorMap tmap;
@@ -523,24 +465,14 @@ int launch_stats_tc16(const float* d_x, int B, int P, int N, const float* w, con
     return PP_ERR_UNSUPPORTED;
   long long* prof = g_opt_pfn_tc_timing ? tc_prof_ptr() : nullptr;
   PP_CUDA(cudaMemsetAsync(range_flag, 0, sizeof(int), st));
-  const tch::PadArgs pa = pad ? *pad : tch::PadArgs{0, 0, nullptr};
-#define PP_TC16(TR, PD, NB, NAME)                                                                                 \
+#define PP_TC16(TR)                                                                                               \
   do {                                                                                                            \
-    PP_CUDA(cudaFuncSetAttribute(tch::k_pfn_stats_tc<TR, PD, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total)); \
-    PP_KERNEL(NAME, st,                                                                                           \
-              (tch::k_pfn_stats_tc<TR, PD, NB><<<nblocks, tch::kThreads, sp.total, st>>>(                         \
-                  tmap, B, P, N, w, bias, bn_w, ext, partials, range_flag, g_opt_pfn_tc_debug, prof, pa)));      \
+    PP_CUDA(cudaFuncSetAttribute(tch::k_pfn_stats_tc<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total)); \
+    PP_KERNEL("k_pfn_stats_tc", st,                                                                               \
+              (tch::k_pfn_stats_tc<TR><<<nblocks, tch::kThreads, sp.total, st>>>(                                 \
+                  tmap, B, P, N, w, bias, bn_w, ext, partials, range_flag, g_opt_pfn_tc_debug, prof)));          \
   } while (0)
-  if (pad) {
-    if (B != 1 || pad->nb < 1 || pad->nb > kSparseMaxSweeps) return PP_ERR_INVALID_ARG;
-    if (pad->nb <= 4) {
-      if (training) PP_TC16(true, true, 4, "k_pfn_pad_tc"); else PP_TC16(false, true, 4, "k_pfn_pad_tc");
-    } else {
-      if (training) PP_TC16(true, true, 8, "k_pfn_pad_tc"); else PP_TC16(false, true, 8, "k_pfn_pad_tc");
-    }
-  } else {
-    if (training) PP_TC16(true, false, 1, "k_pfn_stats_tc"); else PP_TC16(false, false, 1, "k_pfn_stats_tc");
-  }
+  if (training) PP_TC16(true); else PP_TC16(false);
 #undef PP_TC16
   return PP_OK;
 }

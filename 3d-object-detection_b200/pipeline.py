@@ -119,7 +119,7 @@ class _InputPathFunction(torch.autograd.Function):
 
 class InputPath:
     def __init__(self, cfg=None, device=None, data_mean=None, pfn_params=None, anchors=None,
-                 training=True, fused=False):
+                 training=True, fused=False, n_lanes=2):
         if not torch.cuda.is_available():
             raise _lib.PPError("no CUDA device: the input path has no CPU fallback")
         _lib.load()
@@ -153,11 +153,12 @@ class InputPath:
         # two lanes (main + side stream each) for the *_async calls: consecutive steps alternate lanes, so
         # the latency-bound pillarize stage of step k+1 overlaps the encode stage of step k; the encode
         # stages themselves are ordered (they update the BatchNorm running statistics)
-        self._lanes = [(torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)) for _ in range(2)]
+        self._lanes = [(torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+                       for _ in range(max(2, int(n_lanes)))]
         self._lane_no = 0
         self._last_encode = None
-        self._stage = [None, None]
-        self._slot_free = [None, None]
+        self._stage = [None] * len(self._lanes)
+        self._slot_free = [None] * len(self._lanes)
         self._result_pin = [None] * 8      # ring of pinned result buffers: a handle's counters stay valid for 8 more steps
         self._step_no = 0
 
@@ -522,7 +523,7 @@ class InputPath:
         return canvas, npil
 
     def _next_lane(self):
-        lane = self._lanes[self._lane_no & 1]
+        lane = self._lanes[self._lane_no % len(self._lanes)]
         self._lane_no += 1
         return lane
 
@@ -547,7 +548,7 @@ class InputPath:
         ``out`` buffers.  Returns a ``StepHandle``; ``handle.counters()`` waits for this step only and must
         be called before eight further steps have been issued (the pinned result buffers form a ring)."""
         dev = self.device
-        slot = self._step_no & 1
+        slot = self._step_no % len(self._stage)
         self._step_no += 1
         main, side = self._next_lane()
         if self._slot_free[slot] is not None:

@@ -496,6 +496,11 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # the JSON line goes to the process's real stdout; anything native code prints there (NCCL prints its version
+    # banner on stdout) is sent to stderr instead
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     import pp_b200
@@ -508,7 +513,8 @@ def run_ours(args):
     mean = synth.make_data_mean(P, N, seed=0, dense=True)
     prm = synth.make_pfn_params(0)
     fused = not args.dense_path
-    path = pipeline.InputPath(cfg, device=dev, data_mean=mean, pfn_params=prm, training=True, fused=fused)
+    path = pipeline.InputPath(cfg, device=dev, data_mean=mean, pfn_params=prm, training=True, fused=fused,
+                              n_lanes=args.inflight)
     anchors = path.ensure_anchors()
     A = anchors.A
     batch = path.pack_host_batch(wl["sweeps"], wl["gts"], transforms=wl["transforms"])
@@ -523,7 +529,7 @@ def run_ours(args):
                 "targets": (torch.empty((B, A, cfg.num_classes), dtype=torch.float32, device=dev),
                             torch.empty((B, A, 9), dtype=torch.float32, device=dev))}
 
-    outs = [make_out(not fused), make_out(not fused)]
+    outs = [make_out(not fused) for _ in range(max(2, args.inflight))]
     out = outs[0]
 
     def barrier():
@@ -546,7 +552,7 @@ def run_ours(args):
     tick = [0]
 
     def batch_dev(pth=None, oo=None):
-        h = (pth or path).step_device_async(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out=(oo or outs)[tick[0] & 1])
+        h = (pth or path).step_device_async(d_pts, batch["offsets"], gt_dev, batch["gt_offsets"], out=(oo or outs)[tick[0] % len(oo or outs)])
         tick[0] += 1
         inflight.append(h)
         if len(inflight) > args.inflight - 1:
@@ -562,7 +568,7 @@ def run_ours(args):
         # from pinned HOST buffers: the H2D copy (and the on-device aggregation, when configured) and the pillarize
         # stage of this batch overlap the encode stage of the previous one; every batch's counters + status word
         # are read back on the host inside the timed region
-        pending.append(path.step_host_async(batch, out=outs[tick[0] & 1]))
+        pending.append(path.step_host_async(batch, out=outs[tick[0] % len(outs)]))
         tick[0] += 1
         if len(pending) > args.inflight - 1:
             pending.pop(0).counters()
@@ -678,7 +684,8 @@ def run_ours(args):
     training = None
     comparator = None
     if fused and default_cfg and not args.no_dense_reference:
-        path2 = pipeline.InputPath(cfg, device=dev, data_mean=mean, pfn_params=prm, training=True, fused=False, anchors=anchors)
+        path2 = pipeline.InputPath(cfg, device=dev, data_mean=mean, pfn_params=prm, training=True, fused=False, anchors=anchors,
+                                   n_lanes=args.inflight)
         outs2 = []
         for o in outs:
             o2 = dict(o)
@@ -757,7 +764,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks,
             "kernels": kernels, "dense_path": other, "training_rows": training,
         }
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -778,7 +786,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-training-rows", action="store_true", help="skip the PFN backward / loss front-end timings")
     ap.add_argument("--no-dense-reference", action="store_true", help="skip the extra dense_path measurement")
-    ap.add_argument("--inflight", type=int, default=2, help="steps in flight in the streaming loops (>= 2)")
+    ap.add_argument("--inflight", type=int, default=3, help="batches in flight in the streaming loops = stream lanes of the InputPath (>= 2)")
     ap.add_argument("--dense-path", action="store_true",
                     help="time the signature-preserving sequence pp_pillarize -> x [B,9,P,N] -> pp_pfn_scatter "
                          "instead of the fused pp_input_path (x never materialised)")

@@ -217,13 +217,14 @@ int pp_loss_scale_grads(float* d_grad_cls, size_t n_cls, float* d_grad_reg, size
  * pp_profile_report: synchronise the device, write one "name launches total_ms" line per kernel
  * into buf, clear the records, return the bytes needed. */
 int64_t pp_launch_count(void);
-/* Process-wide options.  "pfn_tensor_cores": 1 (default) runs the PFN statistics pass on tcgen05
- * tensor cores (TF32 3-term split) whenever D=9, C=64, N%8==0, N<=256; 0 forces the CUDA-core kernel. */
+/* Process-wide options.  "pfn_tensor_cores": 1 (default) runs the dense PFN statistics pass on tcgen05
+ * tensor cores (fp16 3-term split, TF32 split as the guarded fallback) whenever D=9, C=64, N%8==0, N<=256;
+ * 2 forces the TF32 kernel, 0 the CUDA-core kernel.  "loss_tma": 1 (default) uses the tensor-map TMA kernel for the
+ * classification loss where the shape allows, 0 the generic tile kernel.  Unknown keys: PP_ERR_INVALID_ARG.
+ * (Development knobs -- role timing, stage ablation -- are not part of this header: include/pp_b200_debug.h,
+ * present only in a library built with -DPP_DEBUG.) */
 int pp_set_option(const char* key, int value);
 int pp_profile_enable(int on);
-/* Development aid: with option "pfn_tc_timing"=1, CTA 0 of k_pfn_stats_tc records per-warp wait
- * cycles; this reads them back (128 int64: [warp][wait0, wait1, -, role total]). */
-int pp_debug_tc_timing(int64_t* out64);
 int64_t pp_profile_report(char* buf, int64_t buf_bytes);
 
 /* ------------------------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-"""Print the fused-vs-dense canvas differences and time the fused step (development aid)."""
+"""(needs a debug build: PP_DEBUG=1 python 3d-object-detection_b200/build.py)  Print the fused-vs-dense canvas differences and time the fused step (development aid)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
@@ -46,19 +46,19 @@ for _ in range(20): path.pillarize_encode(pts, offs, out=out)
 e1.record(); torch.cuda.synchronize()
 print("fused K1+K2: %.1f us per batch-4" % (e0.elapsed_time(e1) / 20 * 1e3))
 for dbg in (0, 16, 7, 23):
-    L.pp_set_option(b"pfn_tc_debug", dbg)
+    L.pp_debug_set(b"pfn_tc_debug", dbg)
     for _ in range(2): path.pillarize_encode(pts, offs, out=out)
     L.pp_profile_enable(1)
     for _ in range(5): path.pillarize_encode(pts, offs, out=out)
     rep = _lib.profile_report(); L.pp_profile_enable(0)
     print("dbg=%d k_pfn_pad_tc %.1f us avg over %d launches" % (dbg, rep["k_pfn_pad_tc"][1] / rep["k_pfn_pad_tc"][0] * 1e3, rep["k_pfn_pad_tc"][0]))
-L.pp_set_option(b"pfn_tc_debug", 0)
+L.pp_debug_set(b"pfn_tc_debug", 0)
 import ctypes
-L.pp_set_option(b"pfn_tc_timing", 1)
+L.pp_debug_set(b"pfn_tc_timing", 1)
 path.pillarize_encode(pts, offs, out=out)
 buf = (ctypes.c_int64 * 128)()
 L.pp_debug_tc_timing(buf)
-L.pp_set_option(b"pfn_tc_timing", 0)
+L.pp_debug_set(b"pfn_tc_timing", 0)
 for w in (0, 4, 8, 12, 16, 20, 24, 25):
     v = [buf[w * 4 + k] for k in range(4)]
     role = ("epi e%d j%d q%d (acc_full,busy)" % (w >> 3, (w >> 2) & 1, w & 3) if w < 16 else "conv(raw_full,b_empty)" if w < 24

@@ -1,4 +1,4 @@
-"""Role timing of CTA 0 of k_pfn_pad_tc (development): python scripts/pad_timing.py"""
+"""(needs a debug build: PP_DEBUG=1 python 3d-object-detection_b200/build.py)  Role timing of CTA 0 of k_pfn_pad_tc (development): python scripts/pad_timing.py"""
 import ctypes
 import os
 import sys
@@ -18,13 +18,13 @@ for _ in range(3):
     path.pillarize_encode(pts, offs)
 torch.cuda.synchronize()
 dbg0 = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-L.pp_set_option(b"pfn_tc_debug", dbg0)
-L.pp_set_option(b"pfn_tc_timing", 1)
+L.pp_debug_set(b"pfn_tc_debug", dbg0)
+L.pp_debug_set(b"pfn_tc_timing", 1)
 path.pillarize_encode(pts, offs)
 buf = (ctypes.c_int64 * 128)()
 L.pp_debug_tc_timing(buf)
-L.pp_set_option(b"pfn_tc_timing", 0)
-L.pp_set_option(b"pfn_tc_debug", 0)
+L.pp_debug_set(b"pfn_tc_timing", 0)
+L.pp_debug_set(b"pfn_tc_debug", 0)
 print("role timing with dbg =", dbg0)
 for w in (0, 5, 10, 12, 15, 16, 17):
     v = [buf[w * 4 + k] for k in range(4)]
@@ -32,13 +32,14 @@ for w in (0, 5, 10, 12, 15, 16, 17):
             "producer (wait empty)" if w == 16 else "mma (wait full, wait acc_empty, issue)")
     print("warp %2d %-44s %9d %9d %9d total %9d" % (w, role, v[0], v[1], v[2], v[3]))
 L.pp_profile_enable(1)
-for dbg in (0, 6, 22, 20, 18):
-    L.pp_set_option(b"pfn_tc_debug", dbg)      # bit 1: no MMAs, bit 2: no epilogue loads / arithmetic
+for dbg in (0,):
+    L.pp_debug_set(b"pfn_tc_debug", dbg)      # bit 1: no MMAs, bit 2: no epilogue loads / arithmetic
     for _ in range(5):
         path.pillarize_encode(pts, offs)
     rep = _lib.profile_report()
     if dbg == 0:
         for k, (n, ms) in rep.items():
             print("%-18s %8.2f us" % (k, 1e3 * ms / n))
-    print("dbg=%d k_pfn_pad_tc %8.2f us" % (dbg, 1e3 * rep["k_pfn_pad_tc"][1] / rep["k_pfn_pad_tc"][0]))
-L.pp_set_option(b"pfn_tc_debug", 0)
+    print("dbg=%d k_pfn_pad_tc %8.2f us  k_pfn_real %8.2f us" % (dbg, 1e3 * rep["k_pfn_pad_tc"][1] / rep["k_pfn_pad_tc"][0],
+                                                                 1e3 * rep["k_pfn_real"][1] / rep["k_pfn_real"][0]))
+L.pp_debug_set(b"pfn_tc_debug", 0)

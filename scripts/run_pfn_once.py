@@ -1,4 +1,4 @@
-"""Run the PFN (+scatter) stage a few times (for ncu captures of k_pfn_stats_tc / k_canvas)."""
+"""(needs a debug build: PP_DEBUG=1 python 3d-object-detection_b200/build.py)  Run the PFN (+scatter) stage a few times (for ncu captures of k_pfn_stats_tc / k_canvas)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
@@ -18,12 +18,12 @@ torch.cuda.synchronize()
 print("ok")
 if len(sys.argv) > 2:
     import ctypes
-    L.pp_set_option(b"pfn_tc_timing", 1)
-    if len(sys.argv) > 3: L.pp_set_option(b"pfn_tc_debug", int(sys.argv[3]))
+    L.pp_debug_set(b"pfn_tc_timing", 1)
+    if len(sys.argv) > 3: L.pp_debug_set(b"pfn_tc_debug", int(sys.argv[3]))
     path.encode(x, inds, out=canvas)
     buf = (ctypes.c_int64 * 128)()
     L.pp_debug_tc_timing(buf)
-    L.pp_set_option(b"pfn_tc_timing", 0)
+    L.pp_debug_set(b"pfn_tc_timing", 0)
     for w in range(26):
         v = [buf[w * 4 + k] for k in range(4)]
         role = ("epi e%d j%d q%d (acc_full,busy)" % (w >> 3, (w >> 2) & 1, w & 3) if w < 16 else "conv(raw_full,b_empty)" if w < 24

@@ -36,7 +36,7 @@ for fused in (True, False):
                                                 batch["gt_offsets"], as_list=True, capacity=6)
         cls = torch.randn((2, 54, 40, 40), device="cuda") - 3.0
         reg = torch.randn((2, 48, 40, 40), device="cuda")
-        out = PPLoss(0.4, 1.0, 250.0, 2, torch.device("cuda"))(cls.requires_grad_(True), reg.requires_grad_(True), pos)
+        out = PPLoss(0.4, 1.0, 250.0, 2, torch.device("cuda"))(cls.requires_grad_(True), reg.requires_grad_(True) * 1.0, pos)
         out[4].backward()
         try:
             path.check_status()

@@ -1,4 +1,4 @@
-"""Time the PFN (+scatter) stage alone, train vs eval mode, tensor-core vs CUDA-core kernel."""
+"""(needs a debug build: PP_DEBUG=1 python 3d-object-detection_b200/build.py)  Time the PFN (+scatter) stage alone, train vs eval mode, tensor-core vs CUDA-core kernel."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
@@ -29,6 +29,6 @@ print("train=True tc=0 no data_mean (zero slots skipped):", run(True, 0, dense=F
 print("train=True tc=1 no data_mean:", run(True, 1, dense=False))
 
 for dbg in (1, 2, 4, 3, 5, 6, 7):
-    L.pp_set_option(b"pfn_tc_debug", dbg)
+    L.pp_debug_set(b"pfn_tc_debug", dbg)
     print("dbg=%d (1=no convert, 2=no mma, 4=no epilogue reads) train:" % dbg, run(True, 1)["k_pfn_stats_tc"], "eval:", run(False, 1)["k_pfn_stats_tc"])
-L.pp_set_option(b"pfn_tc_debug", 0)
+L.pp_debug_set(b"pfn_tc_debug", 0)
