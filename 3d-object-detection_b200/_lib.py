@@ -24,6 +24,34 @@ class PPError(RuntimeError):
     pass
 
 
+_vp0, _i320, _i640, _sz0, _f320, _f640 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float, ctypes.c_double
+
+
+class PPStepPlan(ctypes.Structure):
+    """pp_step_plan (include/pp_b200.h), field for field."""
+    _fields_ = [
+        ("stream_main", _vp0), ("stream_side", _vp0), ("stream_copy", _vp0),
+        ("ev_fork", _vp0), ("ev_join", _vp0), ("ev_ready", _vp0), ("ev_slot_free", _vp0), ("ev_prev_encode", _vp0),
+        ("ev_encode_done", _vp0), ("ev_done", _vp0),
+        ("h_blob", _vp0), ("d_blob", _vp0), ("blob_bytes", _sz0),
+        ("n_files", _i320), ("d_file_offsets", _vp0), ("d_file_xforms", _vp0), ("min_dist", _f320),
+        ("d_points", _vp0), ("total_points", _i640), ("point_cols", _i640), ("h_sweep_offsets", _vp0), ("n_sweeps", _i320),
+        ("grid", PPGrid), ("max_points_per_pillar", _i320), ("max_pillars", _i320), ("d_data_mean", _vp0),
+        ("d_mean_prepared", _vp0),
+        ("C", _i320), ("d_conv_w", _vp0), ("d_conv_b", _vp0), ("d_bn_w", _vp0), ("d_bn_b", _vp0), ("d_running_mean", _vp0),
+        ("d_running_var", _vp0),
+        ("d_num_batches_tracked", _vp0), ("training", _i320), ("momentum", _f320), ("eps", _f320), ("canvas_h", _i320),
+        ("canvas_w", _i320),
+        ("d_canvas", _vp0), ("d_indices", _vp0), ("d_num_pillars", _vp0), ("d_ws_input", _vp0), ("ws_input_bytes", _sz0),
+        ("d_a_corners", _vp0), ("d_a_centers", _vp0), ("d_a_wlh", _vp0), ("d_a_yaw", _vp0), ("d_anchor_index", _vp0), ("A", _i640),
+        ("d_g_corners", _vp0), ("d_g_centers", _vp0), ("d_g_wlh", _vp0), ("d_g_yaw", _vp0), ("d_g_cls", _vp0),
+        ("h_gt_offsets", _vp0),
+        ("num_classes", _i320), ("pos_thresh", _f640), ("d_cls", _vp0), ("d_reg", _vp0), ("d_top_anchor", _vp0), ("d_counts", _vp0),
+        ("d_pos_anchor", _vp0), ("d_pos_cls", _vp0), ("d_pos_reg", _vp0), ("d_pos_offsets", _vp0), ("pos_capacity", _i320),
+        ("d_ws_targets", _vp0), ("ws_targets_bytes", _sz0),
+        ("d_status", _vp0), ("h_counters", _vp0)]
+
+
 _lib = None
 _c = ctypes
 _vp, _i32, _i64, _sz, _f32, _f64 = _c.c_void_p, _c.c_int32, _c.c_int64, _c.c_size_t, _c.c_float, _c.c_double
@@ -56,6 +84,8 @@ _SIGNATURES = {
     "pp_input_path": (_c.c_int, [_vp, _i32, _i64, _i64, _i64p, _i32, _gridp, _i32, _i32, _vp, _vp, _i32,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _i32, _i32,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
+    "pp_step": (_c.c_int, [_c.POINTER(PPStepPlan)]),
+    "pp_step_plan_bytes": (_sz, []),
     "pp_input_path_backward_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "pp_input_path_backward": (_c.c_int, [_i64p, _i32, _gridp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _i32,
                                           _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
@@ -112,6 +142,8 @@ def load():
         fn = getattr(L, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    if L.pp_step_plan_bytes() != ctypes.sizeof(PPStepPlan):
+        raise PPError("pp_step_plan layout mismatch: C %d bytes, ctypes %d" % (L.pp_step_plan_bytes(), ctypes.sizeof(PPStepPlan)))
     for name, (res, args) in _DEBUG_SIGNATURES.items():
         fn = getattr(L, name, None)
         if fn is not None:

@@ -11,6 +11,8 @@ parameters) on one GPU and turns raw sweeps + ground-truth boxes into the networ
 Sweeps are independent, so multi-GPU use is one ``InputPath`` per process / GPU over a shard of
 the batch with no collective (``shard_range``).
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -148,6 +150,8 @@ class InputPath:
         # fused=True: the step goes through pp_input_path (x never materialised); False: the
         # signature-preserving pp_pillarize -> x -> pp_pfn_scatter sequence
         self.fused = fused
+        # the streaming calls of the fused path go through ONE C call per batch (pp_step); False: the Python step
+        self.c_step = True
         # host-facing pipeline: copy stream, two device staging buffers, pinned result slots
         self._copy = torch.cuda.Stream(device=self.device)
         # two lanes (main + side stream each) for the *_async calls: consecutive steps alternate lanes, so
@@ -522,6 +526,172 @@ class InputPath:
             self._last_encode.record(main)
         return canvas, npil
 
+    # -- one C call per batch (pp_step) ----------------------------------------------------------------------
+    def _lane_ctx(self, k):
+        """Per-lane state of the C step driver: streams, pre-created events (raw handles), workspaces."""
+        ctx = self.__dict__.setdefault("_cstep_lanes", {}).get(k)
+        if ctx is None:
+            main, side = self._lanes[k]
+
+            def event():
+                e = torch.cuda.Event()
+                e.record(main)                       # materialises the cudaEvent_t; pp_step re-records it
+                return e
+            ctx = {"main": main, "side": side, "fork": event(), "join": event(), "ws_in": None, "ws_tg": None}
+            self._cstep_lanes[k] = ctx
+        return ctx
+
+    def _ring_ctx(self, i):
+        """Per in-flight-step state: completion / upload / encode-order events and the pinned counters."""
+        ring = self.__dict__.setdefault("_cstep_ring", {})
+        ctx = ring.get(i)
+        if ctx is None:
+            def event():
+                e = torch.cuda.Event()
+                e.record(self._copy)
+                return e
+            ctx = {"done": event(), "ready": event(), "encode": event(), "pin": None, "plan": _lib.PPStepPlan()}
+            ring[i] = ctx
+        return ctx
+
+    def _step_c(self, batch, d_pts, offsets, gt_dev, gt_offsets, out):
+        """Issue one batch through pp_step.  ``batch`` (a packed host batch) or ``d_pts`` / ``gt_dev`` (device)."""
+        L = _lib.load()
+        c = self.cfg
+        dev = self.device
+        B = len(offsets) - 1
+        P, N, C = c.max_pillars, c.max_points_per_pillar, c.feature_net_out
+        H, W = c.canvas_height, c.canvas_width
+        net = self.net
+        anchors = self.ensure_anchors()
+        A = anchors.A
+        k = self._lane_no % len(self._lanes)
+        self._lane_no += 1
+        lane = self._lane_ctx(k)
+        no = self._step_no
+        self._step_no += 1
+        R = 8
+        ring = self._ring_ctx(no % R)
+        slot = no % len(self._stage)
+        prep = self.mean_prepared
+        if prep is None and self.data_mean is not None:
+            prep = self.prepare_mean()
+            torch.cuda.current_stream(dev).synchronize()
+        T = int(offsets[-1])
+        Gt = int(gt_offsets[-1])
+        o = out or {}
+        canvas = o.get("canvas")
+        if canvas is None:
+            canvas = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+        if o.get("pillars") is not None:
+            _, inds, npil = o["pillars"]
+        else:
+            inds = torch.empty((B, P, 3), dtype=torch.int64, device=dev)
+            npil = torch.empty(B, dtype=torch.int32, device=dev)
+        pos = None
+        if self.targets_as_list:
+            from .box_utils import Positives
+            cap = 4096 * B
+            pos = Positives(torch.empty(cap, dtype=torch.int32, device=dev), torch.empty((cap, 9), dtype=torch.float32, device=dev),
+                            torch.empty((cap, 9), dtype=torch.float32, device=dev),
+                            torch.empty(B + 1, dtype=torch.int32, device=dev), B, A)
+            cls = reg = None
+        elif o.get("targets") is not None:
+            cls, reg = o["targets"]
+        else:
+            cls = torch.empty((B, A, c.num_classes), dtype=torch.float32, device=dev)
+            reg = torch.empty((B, A, 9), dtype=torch.float32, device=dev)
+        top = torch.empty(max(Gt, 1), dtype=torch.int32, device=dev)
+        counts = torch.empty((B, 4), dtype=torch.int32, device=dev)
+        grid = self._grid_struct()
+        n_in = L.pp_input_path_workspace_bytes(B, T, grid, N, P, C, H, W, 0)
+        if lane["ws_in"] is None or lane["ws_in"].numel() < n_in:
+            lane["ws_in"] = torch.empty(n_in, dtype=torch.uint8, device=dev)
+        n_tg = L.pp_assign_targets_workspace_bytes(B, A, Gt, None)
+        if lane["ws_tg"] is None or lane["ws_tg"].numel() < n_tg:
+            lane["ws_tg"] = torch.empty(n_tg, dtype=torch.uint8, device=dev)
+        pin = ring["pin"]
+        if pin is None or pin.numel() < 5 * B + 1:
+            pin = ring["pin"] = torch.empty(5 * B + 1, dtype=torch.int32).pin_memory()
+        momentum, eps = _bn_args(net.bn1)
+        w = net.conv1.weight
+        if not w.is_contiguous():
+            w = w.detach().contiguous()
+        nbt = net.bn1.num_batches_tracked
+        status = _runtime.status_word(dev)
+        pl = ring["plan"]
+        ptr = lambda t: t.data_ptr() if (t is not None and t.numel() > 0) else None
+        pl.stream_main, pl.stream_side, pl.stream_copy = lane["main"].cuda_stream, lane["side"].cuda_stream, self._copy.cuda_stream
+        pl.ev_fork, pl.ev_join = lane["fork"].cuda_event, lane["join"].cuda_event
+        pl.ev_done, pl.ev_encode_done = ring["done"].cuda_event, ring["encode"].cuda_event
+        pl.ev_prev_encode = self._last_encode.cuda_event if self._last_encode is not None else None
+        if batch is not None:
+            n = batch["blob"].numel()
+            dblob = self._stage[slot]
+            if dblob is None or dblob.numel() < n:
+                dblob = self._stage[slot] = torch.empty(n, dtype=torch.uint8, device=dev)
+            dv = self._blob_views(dblob, batch["layout"], T, batch["ncol"], Gt)
+            gt_dev = {kk: dv[kk] for kk in ("corners", "centers", "wlh", "yaw", "cls")}
+            d_pts = dv["points"][:max(T, 1)]
+            pl.h_blob, pl.d_blob, pl.blob_bytes = batch["blob"].data_ptr(), dblob.data_ptr(), n
+            pl.ev_ready = ring["ready"].cuda_event
+            if self._slot_free[slot] is None:
+                e = torch.cuda.Event()
+                e.record(lane["main"])
+                self._slot_free[slot] = e
+            pl.ev_slot_free = self._slot_free[slot].cuda_event
+            pl.n_files = int(batch.get("n_files") or 0)
+            if pl.n_files:
+                pl.d_file_offsets, pl.d_file_xforms = dv["file_offsets"].data_ptr(), dv["xforms"].data_ptr()
+                pl.min_dist = float(batch["min_dist"])
+            # the upload is ordered after whatever the caller queued on its current stream
+            self._copy.wait_stream(torch.cuda.current_stream(dev))
+        else:
+            pl.h_blob = pl.d_blob = pl.ev_ready = pl.ev_slot_free = None
+            pl.blob_bytes, pl.n_files = 0, 0
+            lane["main"].wait_stream(torch.cuda.current_stream(dev))
+        pl.d_points = d_pts.data_ptr() if T > 0 else None
+        pl.total_points, pl.point_cols = T, int(d_pts.stride(0))
+        pl.h_sweep_offsets = ctypes.cast(_lib.i64_array(offsets), ctypes.c_void_p)
+        pl.n_sweeps = B
+        pl.grid = grid
+        pl.max_points_per_pillar, pl.max_pillars = N, P
+        pl.d_data_mean = self.data_mean.data_ptr() if self.data_mean is not None else None
+        pl.d_mean_prepared = prep.data_ptr() if prep is not None else None
+        pl.C = C
+        pl.d_conv_w, pl.d_conv_b = w.data_ptr(), net.conv1.bias.data_ptr()
+        pl.d_bn_w, pl.d_bn_b = net.bn1.weight.data_ptr(), net.bn1.bias.data_ptr()
+        pl.d_running_mean, pl.d_running_var = net.bn1.running_mean.data_ptr(), net.bn1.running_var.data_ptr()
+        pl.d_num_batches_tracked = nbt.data_ptr() if nbt is not None else None
+        pl.training, pl.momentum, pl.eps = (1 if net.training else 0), momentum, eps
+        pl.canvas_h, pl.canvas_w = H, W
+        pl.d_canvas, pl.d_indices, pl.d_num_pillars = canvas.data_ptr(), inds.data_ptr(), npil.data_ptr()
+        pl.d_ws_input, pl.ws_input_bytes = lane["ws_in"].data_ptr(), lane["ws_in"].numel()
+        pl.d_a_corners, pl.d_a_centers = anchors.corners.data_ptr(), anchors.centers.data_ptr()
+        pl.d_a_wlh, pl.d_a_yaw, pl.d_anchor_index, pl.A = anchors.wlh.data_ptr(), anchors.yaw.data_ptr(), anchors.index.data_ptr(), A
+        pl.d_g_corners, pl.d_g_centers = ptr(gt_dev["corners"]) if Gt else None, ptr(gt_dev["centers"]) if Gt else None
+        pl.d_g_wlh, pl.d_g_yaw, pl.d_g_cls = (ptr(gt_dev["wlh"]), ptr(gt_dev["yaw"]), ptr(gt_dev["cls"])) if Gt else (None, None, None)
+        pl.h_gt_offsets = ctypes.cast(_lib.i64_array(gt_offsets), ctypes.c_void_p)
+        pl.num_classes, pl.pos_thresh = int(c.num_classes), float(c.iou_pos_thresh)
+        pl.d_cls, pl.d_reg = ptr(cls), ptr(reg)
+        pl.d_top_anchor, pl.d_counts = top.data_ptr(), counts.data_ptr()
+        if pos is not None:
+            pl.d_pos_anchor, pl.d_pos_cls, pl.d_pos_reg = pos.anchor.data_ptr(), pos.cls.data_ptr(), pos.reg.data_ptr()
+            pl.d_pos_offsets, pl.pos_capacity = pos.offsets.data_ptr(), pos.anchor.numel()
+        else:
+            pl.d_pos_anchor = pl.d_pos_cls = pl.d_pos_reg = pl.d_pos_offsets = None
+            pl.pos_capacity = 0
+        pl.d_ws_targets, pl.ws_targets_bytes = lane["ws_tg"].data_ptr(), lane["ws_tg"].numel()
+        pl.d_status, pl.h_counters = status.data_ptr(), pin.data_ptr()
+        with _runtime.on_device(dev):
+            rc = L.pp_step(ctypes.byref(pl))
+        _lib.check(rc, "pp_step")
+        self._last_encode = ring["encode"]
+        res = (canvas, pos if pos is not None else cls, reg, npil, counts)
+        h = StepHandle(res, pin, B, ring["done"])
+        h._keep = (top, d_pts, gt_dev)
+        return h
+
     def _next_lane(self):
         lane = self._lanes[self._lane_no % len(self._lanes)]
         self._lane_no += 1
@@ -547,6 +717,8 @@ class InputPath:
         back through a pinned buffer, and nothing blocks the host.  Consecutive calls must not share
         ``out`` buffers.  Returns a ``StepHandle``; ``handle.counters()`` waits for this step only and must
         be called before eight further steps have been issued (the pinned result buffers form a ring)."""
+        if self.fused and self.c_step and self.fused_supported(len(batch["offsets"]) - 1) and batch["points"].dtype == torch.float32:
+            return self._step_c(batch, None, batch["offsets"], None, batch["gt_offsets"], out)
         dev = self.device
         slot = self._step_no % len(self._stage)
         self._step_no += 1
@@ -578,6 +750,9 @@ class InputPath:
     def step_device_async(self, d_pts, offsets, gt_dev, gt_offsets, out=None):
         """``step_device`` on one of the two lanes (see ``step_host_async``); inputs must be ready on the
         current stream.  Returns a ``StepHandle`` (``wait()`` orders the current stream after the step)."""
+        if (self.fused and self.c_step and self.fused_supported(len(offsets) - 1) and d_pts.dtype == torch.float32
+                and d_pts.stride(1) == 1):
+            return self._step_c(None, d_pts, offsets, gt_dev, gt_offsets, out)
         dev = self.device
         main, side = self._next_lane()
         main.wait_stream(torch.cuda.current_stream(dev))

@@ -366,6 +366,47 @@ int pp_assign_targets_list(const double* d_a_corners, const double* d_a_centers,
                            float* d_cls, float* d_reg, int32_t* d_top_anchor, int32_t* d_counts, int32_t* d_status,
                            void* d_workspace, size_t workspace_bytes, pp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * One host call per batch: the whole input path with its stream choreography.
+ * pp_step issues, without blocking the host:
+ *   [copy stream]  (optional, h_blob != NULL) wait ev_slot_free; copy blob_bytes h_blob -> d_blob; with n_files > 0
+ *                  pp_aggregate_sweeps on the points inside it; record ev_ready
+ *   [main stream]  wait ev_ready; record ev_fork
+ *   [side stream]  wait ev_fork; pp_assign_targets (or pp_assign_targets_list when d_pos_anchor != NULL); record ev_join
+ *   [main stream]  pp_input_path PP_STAGE_PILLARIZE; wait ev_prev_encode (the previous batch's encode stage: the
+ *                  BatchNorm running statistics are read-modify-write); pp_input_path PP_STAGE_ENCODE; record
+ *                  ev_encode_done; wait ev_join; record ev_slot_free; copy {num_pillars [B], counts [B,4], status}
+ *                  to h_counters (pinned, 5 B + 1 int32); record ev_done
+ * i.e. what data/dataset.py:88-118 + model/model.py:170-177 (feature_net + scatter) do for one mini-batch.  All
+ * pointer fields are as in pp_input_path / pp_assign_targets[_list] / pp_aggregate_sweeps; events are cudaEvent_t
+ * created by the caller (NULL = that dependency does not exist); streams are cudaStream_t.  The struct is plain
+ * data: fill it once per lane / output set and update the fields that change from batch to batch. */
+typedef struct pp_step_plan {
+  /* streams and events */
+  pp_stream_t stream_main, stream_side, stream_copy;
+  void *ev_fork, *ev_join, *ev_ready, *ev_slot_free, *ev_prev_encode, *ev_encode_done, *ev_done;
+  /* upload */
+  const void* h_blob; void* d_blob; size_t blob_bytes;
+  int32_t n_files; const int64_t* d_file_offsets; const double* d_file_xforms; float min_dist;
+  /* points */
+  const void* d_points; int64_t total_points; int64_t point_cols; const int64_t* h_sweep_offsets; int32_t n_sweeps;
+  /* K1 + K2 */
+  pp_grid grid; int32_t max_points_per_pillar, max_pillars; const float* d_data_mean; const void* d_mean_prepared;
+  int32_t C; const float *d_conv_w, *d_conv_b, *d_bn_w, *d_bn_b; float *d_running_mean, *d_running_var;
+  int64_t* d_num_batches_tracked; int32_t training; float momentum, eps; int32_t canvas_h, canvas_w;
+  float* d_canvas; int64_t* d_indices; int32_t* d_num_pillars; void* d_ws_input; size_t ws_input_bytes;
+  /* K3 */
+  const double *d_a_corners, *d_a_centers, *d_a_wlh, *d_a_yaw; const void* d_anchor_index; int64_t A;
+  const double *d_g_corners, *d_g_centers, *d_g_wlh, *d_g_yaw; const int32_t* d_g_cls; const int64_t* h_gt_offsets;
+  int32_t num_classes; double pos_thresh; float *d_cls, *d_reg; int32_t *d_top_anchor, *d_counts;
+  int32_t* d_pos_anchor; float *d_pos_cls, *d_pos_reg; int32_t* d_pos_offsets; int32_t pos_capacity;
+  void* d_ws_targets; size_t ws_targets_bytes;
+  /* status + counters */
+  int32_t* d_status; int32_t* h_counters;
+} pp_step_plan;
+int pp_step(const pp_step_plan* plan);
+size_t pp_step_plan_bytes(void);   /* sizeof(pp_step_plan): lets a foreign-language binding check its struct layout */
+
 #ifdef __cplusplus
 }
 #endif
