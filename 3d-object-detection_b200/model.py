@@ -9,6 +9,11 @@ tensors raise.  ``PPFeatureScatter`` is the fused module (x, inds) -> canvas.
 Training: the three modules are differentiable with respect to conv1.weight/bias and bn1.weight/bias
 (pp_pfn_backward, csrc/pfn_bwd.cu -- SURVEY.md 8(f) N1), which is what train.py:147 needs; the gradient with
 respect to the input tensor x is not built (x is data in train.py) and asking for it raises.
+
+Checkpoints: parameter names and shapes are the reference's (``conv1.*``, ``bn1.*``; ``strict=True`` loads), but
+the per-slot normalisation constant ``pillar_means.pkl`` depends on the pillarizer's pillar order and must be
+regenerated with ``pp_b200.make_means``; a checkpoint trained against the reference's means
+needs re-validation or fine-tuning.
 """
 import torch
 import torch.nn as nn

@@ -153,3 +153,22 @@ def test_dense_stress_cloud_cap_binds():
     want_x, want_i = glue.pillarize(s.astype(np.float64), max_pillars=30000)
     assert torch.equal(inds[0].cpu(), want_i)
     assert torch.equal(x[0].cpu(), want_x)
+
+
+def test_make_means_equals_reference_recurrence():
+    """pp_b200.make_means (the equivalent of the reference's make_means.py:28-37 over this pillarizer) against the
+    same recurrence over the oracle's network input."""
+    import pp_b200
+    from oracle import glue
+    from pp_b200 import make_means, synth
+    cfg = pp_b200.PPConfig(max_pillars=800, max_points_per_pillar=16)
+    batches = [[synth.make_sweep(10 * b + s)[:5000] for s in range(3)] for b in range(3)]
+    got = make_means.make_means(batches, cfg)
+    means = torch.zeros(9 * 800 * 16)
+    for i, sweeps in enumerate(batches):
+        p = torch.stack([glue.pillarize(s[:, :4].astype(np.float64), None, max_pillars=800, max_points=16)[0] for s in sweeps])
+        m = torch.mean(p.reshape(p.shape[0], -1), dim=0)
+        means = means * (i / (i + 1)) + m * (1 / (i + 1))
+    assert got.shape == means.shape and got.dtype == torch.float32
+    assert torch.allclose(got, means, rtol=1e-6, atol=1e-6)      # torch.mean on the GPU vs CPU: summation order only
+    assert float(got.abs().max()) > 1.0
