@@ -14,6 +14,7 @@ thread_local int g_last_cuda_error = 0;
 int g_opt_pfn_tensor_cores = 1;
 int g_opt_pfn_tc_timing = 0;
 int g_opt_pad_reserve_sms = 0;  // SMs the persistent padding pass of pp_input_path leaves to the other stream lane
+int g_opt_encode_bulk = 1;       // 1: zero stream of the dense targets as cp.async.bulk copies, 0: float4 store loop
 int g_opt_loss_tma = 1;          // 0: generic tile kernel for the classification loss (testing)
 int read_tc_prof(long long* out64);
 int g_opt_pfn_tc_debug = 0;   // development knob: bit0 skip conversion, bit1 skip MMA, bit2 skip epilogue reads
@@ -54,6 +55,7 @@ int pp_set_option(const char* key, int value) {
   if (key == nullptr) return PP_ERR_INVALID_ARG;
   if (strcmp(key, "pfn_tensor_cores") == 0) { pp::g_opt_pfn_tensor_cores = value; return PP_OK; }   // 0 CUDA cores, 1 fp16 split (+TF32 fallback), 2 TF32 split
   if (strcmp(key, "loss_tma") == 0) { pp::g_opt_loss_tma = value; return PP_OK; }
+  if (strcmp(key, "encode_bulk") == 0) { pp::g_opt_encode_bulk = value; return PP_OK; }
   return PP_ERR_INVALID_ARG;
 }
 

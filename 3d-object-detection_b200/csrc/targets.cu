@@ -24,6 +24,7 @@
 
 namespace pp {
 
+extern int g_opt_encode_bulk;
 constexpr double kRadius = 10.0;  // data/pillars.cpp:418-419, hard-coded in the reference
 constexpr int kCandCap = 2048;    // per-GT IoU cache entries handed from pass 0 to pass 1 (overflow is recomputed)
 
@@ -472,6 +473,30 @@ __global__ void __launch_bounds__(256) k_encode_zero(float4* __restrict__ cls4, 
   }
 }
 
+// The same zero stream as bulk copies: each block zeroes a 32 KB shared-memory tile once and one thread streams it
+// out with cp.async.bulk (shared -> global, up to 8 copies of 32 KB in flight): no per-element store instructions,
+// full 32 KB bursts per request.  Both byte counts are multiples of 16.
+constexpr int kZeroTile = 32768;
+__global__ void __launch_bounds__(128) k_encode_zero_bulk(unsigned char* __restrict__ cls, unsigned char* __restrict__ reg,
+                                                          size_t bytes_each) {
+  __shared__ __align__(128) unsigned char s_zero[kZeroTile];
+  for (int i = threadIdx.x; i < kZeroTile / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_zero)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const size_t chunks_each = (bytes_each + kZeroTile - 1) / kZeroTile;
+  const unsigned src = (unsigned)__cvta_generic_to_shared(s_zero);
+  for (size_t c = blockIdx.x; c < 2 * chunks_each; c += gridDim.x) {
+    unsigned char* base = c < chunks_each ? cls : reg;
+    const size_t off = (c < chunks_each ? c : c - chunks_each) * (size_t)kZeroTile;
+    const unsigned n = (unsigned)(bytes_each - off < (size_t)kZeroTile ? bytes_each - off : (size_t)kZeroTile);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base + off), "r"(src), "r"(n) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory");
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(128) k_encode_patch(EncodeArgs ea, GtParams gp, long long A, int B,
                                                       float* __restrict__ cls, float* __restrict__ reg) {
   const size_t words_per_sweep = (size_t)((A + 31) / 32);
@@ -817,8 +842,13 @@ static int assign_impl(const double* d_a_corners, const double* d_a_centers, con
                     ((uintptr_t)d_reg % 16 == 0);
   if (both) {
     const size_t n4 = (size_t)n_sweeps * A * 9 / 4;
-    PP_KERNEL("k_encode_zero", st,
-              (k_encode_zero<<<sm_count() * 8, 256, 0, st>>>((float4*)d_cls, (float4*)d_reg, n4)));
+    if (g_opt_encode_bulk) {
+      PP_KERNEL("k_encode_zero", st,
+                (k_encode_zero_bulk<<<sm_count() * 4, 128, 0, st>>>((unsigned char*)d_cls, (unsigned char*)d_reg, n4 * 16)));
+    } else {
+      PP_KERNEL("k_encode_zero", st,
+                (k_encode_zero<<<sm_count() * 8, 256, 0, st>>>((float4*)d_cls, (float4*)d_reg, n4)));
+    }
     const size_t nwords = (size_t)((A + 31) / 32) * n_sweeps;
     PP_KERNEL("k_encode_patch", st,
               (k_encode_patch<<<(int)((nwords + 127) / 128), 128, 0, st>>>(ea, gp, A, n_sweeps, d_cls, d_reg)));
