@@ -33,7 +33,7 @@ WORKLOAD_B64 = ("batch-64 end-to-end input path (pillarize + PFN + targets), 64 
                 "%d per GPU over %d GPU(s), P=24000 N=200 C=64, 100 GT boxes per sweep vs 540000 anchors")
 WORKLOAD_STRESS = ("dense stress: batch of %d samples per GPU, each a 10-sweep aggregated cloud (~660k raw points, "
                    "pp_aggregate_sweeps on the device), max pillars 30000, N=200, 200 GT boxes per sample vs 540000 anchors")
-MIN_TIMED_S = 0.6      # every timed region lasts at least this long, whatever --steps is
+MIN_TIMED_S = 0.6      # every timed region lasts at least this long, whatever --steps is (--min-timed-s)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -783,6 +783,8 @@ def main():
                          "(64 sweeps per step sharded over the GPUs, strong scaling); stress: configs[4] (10-sweep aggregated "
                          "clouds, P = 30000, 200 GT boxes)")
     ap.add_argument("--no-gpu-comparator", action="store_true", help="skip timing the reference's PPFeatureNet + PPScatter on the GPU")
+    ap.add_argument("--min-timed-s", type=float, default=MIN_TIMED_S,
+                    help="minimum length of every timed region in seconds (profiling runs under ncu pass a small value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-training-rows", action="store_true", help="skip the PFN backward / loss front-end timings")
     ap.add_argument("--no-dense-reference", action="store_true", help="skip the extra dense_path measurement")
@@ -791,6 +793,7 @@ def main():
                     help="time the signature-preserving sequence pp_pillarize -> x [B,9,P,N] -> pp_pfn_scatter "
                          "instead of the fused pp_input_path (x never materialised)")
     args = ap.parse_args()
+    globals()["MIN_TIMED_S"] = args.min_timed_s
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and "RANK" not in os.environ:
