@@ -722,7 +722,7 @@ static int build_map(const int64_t* d_inds, int B, int P, int H, int W, int* map
 // registers (pre-multiplied by sign(gamma): f = s*y, so only a maximum is tracked).  For a pillar with cnt points
 //   slots n <  cnt : y_real and y_pad  -> extreme of y_real, statistics corrections g(y_real) - g(y_pad)
 //   slots cnt <= n < E : y_pad only    -> extreme over the padding slots below the next ladder boundary E
-// (E = 4, 16, 48 or N, see pfn_pad.cu) and the extreme over n >= E comes from the padding table.
+// (E = 2, 4, 8, 16, 48 or N, see pfn_pad.cu) and the extreme over n >= E comes from the padding table.
 // Work unit = group of 8 consecutive live pillars, handed out by an atomic counter (the median pillar holds 2
 // points, p99 22, max 200: static assignment left a 15 % tail).  One batch of loads covers the first four slots
 // of all eight pillars (lane = pillar * 4 + slot: features and per-slot means, 18 loads per lane, plus the eight
@@ -735,6 +735,8 @@ static int build_map(const int64_t* d_inds, int B, int P, int H, int W, int* map
 constexpr int kRealWarps = 8;
 constexpr int kRealRec = 20;       // floats per staged slot: 9 real + 9 padding + 2 pad (16-byte multiples)
 constexpr int kRealGroup = 8;      // pillars per work unit
+constexpr int kRealLongFrom = 48;  // pillars with more slots to evaluate than this go to k_pfn_real_long
+constexpr int kLongWarps = 4;      // warps per block of k_pfn_real_long
 template <int CPL>
 __global__ void __launch_bounds__(kRealWarps * 32, 2) k_pfn_real(CompactPillars cp, int C,
                                                   const float* __restrict__ conv_w,
@@ -743,7 +745,8 @@ __global__ void __launch_bounds__(kRealWarps * 32, 2) k_pfn_real(CompactPillars 
                                                   const float* __restrict__ padtab,
                                                   float* __restrict__ ext_s,
                                                   double* __restrict__ partials2,
-                                                  int* __restrict__ work_counter) {
+                                                  int* __restrict__ work_counter,
+                                                  int* __restrict__ long_count, int* __restrict__ long_list) {
   const int warp = threadIdx.x >> 5;
   const unsigned lane = lane_id();
   extern __shared__ __align__(16) unsigned char real_smem[];
@@ -807,10 +810,19 @@ __global__ void __launch_bounds__(kRealWarps * 32, 2) k_pfn_real(CompactPillars 
     m.cnt = min(cnt_raw, N);
     m.first += off_raw;
     if (!has_mean) { m.row = -1; m.E = m.cnt; }
-    else if (m.cnt <= 4) { m.row = 0; m.E = min(4, N); }
-    else if (m.cnt <= 16) { m.row = 1; m.E = min(16, N); }
-    else if (m.cnt <= 48) { m.row = 2; m.E = min(48, N); }
+    else if (m.cnt <= 2) { m.row = 0; m.E = min(2, N); }
+    else if (m.cnt <= 4) { m.row = 1; m.E = min(4, N); }
+    else if (m.cnt <= 8) { m.row = 2; m.E = min(8, N); }
+    else if (m.cnt <= 16) { m.row = 3; m.E = min(16, N); }
+    else if (m.cnt <= 48) { m.row = 4; m.E = min(48, N); }
     else { m.row = -1; m.E = N; }
+    if (m.E > kRealLongFrom) {
+      // 4 % of the pillars, a third of all slots, and up to 40 us of serial evaluation in one warp (the slowest
+      // warps took twice the median, scripts per-warp timeline): left to k_pfn_real_long, whose blocks deal the
+      // 32-slot chunks of a pillar to their warps
+      long_list[atomicAdd(long_count, 1)] = m.r;
+      m.r = -1;
+    }
   };
   float mx[CPL], ds[CPL], dq[CPL];
   auto eval = [&](const float* rec_base, int k_real, int k_all) {
@@ -884,7 +896,7 @@ __global__ void __launch_bounds__(kRealWarps * 32, 2) k_pfn_real(CompactPillars 
         const int row_k = __shfl_sync(0xffffffffu, mA.row, k);
         const int p_k = __shfl_sync(0xffffffffu, mA.p, k);
         tb[k] = make_float2(0.f, 0.f);
-        if (row_k >= 0) tb[k] = __ldg(reinterpret_cast<const float2*>(padtab + (size_t)p_k * 192 + row_k * 64) + lane);
+        if (row_k >= 0) tb[k] = __ldg(reinterpret_cast<const float2*>(padtab + (size_t)p_k * 320 + row_k * 64) + lane);
       }
       fetch_stage(r_g >= 0 && n < E_g, first_g, p_g, n, cnt_g, tile + lane * kRealRec);
 #pragma unroll
@@ -953,11 +965,148 @@ __global__ void __launch_bounds__(kRealWarps * 32, 2) k_pfn_real(CompactPillars 
   }
 }
 
+// The pillars k_pfn_real left on its list (more than kRealLongFrom slots to evaluate): one pillar per block at a
+// time, its 32-slot chunks dealt to the block's warps, partial extremes combined in shared memory.  Same per-slot
+// arithmetic as k_pfn_real.
+template <int CPL>
+__global__ void __launch_bounds__(kLongWarps * 32, 4) k_pfn_real_long(CompactPillars cp, int C,
+                                                  const float* __restrict__ conv_w,
+                                                  const float* __restrict__ conv_b,
+                                                  const float* __restrict__ bn_w,
+                                                  const float* __restrict__ padtab,
+                                                  float* __restrict__ ext_s,
+                                                  double* __restrict__ partials3,
+                                                  const int* __restrict__ long_count,
+                                                  const int* __restrict__ long_list) {
+  const int warp = threadIdx.x >> 5;
+  const int lane = (int)lane_id();
+  __shared__ __align__(16) float s_tile[kLongWarps][32][kRealRec];
+  __shared__ float s_mx[kLongWarps][64];
+  __shared__ double s_red[kLongWarps][2][64];
+  const int P = cp.P, N = cp.N;
+  const unsigned PN = (unsigned)P * (unsigned)N;
+  const bool has_mean = cp.data_mean != nullptr;
+  float w[CPL][kD], bias[CPL], sgn[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = CPL * lane + j;
+    sgn[j] = bn_w[c] < 0.f ? -1.f : 1.f;
+    bias[j] = sgn[j] * conv_b[c];
+#pragma unroll
+    for (int d = 0; d < kD; ++d) w[j][d] = sgn[j] * conv_w[c * kD + d];
+  }
+  double accS[CPL], accQ[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { accS[j] = 0.0; accQ[j] = 0.0; }
+  const int n_long = *long_count;
+  float* tile = &s_tile[warp][0][0];
+  for (int item = (int)blockIdx.x; item < n_long; item += (int)gridDim.x) {
+    const int r = long_list[item];
+    const int b = r / P, p = r - b * P;
+    const int cnt = min(__ldg(cp.pil_cnt + r), N);
+    const long long first = cp.sw.off[b] + __ldg(cp.pil_off + r);
+    int row = -1, E = cnt;
+    if (has_mean) {
+      if (cnt <= 16) { row = 3; E = min(16, N); }
+      else if (cnt <= 48) { row = 4; E = min(48, N); }
+      else { row = -1; E = N; }
+    }
+    float mx[CPL], ds[CPL], dq[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { mx[j] = -INFINITY; ds[j] = 0.f; dq[j] = 0.f; }
+    for (int n0 = 32 * warp; n0 < E; n0 += 32 * kLongWarps) {
+      const int n = n0 + lane;
+      if (n < E) {
+        const float* f = cp.feat_c + (size_t)first * kD;
+        float fv[kD], mv[kD];
+#pragma unroll
+        for (int d = 0; d < kD; ++d) {
+          fv[d] = n < cnt ? __ldg(f + (unsigned)n * kD + d) : 0.f;
+          mv[d] = has_mean ? __ldg(cp.data_mean + (size_t)p * N + (unsigned)d * PN + (unsigned)n) : 0.f;
+        }
+        float* rec = tile + lane * kRealRec;
+#pragma unroll
+        for (int d = 0; d < kD; ++d) {
+          rec[d] = __fsub_rn(fv[d], mv[d]);                  // data/dataset.py:105
+          rec[kD + d] = __fsub_rn(0.f, mv[d]);               // what the slot holds when it is padding
+        }
+      }
+      __syncwarp();
+      const int k_all = min(32, E - n0), k_real = max(0, min(32, cnt - n0));
+      int k = 0;
+      for (; k < k_real; ++k) {
+        const float4* rec = reinterpret_cast<const float4*>(tile + k * kRealRec);
+        const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4];
+        const float a[kD] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
+        const float q[kD] = {r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w, r4.x, r4.y};
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          float fx = bias[j], fp = bias[j];
+#pragma unroll
+          for (int d = 0; d < kD; ++d) { fx = fmaf(w[j][d], a[d], fx); fp = fmaf(w[j][d], q[d], fp); }
+          mx[j] = fmaxf(mx[j], fx);
+          const float t = fmaf(sgn[j], fx, fabsf(fx)), tp = fmaf(sgn[j], fp, fabsf(fp));   // 2 relu(y), y = s f
+          ds[j] += t - tp;
+          dq[j] += fmaf(t, t, -tp * tp);
+        }
+      }
+      for (; k < k_all; ++k) {
+        const float4* rec = reinterpret_cast<const float4*>(tile + k * kRealRec);
+        const float4 r2 = rec[2], r3 = rec[3], r4 = rec[4];
+        const float q[kD] = {r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w, r4.x, r4.y};
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          float fp = bias[j];
+#pragma unroll
+          for (int d = 0; d < kD; ++d) fp = fmaf(w[j][d], q[d], fp);
+          mx[j] = fmaxf(mx[j], fp);
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      s_mx[warp][CPL * lane + j] = mx[j];
+      accS[j] += (double)ds[j];
+      accQ[j] += (double)dq[j];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float2 tab = make_float2(0.f, 0.f);
+      if (row >= 0) tab = __ldg(reinterpret_cast<const float2*>(padtab + (size_t)p * 320 + row * 64) + lane);
+      const float tb2[2] = {tab.x, tab.y};
+      float* e = ext_s + (size_t)r * C + CPL * lane;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        float m = s_mx[0][CPL * lane + j];
+        for (int wv = 1; wv < kLongWarps; ++wv) m = fmaxf(m, s_mx[wv][CPL * lane + j]);
+        if (has_mean) { if (row >= 0) m = fmaxf(m, sgn[j] * tb2[j]); }
+        else if (cnt < N) m = fmaxf(m, bias[j]);
+        e[j] = sgn[j] * m;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    s_red[warp][0][CPL * lane + j] = accS[j] * 0.5;           // t = 2 relu(y)
+    s_red[warp][1][CPL * lane + j] = accQ[j] * 0.25;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * C) {
+    const int q = threadIdx.x / C, c = threadIdx.x % C;
+    double v = 0.0;
+    for (int wv = 0; wv < kLongWarps; ++wv) v += s_red[wv][q][c];
+    partials3[((size_t)blockIdx.x * 2 + q) * C + c] = v;
+  }
+}
+
 struct SparseWs {
   float* ext_s;        // [B*P, C]
-  float* padtab;       // [P, 3, C]   padding table (pfn_pad.cu)
+  float* padtab;       // [P, 5, C]   padding table (pfn_pad.cu)
   double* partials;    // [nblocks, 2, C]   padding pass
-  double* partials2;   // [nblocks2, 2, C]  k_pfn_real
+  double* partials2;   // [nblocks2 + nblocks3, 2, C]  k_pfn_real, then k_pfn_real_long
+  int* long_list;      // [B*P] rows of the pillars left to k_pfn_real_long
   Affine* affine;
   int* map;
   int* flags;
@@ -965,6 +1114,7 @@ struct SparseWs {
 };
 
 static int real_blocks() { return sm_count() * 2; }
+static int long_blocks() { return sm_count() * 2; }
 constexpr size_t kRealSmem = (size_t)kRealWarps * (2 * 32 * kRealRec * 4 + kRealGroup * 64 * 4) + (PP_MAX_SWEEPS + 1) * 4 + 12;
 
 bool pfn_pad_supported(int N, int C, int P);
@@ -979,13 +1129,14 @@ template <class A>
 static void sparse_layout(A& a, SparseWs* ws, int B, int P, int N, int C, int H, int W, bool own_prep) {
   auto p0 = a.template take<float>((size_t)B * P * C);
   auto p1 = a.template take<double>((size_t)sm_count() * 2 * C);
-  auto p2 = a.template take<double>((size_t)real_blocks() * 2 * C);
+  auto p2 = a.template take<double>((size_t)(real_blocks() + long_blocks()) * 2 * C);
   auto p3 = a.template take<Affine>(64);
   auto p4 = a.template take<int>((size_t)B * H * W + 1);
   auto p5 = a.template take<int>(64);
-  auto p6 = a.template take<float>((size_t)P * 3 * C);
+  auto p6 = a.template take<float>((size_t)P * 5 * C);
   auto p7 = a.template take<char>(own_prep ? mean_prepared_bytes(P, N) : 0);
-  if (ws) { ws->ext_s = p0; ws->partials = p1; ws->partials2 = p2; ws->affine = p3; ws->map = p4; ws->flags = p5; ws->padtab = p6; ws->prep = p7; }
+  auto p8 = a.template take<int>((size_t)B * P);
+  if (ws) { ws->ext_s = p0; ws->partials = p1; ws->partials2 = p2; ws->affine = p3; ws->map = p4; ws->flags = p5; ws->padtab = p6; ws->prep = p7; ws->long_list = p8; }
 }
 
 size_t pfn_sparse_workspace_bytes(int B, int P, int N, int C, int H, int W, bool own_prep) {
@@ -1013,7 +1164,7 @@ int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, c
   if (rc != PP_OK) return rc;
   int nblocks = 0;
   const void* prep = cp.mean_prepared;
-  PP_CUDA(cudaMemsetAsync(ws.flags, 0, 2 * sizeof(int), st));     // [0] range flag of the padding pass, [1] k_pfn_real's work counter
+  PP_CUDA(cudaMemsetAsync(ws.flags, 0, 3 * sizeof(int), st));     // [0] range flag of the padding pass, [1] k_pfn_real's work counter, [2] long-pillar count
   if (cp.data_mean != nullptr) {
     if (own_prep) {
       // a caller without a prepared operand pays a streaming pass over data_mean per call (pp_mean_prepare once
@@ -1034,13 +1185,17 @@ int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, c
   PP_CUDA(cudaFuncSetAttribute(k_pfn_real<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRealSmem));
   PP_KERNEL("k_pfn_real", st,
             k_pfn_real<2><<<nb2, kRealWarps * 32, kRealSmem, st>>>(cp, C, prm.conv_w, prm.conv_b, prm.bn_w, ws.padtab, ws.ext_s,
-                                                           ws.partials2, ws.flags + 1));
+                                                           ws.partials2, ws.flags + 1, ws.flags + 2, ws.long_list));
+  const int nb3 = long_blocks();
+  PP_KERNEL("k_pfn_real_long", st,
+            k_pfn_real_long<2><<<nb3, kLongWarps * 32, 0, st>>>(cp, C, prm.conv_w, prm.conv_b, prm.bn_w, ws.padtab, ws.ext_s,
+                                                                ws.partials2 + (size_t)nb2 * 2 * C, ws.flags + 2, ws.long_list));
   // a mean or weight outside the fp16 range is reported through the status word (by the finalize kernel, which
   // runs anyway)
   SparseFinalize sf{};
   sf.mult = 0.5 * (double)B;
   sf.partials2 = prm.training ? ws.partials2 : nullptr;
-  sf.nparts2 = nb2;
+  sf.nparts2 = nb2 + nb3;
   sf.conv_b = cp.data_mean == nullptr ? prm.conv_b : nullptr;
   sf.pad_count = (double)B * P * N;
   sf.range_flag = cp.data_mean != nullptr ? ws.flags : nullptr;

@@ -3,7 +3,7 @@
 // A padding slot (p, n) of the network input holds x = 0 - data_mean[:, p, n] in every sweep
 // (data/dataset.py:99-105), so y_pad[c, p, n] = W x + b is evaluated ONCE per (p, n), whatever the batch
 // size and whatever the pillars' point counts.  This pass produces
-//   * padtab[p][3][64]: the sign-selected extreme of y_pad over the slot suffixes n >= 4, n >= 16, n >= 48
+//   * padtab[p][5][64]: the sign-selected extreme of y_pad over the slot suffixes n >= 2, 4, 8, 16, 48
 //     (a pillar with cnt points needs the extreme over n >= cnt; k_pfn_real evaluates the few slots between
 //     cnt and the next ladder boundary itself and takes the rest from this table), and
 //   * per-channel sums of |y_pad| and y_pad |y_pad| over all (p, n).  With the first and second moments of
@@ -50,6 +50,8 @@ constexpr int kMaxStages = 8;
 constexpr int kAccCols = 256;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kABytes = 2 * 2048;          // two k-steps of 64 rows x 16 k fp16
+constexpr int kRows = 5;                   // table rows: suffix extremes from slot 2, 4, 8, 16, 48
+constexpr int kPartSlot = 6 * 128;         // floats per hand-over slot: range 0 (4 values), ranges 1 and 2 (1 each) x 128 rows
 
 struct Smem {
   int a_off, stage_off, stage_bytes, stages, part_off, stat_off, bar_off, total;
@@ -60,11 +62,11 @@ __host__ __device__ inline Smem smem_plan(int N) {
   s.a_off = 0;
   s.stage_off = kABytes;                               // 4096: 128-byte aligned
   s.stage_bytes = 2 * 3 * N * 16;                      // pair of pillars x 3 planes x N x 16 B
-  const int fixed = kABytes + 4 * 4 * 128 * 4 + 4 * 2 * 64 * 8 + 512 + 128;
+  const int fixed = kABytes + 4 * kPartSlot * 4 + 4 * 2 * 64 * 8 + 512 + 128;
   int st = (kSmemBudget - fixed) / s.stage_bytes;
   s.stages = st > kMaxStages ? kMaxStages : st;
   s.part_off = s.stage_off + s.stages * s.stage_bytes;
-  s.stat_off = s.part_off + 4 * 4 * 128 * 4;
+  s.stat_off = s.part_off + 4 * kPartSlot * 4;
   s.bar_off = s.stat_off + 4 * 2 * 64 * 8;
   s.total = s.bar_off + 512 + 128;                     // +128: manual base alignment
   return s;
@@ -158,7 +160,7 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
   uint64_t* acc_empty = acc_full + 2;               // [2]
   uint64_t* pbar = acc_empty + 2;                   // [4 slots][4 quarters] partial maxima of ranges 0..2 published
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pbar + 16);
-  float* s_part = reinterpret_cast<float*>(smem + sp.part_off);      // [4 slots][4][128]
+  float* s_part = reinterpret_cast<float*>(smem + sp.part_off);      // [4 slots][6][128]
   double* s_stat = reinterpret_cast<double*>(smem + sp.stat_off);    // [4 ranges][sum |y|, sum y|y|][64]
 
   const int pairs = P >> 1;                          // host guarantees P even
@@ -308,7 +310,7 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
       const long long tq0 = pon ? clock64() : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(e * kAccCols);
       float S[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
-      float m0 = -INFINITY, m1 = -INFINITY, lo = -INFINITY;
+      float m0 = -INFINITY, m1 = -INFINITY, lo2 = -INFINITY, lo4 = -INFINITY, lo8 = -INFINITY;
       bool released = false;
       // accumulator buffer back to the MMA issuer: all lanes' tcgen05.ld have completed (wait::ld is warp-wide)
       auto release = [&]() {
@@ -332,8 +334,10 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
           tmem_ld_wait();
           release();
           float a0 = -INFINITY, a1 = -INFINITY;
-          consume<16, 4, TRAIN>(va, a0, a1, S, Q);
-          lo = fmaxf(a0, a1);
+          consume<16, 8, TRAIN>(va, a0, a1, S, Q);
+          lo8 = fmaxf(a0, a1);                                                       // slots 8..15
+          lo4 = fmaxf(fmaxf(__uint_as_float(va[4]), __uint_as_float(va[5])), fmaxf(__uint_as_float(va[6]), __uint_as_float(va[7])));
+          lo2 = fmaxf(__uint_as_float(va[2]), __uint_as_float(va[3]));
           consume<32, 0, TRAIN>(vb, m0, m1, S, Q);
         } else if (j < 3) {
           uint32_t va[32], vb[16];
@@ -360,8 +364,10 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
         PP_TMEM_LD16(taddr, v);
         tmem_ld_wait();
         float a0 = -INFINITY, a1 = -INFINITY;
-        consume<16, 4, TRAIN>(v, a0, a1, S, Q);
-        lo = fmaxf(a0, a1);
+        consume<16, 8, TRAIN>(v, a0, a1, S, Q);
+        lo8 = fmaxf(a0, a1);
+        lo4 = fmaxf(fmaxf(__uint_as_float(v[4]), __uint_as_float(v[5])), fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
+        lo2 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
         consume_range<TRAIN>(taddr, 16, n1, m0, m1, S, Q);
       } else {
         consume_range<TRAIN>(taddr, n0, n1, m0, m1, S, Q);
@@ -370,26 +376,32 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
       const float m = fmaxf(m0, m1);
       // the four column ranges of a row meet in shared memory; four slots (it & 3): a warp can only be two visits
       // ahead of the j = 3 warp of its quarter when it writes a slot again (the accumulator hand-off orders them)
-      float* part = s_part + (it & 3) * 512;
+      float* part = s_part + (it & 3) * kPartSlot;
       uint64_t* pb = &pbar[(it & 3) * 4 + q];
       if (j < 3) {
-        if (j == 0) { part[rowid] = fmaxf(lo, m); part[128 + rowid] = m; }
-        else part[(j + 1) * 128 + rowid] = m;
+        // range 0: maxima of slots {2,3}, [4,8), [8,16), [16,48); ranges 1, 2: their whole range
+        if (j == 0) { part[rowid] = lo2; part[128 + rowid] = lo4; part[256 + rowid] = lo8; part[384 + rowid] = m; }
+        else part[(j + 3) * 128 + rowid] = m;
         __syncwarp();
         if (lane == 0) mbar_arrive(pb);
         if (pon) pacc[1] += clock64() - tq0;
       } else {
         if (pon) pacc[1] += clock64() - tq0;
         mbar_wait_spin_t(pb, (uint32_t)(it >> 2) & 1u, pon, pacc[2]);
-        const float t = fmaxf(m, fmaxf(part[2 * 128 + rowid], part[3 * 128 + rowid]));
-        const float r4 = fmaxf(part[rowid], t), r16 = fmaxf(part[128 + rowid], t);
+        const float t = fmaxf(m, fmaxf(part[4 * 128 + rowid], part[5 * 128 + rowid]));      // slots >= 48
+        const float r16 = fmaxf(part[384 + rowid], t);
+        const float r8 = fmaxf(part[256 + rowid], r16);
+        const float r4 = fmaxf(part[128 + rowid], r8);
+        const float r2 = fmaxf(part[rowid], r4);
         // TMEM holds 256*s*y; rows of y's sign-selected extreme (max when gamma >= 0, min otherwise); an empty
         // suffix stays -inf (+inf after the sign): neutral for the consumer
         const size_t pillar = 2 * ((size_t)blockIdx.x + (size_t)it * gridDim.x) + h;
-        float* o = padtab + pillar * 192 + c;
-        o[0] = sgn * r4 * (1.f / 256.f);
-        o[64] = sgn * r16 * (1.f / 256.f);
-        o[128] = sgn * t * (1.f / 256.f);
+        float* o = padtab + pillar * (kRows * 64) + c;
+        o[0] = sgn * r2 * (1.f / 256.f);
+        o[64] = sgn * r4 * (1.f / 256.f);
+        o[128] = sgn * r8 * (1.f / 256.f);
+        o[192] = sgn * r16 * (1.f / 256.f);
+        o[256] = sgn * t * (1.f / 256.f);
       }
       if (TRAIN) {
         two_sum(sh, sl, (S[0] + S[1]) + (S[2] + S[3]));
