@@ -144,8 +144,10 @@ __device__ __forceinline__ int find_gt_sweep(const GtParams& gp, long long g) {
 }
 
 // PASS 0: best[a] = max IoU (as bits), top_anchor[g].  PASS 1: arg[a], posmask, counters.
+// (256, 3): at most 85 registers, so that the 400 CTAs of a batch-4 step (one per GT) are one resident wave on
+// 148 SMs; at 100 registers only two CTAs fit an SM and the kernel ran as 1.35 waves
 template <int PASS>
-__global__ void __launch_bounds__(256) k_iou_pass(
+__global__ void __launch_bounds__(256, 3) k_iou_pass(
     const double* __restrict__ a_corners, const double* __restrict__ a_centers,
     const unsigned char* __restrict__ index, long long A, const double* __restrict__ g_corners,
     const double* __restrict__ g_centers, GtParams gp, double pos_thresh,
