@@ -737,11 +737,13 @@ def run_ours(args):
             "dense_path_value": other["value"] if other else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e_max / args.steps, "host_wall_ms_per_step": ms_e_host / args.steps,
-                    "pipeline": "step_host_async: copy stream + 2 staging buffers + 2 kernel lanes, at most two batches "
-                                "in flight; each batch's counters and status word are read back from pinned memory "
-                                "before the next-but-one batch is issued.  The outputs (canvas %d MB, cls + reg targets "
+                    "pipeline": "step_host_async -> pp_step (one host call per batch): copy stream + %d staging buffers + %d "
+                                "kernel lanes with a side stream each for target assignment, at most %d batches in "
+                                "flight; each batch's counters and status word are read back from pinned memory "
+                                "before the batch %d ahead is issued.  The outputs (canvas %d MB, cls + reg targets "
                                 "%d MB per batch) STAY in HBM, where the reference's backbone and loss consume them "
                                 "(model/model.py:170-177, model/loss.py); D2H = per-sweep counters + status" % (
+                                    args.inflight, args.inflight, args.inflight, args.inflight,
                                     B * C * H * W * 4 // 2 ** 20, 2 * B * A * 9 * 4 // 2 ** 20)},
             "roofline": roofline,
             "config": {"workload": wl["workload"], "config": args.config, "sweeps_per_gpu_per_step": sweeps_per_step,
@@ -756,7 +758,8 @@ def run_ours(args):
                        "l2": "no flush: per-batch working set (canvas %d MB, targets %d MB, prepared data_mean %d MB) "
                              ">> 126 MB L2" % (B * C * H * W * 4 // 2 ** 20, 2 * B * A * 9 * 4 // 2 ** 20, P * N * 48 // 2 ** 20),
                        "loop": "streaming: batches alternate between two stream lanes (pillarize stage of batch k+1 "
-                               "overlaps the encode stage of batch k; encode stages ordered), <= %d batches in flight; one "
+                               "overlaps the encode stage of batch k; encode stages ordered), <= %d batches in flight, one host call "
+                               "(pp_step) per batch; one "
                                "driver step = %d back-to-back batches so that the timed region is >= %.1f s; it ends "
                                "after the last batch has completed" % (args.inflight, reps, MIN_TIMED_S),
                        "parallelism": "dp%d (one process per GPU, sweeps sharded, no collective)" % world},
