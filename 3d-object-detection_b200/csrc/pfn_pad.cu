@@ -31,9 +31,12 @@
 // and was bound by the tensor pipe: M = 64 runs at half rate, ~150 cycles per instruction).
 //
 // Roles (576 threads, one persistent CTA per SM, work unit = pair of adjacent pillars at TMEM lane offset 16):
-//   warps 0-15  epilogue, ALL on the same pair: lane quarter q = warp % 4, column range j = warp / 4; two TMEM
-//               accumulator buffers alternate, so the MMAs of pair k+1 run under the epilogue of pair k.
-//               The four column ranges of a row meet in shared memory; the j = 3 warp writes the table rows.
+//   warps 0-15  epilogue in two groups: warps 0-7 own accumulator buffer 0 (even pairs of the CTA), warps 8-15
+//               buffer 1 (odd pairs); lane quarter q = warp % 4, column half = (warp / 4) % 2 ([0,104) | [104,N)).
+//               The groups run half a period apart, so one group's per-visit latencies (barrier wake-up, TMEM
+//               load, hand-over) hide under the other group's arithmetic: 73 -> 62 us against all 16 warps on
+//               the same pair.  The two halves of a row meet in shared memory; the upper-half warp writes the
+//               table rows.  A pure read of the 230 MB operand alone takes 50 us here (scripts/ubench/rd.cu).
 //   warp 16     producer (one bulk copy per pair into an 8-stage ring)
 //   warp 17     TMEM allocation + MMA issuer (4 tcgen05.mma per pair)
 #include "tc_common.cuh"
@@ -51,7 +54,7 @@ constexpr int kAccCols = 256;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kABytes = 2 * 2048;          // two k-steps of 64 rows x 16 k fp16
 constexpr int kRows = 5;                   // table rows: suffix extremes from slot 2, 4, 8, 16, 48
-constexpr int kPartSlot = 6 * 128;         // floats per hand-over slot: range 0 (4 values), ranges 1 and 2 (1 each) x 128 rows
+constexpr int kPartSlot = 5 * 128;         // floats per hand-over slot: five partial maxima of the lower column half x 128 rows
 
 struct Smem {
   int a_off, stage_off, stage_bytes, stages, part_off, stat_off, bar_off, total;
@@ -158,9 +161,9 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
   uint64_t* empty = bars + kMaxStages;              // [kMaxStages] stage read by the MMAs
   uint64_t* acc_full = bars + 2 * kMaxStages;       // [2]
   uint64_t* acc_empty = acc_full + 2;               // [2]
-  uint64_t* pbar = acc_empty + 2;                   // [4 slots][4 quarters] partial maxima of ranges 0..2 published
+  uint64_t* pbar = acc_empty + 2;                   // [group][visit parity][quarter] lower column half published
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pbar + 16);
-  float* s_part = reinterpret_cast<float*>(smem + sp.part_off);      // [4 slots][6][128]
+  float* s_part = reinterpret_cast<float*>(smem + sp.part_off);      // [group][visit parity][5][128]
   double* s_stat = reinterpret_cast<double*>(smem + sp.stat_off);    // [4 ranges][sum |y|, sum y|y|][64]
 
   const int pairs = P >> 1;                          // host guarantees P even
@@ -169,8 +172,8 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
   // ---- one-time setup -------------------------------------------------------------------------
   if (threadIdx.x == 0) {
     for (int i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
-    for (int i = 0; i < 16; ++i) mbar_init(&pbar[i], 3);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 16; ++i) mbar_init(&pbar[i], 1);
     fence_barrier_init();
   }
   // A tile: 64 x 32 fp16, K-major, no swizzle: core matrix = 8 rows x 16 B (8 k), k-chunk stride 128 B,
@@ -280,21 +283,18 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
       if (++s == R) { s = 0; ph ^= 1u; }
     }
   } else {
-    // ===== epilogue: one (pillar-of-pair, channel) row per thread over this warp's column range =====
+    // ===== epilogue, two groups: warps 0-7 own accumulator buffer 0 (even pairs), warps 8-15 buffer 1 (odd pairs).
+    // The groups run half a period apart, so on every SM sub-partition one group's fixed per-visit latencies
+    // (barrier wake-up, TMEM load latency, the hand-over through shared memory) overlap the other group's
+    // arithmetic.  With all 16 warps on the same pair those latencies were exposed on every visit.
     const int q = warp & 3;                // TMEM lane quarter (must equal warp % 4)
-    const int j = warp >> 2;               // column range
+    const int e = warp >> 3;               // accumulator buffer = pair parity
+    const int jh = (warp >> 2) & 1;        // column half: [0, hs) | [hs, N)
     const int h = (int)(lane >> 4);
     const int c = 16 * q + (int)(lane & 15u);
     const int rowid = 32 * q + (int)lane;
     const float sgn = bn_w[c] < 0.f ? -1.f : 1.f;
-    // ranges: [0, e1) | three near-equal parts of [e1, N); e1 = min(N, 48) carries the ladder boundaries 4 and 16
-    const int e1 = N < 48 ? N : 48;
-    const int g = (N - e1) >> 3;
-    const int c1 = e1 + 8 * (g / 3), c2 = c1 + 8 * (g / 3);
-    const int n0 = j == 0 ? 0 : (j == 1 ? e1 : (j == 2 ? c1 : c2));
-    const int n1 = j == 0 ? e1 : (j == 1 ? c1 : (j == 2 ? c2 : N));
-    // running sums of the visits as unevaluated fp32 pairs (hi + lo, TwoSum): the fp64 pipe stays out of the
-    // loop (ncu r2d: 13 % of the warps' stall samples sat on the per-visit F2F + DADD chain)
+    const int hs = N < 104 ? N : 104;
     float sh = 0.f, sl = 0.f, qh = 0.f, ql = 0.f;
     auto two_sum = [](float& hi, float& lo, float b) {
       const float s = __fadd_rn(hi, b);
@@ -302,99 +302,91 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
       lo = __fadd_rn(lo, __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(b, bb)));
       hi = s;
     };
-    for (int it = 0; it < my_pairs; ++it) {
-      const int e = it & 1;
+    const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(e * kAccCols);
+    for (int it = e; it < my_pairs; it += 2) {
       const uint32_t n = (uint32_t)(it >> 1);
       mbar_wait_spin_t(&acc_full[e], n & 1u, pon, pacc[0]);
       tc_fence_after();
       const long long tq0 = pon ? clock64() : 0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(e * kAccCols);
       float S[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
-      float m0 = -INFINITY, m1 = -INFINITY, lo2 = -INFINITY, lo4 = -INFINITY, lo8 = -INFINITY;
-      bool released = false;
-      // accumulator buffer back to the MMA issuer: all lanes' tcgen05.ld have completed (wait::ld is warp-wide)
+      float m0 = -INFINITY, m1 = -INFINITY, lo2 = -INFINITY, lo4 = -INFINITY, lo8 = -INFINITY, m16 = -INFINITY;
       auto release = [&]() {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[e]);
-        released = true;
+      };
+      auto head = [&](const uint32_t* va) {
+        float a0 = -INFINITY, a1 = -INFINITY;
+        consume<16, 8, TRAIN>(va, a0, a1, S, Q);
+        lo8 = fmaxf(a0, a1);                                                       // slots 8..15
+        lo4 = fmaxf(fmaxf(__uint_as_float(va[4]), __uint_as_float(va[5])), fmaxf(__uint_as_float(va[6]), __uint_as_float(va[7])));
+        lo2 = fmaxf(__uint_as_float(va[2]), __uint_as_float(va[3]));
       };
       if (dbg & 4) {
+        release();
       } else if (NT == 200) {
-        // The warp's whole column block goes to registers first and the accumulator buffer is released BEFORE the
-        // arithmetic: the MMAs of the pair after next start ~700 cycles earlier.  With the buffer held until the
-        // end of the visit the hand-off chain (release -> MMA issue + execution -> commit -> epilogue wake-up,
-        // ~1200 cycles) was longer than one epilogue visit (~800) and the epilogue waited ~350 cycles per pair.
-        if (j == 0) {
-          // slots 0..3 never enter a table row (a live pillar holds at least one point and k_pfn_real evaluates
-          // the slots below the first boundary itself); slots 4..15 only enter the first row
-          uint32_t va[16], vb[32];
+        if (jh == 0) {
+          uint32_t va[16], vb[32], vc[32], vd[16], ve[8];
           PP_TMEM_LD16(taddr, va);
           PP_TMEM_LD32(taddr + 16, vb);
           tmem_ld_wait();
-          release();
-          float a0 = -INFINITY, a1 = -INFINITY;
-          consume<16, 8, TRAIN>(va, a0, a1, S, Q);
-          lo8 = fmaxf(a0, a1);                                                       // slots 8..15
-          lo4 = fmaxf(fmaxf(__uint_as_float(va[4]), __uint_as_float(va[5])), fmaxf(__uint_as_float(va[6]), __uint_as_float(va[7])));
-          lo2 = fmaxf(__uint_as_float(va[2]), __uint_as_float(va[3]));
+          head(va);
+          PP_TMEM_LD32(taddr + 48, vc);
+          PP_TMEM_LD16(taddr + 80, vd);
+          PP_TMEM_LD8(taddr + 96, ve);
           consume<32, 0, TRAIN>(vb, m0, m1, S, Q);
-        } else if (j < 3) {
-          uint32_t va[32], vb[16];
-          const uint32_t t0 = taddr + (j == 1 ? 48u : 96u);
-          PP_TMEM_LD32(t0, va);
-          PP_TMEM_LD16(t0 + 32, vb);
+          m16 = fmaxf(m0, m1);                                                     // slots 16..47
+          m0 = m1 = -INFINITY;
           tmem_ld_wait();
           release();
-          consume<32, 0, TRAIN>(va, m0, m1, S, Q);
-          consume<16, 0, TRAIN>(vb, m0, m1, S, Q);
+          consume<32, 0, TRAIN>(vc, m0, m1, S, Q);
+          consume<16, 0, TRAIN>(vd, m0, m1, S, Q);
+          consume<8, 0, TRAIN>(ve, m0, m1, S, Q);
         } else {
-          uint32_t va[32], vb[16], vc[8];
-          PP_TMEM_LD32(taddr + 144, va);
-          PP_TMEM_LD16(taddr + 176, vb);
-          PP_TMEM_LD8(taddr + 192, vc);
+          uint32_t va[32], vb[32], vc[32];
+          PP_TMEM_LD32(taddr + 104, va);
+          PP_TMEM_LD32(taddr + 136, vb);
+          tmem_ld_wait();
+          PP_TMEM_LD32(taddr + 168, vc);
+          consume<32, 0, TRAIN>(va, m0, m1, S, Q);
+          consume<32, 0, TRAIN>(vb, m0, m1, S, Q);
           tmem_ld_wait();
           release();
-          consume<32, 0, TRAIN>(va, m0, m1, S, Q);
-          consume<16, 0, TRAIN>(vb, m0, m1, S, Q);
-          consume<8, 0, TRAIN>(vc, m0, m1, S, Q);
+          consume<32, 0, TRAIN>(vc, m0, m1, S, Q);
         }
-      } else if (j == 0) {
-        uint32_t v[16];
-        PP_TMEM_LD16(taddr, v);
-        tmem_ld_wait();
-        float a0 = -INFINITY, a1 = -INFINITY;
-        consume<16, 8, TRAIN>(v, a0, a1, S, Q);
-        lo8 = fmaxf(a0, a1);
-        lo4 = fmaxf(fmaxf(__uint_as_float(v[4]), __uint_as_float(v[5])), fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
-        lo2 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
-        consume_range<TRAIN>(taddr, 16, n1, m0, m1, S, Q);
       } else {
-        consume_range<TRAIN>(taddr, n0, n1, m0, m1, S, Q);
+        if (jh == 0) {
+          uint32_t v[16];
+          PP_TMEM_LD16(taddr, v);
+          tmem_ld_wait();
+          head(v);
+          consume_range<TRAIN>(taddr, 16, hs < 48 ? hs : 48, m0, m1, S, Q);
+          m16 = fmaxf(m0, m1);
+          m0 = m1 = -INFINITY;
+          if (hs > 48) consume_range<TRAIN>(taddr, 48, hs, m0, m1, S, Q);
+        } else {
+          consume_range<TRAIN>(taddr, hs, N, m0, m1, S, Q);
+        }
+        release();
       }
-      if (!released) release();
       const float m = fmaxf(m0, m1);
-      // the four column ranges of a row meet in shared memory; four slots (it & 3): a warp can only be two visits
-      // ahead of the j = 3 warp of its quarter when it writes a slot again (the accumulator hand-off orders them)
-      float* part = s_part + (it & 3) * kPartSlot;
-      uint64_t* pb = &pbar[(it & 3) * 4 + q];
-      if (j < 3) {
-        // range 0: maxima of slots {2,3}, [4,8), [8,16), [16,48); ranges 1, 2: their whole range
-        if (j == 0) { part[rowid] = lo2; part[128 + rowid] = lo4; part[256 + rowid] = lo8; part[384 + rowid] = m; }
-        else part[(j + 3) * 128 + rowid] = m;
+      // the two column halves of a row meet in shared memory; two slots per group (visit parity): the lower-half
+      // warp can only write a slot again after the accumulator hand-off that follows the upper-half warp's read
+      float* part = s_part + (e * 2 + (int)(n & 1u)) * kPartSlot;
+      uint64_t* pb = &pbar[(e * 2 + (int)(n & 1u)) * 4 + q];
+      if (jh == 0) {
+        part[rowid] = lo2; part[128 + rowid] = lo4; part[256 + rowid] = lo8; part[384 + rowid] = m16; part[512 + rowid] = m;
         __syncwarp();
         if (lane == 0) mbar_arrive(pb);
         if (pon) pacc[1] += clock64() - tq0;
       } else {
         if (pon) pacc[1] += clock64() - tq0;
-        mbar_wait_spin_t(pb, (uint32_t)(it >> 2) & 1u, pon, pacc[2]);
-        const float t = fmaxf(m, fmaxf(part[4 * 128 + rowid], part[5 * 128 + rowid]));      // slots >= 48
+        mbar_wait_spin_t(pb, (n >> 1) & 1u, pon, pacc[2]);
+        const float t = fmaxf(m, part[512 + rowid]);                                        // slots >= 48
         const float r16 = fmaxf(part[384 + rowid], t);
         const float r8 = fmaxf(part[256 + rowid], r16);
         const float r4 = fmaxf(part[128 + rowid], r8);
         const float r2 = fmaxf(part[rowid], r4);
-        // TMEM holds 256*s*y; rows of y's sign-selected extreme (max when gamma >= 0, min otherwise); an empty
-        // suffix stays -inf (+inf after the sign): neutral for the consumer
         const size_t pillar = 2 * ((size_t)blockIdx.x + (size_t)it * gridDim.x) + h;
         float* o = padtab + pillar * (kRows * 64) + c;
         o[0] = sgn * r2 * (1.f / 256.f);
@@ -412,9 +404,10 @@ k_pfn_pad_tc(const unsigned char* __restrict__ hl, int P, int N,
       double accS = (double)sh + (double)sl, accQ = (double)qh + (double)ql;
       accS += __shfl_xor_sync(0xffffffffu, accS, 16);
       accQ += __shfl_xor_sync(0xffffffffu, accQ, 16);
+      const int jj = warp >> 2;
       if (lane < 16) {
-        s_stat[(j * 2 + 0) * 64 + c] = accS * (1.0 / 256.0);                          // sum |y|
-        s_stat[(j * 2 + 1) * 64 + c] = accQ * ((double)sgn / (256.0 * 256.0));        // sum y |y|  (y = s v / 256)
+        s_stat[(jj * 2 + 0) * 64 + c] = accS * (1.0 / 256.0);
+        s_stat[(jj * 2 + 1) * 64 + c] = accQ * ((double)sgn / (256.0 * 256.0));
       }
     }
   }

@@ -26,13 +26,13 @@ L.pp_debug_tc_timing(buf)
 L.pp_debug_set(b"pfn_tc_timing", 0)
 L.pp_debug_set(b"pfn_tc_debug", 0)
 print("role timing with dbg =", dbg0)
-for w in (0, 5, 10, 12, 15, 16, 17):
+for w in (0, 4, 8, 12, 16, 17):
     v = [buf[w * 4 + k] for k in range(4)]
     role = ("epi j%d q%d (wait acc_full, busy, wait pbar)" % (w >> 2, w & 3) if w < 16 else
             "producer (wait empty)" if w == 16 else "mma (wait full, wait acc_empty, issue)")
     print("warp %2d %-44s %9d %9d %9d total %9d" % (w, role, v[0], v[1], v[2], v[3]))
 L.pp_profile_enable(1)
-for dbg in (0,):
+for dbg in (0, 2, 4, 6, 22):
     L.pp_debug_set(b"pfn_tc_debug", dbg)      # bit 1: no MMAs, bit 2: no epilogue loads / arithmetic
     for _ in range(5):
         path.pillarize_encode(pts, offs)
