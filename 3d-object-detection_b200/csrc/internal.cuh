@@ -6,6 +6,8 @@
 
 namespace pp {
 
+constexpr int kFeatStride = 12;   // floats per feat_c record: 9 features padded to three aligned float4
+
 struct SweepParams {
   int n_sweeps;
   int tile_start[PP_MAX_SWEEPS + 1];
@@ -16,7 +18,7 @@ struct SweepParams {
 struct CompactPillars {
   SweepParams sw;            // point offsets of the sweeps (host copy, passed by value to kernels)
   int P, N;
-  const float* feat_c;       // [T, 9] float: decorated features of the kept points, before "- data_mean",
+  const float* feat_c;       // [T, kFeatStride] float (9 used): decorated features of the kept points, before "- data_mean",
                              //   at sw.off[b] + pil_off[b*P+p] + rank
   const int* pil_cnt;        // [B*P] in-range points of the pillar (may exceed N)
   const int* pil_off;        // [B*P] first entry of the pillar's segment (relative to the sweep)

@@ -859,11 +859,11 @@ __global__ void __launch_bounds__(kRealWarps * 32, 2) k_pfn_real(CompactPillars 
   // slot n of the pillar (first point `first`, pillar index p) -> record at tile[slot_in_tile]
   auto fetch_stage = [&](bool on, long long first, int p, int n, int cnt, float* rec) {
     if (!on) return;
-    const float* f = cp.feat_c + (size_t)first * kD;
+    const float* f = cp.feat_c + (size_t)first * kFeatStride;
     float fv[kD], mv[kD];
 #pragma unroll
     for (int d = 0; d < kD; ++d) {
-      fv[d] = n < cnt ? __ldg(f + (unsigned)n * kD + d) : 0.f;
+      fv[d] = n < cnt ? __ldg(f + (unsigned)n * kFeatStride + d) : 0.f;
       mv[d] = has_mean ? __ldg(cp.data_mean + (size_t)p * N + (unsigned)d * PN + (unsigned)n) : 0.f;
     }
 #pragma unroll
@@ -1017,11 +1017,11 @@ __global__ void __launch_bounds__(kLongWarps * 32, 4) k_pfn_real_long(CompactPil
     for (int n0 = 32 * warp; n0 < E; n0 += 32 * kLongWarps) {
       const int n = n0 + lane;
       if (n < E) {
-        const float* f = cp.feat_c + (size_t)first * kD;
+        const float* f = cp.feat_c + (size_t)first * kFeatStride;
         float fv[kD], mv[kD];
 #pragma unroll
         for (int d = 0; d < kD; ++d) {
-          fv[d] = n < cnt ? __ldg(f + (unsigned)n * kD + d) : 0.f;
+          fv[d] = n < cnt ? __ldg(f + (unsigned)n * kFeatStride + d) : 0.f;
           mv[d] = has_mean ? __ldg(cp.data_mean + (size_t)p * N + (unsigned)d * PN + (unsigned)n) : 0.f;
         }
         float* rec = tile + lane * kRealRec;

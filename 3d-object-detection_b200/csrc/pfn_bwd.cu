@@ -420,10 +420,10 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
         const float* src = cp.data_mean + ((size_t)d * P + p) * N;
         for (int ck = t64 & 7; ck * 4 < N; ck += 8) cp_async16(s_mean + (size_t)d * Np + ck * 4, src + ck * 4);
       }
-      const float* src = cp.feat_c + ((size_t)cp.sw.off[s_b2[ms][pl]] + cp.pil_off[(size_t)s_b2[ms][pl] * P + p]) * kBwdD;
+      const float* src = cp.feat_c + ((size_t)cp.sw.off[s_b2[ms][pl]] + cp.pil_off[(size_t)s_b2[ms][pl] * P + p]) * kFeatStride;
       for (int i = t64; i < min(s_cnt2[ms][pl], kLiveStage) * kBwdD; i += 64) {
         const int n = i / kBwdD, d = i - n * kBwdD;
-        cp_async4(s_feat + (size_t)n * kLiveRec + d, src + i);
+        cp_async4(s_feat + (size_t)n * kLiveRec + d, src + (size_t)n * kFeatStride + d);
       }
     }
     cp_async_commit();
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
       const float2 cand = __ldg(ext + (size_t)task * kBwdC + c);   // best padding slot at n >= cnt (pass A)
       const float* tm = s_mean + (size_t)pl * kBwdD * Np;
       const float* tf = s_feat + (size_t)pl * kLiveStage * kLiveRec;
-      const float* gf = cp.feat_c + ((size_t)cp.sw.off[b] + cp.pil_off[(size_t)b * P + p]) * kBwdD;   // the pillar's rows in HBM
+      const float* gf = cp.feat_c + ((size_t)cp.sw.off[b] + cp.pil_off[(size_t)b * P + p]) * kFeatStride;   // the pillar's rows in HBM
       float best = -INFINITY;
       int nbest = 0;
       for (int n = 0; n < cnt; ++n) {                             // the slots that hold a point
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
           xs[8] = f8 - m[8];
         } else {
 #pragma unroll
-          for (int d = 0; d < kBwdD; ++d) xs[d] = __ldg(gf + (size_t)n * kBwdD + d) - m[d];
+          for (int d = 0; d < kBwdD; ++d) xs[d] = __ldg(gf + (size_t)n * kFeatStride + d) - m[d];
         }
         float z = bc;
 #pragma unroll
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(256, 2) k_pfn_bwd_live(CompactPillars cp, int 
 #pragma unroll
       for (int d = 0; d < kBwdD; ++d) {
         const float md = tm[d * Np + nbest];
-        xb[d] = pad_wins ? 0.f - md : (nbest < kLiveStage ? tf[nbest * kLiveRec + d] : __ldg(gf + (size_t)nbest * kBwdD + d)) - md;
+        xb[d] = pad_wins ? 0.f - md : (nbest < kLiveStage ? tf[nbest * kLiveRec + d] : __ldg(gf + (size_t)nbest * kFeatStride + d)) - md;
       }
       float zs = bc;
 #pragma unroll

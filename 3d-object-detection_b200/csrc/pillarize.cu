@@ -69,85 +69,142 @@ __device__ __forceinline__ void load_xyz(const T* __restrict__ pts, long long i,
 }
 
 // ------------------------------------------------------------------------------------------
+// The stages are latency-bound single waves of dependent, mostly uncoalesced accesses (~10 MB of traffic in
+// all): what they cost is launch + drain latency and the number of memory WAVEFRONTS the SM's load/store unit
+// has to take (a fully divergent warp instruction = 32 of them), not bytes.  Hence: warp-aggregated atomics, one
+// coalesced 16-byte point -> pillar record (point_seg) instead of the cell -> slot -> pillar chain in every stage,
+// 48-byte feature records written as three aligned float4, long running-mean chains on their own warps.
+// (One persistent cooperative kernel with grid barriers instead of six launches was tried: 68 us instead of ~85,
+// but it owns every SM while it spins, so target assignment on the side stream no longer ran next to it and the
+// step got slower, 474 us per batch instead of 357.)
 template <typename T>
-__global__ void __launch_bounds__(256) k_bin(const T* __restrict__ pts, long long sp, long long sc,
-                                             bool vec4, SweepParams sw, GridDev g,
-                                             int* __restrict__ cell_of_point,
-                                             int* __restrict__ cell_first,
-                                             int* __restrict__ cell_count,
-                                             int* __restrict__ status) {
+struct K1 {
+  const T* pts;
+  long long sp, sc;
+  bool vec4;
+  SweepParams sw;
+  GridDev g;
+  int P, N;
+  int *cell_of_point, *cell_first, *cell_count, *tile_count, *cell_slot;
+  int *pil_cnt, *pil_off, *pil_cell, *pil_cursor, *list_cursor, *list_u, *rank_of_point;
+  int *big_count, *big_list, *long_count, *long_list, *tile_ticket;
+  int2* pil_oc;            // per pillar {segment offset, count} (one 8-byte read in st_scatter)
+  int4* point_seg;         // per point {absolute segment start, pillar index or -1, count, 0}
+  double4* terms;
+  double* pil_mean;
+  long long* indices;      // may be null (compact path)
+  int* num_pillars;
+  float* feat_c;           // null: no decoration stage (compact path emits fp64 rows itself)
+  int* status;
+};
+
+constexpr int kMeanLong = 32;   // pillars with more points run their running-mean chain warp-cooperatively
+constexpr unsigned kTileReady = 0x80000000u;
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ---- stage: range filter + floor binning in fp64, first index and count of every cell
+template <typename T>
+__device__ __forceinline__ void st_bin(const K1<T>& a, long long i0, long long stride) {
+  const SweepParams& sw = a.sw;
+  const GridDev& g = a.g;
   const long long total = sw.off[sw.n_sweeps];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int b = find_sweep(sw, i);
-    double x, y, z, r;
-    load_xyz(pts, i, sp, sc, vec4, x, y, z, r);
-    int cell = -1;
-    // data/pillars.cpp:271-275 (half-open box; written as the reference writes it)
-    if (!((x >= g.x_max) || (x < g.x_min) || (y >= g.y_max) || (y < g.y_min) ||
-          (z >= g.z_max) || (z < g.z_min))) {
-      // data/pillars.cpp:278-279, IEEE double subtract / divide / floor
-      const double fx = floor(__ddiv_rn(__dsub_rn(x, g.x_min), g.x_step));
-      const double fy = floor(__ddiv_rn(__dsub_rn(y, g.y_min), g.y_step));
-      if (fx >= 0.0 && fx < (double)g.nx && fy >= 0.0 && fy < (double)g.ny) {
-        cell = (int)fy * g.nx + (int)fx;
-      } else {
-        atomicOr(status, PP_STATUS_BAD_POINT);  // NaN/Inf: out of contract, dropped
+  const int lane = (int)lane_id();
+  for (long long base = i0 - lane; base < total; base += stride) {      // warp-uniform trip count
+    const long long i = base + lane;
+    int cell = -1, b = 0;
+    if (i < total) {
+      b = find_sweep(sw, i);
+      double x, y, z, r;
+      load_xyz(a.pts, i, a.sp, a.sc, a.vec4, x, y, z, r);
+      // data/pillars.cpp:271-275 (half-open box; written as the reference writes it)
+      if (!((x >= g.x_max) || (x < g.x_min) || (y >= g.y_max) || (y < g.y_min) ||
+            (z >= g.z_max) || (z < g.z_min))) {
+        // data/pillars.cpp:278-279, IEEE double subtract / divide / floor
+        const double fx = floor(__ddiv_rn(__dsub_rn(x, g.x_min), g.x_step));
+        const double fy = floor(__ddiv_rn(__dsub_rn(y, g.y_min), g.y_step));
+        if (fx >= 0.0 && fx < (double)g.nx && fy >= 0.0 && fy < (double)g.ny) {
+          cell = (int)fy * g.nx + (int)fx;
+        } else {
+          atomicOr(a.status, PP_STATUS_BAD_POINT);  // NaN/Inf: out of contract, dropped
+        }
       }
+      a.cell_of_point[i] = cell;
     }
-    cell_of_point[i] = cell;
-    if (cell >= 0) {
+    // neighbours in the input often share a cell: one pair of atomics per distinct (sweep, cell) of the warp.
+    // The group's lowest lane holds its smallest index (lanes are in input order).
+    const int key = cell >= 0 ? b * g.ncell + cell : -1 - lane;          // < 2^31 (checked by the host)
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    if (cell >= 0 && (grp & ((1u << lane) - 1u)) == 0u) {
       const int il = (int)(i - sw.off[b]);
-      atomicMin(&cell_first[(size_t)b * g.ncell + cell], il);
-      atomicAdd(&cell_count[(size_t)b * g.ncell + cell], 1);
+      // first index as an inverted maximum: the table starts at zero like the counters (one memset)
+      atomicMax(&a.cell_first[(size_t)key], 0x7fffffff - il);
+      atomicAdd(&a.cell_count[(size_t)key], __popc(grp));
     }
   }
 }
 
-__device__ __forceinline__ bool first_touch_flag(const SweepParams& sw, const GridDev& g, int t,
-                                                 int& b, int& il, int& cell,
-                                                 const int* __restrict__ cell_of_point,
-                                                 const int* __restrict__ cell_first) {
+template <typename T>
+__device__ __forceinline__ bool first_touch_flag(const K1<T>& a, int t, int& b, int& il, int& cell) {
+  const SweepParams& sw = a.sw;
   b = find_tile_sweep(sw, t);
   il = (t - sw.tile_start[b]) * kTile + (int)threadIdx.x;
   const long long n_b = sw.off[b + 1] - sw.off[b];
   cell = -1;
-  if (il < n_b) cell = cell_of_point[sw.off[b] + il];
-  return cell >= 0 && cell_first[(size_t)b * g.ncell + cell] == il;
+  if (il < n_b) cell = a.cell_of_point[sw.off[b] + il];
+  return cell >= 0 && a.cell_first[(size_t)b * a.g.ncell + cell] == 0x7fffffff - il;
 }
 
-__global__ void __launch_bounds__(kTile) k_tilecount(SweepParams sw, GridDev g,
-                                                     const int* __restrict__ cell_of_point,
-                                                     const int* __restrict__ cell_first,
-                                                     int* __restrict__ tile_count) {
+// ---- stage: number of first-touch points of tile t, published with a ready bit (st_assign of a later tile
+// of the same sweep polls it: every block publishes all its tiles before it waits for anything)
+template <typename T>
+__device__ __forceinline__ void st_tilecount(const K1<T>& a, int t) {
   __shared__ int warp_cnt[kTile / 32];
   int b, il, cell;
-  const bool flag = first_touch_flag(sw, g, blockIdx.x, b, il, cell, cell_of_point, cell_first);
+  const bool flag = first_touch_flag(a, t, b, il, cell);
   const unsigned m = __ballot_sync(0xffffffffu, flag);
   if (lane_id() == 0) warp_cnt[threadIdx.x >> 5] = __popc(m);
   __syncthreads();
   if (threadIdx.x < 32) {
     int v = warp_cnt[threadIdx.x];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) tile_count[blockIdx.x] = v;
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicExch(reinterpret_cast<unsigned*>(&a.tile_count[t]), (unsigned)v | kTileReady);
+    }
   }
+  __syncthreads();
 }
 
-__global__ void __launch_bounds__(kTile) k_assign(
-    SweepParams sw, GridDev g, int P, const int* __restrict__ cell_of_point,
-    const int* __restrict__ cell_first, const int* __restrict__ cell_count,
-    const int* __restrict__ tile_count, int* __restrict__ cell_slot, int* __restrict__ pil_cnt,
-    int* __restrict__ pil_off, int* __restrict__ pil_cell, int* __restrict__ list_cursor,
-    int* __restrict__ big_count, int* __restrict__ big_list, int* __restrict__ num_pillars) {
+// ---- stage: pillar slot of every first-touch point (exclusive scan in input order), list segments
+template <typename T>
+__device__ __forceinline__ void st_assign(const K1<T>& a, int t) {
   __shared__ int warp_sum[kTile / 32];
-  __shared__ int s_base;
-  const int t = blockIdx.x;
+  __shared__ int warp_cnt[kTile / 32];
+  __shared__ int s_base, s_seg_base;
+  const SweepParams& sw = a.sw;
+  const GridDev& g = a.g;
+  const int P = a.P;
   int b, il, cell;
-  const bool flag = first_touch_flag(sw, g, t, b, il, cell, cell_of_point, cell_first);
+  const bool flag = first_touch_flag(a, t, b, il, cell);
+  // the cell's point count is needed once the slot is known: fetch it under the wait for the earlier tiles
+  const size_t ci = flag ? (size_t)b * g.ncell + cell : 0;
+  const int cnt_cell = flag ? a.cell_count[ci] : 0;
 
   // base = number of first-touch points in the earlier tiles of this sweep
   int part = 0;
-  for (int k = sw.tile_start[b] + (int)threadIdx.x; k < t; k += kTile) part += tile_count[k];
+  for (int k = sw.tile_start[b] + (int)threadIdx.x; k < t; k += kTile) {
+    unsigned v;
+    const long long t0 = clock64();
+    while (((v = ld_acquire(reinterpret_cast<const unsigned*>(&a.tile_count[k]))) & kTileReady) == 0u) {
+      if (clock64() - t0 > 4000000000ll) __trap();
+    }
+    part += (int)(v & ~kTileReady);
+  }
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   if (lane_id() == 0) warp_sum[threadIdx.x >> 5] = part;
   __syncthreads();
@@ -162,7 +219,6 @@ __global__ void __launch_bounds__(kTile) k_assign(
   // exclusive scan of the flags inside the tile
   const unsigned m = __ballot_sync(0xffffffffu, flag);
   const int in_warp = __popc(m & ((1u << lane_id()) - 1u));
-  __syncthreads();  // warp_sum reuse
   if (lane_id() == 0) warp_sum[threadIdx.x >> 5] = __popc(m);
   __syncthreads();
   int before = 0, total = 0;
@@ -174,19 +230,15 @@ __global__ void __launch_bounds__(kTile) k_assign(
   // kept pillars reserve a list segment of `cnt` entries: block-scan the counts and take ONE
   // atomicAdd per tile (segments only have to be disjoint, not ordered)
   int slot = -1, cnt = 0;
-  size_t ci = 0;
   if (flag) {
     slot = base + before + in_warp;
-    ci = (size_t)b * g.ncell + cell;
-    if (slot < P) cnt = cell_count[ci];
+    if (slot < P) cnt = cnt_cell;
   }
   int incl = cnt;
   for (int o = 1; o < 32; o <<= 1) {
     const int v = __shfl_up_sync(0xffffffffu, incl, o);
     if ((int)lane_id() >= o) incl += v;
   }
-  __shared__ int warp_cnt[kTile / 32];
-  __shared__ int s_seg_base;
   if (lane_id() == 31) warp_cnt[threadIdx.x >> 5] = incl;
   __syncthreads();
   int cnt_before = 0, cnt_total = 0;
@@ -195,45 +247,67 @@ __global__ void __launch_bounds__(kTile) k_assign(
     if (w < (int)(threadIdx.x >> 5)) cnt_before += v;
     cnt_total += v;
   }
-  if (threadIdx.x == 0) s_seg_base = cnt_total > 0 ? atomicAdd(&list_cursor[b], cnt_total) : 0;
+  if (threadIdx.x == 0) s_seg_base = cnt_total > 0 ? atomicAdd(&a.list_cursor[b], cnt_total) : 0;
   __syncthreads();
   if (flag) {
     if (slot < P) {
       const int off = s_seg_base + cnt_before + incl - cnt;
       const size_t pi = (size_t)b * P + slot;
-      cell_slot[ci] = slot;
-      pil_cnt[pi] = cnt;
-      pil_off[pi] = off;
-      pil_cell[pi] = cell;
-      if (cnt > kBig) big_list[atomicAdd(big_count, 1)] = (int)pi;
+      a.cell_slot[ci] = slot;
+      a.pil_cnt[pi] = cnt;
+      a.pil_off[pi] = off;
+      a.pil_oc[pi] = make_int2(off, cnt);
+      a.pil_cell[pi] = cell;
+      if (cnt > kBig) a.big_list[atomicAdd(a.big_count, 1)] = (int)pi;
+      else if (cnt > kMeanLong) a.long_list[atomicAdd(a.long_count, 1)] = (int)pi;
     } else {
-      cell_slot[ci] = -1;  // pillar beyond the max_pillars cap: data/pillars.cpp:339
+      a.cell_slot[ci] = -1;  // pillar beyond the max_pillars cap: data/pillars.cpp:339
     }
   }
   const int ntiles_b = sw.tile_start[b + 1] - sw.tile_start[b];
   if (threadIdx.x == 0 && t - sw.tile_start[b] == ntiles_b - 1) {
     const int np = base + total;
-    num_pillars[b] = np < P ? np : P;
+    a.num_pillars[b] = np < P ? np : P;
   }
+  __syncthreads();   // shared scratch is reused by the block's next tile
 }
 
-__global__ void __launch_bounds__(256) k_scatter(SweepParams sw, GridDev g, int P,
-                                                 const int* __restrict__ cell_of_point,
-                                                 const int* __restrict__ cell_slot,
-                                                 const int* __restrict__ pil_off,
-                                                 int* __restrict__ pil_cursor,
-                                                 int* __restrict__ list_u) {
+// ---- stage: append every kept point to its pillar's segment (unordered).  The point's pillar, segment and count
+// go to point_seg with one coalesced 16-byte store: the later per-point stages start from there instead of
+// repeating the cell -> slot -> pillar chain of random 4-byte reads (these stages are bound by the number of
+// memory wavefronts the SM's load/store unit takes for uncoalesced accesses, not by bytes).
+template <typename T>
+__device__ __forceinline__ void st_scatter(const K1<T>& a, long long i0, long long stride) {
+  const SweepParams& sw = a.sw;
   const long long total = sw.off[sw.n_sweeps];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cell = cell_of_point[i];
-    if (cell < 0) continue;
-    const int b = find_sweep(sw, i);
-    const int slot = cell_slot[(size_t)b * g.ncell + cell];
-    if (slot < 0) continue;
-    const size_t pi = (size_t)b * P + slot;
-    const int pos = atomicAdd(&pil_cursor[pi], 1);
-    list_u[sw.off[b] + pil_off[pi] + pos] = (int)(i - sw.off[b]);
+  const int lane = (int)lane_id();
+  for (long long base = i0 - lane; base < total; base += stride) {      // warp-uniform trip count
+    const long long i = base + lane;
+    int pi = -1, b = 0;
+    if (i < total) {
+      const int cell = a.cell_of_point[i];
+      if (cell >= 0) {
+        b = find_sweep(sw, i);
+        const int slot = a.cell_slot[(size_t)b * a.g.ncell + cell];
+        if (slot >= 0) pi = b * a.P + slot;
+      }
+    }
+    // one cursor atomic per pillar of the warp
+    const unsigned grp = __match_any_sync(0xffffffffu, pi >= 0 ? pi : -1 - lane);
+    const unsigned lower = grp & ((1u << lane) - 1u);
+    int pos = 0;
+    if (pi >= 0 && lower == 0u) pos = atomicAdd(&a.pil_cursor[pi], __popc(grp));
+    pos = __shfl_sync(0xffffffffu, pos, __ffs(grp) - 1) + __popc(lower);
+    if (i < total) {
+      int4 ps = make_int4(0, -1, 0, 0);
+      if (pi >= 0) {
+        const int2 oc = a.pil_oc[pi];
+        const int segbase = (int)sw.off[b] + oc.x;
+        a.list_u[segbase + pos] = (int)(i - sw.off[b]);
+        ps = make_int4(segbase, pi, oc.y, 0);
+      }
+      a.point_seg[i] = ps;
+    }
   }
 }
 
@@ -241,7 +315,7 @@ __global__ void __launch_bounds__(256) k_scatter(SweepParams sw, GridDev g, int 
 //   m <- m*(n/(n+1)) + x/(n+1)
 // for the point of rank n: {a = n/(n+1), x/(n+1), y/(n+1), z/(n+1)} (the first point initialises the
 // mean: a = 0, terms = x, y, z).  The four IEEE divisions do not depend on m, so they are done here,
-// one point per thread with every lane busy, and k_mean is left with the bare multiply-add chain.
+// one point per thread with every lane busy, and the mean stage is left with the bare multiply-add chain.
 template <typename T>
 __device__ __forceinline__ void mean_terms(const T* __restrict__ pts, long long gi, long long sp, long long sc,
                                            bool vec4, int rank, double4* __restrict__ out) {
@@ -257,80 +331,62 @@ __device__ __forceinline__ void mean_terms(const T* __restrict__ pts, long long 
   *out = t;
 }
 
+// ---- stage: rank of every kept point inside its pillar = number of smaller indices in the segment
 template <typename T>
-__global__ void __launch_bounds__(256) k_rank(const T* __restrict__ pts, long long sp, long long sc, bool vec4,
-                                              SweepParams sw, GridDev g, int P,
-                                              const int* __restrict__ cell_of_point,
-                                              const int* __restrict__ cell_slot,
-                                              const int* __restrict__ pil_cnt,
-                                              const int* __restrict__ pil_off,
-                                              const int* __restrict__ list_u,
-                                              double4* __restrict__ terms,
-                                              int* __restrict__ rank_of_point) {
+__device__ __forceinline__ void st_rank(const K1<T>& a, long long i0, long long stride) {
+  const SweepParams& sw = a.sw;
   const long long total = sw.off[sw.n_sweeps];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cell = cell_of_point[i];
+  for (long long i = i0; i < total; i += stride) {
+    const int4 ps = a.point_seg[i];
     int rank = -1;
-    if (cell >= 0) {
-      const int b = find_sweep(sw, i);
-      const int slot = cell_slot[(size_t)b * g.ncell + cell];
-      if (slot >= 0) {
-        const size_t pi = (size_t)b * P + slot;
-        const int c = pil_cnt[pi];
-        if (c <= kBig) {
-          const int il = (int)(i - sw.off[b]);
-          const int* seg = list_u + sw.off[b] + pil_off[pi];
-          rank = 0;
-          for (int k = 0; k < c; ++k) rank += (seg[k] < il) ? 1 : 0;
-          mean_terms(pts, i, sp, sc, vec4, rank, terms + sw.off[b] + pil_off[pi] + rank);
-        } else {
-          rank = -2;  // filled by k_rank_big
-        }
+    if (ps.y >= 0) {
+      const int c = ps.z;
+      if (c <= kBig) {
+        const int il = (int)(i - sw.off[find_sweep(sw, i)]);
+        const int* seg = a.list_u + ps.x;
+        rank = 0;
+        for (int k = 0; k < c; ++k) rank += (seg[k] < il) ? 1 : 0;
+        mean_terms(a.pts, i, a.sp, a.sc, a.vec4, rank, a.terms + ps.x + rank);
+      } else {
+        rank = -2;  // filled by st_rank_big
       }
     }
-    if (rank != -2) rank_of_point[i] = rank;
+    if (rank != -2) a.rank_of_point[i] = rank;
   }
 }
 
 // One block per big pillar: ordered stream compaction of the sweep's points that fall in its cell.
 template <typename T>
-__global__ void __launch_bounds__(kTile) k_rank_big(const T* __restrict__ pts, long long sp, long long sc, bool vec4,
-                                                    SweepParams sw, int P,
-                                                    const int* __restrict__ cell_of_point,
-                                                    const int* __restrict__ pil_off,
-                                                    const int* __restrict__ pil_cell,
-                                                    const int* __restrict__ big_count,
-                                                    const int* __restrict__ big_list,
-                                                    double4* __restrict__ terms,
-                                                    int* __restrict__ rank_of_point) {
-  __shared__ int warp_sum[kTile / 32];
-  const int nbig = *big_count;
+__device__ __forceinline__ void st_rank_big(const K1<T>& a) {
+  __shared__ int warp_sum[32];
+  const SweepParams& sw = a.sw;
+  const int nbig = __ldcg(a.big_count);
+  const int nwarps = (int)(blockDim.x >> 5);
   for (int k = blockIdx.x; k < nbig; k += gridDim.x) {
-    const int pi = big_list[k];
-    const int b = pi / P;
-    const int cell = pil_cell[pi];
+    const int pi = a.big_list[k];
+    const int b = pi / a.P;
+    const int cell = a.pil_cell[pi];
     const long long n_b = sw.off[b + 1] - sw.off[b];
-    double4* out = terms + sw.off[b] + pil_off[pi];
+    double4* out = a.terms + sw.off[b] + a.pil_off[pi];
     int running = 0;
-    for (long long s = 0; s < n_b; s += kTile) {
+    for (long long s = 0; s < n_b; s += blockDim.x) {
       const long long il = s + threadIdx.x;
-      const bool flag = il < n_b && cell_of_point[sw.off[b] + il] == cell;
+      const bool flag = il < n_b && a.cell_of_point[sw.off[b] + il] == cell;
       const unsigned m = __ballot_sync(0xffffffffu, flag);
       const int in_warp = __popc(m & ((1u << lane_id()) - 1u));
       __syncthreads();
       if (lane_id() == 0) warp_sum[threadIdx.x >> 5] = __popc(m);
       __syncthreads();
       int before = 0, total = 0;
-      for (int w = 0; w < kTile / 32; ++w) {
+      for (int w = 0; w < nwarps; ++w) {
         const int v = warp_sum[w];
         if (w < (int)(threadIdx.x >> 5)) before += v;
         total += v;
       }
       if (flag) {
         const int rank = running + before + in_warp;
-        mean_terms(pts, sw.off[b] + il, sp, sc, vec4, rank, out + rank);
-        rank_of_point[sw.off[b] + il] = rank;
+        mean_terms(a.pts, sw.off[b] + il, a.sp, a.sc, a.vec4, rank, out + rank);
+        a.rank_of_point[sw.off[b] + il] = rank;
       }
       running += total;
     }
@@ -340,78 +396,108 @@ __global__ void __launch_bounds__(kTile) k_rank_big(const T* __restrict__ pts, l
 
 __device__ __forceinline__ double4 ld_terms(const double4* __restrict__ p) {
   const double2* q = reinterpret_cast<const double2*>(p);
-  const double2 a = __ldg(q), b = __ldg(q + 1);
+  const double2 a = __ldcg(q), b = __ldcg(q + 1);     // written earlier in this launch: L2, not the read-only path
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
-// One thread per pillar slot: the sequential multiply-add chain of the reference's running mean over
-// the terms k_rank prepared (32-byte records, contiguous per pillar, L2-resident), evaluated in input
-// order with separately rounded IEEE operations.  The records of the next steps are loaded ahead of
-// the chain (4-deep), so a pillar costs ~2 dependent fp64 operations per point (median pillar: 2
-// points, longest of a Lyft-shaped sweep: ~300).
-__global__ void __launch_bounds__(128) k_mean(SweepParams sw, GridDev g, int P,
-                                              const int* __restrict__ num_pillars,
-                                              const int* __restrict__ pil_cnt,
-                                              const int* __restrict__ pil_off,
-                                              const int* __restrict__ pil_cell,
-                                              const double4* __restrict__ terms,
-                                              double* __restrict__ pil_mean,
-                                              long long* __restrict__ indices) {
-  const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (grp >= (long long)sw.n_sweeps * P) return;
-  const int b = (int)(grp / P);
-  const int slot = (int)(grp - (long long)b * P);
-  if (slot >= num_pillars[b]) {
-    if (indices != nullptr) { indices[grp * 3 + 0] = 0; indices[grp * 3 + 1] = 0; indices[grp * 3 + 2] = 0; }
+template <typename T>
+__device__ __forceinline__ void mean_store(const K1<T>& a, long long grp, double m0, double m1, double m2) {
+  a.pil_mean[grp * 3 + 0] = m0;
+  a.pil_mean[grp * 3 + 1] = m1;
+  a.pil_mean[grp * 3 + 2] = m2;
+  if (a.indices != nullptr) {
+    const int cell = a.pil_cell[grp];
+    const double cx = (double)(cell % a.g.nx);
+    const double cy = __dsub_rn(__dsub_rn(a.g.canvas_height, 1.0), (double)(cell / a.g.nx));
+    a.indices[grp * 3 + 0] = 1;                 // data/pillars.cpp:390-392, then .long()
+    a.indices[grp * 3 + 1] = (long long)cx;
+    a.indices[grp * 3 + 2] = (long long)cy;
+  }
+}
+
+// ---- stage: the sequential multiply-add chain of the reference's running mean over the terms st_rank
+// prepared (32-byte records, contiguous per pillar, L2-resident), in input order with separately rounded IEEE
+// operations.  One thread per pillar slot up to kMeanLong points (records loaded four steps ahead of the
+// chain); longer pillars (0.4 % of them, up to a few hundred points) take a whole warp (st_mean_long).  As one
+// thread per pillar the longest pillar alone set the stage's duration (31 us).
+constexpr int kMeanBlock = 256;
+
+template <typename T>
+__device__ __forceinline__ void st_mean_slots(const K1<T>& a, long long grp) {
+  const SweepParams& sw = a.sw;
+  if (grp >= (long long)sw.n_sweeps * a.P) return;
+  const int b = (int)(grp / a.P);
+  const int slot = (int)(grp - (long long)b * a.P);
+  if (slot >= a.num_pillars[b]) {
+    if (a.indices != nullptr) { a.indices[grp * 3 + 0] = 0; a.indices[grp * 3 + 1] = 0; a.indices[grp * 3 + 2] = 0; }
     return;
   }
-  const int c = pil_cnt[grp];
-  const double4* seg = terms + sw.off[b] + pil_off[grp];
+  const int2 oc = a.pil_oc[grp];
+  const int c = oc.y;
+  if (c > kMeanLong) return;
+  const double4* seg = a.terms + sw.off[b] + oc.x;
   double4 t = ld_terms(seg);                          // rank 0: a = 0, terms = the point itself
   double m0 = t.y, m1 = t.z, m2 = t.w;             // data/pillars.cpp:313-317
   constexpr int kAhead = 4;
-  int k = 1;
-  if (k + kAhead <= c) {
-    double4 u[kAhead], v[kAhead];
+  double4 u[kAhead];
 #pragma unroll
-    for (int j = 0; j < kAhead; ++j) u[j] = ld_terms(seg + k + j);
-    for (; k + kAhead <= c; k += kAhead) {
-      const bool more = k + 2 * kAhead <= c;
-      // long pillars are bound by the L2 round trip of their record stream, not by the arithmetic
-      // chain: pull the 128-byte line eight batches ahead into L1
-      if (k + 9 * kAhead <= c) asm volatile("prefetch.global.L1 [%0];" ::"l"(seg + k + 8 * kAhead));
-      if (more) {
+  for (int j = 0; j < kAhead; ++j)
+    if (1 + j < c) u[j] = ld_terms(seg + 1 + j);
+  for (int k = 1; k < c; k += kAhead) {
 #pragma unroll
-        for (int j = 0; j < kAhead; ++j) v[j] = ld_terms(seg + k + kAhead + j);   // in flight during the chain below
-      }
-#pragma unroll
-      for (int j = 0; j < kAhead; ++j) {
-        m0 = __dadd_rn(__dmul_rn(m0, u[j].x), u[j].y);   // data/pillars.cpp:324-326
-        m1 = __dadd_rn(__dmul_rn(m1, u[j].x), u[j].z);
-        m2 = __dadd_rn(__dmul_rn(m2, u[j].x), u[j].w);
-      }
-      if (more) {
-#pragma unroll
-        for (int j = 0; j < kAhead; ++j) u[j] = v[j];
+    for (int j = 0; j < kAhead; ++j) {
+      if (k + j < c) {
+        const double4 v = u[j];
+        if (k + j + kAhead < c) u[j] = ld_terms(seg + k + j + kAhead);
+        m0 = __dadd_rn(__dmul_rn(m0, v.x), v.y);   // data/pillars.cpp:324-326
+        m1 = __dadd_rn(__dmul_rn(m1, v.x), v.z);
+        m2 = __dadd_rn(__dmul_rn(m2, v.x), v.w);
       }
     }
   }
-  for (; k < c; ++k) {
-    const double4 u = ld_terms(seg + k);
-    m0 = __dadd_rn(__dmul_rn(m0, u.x), u.y);
-    m1 = __dadd_rn(__dmul_rn(m1, u.x), u.z);
-    m2 = __dadd_rn(__dmul_rn(m2, u.x), u.w);
-  }
-  pil_mean[grp * 3 + 0] = m0;
-  pil_mean[grp * 3 + 1] = m1;
-  pil_mean[grp * 3 + 2] = m2;
-  if (indices != nullptr) {
-    const int cell = pil_cell[grp];
-    const double cx = (double)(cell % g.nx);
-    const double cy = __dsub_rn(__dsub_rn(g.canvas_height, 1.0), (double)(cell / g.nx));
-    indices[grp * 3 + 0] = 1;                 // data/pillars.cpp:390-392, then .long()
-    indices[grp * 3 + 1] = (long long)cx;
-    indices[grp * 3 + 2] = (long long)cy;
+  mean_store(a, grp, m0, m1, m2);
+}
+
+// Long pillars (more than kMeanLong points; the big ones of st_rank_big included): one warp each.  The lanes load
+// 32 records at once, park them in shared memory and every lane walks the chain over broadcast reads: two LDS.128
+// and six fp64 operations per step (~47 cycles) instead of an L2 round trip every four steps.
+template <typename T>
+__device__ __forceinline__ void st_mean_long(const K1<T>& a, int w0, int wstride) {
+  __shared__ double4 s_rec[kMeanBlock / 32][32];
+  const SweepParams& sw = a.sw;
+  const unsigned lane = lane_id();
+  double4* rec = s_rec[threadIdx.x >> 5];
+  const int nl0 = __ldcg(a.long_count), nlong = nl0 + __ldcg(a.big_count);
+  for (int w = w0; w < nlong; w += wstride) {
+    const long long grp = w < nl0 ? a.long_list[w] : a.big_list[w - nl0];
+    const int b = (int)(grp / a.P);
+    const int2 oc = a.pil_oc[grp];
+    const int c = oc.y;
+    const double4* seg = a.terms + sw.off[b] + oc.x;
+    double4 cur = make_double4(0.0, 0.0, 0.0, 0.0);
+    if ((int)lane < c) cur = ld_terms(seg + lane);
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+    for (int k0 = 0; k0 < c; k0 += 32) {
+      rec[lane] = cur;
+      __syncwarp();
+      if (k0 + 32 + (int)lane < c) cur = ld_terms(seg + k0 + 32 + lane);      // in flight during the chain below
+      const int n = c - k0 < 32 ? c - k0 : 32;
+      int j = 0;
+      if (k0 == 0) {                                    // rank 0: the point itself (data/pillars.cpp:313-317)
+        const double4 v = rec[0];
+        m0 = v.y; m1 = v.z; m2 = v.w;
+        j = 1;
+      }
+#pragma unroll 4
+      for (; j < n; ++j) {
+        const double4 v = rec[j];
+        m0 = __dadd_rn(__dmul_rn(m0, v.x), v.y);       // data/pillars.cpp:324-326
+        m1 = __dadd_rn(__dmul_rn(m1, v.x), v.z);
+        m2 = __dadd_rn(__dmul_rn(m2, v.x), v.w);
+      }
+      __syncwarp();                                     // all lanes have read the chunk before it is overwritten
+    }
+    if (lane == 0) mean_store(a, grp, m0, m1, m2);
   }
 }
 
@@ -429,38 +515,81 @@ __device__ __forceinline__ void point_features(double x, double y, double z, dou
 
 constexpr int kFeatGroup = 3;   // features per thread in k_emit_dense (9 = 3 groups -> grid.y)
 
-// Per kept point (rank < N inside a kept pillar): the nine decorated features in fp64, rounded once
-// to fp32 (torch .float(), data/dataset.py:101), stored compactly at the point's position in its
-// pillar's ordered segment.  Keeps all fp64 math out of the streaming kernel below.
+// ---- stage: per kept point (rank < N inside a kept pillar) the nine decorated features in fp64, rounded once
+// to fp32 (torch .float(), data/dataset.py:101), stored compactly at the point's position in its pillar's
+// ordered segment.  Keeps all fp64 math out of the streaming kernels downstream.
 template <typename T>
-__global__ void __launch_bounds__(256) k_feat(const T* __restrict__ pts, long long sp, long long sc,
-                                              bool vec4, SweepParams sw, GridDev g, int P, int N,
-                                              const int* __restrict__ cell_of_point,
-                                              const int* __restrict__ cell_slot,
-                                              const int* __restrict__ rank_of_point,
-                                              const int* __restrict__ pil_off,
-                                              const double* __restrict__ pil_mean,
-                                              float* __restrict__ feat_c) {
+__device__ __forceinline__ void st_feat(const K1<T>& a, long long i0, long long stride) {
+  const SweepParams& sw = a.sw;
+  const GridDev& g = a.g;
   const long long total = sw.off[sw.n_sweeps];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cell = cell_of_point[i];
-    if (cell < 0) continue;
-    const int b = find_sweep(sw, i);
-    const int slot = cell_slot[(size_t)b * g.ncell + cell];
-    if (slot < 0) continue;
-    const int rank = rank_of_point[i];
-    if (rank >= N) continue;                       // data/pillars.cpp:371 first-N cap
-    const size_t pi = (size_t)b * P + slot;
-    double x, y, z, r, ft[9];
-    load_xyz(pts, i, sp, sc, vec4, x, y, z, r);
+  for (long long i = i0; i < total; i += stride) {
+    const int4 ps = a.point_seg[i];
+    if (ps.y < 0) continue;
+    const int rank = a.rank_of_point[i];
+    if (rank >= a.N) continue;                       // data/pillars.cpp:371 first-N cap
+    const int cell = a.cell_of_point[i];
+    double x, y, z, r, ft[9], mean[3];
+    load_xyz(a.pts, i, a.sp, a.sc, a.vec4, x, y, z, r);
     const double cx = (double)(cell % g.nx);
     const double cy = __dsub_rn(__dsub_rn(g.canvas_height, 1.0), (double)(cell / g.nx));
-    point_features(x, y, z, r, cx, cy, pil_mean + pi * 3, ft);
-    float* o = feat_c + (size_t)(sw.off[b] + pil_off[pi] + rank) * 9;
-#pragma unroll
-    for (int d = 0; d < 9; ++d) o[d] = (float)ft[d];
+    const double* pm = a.pil_mean + (size_t)ps.y * 3;
+    mean[0] = __ldcg(pm); mean[1] = __ldcg(pm + 1); mean[2] = __ldcg(pm + 2);
+    point_features(x, y, z, r, cx, cy, mean, ft);
+    // 48-byte records: three aligned 16-byte stores instead of nine scattered 4-byte ones
+    float4* o = reinterpret_cast<float4*>(a.feat_c + (size_t)(ps.x + rank) * kFeatStride);
+    o[0] = make_float4((float)ft[0], (float)ft[1], (float)ft[2], (float)ft[3]);
+    o[1] = make_float4((float)ft[4], (float)ft[5], (float)ft[6], (float)ft[7]);
+    o[2] = make_float4((float)ft[8], 0.f, 0.f, 0.f);
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bin(const K1<T> a) {
+  const SweepParams& sw = a.sw;
+  if (blockIdx.x == 0 && (int)threadIdx.x < sw.n_sweeps && sw.off[threadIdx.x + 1] == sw.off[threadIdx.x])
+    a.num_pillars[threadIdx.x] = 0;                  // a sweep without points has no tile to report its count
+  st_bin(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+// One block per 1024-point tile.  Tiles are taken in the order the blocks start (ticket), so the tiles a block
+// waits for in st_assign belong to blocks that are already running, and those publish their count before they
+// wait for anything themselves.
+template <typename T>
+__global__ void __launch_bounds__(kTile) k_assign(const K1<T> a) {
+  __shared__ int s_t;
+  if (threadIdx.x == 0) s_t = atomicAdd(a.tile_ticket, 1);
+  __syncthreads();
+  const int t = s_t;
+  st_tilecount(a, t);
+  st_assign(a, t);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_scatter(const K1<T> a) {
+  st_scatter(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_rank(const K1<T> a) {
+  st_rank(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+  st_rank_big(a);
+}
+
+// blocks [0, long_blocks): long pillars, dealt block-minor so that consecutive entries go to different SMs (the
+// chains of one SM share its fp64 pipe); they come first in the grid and start with the launch.  The other blocks:
+// one thread per pillar slot.
+template <typename T>
+__global__ void __launch_bounds__(kMeanBlock) k_mean(const K1<T> a, int long_blocks) {
+  if ((int)blockIdx.x < long_blocks)
+    st_mean_long(a, (int)blockIdx.x + (int)(threadIdx.x >> 5) * long_blocks, (kMeanBlock / 32) * long_blocks);
+  else
+    st_mean_slots(a, (long long)(blockIdx.x - long_blocks) * kMeanBlock + threadIdx.x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_feat(const K1<T> a) {
+  st_feat(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
 // Dense emit: x[b,d,p,n] = float(feature) - data_mean[d,p,n] for every slot (data/dataset.py:99-105).
@@ -496,7 +625,7 @@ __global__ void __launch_bounds__(256) k_emit_dense(
       int c = 0;
       if (p < num_pillars[b]) c = min(pil_cnt[pi], N);  // data/pillars.cpp:371 first-N cap
       float* ob = xout + (size_t)b * 9 * PN + e;
-      const float* fc = (n0 < c) ? feat_c + (size_t)(sw.off[b] + pil_off[pi] + n0) * 9 + d0 : nullptr;
+      const float* fc = (n0 < c) ? feat_c + (size_t)(sw.off[b] + pil_off[pi] + n0) * kFeatStride + d0 : nullptr;
 #pragma unroll
       for (int d = 0; d < kFeatGroup; ++d) {
         vec_t v;
@@ -504,7 +633,7 @@ __global__ void __launch_bounds__(256) k_emit_dense(
         const float* mf = reinterpret_cast<const float*>(&m[d]);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-          const float f = (fc != nullptr && n0 + k < c) ? fc[k * 9 + d] : 0.f;
+          const float f = (fc != nullptr && n0 + k < c) ? fc[k * kFeatStride + d] : 0.f;
           vf[k] = __fsub_rn(f, mf[k]);            // feature (or 0) - mean, like the reference
         }
         __stcs(reinterpret_cast<vec_t*>(ob + (d0 + d) * PN), v);
@@ -564,12 +693,13 @@ __global__ void k_pillar_xy(GridDev g, int P, const int* __restrict__ num_pillar
 struct PillarWs {
   int *cell_first, *cell_slot, *cell_of_point, *rank_of_point, *tile_count, *list_u;
   double4* terms;   // per point, in its pillar's ordered segment: {n/(n+1), x/(n+1), y/(n+1), z/(n+1)}
-  int *pil_cnt, *pil_off, *pil_cell, *big_list, *num_pillars_scratch;
+  int *pil_cnt, *pil_off, *pil_cell, *big_list, *long_list, *num_pillars_scratch;
+  int2* pil_oc;
+  int4* point_seg;
   double* pil_mean;
   float* feat_c;
-  // zero-initialised block (one memset)
-  int* zero_begin;
-  int *cell_count, *pil_cursor, *list_cursor, *big_count, *n_rows;
+  // zero-initialised block (one memset), starts at cell_count
+  int *cell_count, *pil_cursor, *list_cursor, *big_count, *long_count, *tile_ticket, *n_rows;
   size_t zero_bytes;
 };
 
@@ -605,23 +735,28 @@ static void layout(A& a, PillarWs* ws, int B, long long T, long long ntiles, int
   TAKE(pil_cursor, int, np);
   TAKE(list_cursor, int, PP_MAX_SWEEPS);
   TAKE(big_count, int, 1);
+  TAKE(long_count, int, 1);
   TAKE(n_rows, int, 1);
+  TAKE(tile_ticket, int, 1);
   TAKE(num_pillars_scratch, int, PP_MAX_SWEEPS);
+  TAKE(tile_count, int, (size_t)ntiles + 1);
+  TAKE(cell_first, int, nc);
   if (ws) { ws->zero_bytes = a.used - z0; }
   // --- rest
-  TAKE(cell_first, int, nc);
   TAKE(cell_slot, int, nc);
   TAKE(cell_of_point, int, t);
   TAKE(rank_of_point, int, t);
-  TAKE(tile_count, int, (size_t)ntiles + 1);
   TAKE(list_u, int, t);
   TAKE(terms, double4, t);
   TAKE(pil_cnt, int, np);
   TAKE(pil_off, int, np);
   TAKE(pil_cell, int, np);
+  TAKE(pil_oc, int2, np);
+  TAKE(point_seg, int4, t);
   TAKE(big_list, int, t / kBig + 2);
+  TAKE(long_list, int, t / kMeanLong + 2);
   TAKE(pil_mean, double, np * 3);
-  TAKE(feat_c, float, t * 9);
+  TAKE(feat_c, float, t * kFeatStride);
 #undef TAKE
 }
 
@@ -633,33 +768,31 @@ struct SizeArena {
 
 template <typename T>
 static int run_stages(const T* pts, long long sp, long long sc, bool vec4, const SweepParams& sw,
-                      const GridDev& g, int P, PillarWs& ws, int* d_num_pillars,
-                      long long* d_indices, int* d_status, cudaStream_t st) {
+                      const GridDev& g, int P, int N, PillarWs& ws, int* d_num_pillars,
+                      long long* d_indices, float* d_feat, int* d_status, cudaStream_t st) {
   const long long total = sw.off[sw.n_sweeps];
   const int ntiles = sw.tile_start[sw.n_sweeps];
-  const int B = sw.n_sweeps;
   PP_CUDA(cudaMemsetAsync(ws.cell_count, 0, ws.zero_bytes, st));
-  PP_CUDA(cudaMemsetAsync(ws.cell_first, 0x7f, (size_t)B * g.ncell * sizeof(int), st));
-  PP_CUDA(cudaMemsetAsync(d_num_pillars, 0, (size_t)B * sizeof(int), st));
+  K1<T> a;
+  a.pts = pts; a.sp = sp; a.sc = sc; a.vec4 = vec4; a.sw = sw; a.g = g; a.P = P; a.N = N;
+  a.cell_of_point = ws.cell_of_point; a.cell_first = ws.cell_first; a.cell_count = ws.cell_count;
+  a.tile_count = ws.tile_count; a.cell_slot = ws.cell_slot; a.pil_cnt = ws.pil_cnt; a.pil_off = ws.pil_off;
+  a.pil_cell = ws.pil_cell; a.pil_cursor = ws.pil_cursor; a.list_cursor = ws.list_cursor; a.list_u = ws.list_u;
+  a.rank_of_point = ws.rank_of_point; a.big_count = ws.big_count; a.big_list = ws.big_list;
+  a.long_count = ws.long_count; a.long_list = ws.long_list; a.tile_ticket = ws.tile_ticket;
+  a.pil_oc = ws.pil_oc; a.point_seg = ws.point_seg; a.terms = ws.terms; a.pil_mean = ws.pil_mean;
+  a.indices = d_indices; a.num_pillars = d_num_pillars; a.feat_c = d_feat; a.status = d_status;
   const int pt_blocks = (int)((total + 255) / 256);
+  PP_KERNEL("k_bin", st, k_bin<T><<<pt_blocks > 0 ? pt_blocks : 1, 256, 0, st>>>(a));
   if (total > 0) {
-    PP_KERNEL("k_bin", st, k_bin<T><<<pt_blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, ws.cell_of_point, ws.cell_first,
-                                        ws.cell_count, d_status));
-    PP_KERNEL("k_tilecount", st, k_tilecount<<<ntiles, kTile, 0, st>>>(sw, g, ws.cell_of_point, ws.cell_first, ws.tile_count));
-    PP_KERNEL("k_assign", st, k_assign<<<ntiles, kTile, 0, st>>>(sw, g, P, ws.cell_of_point, ws.cell_first, ws.cell_count,
-                                       ws.tile_count, ws.cell_slot, ws.pil_cnt, ws.pil_off,
-                                       ws.pil_cell, ws.list_cursor, ws.big_count, ws.big_list,
-                                       d_num_pillars));
-    PP_KERNEL("k_scatter", st, k_scatter<<<pt_blocks, 256, 0, st>>>(sw, g, P, ws.cell_of_point, ws.cell_slot, ws.pil_off,
-                                         ws.pil_cursor, ws.list_u));
-    PP_KERNEL("k_rank", st, k_rank<T><<<pt_blocks, 256, 0, st>>>(pts, sp, sc, vec4, sw, g, P, ws.cell_of_point, ws.cell_slot,
-                                         ws.pil_cnt, ws.pil_off, ws.list_u, ws.terms, ws.rank_of_point));
-    PP_KERNEL("k_rank_big", st, k_rank_big<T><<<64, kTile, 0, st>>>(pts, sp, sc, vec4, sw, P, ws.cell_of_point, ws.pil_off,
-                                        ws.pil_cell, ws.big_count, ws.big_list, ws.terms, ws.rank_of_point));
+    PP_KERNEL("k_assign", st, k_assign<T><<<ntiles, kTile, 0, st>>>(a));
+    PP_KERNEL("k_scatter", st, k_scatter<T><<<pt_blocks, 256, 0, st>>>(a));
+    PP_KERNEL("k_rank", st, k_rank<T><<<pt_blocks, 256, 0, st>>>(a));
   }
-  const long long groups = (long long)B * P;
-  PP_KERNEL("k_mean", st, k_mean<<<(int)((groups + 127) / 128), 128, 0, st>>>(sw, g, P, d_num_pillars, ws.pil_cnt, ws.pil_off,
-                                         ws.pil_cell, ws.terms, ws.pil_mean, d_indices));
+  const long long groups = (long long)sw.n_sweeps * P;
+  const int long_blocks = total > 0 ? sm_count() : 0;
+  PP_KERNEL("k_mean", st, k_mean<T><<<long_blocks + (int)((groups + kMeanBlock - 1) / kMeanBlock), kMeanBlock, 0, st>>>(a, long_blocks));
+  if (d_feat != nullptr && total > 0) PP_KERNEL("k_feat", st, k_feat<T><<<pt_blocks, 256, 0, st>>>(a));
   return PP_OK;
 }
 
@@ -722,16 +855,9 @@ static int pillarize_impl(const T* pts, long long sp, long long sc, const int64_
   layout(arena, &ws, B, sw.off[B], sw.tile_start[B], g.ncell, P);
   if (!arena.ok) return PP_ERR_WORKSPACE;
   const bool vec4 = sizeof(T) == 4 && sp == 4 && sc == 1 && ((uintptr_t)pts % 16) == 0;
-  rc = run_stages<T>(pts, sp, sc, vec4, sw, g, P, ws, d_num_pillars, (long long*)d_indices,
+  rc = run_stages<T>(pts, sp, sc, vec4, sw, g, P, N, ws, d_num_pillars, (long long*)d_indices, ws.feat_c,
                      d_status, st);
   if (rc != PP_OK) return rc;
-  const long long total = sw.off[B];
-  if (total > 0) {
-    PP_KERNEL("k_feat", st,
-              k_feat<T><<<(int)((total + 255) / 256), 256, 0, st>>>(
-                  pts, sp, sc, vec4, sw, g, P, N, ws.cell_of_point, ws.cell_slot, ws.rank_of_point,
-                  ws.pil_off, ws.pil_mean, ws.feat_c));
-  }
   rc = emit_dense(sw, P, N, d_mean, d_x, d_num_pillars, ws, st);
   if (rc != PP_OK) return rc;
   return PP_OK;
@@ -762,15 +888,8 @@ static int input_path_impl(const T* pts, long long sp, long long sc, const int64
   const size_t k1_bytes = arena.used;
   if (stages & 1) {
     const bool vec4 = sizeof(T) == 4 && sp == 4 && sc == 1 && ((uintptr_t)pts % 16) == 0;
-    rc = run_stages<T>(pts, sp, sc, vec4, sw, g, P, ws, d_num_pillars, (long long*)d_indices, d_status, st);
+    rc = run_stages<T>(pts, sp, sc, vec4, sw, g, P, N, ws, d_num_pillars, (long long*)d_indices, ws.feat_c, d_status, st);
     if (rc != PP_OK) return rc;
-    const long long total = sw.off[B];
-    if (total > 0) {
-      PP_KERNEL("k_feat", st,
-                k_feat<T><<<(int)((total + 255) / 256), 256, 0, st>>>(
-                    pts, sp, sc, vec4, sw, g, P, N, ws.cell_of_point, ws.cell_slot, ws.rank_of_point,
-                    ws.pil_off, ws.pil_mean, ws.feat_c));
-    }
     if (d_x != nullptr) {
       rc = emit_dense(sw, P, N, d_mean, d_x, d_num_pillars, ws, st);
       if (rc != PP_OK) return rc;
@@ -805,7 +924,7 @@ static int compact_impl(const T* pts, long long sp, long long sc, int64_t n_poin
   layout(arena, &ws, 1, n_points, sw.tile_start[1], g.ncell, P);
   if (!arena.ok) return PP_ERR_WORKSPACE;
   const bool vec4 = sizeof(T) == 4 && sp == 4 && sc == 1 && ((uintptr_t)pts % 16) == 0;
-  rc = run_stages<T>(pts, sp, sc, vec4, sw, g, P, ws, ws.num_pillars_scratch, nullptr, d_status, st);
+  rc = run_stages<T>(pts, sp, sc, vec4, sw, g, P, N, ws, ws.num_pillars_scratch, nullptr, nullptr, d_status, st);
   if (rc != PP_OK) return rc;
   if (n_points > 0) {
     PP_CUDA(cudaMemsetAsync(d_slot, 0xff, (size_t)n_points * sizeof(int), st));
