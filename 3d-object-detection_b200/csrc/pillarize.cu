@@ -331,27 +331,63 @@ __device__ __forceinline__ void mean_terms(const T* __restrict__ pts, long long 
   *out = t;
 }
 
-// ---- stage: rank of every kept point inside its pillar = number of smaller indices in the segment
+// ---- stage: rank of every kept point inside its pillar = number of smaller indices in the segment.
+// One thread per point for pillars up to kMeanLong points; longer ones by st_rank_long / st_rank_big.
 template <typename T>
 __device__ __forceinline__ void st_rank(const K1<T>& a, long long i0, long long stride) {
   const SweepParams& sw = a.sw;
   const long long total = sw.off[sw.n_sweeps];
   for (long long i = i0; i < total; i += stride) {
     const int4 ps = a.point_seg[i];
-    int rank = -1;
-    if (ps.y >= 0) {
-      const int c = ps.z;
-      if (c <= kBig) {
-        const int il = (int)(i - sw.off[find_sweep(sw, i)]);
-        const int* seg = a.list_u + ps.x;
-        rank = 0;
-        for (int k = 0; k < c; ++k) rank += (seg[k] < il) ? 1 : 0;
-        mean_terms(a.pts, i, a.sp, a.sc, a.vec4, rank, a.terms + ps.x + rank);
-      } else {
-        rank = -2;  // filled by st_rank_big
+    if (ps.y < 0) { a.rank_of_point[i] = -1; continue; }
+    const int c = ps.z;
+    if (c > kMeanLong) continue;
+    const int il = (int)(i - sw.off[find_sweep(sw, i)]);
+    const int* seg = a.list_u + ps.x;
+    int rank = 0;
+    for (int k = 0; k < c; ++k) rank += (seg[k] < il) ? 1 : 0;
+    mean_terms(a.pts, i, a.sp, a.sc, a.vec4, rank, a.terms + ps.x + rank);
+    a.rank_of_point[i] = rank;
+  }
+}
+
+// Pillars with kMeanLong < c <= kBig points: 128 threads each.  The segment's indices go to shared memory once and
+// every thread ranks its element against broadcast 16-byte reads (one wavefront serves a whole warp).  As one
+// thread per point every lane of a warp walked a different pillar's segment: c wavefronts per point, 200 us of
+// the dense-cloud configuration (10-sweep clouds, most pillars hold 100+ points).  (One WARP per pillar left a
+// 12k-instruction serial tail on the longest pillar: +10 us on the default configuration.)
+constexpr int kRankBlock = 256;
+constexpr int kRankGroup = 128;      // threads per long pillar: two pillars per block, each behind its own named barrier
+template <typename T>
+__device__ __forceinline__ void st_rank_long(const K1<T>& a, int long_blocks) {
+  __shared__ __align__(16) int s_seg_all[kRankBlock / kRankGroup][kBig + 4];
+  const SweepParams& sw = a.sw;
+  const int grp_id = (int)threadIdx.x / kRankGroup, t = (int)threadIdx.x % kRankGroup;
+  int* s_seg = s_seg_all[grp_id];
+  const int ngroups = long_blocks * (kRankBlock / kRankGroup);
+  const int nl = __ldcg(a.long_count);
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp_id), "r"(kRankGroup) : "memory"); };
+  for (int w = (int)blockIdx.x + grp_id * long_blocks; w < nl; w += ngroups) {
+    const long long grp = a.long_list[w];
+    const int b = (int)(grp / a.P);
+    const int2 oc = a.pil_oc[grp];
+    const int c = oc.y, c4 = (c + 3) & ~3;
+    const long long segbase = sw.off[b] + oc.x;
+    group_sync();                                        // the previous pillar's readers are done
+    for (int k = t; k < c4; k += kRankGroup) s_seg[k] = k < c ? a.list_u[segbase + k] : 0x7fffffff;
+    group_sync();
+    for (int e = t; e < c; e += kRankGroup) {
+      const int il = s_seg[e];
+      int rank = 0;
+#pragma unroll 4
+      for (int k = 0; k < c4; k += 4) {
+        const int4 v = *reinterpret_cast<const int4*>(s_seg + k);
+        rank += (v.x < il) + (v.y < il) + (v.z < il) + (v.w < il);
       }
+      const long long gi = sw.off[b] + il;
+      mean_terms(a.pts, gi, a.sp, a.sc, a.vec4, rank, a.terms + segbase + rank);
+      a.rank_of_point[gi] = rank;
     }
-    if (rank != -2) a.rank_of_point[i] = rank;
   }
 }
 
@@ -570,9 +606,13 @@ __global__ void __launch_bounds__(256) k_scatter(const K1<T> a) {
   st_scatter(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
+// blocks [0, long_blocks): one block per long pillar; the others: one thread per point; all: big pillars
 template <typename T>
-__global__ void __launch_bounds__(256) k_rank(const K1<T> a) {
-  st_rank(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+__global__ void __launch_bounds__(kRankBlock) k_rank(const K1<T> a, int long_blocks) {
+  if ((int)blockIdx.x < long_blocks)
+    st_rank_long(a, long_blocks);
+  else
+    st_rank(a, (long long)(blockIdx.x - long_blocks) * blockDim.x + threadIdx.x, (long long)(gridDim.x - long_blocks) * blockDim.x);
   st_rank_big(a);
 }
 
@@ -787,10 +827,10 @@ static int run_stages(const T* pts, long long sp, long long sc, bool vec4, const
   if (total > 0) {
     PP_KERNEL("k_assign", st, k_assign<T><<<ntiles, kTile, 0, st>>>(a));
     PP_KERNEL("k_scatter", st, k_scatter<T><<<pt_blocks, 256, 0, st>>>(a));
-    PP_KERNEL("k_rank", st, k_rank<T><<<pt_blocks, 256, 0, st>>>(a));
+    PP_KERNEL("k_rank", st, k_rank<T><<<2 * sm_count() + pt_blocks, kRankBlock, 0, st>>>(a, 2 * sm_count()));
   }
   const long long groups = (long long)sw.n_sweeps * P;
-  const int long_blocks = total > 0 ? sm_count() : 0;
+  const int long_blocks = total > 0 ? 2 * sm_count() : 0;   // 16 chains per SM keep its fp64 pipe busy without queueing
   PP_KERNEL("k_mean", st, k_mean<T><<<long_blocks + (int)((groups + kMeanBlock - 1) / kMeanBlock), kMeanBlock, 0, st>>>(a, long_blocks));
   if (d_feat != nullptr && total > 0) PP_KERNEL("k_feat", st, k_feat<T><<<pt_blocks, 256, 0, st>>>(a));
   return PP_OK;
