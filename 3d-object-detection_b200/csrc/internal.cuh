@@ -18,6 +18,8 @@ struct SweepParams {
 struct CompactPillars {
   SweepParams sw;            // point offsets of the sweeps (host copy, passed by value to kernels)
   int P, N;
+  const int* cell_map;       // [B, H*W]: slot + 1 of the pillar on each canvas cell, 0 = none (written by K1's mean stage
+                             // when the canvas size is known; saves the index -> map kernel and its memset), or null
   const float* feat_c;       // [T, kFeatStride] float (9 used): decorated features of the kept points, before "- data_mean",
                              //   at sw.off[b] + pil_off[b*P+p] + rank
   const int* pil_cnt;        // [B*P] in-range points of the pillar (may exceed N)

@@ -467,7 +467,7 @@ constexpr int kStage = 20;      // occupied cells staged per unit
 template <int FROM_EXT>
 __global__ void __launch_bounds__(256) k_canvas(const float* __restrict__ src,
                                                 const Affine* __restrict__ affine,
-                                                const int* __restrict__ map, int B, int P, int C, int HW,
+                                                const int* __restrict__ map, int map_bias, int B, int P, int C, int HW,
                                                 bool vec_ok, float* __restrict__ canvas) {
   constexpr int kCells = 128;
   __shared__ Affine s_aff[64];
@@ -504,7 +504,8 @@ __global__ void __launch_bounds__(256) k_canvas(const float* __restrict__ src,
     };
     const int cell0 = grp * kCells;
     if (vec_ok && cell0 + kCells <= HW) {
-      const int4 sl = __ldg(reinterpret_cast<const int4*>(mb + cell0) + lane);
+      int4 sl = __ldg(reinterpret_cast<const int4*>(mb + cell0) + lane);
+      sl.x -= map_bias; sl.y -= map_bias; sl.z -= map_bias; sl.w -= map_bias;   // K1's map holds slot + 1 (0 = none)
       float4* o = reinterpret_cast<float4*>(cb + cell0) + lane;
       const size_t cs = (size_t)HW / 4;                 // float4 stride between channels
       const int mine = (sl.x >= 0) + (sl.y >= 0) + (sl.z >= 0) + (sl.w >= 0);
@@ -563,7 +564,7 @@ __global__ void __launch_bounds__(256) k_canvas(const float* __restrict__ src,
       }
     } else {
       for (int j = lane; j < kCells && cell0 + j < HW; j += 32) {
-        const int slot = mb[cell0 + j];
+        const int slot = mb[cell0 + j] - map_bias;
         for (int c = c0; c < c1; ++c) cb[(size_t)c * HW + cell0 + j] = slot >= 0 ? value(slot, c) : 0.f;
       }
     }
@@ -674,7 +675,7 @@ static bool pfn_args_ok(const void* x, int B, int D, int P, int N, int C, const 
 }
 
 static int canvas_launch(int from_ext, const float* src, const Affine* aff, const int* map, int B,
-                         int P, int C, int H, int W, float* d_canvas, cudaStream_t st) {
+                         int P, int C, int H, int W, float* d_canvas, cudaStream_t st, int map_bias = 0) {
   const int HW = H * W;
   const bool vec_ok = (HW % 4 == 0) && ((uintptr_t)d_canvas % 16 == 0);
   // exactly one resident wave (8 CTAs of 8 warps per SM), fewer when there is less work than that
@@ -687,11 +688,11 @@ static int canvas_launch(int from_ext, const float* src, const Affine* aff, cons
   const long long cap = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
   if (gx > cap) gx = cap;
   if (from_ext == 2) {
-    PP_KERNEL("k_canvas", st, k_canvas<2><<<(int)gx, 256, 0, st>>>(src, aff, map, B, P, C, HW, vec_ok, d_canvas));
+    PP_KERNEL("k_canvas", st, k_canvas<2><<<(int)gx, 256, 0, st>>>(src, aff, map, map_bias, B, P, C, HW, vec_ok, d_canvas));
   } else if (from_ext == 3) {
-    PP_KERNEL("k_canvas", st, k_canvas<3><<<(int)gx, 256, 0, st>>>(src, aff, map, B, P, C, HW, vec_ok, d_canvas));
+    PP_KERNEL("k_canvas", st, k_canvas<3><<<(int)gx, 256, 0, st>>>(src, aff, map, map_bias, B, P, C, HW, vec_ok, d_canvas));
   } else {
-    PP_KERNEL("k_canvas", st, k_canvas<0><<<(int)gx, 256, 0, st>>>(src, aff, map, B, P, C, HW, vec_ok, d_canvas));
+    PP_KERNEL("k_canvas", st, k_canvas<0><<<(int)gx, 256, 0, st>>>(src, aff, map, map_bias, B, P, C, HW, vec_ok, d_canvas));
   }
   return PP_OK;
 }
@@ -1160,8 +1161,11 @@ int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, c
   SparseWs ws{};
   sparse_layout(arena, &ws, B, P, N, C, H, W, own_prep);
   if (!arena.ok) return PP_ERR_WORKSPACE;
-  int rc = build_map(d_inds, B, P, H, W, ws.map, d_status, st);
-  if (rc != PP_OK) return rc;
+  int rc = PP_OK;
+  if (cp.cell_map == nullptr) {                 // a caller without K1's map (indices from elsewhere)
+    rc = build_map(d_inds, B, P, H, W, ws.map, d_status, st);
+    if (rc != PP_OK) return rc;
+  }
   int nblocks = 0;
   const void* prep = cp.mean_prepared;
   PP_CUDA(cudaMemsetAsync(ws.flags, 0, 3 * sizeof(int), st));     // [0] range flag of the padding pass, [1] k_pfn_real's work counter, [2] long-pillar count
@@ -1211,7 +1215,8 @@ int pfn_sparse_scatter(const CompactPillars& cp, const int64_t* d_inds, int C, c
             k_bn_finalize<<<1, 64 * kFinSegs, 0, st>>>(C, nblocks, (double)B * P * N, prm.training, prm.momentum, prm.eps, sf,
                                             ws.partials, prm.bn_w, prm.bn_b, prm.running_mean, prm.running_var,
                                             (long long*)prm.num_batches_tracked, ws.affine));
-  return canvas_launch(3, ws.ext_s, ws.affine, ws.map, B, P, C, H, W, d_canvas, st);
+  return canvas_launch(3, ws.ext_s, ws.affine, cp.cell_map != nullptr ? cp.cell_map : ws.map, B, P, C, H, W, d_canvas, st,
+                       cp.cell_map != nullptr ? 1 : 0);
 }
 
 }  // namespace pp

@@ -88,6 +88,8 @@ struct K1 {
   int *cell_of_point, *cell_first, *cell_count, *tile_count, *cell_slot;
   int *pil_cnt, *pil_off, *pil_cell, *pil_cursor, *list_cursor, *list_u, *rank_of_point;
   int *big_count, *big_list, *long_count, *long_list, *tile_ticket;
+  int* map;                // [B, map_h * map_w] canvas cell -> slot + 1 (null: not wanted)
+  int map_h, map_w;
   int2* pil_oc;            // per pillar {segment offset, count} (one 8-byte read in st_scatter)
   int4* point_seg;         // per point {absolute segment start, pillar index or -1, count, 0}
   double4* terms;
@@ -448,6 +450,15 @@ __device__ __forceinline__ void mean_store(const K1<T>& a, long long grp, double
     a.indices[grp * 3 + 0] = 1;                 // data/pillars.cpp:390-392, then .long()
     a.indices[grp * 3 + 1] = (long long)cx;
     a.indices[grp * 3 + 2] = (long long)cy;
+    if (a.map != nullptr) {                     // model/model.py:59-61: out[b, :, y_inds, x_inds]; one pillar per cell
+      const long long ix = (long long)cx, iy = (long long)cy;
+      if (ix < 0 || ix >= a.map_w || iy < 0 || iy >= a.map_h) {
+        atomicOr(a.status, PP_STATUS_BAD_INDEX);
+      } else {
+        const long long b = grp / a.P;
+        a.map[(size_t)b * a.map_h * a.map_w + (size_t)iy * a.map_w + (size_t)ix] = (int)(grp - b * a.P) + 1;
+      }
+    }
   }
 }
 
@@ -736,6 +747,7 @@ struct PillarWs {
   int *pil_cnt, *pil_off, *pil_cell, *big_list, *long_list, *num_pillars_scratch;
   int2* pil_oc;
   int4* point_seg;
+  int* map;                // zero block
   double* pil_mean;
   float* feat_c;
   // zero-initialised block (one memset), starts at cell_count
@@ -762,7 +774,7 @@ static bool make_grid(const pp_grid* grid, GridDev& g) {
 }
 
 template <class A>
-static void layout(A& a, PillarWs* ws, int B, long long T, long long ntiles, int ncell, int P) {
+static void layout(A& a, PillarWs* ws, int B, long long T, long long ntiles, int ncell, int P, long long map_cells = 0) {
   const size_t nc = (size_t)B * ncell, np = (size_t)B * P, t = (size_t)(T > 0 ? T : 1);
 #define TAKE(field, type, count)                    \
   do {                                              \
@@ -781,7 +793,8 @@ static void layout(A& a, PillarWs* ws, int B, long long T, long long ntiles, int
   TAKE(num_pillars_scratch, int, PP_MAX_SWEEPS);
   TAKE(tile_count, int, (size_t)ntiles + 1);
   TAKE(cell_first, int, nc);
-  if (ws) { ws->zero_bytes = a.used - z0; }
+  TAKE(map, int, (size_t)B * (size_t)map_cells);
+  if (ws) { ws->zero_bytes = a.used - z0; if (map_cells == 0) ws->map = nullptr; }
   // --- rest
   TAKE(cell_slot, int, nc);
   TAKE(cell_of_point, int, t);
@@ -809,7 +822,7 @@ struct SizeArena {
 template <typename T>
 static int run_stages(const T* pts, long long sp, long long sc, bool vec4, const SweepParams& sw,
                       const GridDev& g, int P, int N, PillarWs& ws, int* d_num_pillars,
-                      long long* d_indices, float* d_feat, int* d_status, cudaStream_t st) {
+                      long long* d_indices, float* d_feat, int* d_status, cudaStream_t st, int map_h = 0, int map_w = 0) {
   const long long total = sw.off[sw.n_sweeps];
   const int ntiles = sw.tile_start[sw.n_sweeps];
   PP_CUDA(cudaMemsetAsync(ws.cell_count, 0, ws.zero_bytes, st));
@@ -822,6 +835,7 @@ static int run_stages(const T* pts, long long sp, long long sc, bool vec4, const
   a.long_count = ws.long_count; a.long_list = ws.long_list; a.tile_ticket = ws.tile_ticket;
   a.pil_oc = ws.pil_oc; a.point_seg = ws.point_seg; a.terms = ws.terms; a.pil_mean = ws.pil_mean;
   a.indices = d_indices; a.num_pillars = d_num_pillars; a.feat_c = d_feat; a.status = d_status;
+  a.map = (map_h > 0 && map_w > 0) ? ws.map : nullptr; a.map_h = map_h; a.map_w = map_w;
   const int pt_blocks = (int)((total + 255) / 256);
   PP_KERNEL("k_bin", st, k_bin<T><<<pt_blocks > 0 ? pt_blocks : 1, 256, 0, st>>>(a));
   if (total > 0) {
@@ -923,12 +937,12 @@ static int input_path_impl(const T* pts, long long sp, long long sc, const int64
   if (!pfn_sparse_supported(B, P, N, C, d_mean)) return PP_ERR_UNSUPPORTED;
   Arena arena(d_ws, ws_bytes);
   PillarWs ws{};
-  layout(arena, &ws, B, sw.off[B], sw.tile_start[B], g.ncell, P);
+  layout(arena, &ws, B, sw.off[B], sw.tile_start[B], g.ncell, P, (long long)H * W);
   if (!arena.ok) return PP_ERR_WORKSPACE;
   const size_t k1_bytes = arena.used;
   if (stages & 1) {
     const bool vec4 = sizeof(T) == 4 && sp == 4 && sc == 1 && ((uintptr_t)pts % 16) == 0;
-    rc = run_stages<T>(pts, sp, sc, vec4, sw, g, P, N, ws, d_num_pillars, (long long*)d_indices, ws.feat_c, d_status, st);
+    rc = run_stages<T>(pts, sp, sc, vec4, sw, g, P, N, ws, d_num_pillars, (long long*)d_indices, ws.feat_c, d_status, st, H, W);
     if (rc != PP_OK) return rc;
     if (d_x != nullptr) {
       rc = emit_dense(sw, P, N, d_mean, d_x, d_num_pillars, ws, st);
@@ -936,9 +950,9 @@ static int input_path_impl(const T* pts, long long sp, long long sc, const int64
     }
   }
   if (!(stages & 2)) return PP_OK;
-  CompactPillars cp;
+  CompactPillars cp{};
   cp.sw = sw; cp.P = P; cp.N = N;
-  cp.feat_c = ws.feat_c; cp.pil_cnt = ws.pil_cnt; cp.pil_off = ws.pil_off;
+  cp.feat_c = ws.feat_c; cp.pil_cnt = ws.pil_cnt; cp.pil_off = ws.pil_off; cp.cell_map = ws.map;
   cp.num_pillars = d_num_pillars; cp.data_mean = d_mean; cp.mean_prepared = d_mean != nullptr ? d_mean_prep : nullptr;
   return pfn_sparse_scatter(cp, d_indices, C, prm, H, W, d_canvas, d_status, (char*)d_ws + k1_bytes,
                             ws_bytes - k1_bytes, st);
@@ -985,16 +999,21 @@ static int compact_impl(const T* pts, long long sp, long long sc, int64_t n_poin
 
 extern "C" {
 
-size_t pp_pillarize_workspace_bytes(int32_t n_sweeps, int64_t total_points, const pp_grid* grid,
-                                    int32_t max_pillars) {
+static size_t k1_workspace_bytes(int32_t n_sweeps, int64_t total_points, const pp_grid* grid, int32_t max_pillars,
+                                 long long map_cells) {
   pp::GridDev g;
   if (!pp::make_grid(grid, g) || n_sweeps < 1 || n_sweeps > PP_MAX_SWEEPS || total_points < 0 ||
       max_pillars < 1)
     return 0;
   pp::SizeArena a;
   const long long ntiles = total_points / pp::kTile + n_sweeps + 1;
-  pp::layout(a, (pp::PillarWs*)nullptr, n_sweeps, total_points, ntiles, g.ncell, max_pillars);
+  pp::layout(a, (pp::PillarWs*)nullptr, n_sweeps, total_points, ntiles, g.ncell, max_pillars, map_cells);
   return a.used + pp::kAlign;
+}
+
+size_t pp_pillarize_workspace_bytes(int32_t n_sweeps, int64_t total_points, const pp_grid* grid,
+                                    int32_t max_pillars) {
+  return k1_workspace_bytes(n_sweeps, total_points, grid, max_pillars, 0);
 }
 
 int pp_pillarize(const void* d_points, int32_t point_dtype, int64_t stride_point,
@@ -1019,8 +1038,9 @@ int pp_pillarize(const void* d_points, int32_t point_dtype, int64_t stride_point
 size_t pp_input_path_workspace_bytes(int32_t n_sweeps, int64_t total_points, const pp_grid* grid,
                                      int32_t max_points_per_pillar, int32_t max_pillars, int32_t C, int32_t canvas_h,
                                      int32_t canvas_w, int32_t prepare_in_workspace) {
-  const size_t k1 = pp_pillarize_workspace_bytes(n_sweeps, total_points, grid, max_pillars);
-  if (k1 == 0 || C < 1 || canvas_h < 1 || canvas_w < 1 || max_points_per_pillar < 1) return 0;
+  if (C < 1 || canvas_h < 1 || canvas_w < 1 || max_points_per_pillar < 1) return 0;
+  const size_t k1 = k1_workspace_bytes(n_sweeps, total_points, grid, max_pillars, (long long)canvas_h * canvas_w);
+  if (k1 == 0) return 0;
   return k1 + pp::pfn_sparse_workspace_bytes(n_sweeps, max_pillars, max_points_per_pillar, C, canvas_h, canvas_w,
                                              prepare_in_workspace != 0);
 }
@@ -1091,9 +1111,9 @@ int pp_input_path_backward(const int64_t* h_sweep_offsets, int32_t n_sweeps, con
   // the forward's K1 state, found by laying the same workspace out again (pp_input_path, stage 1)
   Arena arena(const_cast<void*>(d_forward_workspace), forward_workspace_bytes);
   PillarWs ws{};
-  layout(arena, &ws, n_sweeps, sw.off[n_sweeps], sw.tile_start[n_sweeps], g.ncell, P);
+  layout(arena, &ws, n_sweeps, sw.off[n_sweeps], sw.tile_start[n_sweeps], g.ncell, P, (long long)canvas_h * canvas_w);
   if (!arena.ok) return PP_ERR_WORKSPACE;
-  CompactPillars cp;
+  CompactPillars cp{};
   cp.sw = sw; cp.P = P; cp.N = N;
   cp.feat_c = ws.feat_c; cp.pil_cnt = ws.pil_cnt; cp.pil_off = ws.pil_off;
   cp.num_pillars = d_num_pillars; cp.data_mean = d_data_mean; cp.mean_prepared = nullptr;

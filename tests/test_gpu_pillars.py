@@ -69,6 +69,26 @@ def test_pillar_with_more_points_than_the_block_scan_threshold():
     np.testing.assert_array_equal(t1, t0)
 
 
+def test_pillar_sizes_at_the_kernel_path_boundaries():
+    """Pillars of exactly 1, 2, 32, 33 (thread -> warp / group paths of the rank and running-mean stages), 128, 129,
+    256, 257 (group size of the shared-memory ranking), 1024 and 1025 points (block-scan path), interleaved in the
+    input so that every segment is filled out of order: membership, order, running mean and features stay exact."""
+    rng = np.random.default_rng(21)
+    sizes = [1, 2, 32, 33, 128, 129, 256, 257, 1024, 1025]
+    chunks = []
+    for k, c in enumerate(sizes):
+        x0, y0 = -50.0 + 3.0 * k, 10.0 + 2.0 * (k % 3)            # one 0.2 x 0.2 cell each
+        chunks.append(np.stack([rng.uniform(x0 + 0.01, x0 + 0.19, c), rng.uniform(y0 + 0.01, y0 + 0.19, c),
+                                rng.uniform(-2, 2, c), rng.uniform(0, 1, c)], 1))
+    pts = np.concatenate(chunks)
+    pts = f32_exact(pts[rng.permutation(len(pts))])
+    for N in (200, 40):
+        (t0, i0), (t1, i1) = _both(pts, 16, N)
+        assert int(i0[:, 0].sum()) == len(sizes)
+        np.testing.assert_array_equal(i1, i0)
+        np.testing.assert_array_equal(t1, t0)
+
+
 def test_non_float32_representable_doubles():
     """The drop-in takes arbitrary doubles, like the reference (binning in fp64)."""
     rng = np.random.default_rng(6)
