@@ -20,7 +20,7 @@ case $what in
   full)
     python scripts/run_fused_once.py 3 > $out/${tag}_plain.log 2>&1 &&
     ncu --set full --import-source on --clock-control none \
-        -k regex:"k_pfn_pad_tc|k_pfn_real|k_canvas|k_bn_finalize|k_mean|k_feat|k_rank|k_bin|k_assign|k_scatter|k_build_map" \
-        -s 24 -c 12 -o $out/${tag}_full -f python scripts/run_fused_once.py 3 > $out/${tag}_ncu_full.log 2>&1 ;;
+        -k regex:"k_pfn_pad_tc|k_pfn_real|k_canvas|k_bn_finalize|k_mean|k_feat|k_rank|k_bin|k_assign|k_scatter" \
+        -s 22 -c 11 -o $out/${tag}_full -f python scripts/run_fused_once.py 3 > $out/${tag}_ncu_full.log 2>&1 ;;
 esac
 ls -la $out | tail -5
