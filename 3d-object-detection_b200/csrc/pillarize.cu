@@ -313,6 +313,17 @@ __device__ __forceinline__ void st_scatter(const K1<T>& a, long long i0, long lo
   }
 }
 
+// one 256-bit access per 32-byte record (sm_100: LDG.256 / STG.256): a record fetched by a single lane costs one
+// memory wavefront instead of two
+__device__ __forceinline__ double4 ld_terms(const double4* __restrict__ p) {
+  double4 v;
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_terms(double4* p, const double4& v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+
 // Per-point terms of the reference's running mean (data/pillars.cpp:311-328)
 //   m <- m*(n/(n+1)) + x/(n+1)
 // for the point of rank n: {a = n/(n+1), x/(n+1), y/(n+1), z/(n+1)} (the first point initialises the
@@ -330,7 +341,7 @@ __device__ __forceinline__ void mean_terms(const T* __restrict__ pts, long long 
     const double n1 = __dadd_rn((double)rank, 1.0);
     t = make_double4(__ddiv_rn((double)rank, n1), __ddiv_rn(x, n1), __ddiv_rn(y, n1), __ddiv_rn(z, n1));
   }
-  *out = t;
+  st_terms(out, t);
 }
 
 // ---- stage: rank of every kept point inside its pillar = number of smaller indices in the segment.
@@ -432,17 +443,10 @@ __device__ __forceinline__ void st_rank_big(const K1<T>& a) {
   }
 }
 
-__device__ __forceinline__ double4 ld_terms(const double4* __restrict__ p) {
-  const double2* q = reinterpret_cast<const double2*>(p);
-  const double2 a = __ldcg(q), b = __ldcg(q + 1);     // written earlier in this launch: L2, not the read-only path
-  return make_double4(a.x, a.y, b.x, b.y);
-}
 
 template <typename T>
 __device__ __forceinline__ void mean_store(const K1<T>& a, long long grp, double m0, double m1, double m2) {
-  a.pil_mean[grp * 3 + 0] = m0;
-  a.pil_mean[grp * 3 + 1] = m1;
-  a.pil_mean[grp * 3 + 2] = m2;
+  st_terms(reinterpret_cast<double4*>(a.pil_mean) + grp, make_double4(m0, m1, m2, 0.0));   // 32-byte record per pillar
   if (a.indices != nullptr) {
     const int cell = a.pil_cell[grp];
     const double cx = (double)(cell % a.g.nx);
@@ -580,8 +584,8 @@ __device__ __forceinline__ void st_feat(const K1<T>& a, long long i0, long long 
     load_xyz(a.pts, i, a.sp, a.sc, a.vec4, x, y, z, r);
     const double cx = (double)(cell % g.nx);
     const double cy = __dsub_rn(__dsub_rn(g.canvas_height, 1.0), (double)(cell / g.nx));
-    const double* pm = a.pil_mean + (size_t)ps.y * 3;
-    mean[0] = __ldcg(pm); mean[1] = __ldcg(pm + 1); mean[2] = __ldcg(pm + 2);
+    const double4 pm = ld_terms(reinterpret_cast<const double4*>(a.pil_mean) + ps.y);
+    mean[0] = pm.x; mean[1] = pm.y; mean[2] = pm.z;
     point_features(x, y, z, r, cx, cy, mean, ft);
     // 48-byte records: three aligned 16-byte stores instead of nine scattered 4-byte ones
     float4* o = reinterpret_cast<float4*>(a.feat_c + (size_t)(ps.x + rank) * kFeatStride);
@@ -715,7 +719,7 @@ __global__ void __launch_bounds__(256) k_emit_compact(
     load_xyz(pts, i, sp, sc, vec4, x, y, z, r);
     const double cx = (double)(cell % g.nx);
     const double cy = __dsub_rn(__dsub_rn(g.canvas_height, 1.0), (double)(cell / g.nx));
-    point_features(x, y, z, r, cx, cy, pil_mean + (size_t)slot * 3, ft);
+    point_features(x, y, z, r, cx, cy, pil_mean + (size_t)slot * 4, ft);
 #pragma unroll
     for (int d = 0; d < 9; ++d) rows[q * 9 + d] = ft[d];
     slot_out[q] = slot * N + rank;
@@ -808,7 +812,7 @@ static void layout(A& a, PillarWs* ws, int B, long long T, long long ntiles, int
   TAKE(point_seg, int4, t);
   TAKE(big_list, int, t / kBig + 2);
   TAKE(long_list, int, t / kMeanLong + 2);
-  TAKE(pil_mean, double, np * 3);
+  TAKE(pil_mean, double, np * 4);
   TAKE(feat_c, float, t * kFeatStride);
 #undef TAKE
 }
