@@ -164,10 +164,8 @@ __device__ __forceinline__ bool first_touch_flag(const K1<T>& a, int t, int& b, 
 // ---- stage: number of first-touch points of tile t, published with a ready bit (st_assign of a later tile
 // of the same sweep polls it: every block publishes all its tiles before it waits for anything)
 template <typename T>
-__device__ __forceinline__ void st_tilecount(const K1<T>& a, int t) {
+__device__ __forceinline__ void st_tilecount(const K1<T>& a, int t, bool flag) {
   __shared__ int warp_cnt[kTile / 32];
-  int b, il, cell;
-  const bool flag = first_touch_flag(a, t, b, il, cell);
   const unsigned m = __ballot_sync(0xffffffffu, flag);
   if (lane_id() == 0) warp_cnt[threadIdx.x >> 5] = __popc(m);
   __syncthreads();
@@ -184,19 +182,13 @@ __device__ __forceinline__ void st_tilecount(const K1<T>& a, int t) {
 
 // ---- stage: pillar slot of every first-touch point (exclusive scan in input order), list segments
 template <typename T>
-__device__ __forceinline__ void st_assign(const K1<T>& a, int t) {
+__device__ __forceinline__ void st_assign(const K1<T>& a, int t, bool flag, int b, int cell, size_t ci, int cnt_cell) {
   __shared__ int warp_sum[kTile / 32];
   __shared__ int warp_cnt[kTile / 32];
   __shared__ int s_base, s_seg_base;
   const SweepParams& sw = a.sw;
   const GridDev& g = a.g;
   const int P = a.P;
-  int b, il, cell;
-  const bool flag = first_touch_flag(a, t, b, il, cell);
-  // the cell's point count is needed once the slot is known: fetch it under the wait for the earlier tiles
-  const size_t ci = flag ? (size_t)b * g.ncell + cell : 0;
-  const int cnt_cell = flag ? a.cell_count[ci] : 0;
-
   // base = number of first-touch points in the earlier tiles of this sweep
   int part = 0;
   for (int k = sw.tile_start[b] + (int)threadIdx.x; k < t; k += kTile) {
@@ -612,8 +604,13 @@ __global__ void __launch_bounds__(kTile) k_assign(const K1<T> a) {
   if (threadIdx.x == 0) s_t = atomicAdd(a.tile_ticket, 1);
   __syncthreads();
   const int t = s_t;
-  st_tilecount(a, t);
-  st_assign(a, t);
+  int b, il, cell;
+  const bool flag = first_touch_flag(a, t, b, il, cell);    // one random read per point, shared by both stages
+  // the cell's point count is needed once the slot is known: requested now, under the count exchange between tiles
+  const size_t ci = flag ? (size_t)b * a.g.ncell + cell : 0;
+  const int cnt_cell = flag ? a.cell_count[ci] : 0;
+  st_tilecount(a, t, flag);
+  st_assign(a, t, flag, b, cell, ci, cnt_cell);
 }
 
 template <typename T>
