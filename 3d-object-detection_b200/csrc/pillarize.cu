@@ -5,21 +5,22 @@
 // Order-exactness: pillars are numbered by the input index of their first
 // in-range point; inside a pillar points keep input order; the first N are emitted; the mean is
 // the reference's sequential running mean over ALL in-range points of the pillar.  atomics only
-// ever decide things that do not depend on order (min index, counts, list placement before the
+// ever decide things that do not depend on order (first index, counts, list placement before the
 // rank pass), so the result is deterministic and identical to the sequential CPU algorithm.
 //
-// Stages (one launch each, all sweeps of the batch in the same launch):
-//   k_bin        per point: range filter + floor binning in fp64, atomicMin(first index of cell),
-//                atomicAdd(count of cell)
-//   k_tilecount  per 1024-point tile: number of first-touch points
-//   k_assign     per tile: exclusive scan of first-touch flags -> pillar slot of each cell,
-//                list segment of each kept pillar
-//   k_scatter    per point: append its index to its pillar's segment (unordered)
-//   k_rank       per point: rank = number of smaller indices in the segment; the point's running-mean
-//                terms (four IEEE divisions) go to its place in the ordered segment
-//   k_rank_big   pillars with more than kBig points: ordered compaction by a block scan instead
-//   k_mean       per pillar (one thread): sequential multiply-add chain of the running mean, indices row
-//   k_emit_*     dense [B,9,P,N] float with fused "- data_mean", or compact fp64 rows
+// Stages (one launch each after ONE memset of the workspace's zero block; all sweeps of the batch in the same launch):
+//   k_bin      per point: range filter + floor binning in fp64; first index (atomicMax of the inverted index) and
+//              count of its cell, one pair of atomics per distinct cell of a warp
+//   k_assign   per 1024-point tile (ticket order): first-touch count published to the later tiles, exclusive scan of
+//              the first-touch flags -> pillar slot of each cell, list segment of each kept pillar, long / big lists
+//   k_scatter  per point: append its index to its pillar's segment (unordered); point -> pillar record
+//   k_rank     rank = number of smaller indices in the segment (per point / 128 threads per long pillar / block scan
+//              for pillars with more than kBig points); the point's running-mean terms (four IEEE divisions) go to
+//              its place in the ordered segment
+//   k_mean     sequential multiply-add chain of the running mean (one thread per pillar, one warp per long pillar);
+//              indices row and canvas cell map
+//   k_feat     per kept point: the nine decorated features, fp64 -> one rounding to fp32
+//   k_emit_*   dense [B,9,P,N] float with fused "- data_mean", or compact fp64 rows
 #include <type_traits>
 
 #include "internal.cuh"
